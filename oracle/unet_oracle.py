@@ -1,0 +1,363 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU fp32 restatement of the reference UNet training hot path.
+
+This is the *oracle*: a functional (dict-of-tensors) restatement, in plain PyTorch-CPU fp32
+ops, of what the reference computes on the path named by BASELINE.json's north_star:
+
+  * ``unet/unet_parts.py:7-24``   DoubleConv  -> :func:`double_conv`
+  * ``unet/unet_parts.py:26-37``  Down        -> :func:`down`
+  * ``unet/unet_parts.py:62-98``  Up          -> :func:`up`
+  * ``unet/unet_parts.py:100-106`` OutConv    -> :func:`out_conv`
+  * ``unet/unet_model.py:8-38``   UNet        -> :func:`unet_forward`, :func:`build_state`
+  * ``utils/dice_score.py:5-36``  dice        -> :func:`dice_coeff` / :func:`multiclass_dice_coeff` / :func:`dice_loss`
+  * ``utils/boundary_loss.py:5-118``          -> :func:`boundary_loss` (literal) and
+                                                 :func:`boundary_loss_counts` (closed form)
+  * ``train.py:116-147``          loss composition -> :func:`train_loss`
+
+The arithmetic of the reference lives in a third-party dependency (PyTorch ATen/oneDNN,
+pinned ``torch~=2.7.1+cu126`` in ``requirements.txt:7``; this image has torch 2.11.0+cu128),
+so the restatement calls the same ``torch.nn.functional`` primitives on CPU in fp32.
+
+PARITY PINNING: the reference ships no tests or golden vectors.  The oracle is
+pinned instead against outputs of the *reference itself*, imported from /root/reference in the
+build container by ``tests/golden/make_golden.py`` (committed, with the fixtures it produced under
+``tests/golden/``).  ``tests/test_oracle.py`` re-checks the oracle against those fixtures on
+every run, with no access to /root/reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+BN_EPS = 1e-5        # nn.BatchNorm2d default, unet_parts.py:16,19
+BN_MOMENTUM = 0.1    # nn.BatchNorm2d default
+
+
+# --------------------------------------------------------------------------------------
+# parameters: same tensors the reference constructor draws under the same torch seed
+# --------------------------------------------------------------------------------------
+def _dc_channels(n_channels: int, bilinear: bool):
+    """(prefix, c_in, c_mid, c_out) of the 9 DoubleConv blocks, in construction order
+    (unet_model.py:15-24; bilinear halves down4/up widths through ``factor``, and Up passes
+    mid = in // 2 when bilinear, unet_parts.py:71)."""
+    f = 2 if bilinear else 1
+    enc = [("inc.double_conv", n_channels, 64, 64),
+           ("down1.maxpool_conv.1.double_conv", 64, 128, 128),
+           ("down2.maxpool_conv.1.double_conv", 128, 256, 256),
+           ("down3.maxpool_conv.1.double_conv", 256, 512, 512),
+           ("down4.maxpool_conv.1.double_conv", 512, 1024 // f, 1024 // f)]
+    dec = []
+    for name, cin, cout in (("up1", 1024, 512 // f), ("up2", 512, 256 // f),
+                            ("up3", 256, 128 // f), ("up4", 128, 64)):
+        mid = cin // 2 if bilinear else cout
+        dec.append((name + ".conv.double_conv", cin, mid, cout))
+    return enc, dec
+
+
+def build_state(n_channels: int, n_classes: int, bilinear: bool = False, seed: int | None = 0):
+    """State dict with the reference's 118 (or 110, bilinear) keys and default PyTorch init.
+
+    Layers are instantiated in the reference's construction order so that, under the same
+    ``torch.manual_seed``, the random draws are identical to ``UNet(n_channels, n_classes,
+    bilinear)`` (unet_model.py:9-25).  Checked bit-for-bit by tests/golden/make_golden.py.
+    """
+    if seed is not None:
+        torch.manual_seed(seed)
+    st = OrderedDict()
+
+    def add_dc(prefix, cin, cmid, cout):
+        for idx, (a, b) in ((0, (cin, cmid)), (3, (cmid, cout))):
+            conv = nn.Conv2d(a, b, kernel_size=3, padding=1, bias=False)
+            st[f"{prefix}.{idx}.weight"] = conv.weight.detach().clone()
+            st[f"{prefix}.{idx + 1}.weight"] = torch.ones(b)
+            st[f"{prefix}.{idx + 1}.bias"] = torch.zeros(b)
+            st[f"{prefix}.{idx + 1}.running_mean"] = torch.zeros(b)
+            st[f"{prefix}.{idx + 1}.running_var"] = torch.ones(b)
+            st[f"{prefix}.{idx + 1}.num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    enc, dec = _dc_channels(n_channels, bilinear)
+    for e in enc:
+        add_dc(*e)
+    for prefix, cin, cmid, cout in dec:
+        upname = prefix.split(".")[0]
+        if not bilinear:   # unet_parts.py:73 -- ConvTranspose2d is built before the DoubleConv
+            t = nn.ConvTranspose2d(cin, cin // 2, kernel_size=2, stride=2)
+            st[f"{upname}.up.weight"] = t.weight.detach().clone()
+            st[f"{upname}.up.bias"] = t.bias.detach().clone()
+        add_dc(prefix, cin, cmid, cout)
+    oc = nn.Conv2d(64, n_classes, kernel_size=1)     # unet_parts.py:103
+    st["outc.conv.weight"] = oc.weight.detach().clone()
+    st["outc.conv.bias"] = oc.bias.detach().clone()
+    return st
+
+
+def param_names(state):
+    return [k for k in state if not (k.endswith("running_mean") or k.endswith("running_var")
+                                     or k.endswith("num_batches_tracked"))]
+
+
+# --------------------------------------------------------------------------------------
+# forward pieces
+# --------------------------------------------------------------------------------------
+def double_conv(st, prefix, x, training=True):
+    """(conv3x3 pad1 no-bias -> BatchNorm2d -> ReLU) x 2   (unet_parts.py:14-24)."""
+    for idx in (0, 3):
+        x = F.conv2d(x, st[f"{prefix}.{idx}.weight"], None, padding=1)
+        bn = f"{prefix}.{idx + 1}"
+        x = F.batch_norm(x, st[bn + ".running_mean"], st[bn + ".running_var"],
+                         st[bn + ".weight"], st[bn + ".bias"], training, BN_MOMENTUM, BN_EPS)
+        if training:
+            st[bn + ".num_batches_tracked"] += 1
+        x = F.relu(x)
+    return x
+
+
+def down(st, name, x, training=True):
+    """MaxPool2d(2) then DoubleConv  (unet_parts.py:31-37)."""
+    return double_conv(st, f"{name}.maxpool_conv.1.double_conv", F.max_pool2d(x, 2), training)
+
+
+def up(st, name, x1, x2, bilinear, training=True):
+    """Upsample x1, pad to x2, cat([x2, x1]) (skip first), DoubleConv  (unet_parts.py:80-98)."""
+    if bilinear:
+        x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+    else:
+        x1 = F.conv_transpose2d(x1, st[f"{name}.up.weight"], st[f"{name}.up.bias"], stride=2)
+    dy = x2.size(2) - x1.size(2)
+    dx = x2.size(3) - x1.size(3)
+    x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    return double_conv(st, f"{name}.conv.double_conv", torch.cat([x2, x1], dim=1), training)
+
+
+def out_conv(st, x):
+    """1x1 conv with bias  (unet_parts.py:103-106)."""
+    return F.conv2d(x, st["outc.conv.weight"], st["outc.conv.bias"])
+
+
+def unet_forward(st, x, bilinear=False, training=True):
+    """UNet.forward wiring  (unet_model.py:27-38)."""
+    x1 = double_conv(st, "inc.double_conv", x, training)
+    x2 = down(st, "down1", x1, training)
+    x3 = down(st, "down2", x2, training)
+    x4 = down(st, "down3", x3, training)
+    x5 = down(st, "down4", x4, training)
+    y = up(st, "up1", x5, x4, bilinear, training)
+    y = up(st, "up2", y, x3, bilinear, training)
+    y = up(st, "up3", y, x2, bilinear, training)
+    y = up(st, "up4", y, x1, bilinear, training)
+    return out_conv(st, y)
+
+
+# --------------------------------------------------------------------------------------
+# dice  (utils/dice_score.py)
+# --------------------------------------------------------------------------------------
+def dice_coeff(inp, tgt, reduce_batch_first=False, epsilon=1e-6):
+    """dice_score.py:5-25."""
+    assert inp.size() == tgt.size()
+    assert inp.dim() == 3 or not reduce_batch_first
+    dims = (-1, -2) if inp.dim() == 2 or not reduce_batch_first else (-1, -2, -3)
+    inter = 2 * (inp * tgt).sum(dim=dims)
+    sets = inp.sum(dim=dims) + tgt.sum(dim=dims)
+    sets = torch.where(sets == 0, inter, sets)
+    return ((inter + epsilon) / (sets + epsilon)).mean()
+
+
+def multiclass_dice_coeff(inp, tgt, reduce_batch_first=False, epsilon=1e-6):
+    """dice_score.py:28-30 -- flatten(0,1) then the 3-D path."""
+    return dice_coeff(inp.flatten(0, 1), tgt.flatten(0, 1), reduce_batch_first, epsilon)
+
+
+def dice_loss(inp, tgt, multiclass=False):
+    """dice_score.py:33-36."""
+    fn = multiclass_dice_coeff if multiclass else dice_coeff
+    return 1 - fn(inp, tgt, reduce_batch_first=True)
+
+
+# --------------------------------------------------------------------------------------
+# boundary loss  (utils/boundary_loss.py) -- literal restatement
+# --------------------------------------------------------------------------------------
+def _edge_mask(b, h, w, edge_width):
+    """boundary_loss.py:48-59."""
+    m = torch.zeros((b, h, w), dtype=torch.bool)
+    if edge_width == 0:
+        return m
+    m[:, :edge_width, :] = True
+    m[:, -edge_width:, :] = True
+    m[:, :, :edge_width] = True
+    m[:, :, -edge_width:] = True
+    return m
+
+
+def _boundary_of(mask):
+    """boundary_loss.py:98-112: binarise > 0.5, 3x3 ones conv, dilated != eroded."""
+    binary = (mask > 0.5).float()
+    k = torch.ones((1, 1, 3, 3))
+    s = F.conv2d(binary, k, padding=1)
+    return ((s > 0) != (s == 9)).float()
+
+
+def _region_loss(pred, target, region, smooth):
+    """boundary_loss.py:62-95."""
+    if not region.any():
+        return torch.tensor(0.0)
+    pr = pred[region]
+    tr = target[region].float()
+    b = pred.size(0)
+    n = pr.numel() // b
+    pb = _boundary_of(pr.view(b, 1, n, 1)).view(-1)
+    tb = _boundary_of(tr.view(b, 1, n, 1)).view(-1)
+    inter = (pb * tb).sum()
+    union = pb.sum() + tb.sum() - inter
+    iou = (inter + smooth) / (union + smooth)
+    p = pb.clamp(1e-6, 1 - 1e-6).clamp(1e-12, 1 - 1e-12)       # :90 and :117
+    logits = torch.log(p / (1 - p))
+    bce = F.binary_cross_entropy_with_logits(logits, tb, reduction="sum") / pb.size(0)
+    return (1 - iou) + 0.5 * bce
+
+
+def boundary_loss(pred_mask, target_mask, edge_width=64, edge_weight=5.0, smooth=1e-6):
+    """boundary_loss.py:5-45."""
+    if pred_mask.dim() == 4:
+        pred_mask = pred_mask[:, 1, :, :] if pred_mask.size(1) > 1 else pred_mask.squeeze(1)
+    if pred_mask.min() < -10 or pred_mask.max() > 10:
+        pred_mask = torch.sigmoid(pred_mask)
+    b, h, w = pred_mask.shape
+    edge = _edge_mask(b, h, w, edge_width)
+    tgt = (target_mask == 255).float()
+    normal = _region_loss(pred_mask, tgt, ~edge, smooth)
+    edge_l = _region_loss(pred_mask, tgt, edge, smooth)
+    return (normal + edge_weight * edge_l) / (1 + edge_weight)
+
+
+# fp32 constants of the BCE-with-logits term for the four (pred_boundary, target_boundary)
+# combinations, evaluated exactly as boundary_loss.py:90-93 does in float32.
+def _bce_constants():
+    pb = torch.tensor([0.0, 0.0, 1.0, 1.0])
+    tb = torch.tensor([0.0, 1.0, 0.0, 1.0])
+    p = pb.clamp(1e-6, 1 - 1e-6).clamp(1e-12, 1 - 1e-12)
+    lg = torch.log(p / (1 - p))
+    v = F.binary_cross_entropy_with_logits(lg, tb, reduction="none")
+    return [float(x) for x in v]          # order: (0,0) (0,1) (1,0) (1,1)
+
+
+def region_loss_from_counts(n, p, t, i, smooth=1e-6):
+    """Closed form of boundary_loss.py:62-95 given integer counts of one region:
+    n pixels, p = sum(pred_boundary), t = sum(target_boundary), i = sum(both)."""
+    if n == 0:
+        return 0.0
+    c00, c01, c10, c11 = _bce_constants()
+    iou = (i + smooth) / (p + t - i + smooth)
+    bce = (c11 * i + c10 * (p - i) + c01 * (t - i) + c00 * (n - p - t + i)) / n
+    return (1.0 - iou) + 0.5 * bce
+
+
+def boundary_counts(pred, target, edge_width):
+    """Integer counts (N, P, T, I) for the inner and edge regions, numpy, following
+    boundary_loss.py:28-29 (data-dependent sigmoid), :37 (target == 255), :48-59 (frame),
+    :68-74 (row-major compaction per image) and :98-112 (3-tap OR over the compacted run)."""
+    if pred.dim() == 4:
+        pred = pred[:, 1] if pred.size(1) > 1 else pred.squeeze(1)
+    if pred.min() < -10 or pred.max() > 10:
+        pred = torch.sigmoid(pred)
+    b, h, w = pred.shape
+    edge = _edge_mask(b, h, w, edge_width).numpy()
+    pbin = (pred > 0.5).numpy()
+    tbin = ((target == 255).float() > 0.5).numpy()
+    out = {}
+    for name, reg in (("inner", ~edge), ("edge", edge)):
+        n = int(reg.sum())
+        if n == 0:
+            out[name] = (0, 0, 0, 0)
+            continue
+        per = n // b
+
+        def dil(bits):
+            seq = bits[reg].reshape(b, per)
+            pad = np.zeros((b, per + 2), dtype=bool)
+            pad[:, 1:-1] = seq
+            return pad[:, :-2] | pad[:, 1:-1] | pad[:, 2:]
+        pb, tb = dil(pbin), dil(tbin)
+        out[name] = (n, int(pb.sum()), int(tb.sum()), int((pb & tb).sum()))
+    return out
+
+
+def boundary_loss_counts(pred, target, edge_width=64, edge_weight=5.0, smooth=1e-6):
+    """boundary_loss evaluated through the integer-count closed form (float64)."""
+    c = boundary_counts(pred, target, edge_width)
+    normal = region_loss_from_counts(*c["inner"], smooth=smooth)
+    edge = region_loss_from_counts(*c["edge"], smooth=smooth)
+    return (normal + edge_weight * edge) / (1 + edge_weight)
+
+
+# --------------------------------------------------------------------------------------
+# loss composition of the training step  (train.py:116-147)
+# --------------------------------------------------------------------------------------
+def train_loss(logits, masks, n_classes, boundary_coeff=0.0, edge_width=51, edge_weight=7):
+    """n_classes > 1: CrossEntropy + multiclass dice on softmax / one-hot (train.py:136-142),
+    plus ``boundary_coeff * boundary_loss(logits, masks.float(), 51, 7)`` (the train.py:143-147 form).
+    n_classes == 1: BCEWithLogits + dice(sigmoid) + 0.25 * boundary (train.py:118-134; the
+    ``true_masks //= 2`` remap is the caller's job)."""
+    if n_classes == 1:
+        lg = logits.squeeze(1)
+        t = masks.float()
+        loss = F.binary_cross_entropy_with_logits(lg, t)
+        loss = loss + dice_loss(torch.sigmoid(lg), t, multiclass=False)
+        return loss + 0.25 * boundary_loss(lg, t, edge_width=51, edge_weight=15)
+    loss = F.cross_entropy(logits, masks)
+    loss = loss + dice_loss(F.softmax(logits, dim=1).float(),
+                            F.one_hot(masks, n_classes).permute(0, 3, 1, 2).float(),
+                            multiclass=True)
+    if boundary_coeff:
+        loss = loss + boundary_coeff * boundary_loss(logits, masks.float(),
+                                                     edge_width=edge_width, edge_weight=edge_weight)
+    return loss
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs and a full step
+# --------------------------------------------------------------------------------------
+def synthetic_batch(batch, n_channels, n_classes, h, w, rank=0):
+    """Images uniform [0,1) with generator seed 1+rank (cf. /255 in data_loading.py:86-87),
+    class-index masks with generator seed 2+rank."""
+    gi = torch.Generator().manual_seed(1 + 1000 * rank)
+    gm = torch.Generator().manual_seed(2 + 1000 * rank)
+    img = torch.rand(batch, n_channels, h, w, generator=gi)
+    msk = torch.randint(0, max(n_classes, 2), (batch, h, w), generator=gm, dtype=torch.long)
+    return img, msk
+
+
+def training_step(st, images, masks, n_classes, bilinear=False, boundary_coeff=0.0):
+    """Forward + loss + backward on CPU fp32.  Returns (logits, loss, {name: grad})."""
+    names = param_names(st)
+    leaves = {k: st[k].detach().clone().requires_grad_(True) for k in names}
+    work = OrderedDict((k, leaves[k] if k in leaves else v.clone()) for k, v in st.items())
+    logits = unet_forward(work, images, bilinear, training=True)
+    loss = train_loss(logits, masks, n_classes, boundary_coeff)
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names])
+    for k in st:                       # running stats were updated in the working copy
+        if k not in leaves:
+            st[k] = work[k]
+    return logits.detach(), loss.detach(), dict(zip(names, grads))
+
+
+def rel_err(a, b):
+    """The tolerance metric of north_star: max-abs error relative to max-abs of the oracle."""
+    a = a.detach().float().cpu().reshape(-1)
+    b = b.detach().float().cpu().reshape(-1)
+    d = (a - b).abs().max().item()
+    s = b.abs().max().item()
+    return d / s if s > 0 else d
+
+
+def rel_l2(a, b):
+    a = a.detach().double().cpu().reshape(-1)
+    b = b.detach().double().cpu().reshape(-1)
+    n = b.norm().item()
+    return (a - b).norm().item() / n if n > 0 else (a - b).norm().item()
