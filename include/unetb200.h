@@ -1,0 +1,237 @@
+/*
+ * unetb200.h -- C ABI of the B200-native UNet training hot path (libunetb200.so, sm_100a).
+ *
+ * The reference (Florescence/UNet-Medical-Image-Contour-Segmentation) has no native layer: its hot
+ * path is the set of PyTorch library calls made by unet/unet_parts.py, unet/unet_model.py,
+ * utils/dice_score.py and utils/boundary_loss.py.  Each entry point below replaces one of those
+ * library calls (cited as reference file:line) on raw device pointers.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; nothing is allocated or freed by
+ *     the library (the caller owns inputs, outputs, saved tensors and workspaces);
+ *   - activations are NHWC with an explicit pixel stride `ld` (in elements, >= C): element
+ *     (n,h,w,c) lives at base[((n*H + h)*W + w)*ld + c].  ld > C addresses a channel slice of a
+ *     wider buffer (this is how the skip concat of unet_parts.py:95 is fused away);
+ *   - `dtype` is UNETB200_F32 or UNETB200_BF16 (storage type of activations / packed weights);
+ *     all accumulation is fp32, cross-tile statistics are fp64;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it and never
+ *     synchronises the device;
+ *   - return value: 0 on success, negative on error (UNETB200_E_*); unetb200_last_error() returns
+ *     a thread-local message.  Entry points are re-entrant (forward is called from the Python main
+ *     thread, backward from the autograd engine's device thread).
+ */
+#ifndef UNETB200_H_
+#define UNETB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNETB200_F32 0
+#define UNETB200_BF16 1
+
+#define UNETB200_OK 0
+#define UNETB200_E_INVALID (-1)   /* bad argument / unsupported shape (Python raises ValueError) */
+#define UNETB200_E_CUDA (-2)      /* CUDA runtime / driver error (Python raises RuntimeError)     */
+#define UNETB200_E_NOMEM (-3)     /* workspace too small                                           */
+
+#define UNETB200_ALGO_AUTO 0
+#define UNETB200_ALGO_SIMT 1      /* CUDA-core implicit GEMM, fp32 FMA (any shape; exactness mode)  */
+#define UNETB200_ALGO_TC 2        /* tcgen05 / TMEM / TMA implicit GEMM (bf16, or fp32 read as tf32) */
+#define UNETB200_ALGO_PREFER_TC 3 /* TC when the shape fits (also for fp32 -> tf32), SIMT otherwise     */
+
+int unetb200_version(void);
+const char* unetb200_last_error(void);
+/* host pointers out */
+int unetb200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generalised convolution as an implicit GEMM   D[m][n] = sum_{t,c} A[m][(t,c)] * Wp[n][(t,c)]
+ *
+ *   m  runs over the "M grid" (b, i, j), b < B, i < Hm, j < Wm;
+ *   A[m][(t,c)] = x[b, i*in_scale + tap_dy[t] + in_off_y, j*in_scale + tap_dx[t] + in_off_x, c]
+ *                 (zero outside [0,Hin) x [0,Win): this is the conv padding);
+ *   n = q*Cq + co with q < nquad (1 or 4), Cq = N / nquad; D[m][n] is stored at
+ *   y[b, i*out_scale + (q>>1) + out_off_y, j*out_scale + (q&1) + out_off_x, co]  (+ bias[co]).
+ *
+ * It covers, with different packed weights:
+ *   nn.Conv2d 3x3 pad 1 fprop  (unet_parts.py:15,18)      9 taps (kh-1,kw-1), scales 1
+ *   its dgrad (autograd of the same)                      9 taps, rot180 / transposed weights
+ *   nn.ConvTranspose2d k2 s2 fprop (unet_parts.py:73)     1 tap, nquad 4, out_scale 2, bias
+ *   its dgrad                                             4 taps (a,c), in_scale 2
+ *   nn.Conv2d 1x1 (unet_parts.py:103)                     1 tap
+ * ------------------------------------------------------------------------------------------- */
+typedef struct unetb200_gconv {
+  int32_t dtype;              /* storage dtype of x, Wp, y (and gy for wgrad)                       */
+  int32_t algo;               /* UNETB200_ALGO_*                                                     */
+  int32_t B, Hm, Wm;          /* M grid                                                              */
+  int32_t Cin;                /* channels per tap                                                    */
+  int32_t ntaps;              /* 1..9                                                                */
+  int32_t tap_dy[9], tap_dx[9];
+  int32_t in_scale;           /* 1 or 2                                                              */
+  int32_t in_off_y, in_off_x;
+  int32_t Hin, Win;           /* source grid                                                         */
+  int64_t ld_in;              /* source pixel stride, elements                                       */
+  int32_t N;                  /* GEMM N = nquad * Cq                                                 */
+  int32_t nquad;              /* 1 or 4                                                              */
+  int32_t out_scale;          /* 1 or 2                                                              */
+  int32_t out_off_y, out_off_x;
+  int32_t Hout, Wout;         /* destination grid                                                    */
+  int64_t ld_out;             /* destination pixel stride, elements                                  */
+} unetb200_gconv_t;           /* HOST struct */
+
+/* y = gconv(x, Wp) (+bias).  `stats` (nullable) = double[2*Cq], accumulated (+=) with the
+ * per-channel sum and sum of squares of the values as stored (i.e. after rounding to `dtype`):
+ * the BatchNorm batch statistics of unet_parts.py:16,19 fused into the conv epilogue.
+ * Returns the algorithm actually used through *algo_used (host, nullable). */
+int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp,
+                         const float* bias, void* y, double* stats, int* algo_used, void* stream);
+
+/* Weight gradient of the same generalised conv:
+ *   dWp[(t,c)][n] = sum_m A[m][(t,c)] * G[m][n],  G[m][n] = gy at the destination of (m,n).
+ * The reduction over m is split `splits` ways; partial s is written (not accumulated) to
+ * partials + s*K*N floats, K = ntaps*Cin.  unetb200_gconv_wgrad_plan returns the split count the
+ * chosen algorithm wants (host out-params) so the caller can size `partials`. */
+int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_used);
+int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials,
+                         int splits, void* stream);
+/* dst[t*st + c*sc + q*sq + co*sn] (=|+=) sum_s partials[s][(t,c)][n], n = q*Cq + co: reduces the
+ * splits and scatters into the parameter's own layout (OIHW for Conv2d, IOHW for ConvTranspose2d),
+ * deterministic. */
+int unetb200_wgrad_reduce(const float* partials, int splits, int ntaps, int Cin, int N, int Cq,
+                          float* dst, int64_t st, int64_t sc, int64_t sq, int64_t sn, int accumulate,
+                          void* stream);
+
+/* dst[i0][i1][i2] = cast(src[off + i0*s0 + i1*s1 + i2*s2]) (strides may be negative): packs an fp32
+ * parameter (OIHW / IOHW) into the K-major [N][(t,c)] operand layout of gconv, any tap order. */
+int unetb200_pack_weights(const float* src, void* dst, int dst_dtype, int64_t n0, int64_t n1,
+                          int64_t n2, int64_t s0, int64_t s1, int64_t s2, int64_t off, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm2d + ReLU (+ MaxPool2d) -- unet_parts.py:16-17,19-20,32.  Memory-bound, vectorised.
+ * ------------------------------------------------------------------------------------------- */
+/* stats = double[2*C] (sum, sumsq) over `count` values per channel.  Writes save_mean,
+ * save_invstd (biased variance, eps inside the sqrt), scale = gamma*invstd, shift = beta -
+ * mean*scale, and (if non-null) running_mean/var with `momentum` and the unbiased variance. */
+int unetb200_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta,
+                         float eps, float momentum, float* running_mean, float* running_var,
+                         float* save_mean, float* save_invstd, float* scale, float* shift, int C,
+                         void* stream);
+/* eval mode: scale/shift from the running statistics */
+int unetb200_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* scale, float* shift,
+                            float* save_mean, float* save_invstd, int C, void* stream);
+/* z = relu(y*scale + shift); if pooled != NULL also pooled = maxpool2x2(z) (floor mode). */
+int unetb200_bn_relu_apply(const void* y, int64_t ld_y, const float* scale, const float* shift,
+                           void* z, int64_t ld_z, void* pooled, int64_t ld_p, int dtype, int B,
+                           int H, int W, int C, void* stream);
+int unetb200_maxpool2_fwd(const void* x, int64_t ld_x, void* p, int64_t ld_p, int dtype, int B,
+                          int H, int W, int C, void* stream);
+/* gx (=|+=) scatter of gp to the FIRST maximum of each 2x2 window in row-major order (ATen's tie
+ * rule); positions outside any window (odd H/W) get 0. */
+int unetb200_maxpool2_bwd(const void* x, int64_t ld_x, const void* gp, int64_t ld_gp, void* gx,
+                          int64_t ld_gx, int accumulate, int dtype, int B, int H, int W, int C,
+                          void* stream);
+/* g = gz * (y*scale+shift > 0);  sums[0][c] += sum g,  sums[1][c] += sum g*xhat,
+ * xhat = (y-mean)*invstd.  `sums` must be zeroed by the caller. */
+int unetb200_bn_relu_bwd_reduce(const void* gz, int64_t ld_gz, const void* y, int64_t ld_y,
+                                const float* scale, const float* shift, const float* mean,
+                                const float* invstd, double* sums, int dtype, int B, int H, int W,
+                                int C, void* stream);
+/* dgamma = sums[1], dbeta = sums[0]; coef[0][c] = mean(g), coef[1][c] = mean(g*xhat)
+ * (both 0 when `training` == 0: eval-mode BN has no batch-statistics term). */
+int unetb200_bn_bwd_finalize(const double* sums, int64_t count, int training, float* dgamma,
+                             float* dbeta, float* coef, int C, void* stream);
+/* gy = scale * (g - coef0 - xhat*coef1) */
+int unetb200_bn_relu_bwd_apply(const void* gz, int64_t ld_gz, const void* y, int64_t ld_y,
+                               const float* scale, const float* shift, const float* mean,
+                               const float* invstd, const float* coef, void* gy, int64_t ld_gy,
+                               int dtype, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) -- unet_parts.py:70, and the
+ * F.pad placement of unet_parts.py:85-88 (output written at (off_y, off_x) of an Hout x Wout grid).
+ * ------------------------------------------------------------------------------------------- */
+int unetb200_upsample2x_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, int dtype, int B,
+                            int h, int w, int C, int Hout, int Wout, int off_y, int off_x,
+                            void* stream);
+int unetb200_upsample2x_bwd(const void* gy, int64_t ld_gy, void* gx, int64_t ld_gx, int dtype,
+                            int B, int h, int w, int C, int Hout, int Wout, int off_y, int off_x,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * layout / dtype plumbing
+ * ------------------------------------------------------------------------------------------- */
+/* dst NHWC(ld_dst) <- src with arbitrary element strides (sn, sc, sh, sw), with dtype cast */
+int unetb200_gather_nhwc(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh,
+                         int64_t sw, void* dst, int dst_dtype, int64_t ld_dst, int B, int C, int H,
+                         int W, void* stream);
+/* dst[p*ld_dst + c] = cast(src[p*ld_src + c]) for p < npix, c < C (channel-slice copy) */
+int unetb200_copy_channels(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype,
+                           int64_t ld_dst, int64_t npix, int C, void* stream);
+/* zero a channel slice */
+int unetb200_zero_channels(void* dst, int dtype, int64_t ld_dst, int64_t npix, int C, void* stream);
+/* out[c] = sum_p g[p*ld + c]   (bias gradient of ConvTranspose2d); acc = double[C] workspace */
+int unetb200_channel_sum(const void* g, int dtype, int64_t ld, int64_t npix, int C, double* acc,
+                         float* out, void* stream);
+/* a += b on NHWC channel slices (skip-gradient accumulation) */
+int unetb200_add_channels(void* a, int64_t ld_a, const void* b, int64_t ld_b, int dtype,
+                          int64_t npix, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * OutConv: 1x1 conv with bias to n_classes <= 8 channels -- unet_parts.py:103.  Memory-bound.
+ * logits are NHWC [npix][ncls] of `dtype`; w, bias, dw, dbias are fp32 in the parameter layout.
+ * ------------------------------------------------------------------------------------------- */
+int unetb200_outconv_fwd(const void* x, int64_t ld_x, const float* w, const float* bias,
+                         void* logits, int dtype, int64_t npix, int C, int ncls, void* stream);
+/* gx = glogits . w ; dw, dbias (overwritten).  workspace: float[outconv_bwd_workspace] */
+int64_t unetb200_outconv_bwd_workspace(int64_t npix, int C, int ncls);
+int unetb200_outconv_bwd(const void* x, int64_t ld_x, const float* w, const void* glogits,
+                         void* gx, int64_t ld_gx, float* dw, float* dbias, float* workspace,
+                         int dtype, int64_t npix, int C, int ncls, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * losses
+ * ------------------------------------------------------------------------------------------- */
+/* Fused criterion of train.py:137-142: CrossEntropyLoss(logits, target) +
+ * dice_loss(softmax(logits), one_hot(target), multiclass=True) (dice_score.py:5-36: one global
+ * ratio).  logits NHWC [npix][C] (`dtype`), target int64[npix].
+ *   acc   : double[4] workspace (zeroed by the callee)
+ *   out   : float[4] = {ce + dice_loss, ce, dice_loss, dice_coeff}
+ *   coefs : float[4] saved for backward                                                        */
+int unetb200_ce_dice_fwd(const void* logits, int dtype, const int64_t* target, int64_t npix, int C,
+                         float epsilon, double* acc, float* out, float* coefs, void* stream);
+/* glogits = gscale[0] * d(ce + dice_loss)/dlogits  (gscale: device float, upstream gradient) */
+int unetb200_ce_dice_bwd(const void* logits, int dtype, const int64_t* target, int64_t npix, int C,
+                         const float* coefs, const float* gscale, void* glogits, void* stream);
+
+/* dice_coeff (dice_score.py:5-25) on fp32 contiguous input/target viewed as [G][L]: per group
+ * inter = 2*sum(x*t), sets = sum x + sum t, sets==0 -> inter, dice = (inter+eps)/(sets+eps);
+ * out[0] = mean over groups.  acc: double[3*G] workspace.  saved: float[2*G] for backward. */
+int unetb200_dice_fwd(const float* x, const float* t, int64_t G, int64_t L, float epsilon,
+                      double* acc, float* out, float* saved, void* stream);
+/* gx = gscale[0] * d(mean dice)/dx */
+int unetb200_dice_bwd(const float* x, const float* t, int64_t G, int64_t L, float epsilon,
+                      const float* saved, const float* gscale, float* gx, void* stream);
+
+/* boundary_loss (boundary_loss.py:5-118) as one integer-count pass + a scalar finalize; no host
+ * synchronisation (the reference's .min()/.max()/.any() syncs disappear).  pred is addressed as
+ * pred[b*sb + h*sh + w*sw] (elements of pred_dtype; the caller has already selected channel 1 /
+ * squeezed, boundary_loss.py:20-25); target likewise (tgt_dtype: UNETB200_F32, or 2 = int64).
+ *   work : int64[16] + float[2] workspace (zeroed by the callee), see boundary.cu
+ *   out  : float[1] loss                                                                         */
+#define UNETB200_I64 2
+int unetb200_boundary_loss(const void* pred, int pred_dtype, int64_t sb, int64_t sh, int64_t sw,
+                           const void* target, int tgt_dtype, int64_t tb, int64_t th, int64_t tw,
+                           int B, int H, int W, int edge_width, float edge_weight, float smooth,
+                           void* work, float* out, void* stream);
+int64_t unetb200_boundary_work_bytes(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETB200_H_ */

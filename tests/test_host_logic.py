@@ -1,0 +1,83 @@
+"""CPU: host-side logic -- NHWC stride detection, channel-slice aliasing, weight packing index maps,
+precision policy."""
+import torch
+
+from unetb200 import functional as UF
+from unetb200 import ops
+
+
+def test_nhwc_ld():
+    t = torch.empty(2, 5, 6, 8).permute(0, 3, 1, 2)          # logical [2,8,5,6], NHWC
+    assert ops.nhwc_ld(t) == 8
+    assert ops.nhwc_ld(t[:, :3]) == 8                         # channel slice keeps the pixel stride
+    assert ops.nhwc_ld(torch.empty(2, 8, 5, 6)) is None       # NCHW contiguous
+    assert ops.nhwc_ld(torch.empty(2, 1, 5, 6)) == 1          # C == 1: both layouts coincide
+    assert ops.nhwc_ld(torch.empty(2, 8, 5, 6).contiguous(memory_format=torch.channels_last)) == 8
+    s = ops.channel_slice(t, 2, 4)
+    assert s.shape == (2, 4, 5, 6) and s.data_ptr() == t.data_ptr() + 2 * 4 and ops.nhwc_ld(s) == 8
+    assert s._base is None                                    # alias without an autograd view relation
+    t.zero_()
+    s.fill_(1.0)
+    assert t[:, 2:6].eq(1).all() and t[:, :2].eq(0).all() and t[:, 6:].eq(0).all()
+
+
+def _emulate_pack(w, n0, n1, n2, s0, s1, s2, off):
+    # dst[i0][i1][i2] = storage[off + i0*s0 + i1*s1 + i2*s2]   (what unetb200_pack_weights does)
+    flat = torch.as_strided(w, (w.untyped_storage().nbytes() // w.element_size(),), (1,), 0)
+    i0 = torch.arange(n0).view(n0, 1, 1)
+    i1 = torch.arange(n1).view(1, n1, 1)
+    i2 = torch.arange(n2).view(1, 1, n2)
+    return flat[w.storage_offset() + off + i0 * s0 + i1 * s1 + i2 * s2]
+
+
+def _capture_pack(fn, w, monkeypatch):
+    got = {}
+
+    def fake(wt, dtype, n0, n1, n2, s0, s1, s2, off=0):
+        got["v"] = _emulate_pack(wt, n0, n1, n2, s0, s1, s2, off)
+        return got["v"].reshape(n0, n1 * n2)
+    monkeypatch.setattr(UF, "_pack", fake)
+    fn(w, torch.float32)
+    return got["v"]
+
+
+def test_pack_index_maps(monkeypatch):
+    g = torch.Generator().manual_seed(0)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        w = torch.randn(6, 4, 3, 3, generator=g).contiguous(memory_format=fmt)       # OIHW
+        p = _capture_pack(UF.pack3x3_fprop, w, monkeypatch)                           # [co][t][ci]
+        assert torch.equal(p, w.permute(0, 2, 3, 1).reshape(6, 9, 4))
+        p = _capture_pack(UF.pack3x3_dgrad, w, monkeypatch)                           # [ci][t'][co], flipped taps
+        assert torch.equal(p, w.flip(2, 3).permute(1, 2, 3, 0).reshape(4, 9, 6))
+        wt = torch.randn(8, 5, 2, 2, generator=g).contiguous(memory_format=fmt)      # IOHW
+        p = _capture_pack(UF.packT_fprop, wt, monkeypatch)                            # [q][co][ci]
+        assert torch.equal(p, wt.permute(2, 3, 1, 0).reshape(4, 5, 8))
+        p = _capture_pack(UF.packT_dgrad, wt, monkeypatch)                            # [ci][q][co]
+        assert torch.equal(p, wt.permute(0, 2, 3, 1).reshape(8, 4, 5))
+
+
+def test_dgrad_packing_is_the_conv_transpose():
+    """conv3x3(dy, flipped/transposed W) == autograd dgrad of conv3x3(x, W): validates the tap algebra
+    the CUDA dgrad relies on."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, 7, 6, generator=g, requires_grad=True)
+    w = torch.randn(5, 4, 3, 3, generator=g)
+    dy = torch.randn(2, 5, 7, 6, generator=g)
+    F.conv2d(x, w, padding=1).backward(dy)
+    wd = w.flip(2, 3).permute(1, 0, 2, 3)                     # [ci][co][kh'][kw']
+    assert torch.allclose(F.conv2d(dy, wd, padding=1), x.grad, atol=1e-4)
+
+
+def test_precision_policy(monkeypatch):
+    from unetb200._lib import ALGO_AUTO, ALGO_PREFER_TC, ALGO_SIMT
+    assert UF.conv_algo(torch.bfloat16) == ALGO_AUTO
+    monkeypatch.setenv("UNET_B200_PRECISION", "fp32")
+    assert UF.conv_algo(torch.float32) == ALGO_SIMT
+    monkeypatch.setenv("UNET_B200_PRECISION", "tf32")
+    assert UF.conv_algo(torch.float32) == ALGO_PREFER_TC
+    x = torch.zeros(1)
+    assert UF.compute_dtype(x) == torch.float32
+    assert UF.compute_dtype(x.bfloat16()) == torch.bfloat16
+    with torch.autocast("cuda", enabled=True):
+        assert UF.compute_dtype(x) == torch.bfloat16

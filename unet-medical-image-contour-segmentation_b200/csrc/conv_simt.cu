@@ -1,0 +1,475 @@
+// CUDA-core (fp32 FMA) implicit-GEMM engine for the generalised convolution of unetb200.h.
+// It handles every shape (C_in = 1 or 3 first layer, widths that do not fill a UMMA tile, unaligned
+// channel slices) and is the arithmetic of the fp32 "exactness" mode.  Large bf16 layers are
+// dispatched to the tcgen05 engine in conv_tc.cu instead.
+#include "gconv.cuh"
+
+namespace ub {
+
+constexpr int FBM = 128, FBN = 64, FBK = 16;   // fprop tile
+constexpr int WBK = 64, WBN = 64, WBM = 16;    // wgrad tile (K rows x N cols, M step)
+
+int gconv_validate(const unetb200_gconv_t* d, GconvDev* o) {
+  UB_CHECK_ARG(d != nullptr, "gconv: null descriptor");
+  UB_CHECK_ARG(d->dtype == UNETB200_F32 || d->dtype == UNETB200_BF16, "gconv: dtype %d", d->dtype);
+  UB_CHECK_ARG(d->B > 0 && d->Hm > 0 && d->Wm > 0 && d->Cin > 0, "gconv: bad M grid / Cin");
+  UB_CHECK_ARG(d->ntaps >= 1 && d->ntaps <= 9, "gconv: ntaps %d", d->ntaps);
+  UB_CHECK_ARG(d->in_scale == 1 || d->in_scale == 2, "gconv: in_scale %d", d->in_scale);
+  UB_CHECK_ARG(d->out_scale == 1 || d->out_scale == 2, "gconv: out_scale %d", d->out_scale);
+  UB_CHECK_ARG(d->nquad == 1 || d->nquad == 4, "gconv: nquad %d", d->nquad);
+  UB_CHECK_ARG(d->N > 0 && d->N % d->nquad == 0, "gconv: N %d not divisible by nquad %d", d->N, d->nquad);
+  UB_CHECK_ARG(d->nquad == 1 || d->out_scale == 2, "gconv: nquad 4 needs out_scale 2");
+  UB_CHECK_ARG(d->Hin > 0 && d->Win > 0 && d->Hout > 0 && d->Wout > 0, "gconv: bad grids");
+  UB_CHECK_ARG(d->ld_in >= d->Cin && d->ld_out >= d->N / d->nquad, "gconv: pixel stride smaller than channels");
+  UB_CHECK_ARG(d->out_off_y >= 0 && d->out_off_x >= 0 &&
+                   (d->Hm - 1) * d->out_scale + (d->nquad == 4 ? 1 : 0) + d->out_off_y < d->Hout &&
+                   (d->Wm - 1) * d->out_scale + (d->nquad == 4 ? 1 : 0) + d->out_off_x < d->Wout,
+               "gconv: output does not fit the destination grid");
+  o->B = d->B; o->Hm = d->Hm; o->Wm = d->Wm; o->Cin = d->Cin; o->ntaps = d->ntaps;
+  for (int t = 0; t < 9; ++t) { o->tap_dy[t] = d->tap_dy[t]; o->tap_dx[t] = d->tap_dx[t]; }
+  o->in_scale = d->in_scale; o->in_off_y = d->in_off_y; o->in_off_x = d->in_off_x;
+  o->Hin = d->Hin; o->Win = d->Win; o->ld_in = d->ld_in;
+  o->N = d->N; o->nquad = d->nquad; o->Cq = d->N / d->nquad; o->out_scale = d->out_scale;
+  o->out_off_y = d->out_off_y; o->out_off_x = d->out_off_x; o->Hout = d->Hout; o->Wout = d->Wout;
+  o->ld_out = d->ld_out;
+  o->M = (long long)d->B * d->Hm * d->Wm;
+  o->K = d->ntaps * d->Cin;
+  return 0;
+}
+
+__device__ __forceinline__ void decode_m(const GconvDev& d, long long m, int& b, int& i, int& j) {
+  j = (int)(m % d.Wm);
+  long long r = m / d.Wm;
+  i = (int)(r % d.Hm);
+  b = (int)(r / d.Hm);
+}
+// source element offset of (b,i,j) under tap t, or -1 when it falls in the padding
+__device__ __forceinline__ long long src_offset(const GconvDev& d, int b, int i, int j, int t) {
+  int si = i * d.in_scale + d.tap_dy[t] + d.in_off_y;
+  int sj = j * d.in_scale + d.tap_dx[t] + d.in_off_x;
+  if (si < 0 || si >= d.Hin || sj < 0 || sj >= d.Win) return -1;
+  return (((long long)b * d.Hin + si) * d.Win + sj) * d.ld_in;
+}
+__device__ __forceinline__ long long dst_offset(const GconvDev& d, int b, int i, int j, int q) {
+  int oi = i * d.out_scale + (q >> 1) + d.out_off_y;
+  int oj = j * d.out_scale + (q & 1) + d.out_off_x;
+  return (((long long)b * d.Hout + oi) * d.Wout + oj) * d.ld_out;
+}
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float v[4]);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float v[4]) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float v[4]) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4(float* p, const float v[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
+  uint2 r;
+  r.x = pack_bf16x2(v[0], v[1]);
+  r.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// ------------------------------------------------------------------------------------------
+// fprop: D[128 x 64] tile per block, 256 threads, 8x4 micro-tile, K chunks of 16
+// ------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
+                        T* __restrict__ y, double* __restrict__ stats) {
+  __shared__ __align__(16) float As[FBK][FBM + 4];
+  __shared__ __align__(16) float Bs[FBK][FBN + 4];
+  __shared__ int pb[FBM], pi[FBM], pj[FBM];
+  __shared__ float sstat[2][FBN];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * FBM;
+  const int n0 = blockIdx.y * FBN;
+  for (int t = tid; t < FBM; t += 256) {
+    long long m = m0 + t;
+    int b = -1, i = 0, j = 0;
+    if (m < d.M) decode_m(d, m, b, i, j);
+    pb[t] = b; pi[t] = i; pj[t] = j;
+  }
+  if (tid < FBN) { sstat[0][tid] = 0.f; sstat[1][tid] = 0.f; }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  for (int k0 = 0; k0 < d.K; k0 += FBK) {
+    if (VEC) {
+      {  // A: thread -> pixel tid/2, 8 channels
+        const int ml = tid >> 1, kv = (tid & 1) * 8;
+        const int k = k0 + kv;
+        const int t = k / d.Cin, c = k - t * d.Cin;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (pb[ml] >= 0) {
+          long long off = src_offset(d, pb[ml], pi[ml], pj[ml], t);
+          if (off >= 0) load8(x + off + c, v);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) As[kv + e][ml] = v[e];
+      }
+      {  // B: thread -> row n tid/4, 4 consecutive k
+        const int nl = tid >> 2, k4 = (tid & 3) * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (n0 + nl < d.N) load4<T>(wp + (long long)(n0 + nl) * d.K + k0 + k4, v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) Bs[k4 + e][nl] = v[e];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int e = tid + r * 256;
+        const int kl = e & 15, ml = e >> 4;
+        const int k = k0 + kl;
+        float v = 0.f;
+        if (k < d.K && pb[ml] >= 0) {
+          const int t = k / d.Cin, c = k - t * d.Cin;
+          long long off = src_offset(d, pb[ml], pi[ml], pj[ml], t);
+          if (off >= 0) v = Elem<T>::ld(x + off + c);
+        }
+        As[kl][ml] = v;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int e = tid + r * 256;
+        const int kl = e & 15, nl = e >> 4;
+        const int k = k0 + kl;
+        float v = 0.f;
+        if (k < d.K && n0 + nl < d.N) v = Elem<T>::ld(wp + (long long)(n0 + nl) * d.K + k);
+        Bs[kl][nl] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < FBK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], b[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+
+  // epilogue
+  const int nb = n0 + tx * 4;
+  float bs[4] = {0.f, 0.f, 0.f, 0.f};
+  int qq[4], cc[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    int n = nb + c;
+    qq[c] = (n < d.N) ? n / d.Cq : 0;
+    cc[c] = (n < d.N) ? n - qq[c] * d.Cq : 0;
+    if (bias && n < d.N) bs[c] = Elem<T>::round(bias[cc[c]]);
+  }
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int ml = ty * 8 + r;
+    if (pb[ml] < 0) continue;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      v[c] = Elem<T>::round(acc[r][c] + bs[c]);
+      if (nb + c < d.N) { s1[c] += v[c]; s2[c] += v[c] * v[c]; }
+    }
+    if (VEC) {
+      if (nb < d.N) store4(y + dst_offset(d, pb[ml], pi[ml], pj[ml], qq[0]) + cc[0], v);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (nb + c < d.N) Elem<T>::st(y + dst_offset(d, pb[ml], pi[ml], pj[ml], qq[c]) + cc[c], v[c]);
+    }
+  }
+  if (stats) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      // the two ty rows of a warp first, then shared-memory atomics across the 8 warps
+      float a = s1[c] + __shfl_xor_sync(0xffffffffu, s1[c], 16);
+      float b = s2[c] + __shfl_xor_sync(0xffffffffu, s2[c], 16);
+      if ((tid & 16) == 0) { atomicAdd(&sstat[0][tx * 4 + c], a); atomicAdd(&sstat[1][tx * 4 + c], b); }
+    }
+    __syncthreads();
+    if (tid < FBN && n0 + tid < d.N) {
+      int co = (n0 + tid) % d.Cq;
+      atomicAdd(stats + co, (double)sstat[0][tid]);
+      atomicAdd(stats + d.Cq + co, (double)sstat[1][tid]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dWp[64 k x 64 n] tile per block, reduction over a slice of m, 4x4 micro-tile
+// ------------------------------------------------------------------------------------------
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+gconv_wgrad_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ partials,
+                        long long m_per_split) {
+  __shared__ __align__(16) float As[WBM][WBK + 4];
+  __shared__ __align__(16) float Gs[WBM][WBN + 4];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * WBK, n0 = blockIdx.y * WBN;
+  const long long mb = (long long)blockIdx.z * m_per_split;
+  long long me = mb + m_per_split;
+  if (me > d.M) me = d.M;
+  const int tk = tid >> 4, tn = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+  for (long long m0 = mb; m0 < me; m0 += WBM) {
+    if (VEC) {
+      const int ml = tid >> 4, q4 = (tid & 15) * 4;
+      const long long m = m0 + ml;
+      float va[4] = {0.f, 0.f, 0.f, 0.f}, vg[4] = {0.f, 0.f, 0.f, 0.f};
+      if (m < me) {
+        int b, i, j;
+        decode_m(d, m, b, i, j);
+        const int k = k0 + q4;
+        if (k < d.K) {
+          const int t = k / d.Cin, c = k - t * d.Cin;
+          long long off = src_offset(d, b, i, j, t);
+          if (off >= 0) load4<T>(x + off + c, va);
+        }
+        const int n = n0 + q4;
+        if (n < d.N) {
+          const int q = n / d.Cq, co = n - q * d.Cq;
+          load4<T>(gy + dst_offset(d, b, i, j, q) + co, vg);
+        }
+      }
+      *reinterpret_cast<float4*>(&As[ml][q4]) = make_float4(va[0], va[1], va[2], va[3]);
+      *reinterpret_cast<float4*>(&Gs[ml][q4]) = make_float4(vg[0], vg[1], vg[2], vg[3]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int e = tid + r * 256;
+        const int ml = e >> 6, kl = e & 63;
+        const long long m = m0 + ml;
+        float va = 0.f, vg = 0.f;
+        if (m < me) {
+          int b, i, j;
+          decode_m(d, m, b, i, j);
+          const int k = k0 + kl;
+          if (k < d.K) {
+            const int t = k / d.Cin, c = k - t * d.Cin;
+            long long off = src_offset(d, b, i, j, t);
+            if (off >= 0) va = Elem<T>::ld(x + off + c);
+          }
+          const int n = n0 + kl;
+          if (n < d.N) {
+            const int q = n / d.Cq, co = n - q * d.Cq;
+            vg = Elem<T>::ld(gy + dst_offset(d, b, i, j, q) + co);
+          }
+        }
+        As[ml][kl] = va;
+        Gs[ml][kl] = vg;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < WBM; ++mm) {
+      float4 a4 = *reinterpret_cast<const float4*>(&As[mm][tk * 4]);
+      float4 g4 = *reinterpret_cast<const float4*>(&Gs[mm][tn * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], g[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+  float* out = partials + (long long)blockIdx.z * d.K * d.N;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = k0 + tk * 4 + r;
+    if (k >= d.K) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + tn * 4 + c;
+      if (n < d.N) out[(long long)k * d.N + n] = acc[r][c];
+    }
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, int splits, int Cin, long long K, int N,
+                                    int Cq, float* __restrict__ dst, long long st, long long sc, long long sq,
+                                    long long sn, int accumulate) {
+  const long long total = K * N;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < splits; ++p) s += partials[(long long)p * total + idx];
+    const long long k = idx / N;
+    const int n = (int)(idx - k * N);
+    const long long t = k / Cin, c = k - t * Cin;
+    const int q = n / Cq, co = n - q * Cq;
+    float* o = dst + t * st + c * sc + q * sq + (long long)co * sn;
+    *o = accumulate ? *o + s : s;
+  }
+}
+
+template <typename D>
+__global__ void pack_weights_kernel(const float* __restrict__ src, D* __restrict__ dst, long long n0, long long n1,
+                                    long long n2, long long s0, long long s1, long long s2, long long off) {
+  const long long total = n0 * n1 * n2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long i2 = idx % n2;
+    long long r = idx / n2;
+    long long i1 = r % n1, i0 = r / n1;
+    Elem<D>::st(dst + idx, src[off + i0 * s0 + i1 * s1 + i2 * s2]);
+  }
+}
+
+static bool simt_vec_ok(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y) {
+  const size_t esz = d->dtype == UNETB200_BF16 ? 2 : 4;
+  const int Cq = d->N / d->nquad;
+  return d->Cin % 16 == 0 && Cq % 4 == 0 && d->ld_in % 8 == 0 && d->ld_out % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(x) % (8 * esz)) == 0 && (!wp || (reinterpret_cast<uintptr_t>(wp) % 16) == 0) &&
+         (reinterpret_cast<uintptr_t>(y) % (4 * esz)) == 0;
+}
+
+static int simt_wgrad_splits(const GconvDev& g) {
+  long long tiles = (long long)((g.K + WBK - 1) / WBK) * ((g.N + WBN - 1) / WBN);
+  long long want = ((long long)sm_count() * 6 + tiles - 1) / tiles;
+  long long max_by_m = (g.M + 255) / 256;
+  if (want > max_by_m) want = max_by_m;
+  if (want > 1024) want = 1024;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+}  // namespace ub
+
+using namespace ub;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
+                         double* stats, int* algo_used, void* stream) {
+  GconvDev g;
+  int rc = gconv_validate(d, &g);
+  if (rc) return rc;
+  UB_CHECK_ARG(x && wp && y, "gconv_fprop: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int algo = d->algo;
+  if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_fprop_supported(d, x, wp, y) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
+  if (algo_used) *algo_used = algo;
+  if (algo == UNETB200_ALGO_TC) {
+    UB_CHECK_ARG(tc_fprop_supported(d, x, wp, y), "gconv_fprop: tcgen05 path requested but shape/alignment unsupported");
+    return tc_fprop(d, g, x, wp, bias, y, stats, s);
+  }
+  UB_CHECK_ARG(algo == UNETB200_ALGO_SIMT, "gconv_fprop: unknown algo %d", algo);
+  dim3 grid((unsigned)((g.M + FBM - 1) / FBM), (unsigned)((g.N + FBN - 1) / FBN));
+  const bool vec = simt_vec_ok(d, x, wp, y) && (g.K % 4 == 0);
+  if (d->dtype == UNETB200_BF16) {
+    if (vec) gconv_fprop_simt_kernel<bf16, true><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats);
+    else gconv_fprop_simt_kernel<bf16, false><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats);
+  } else {
+    if (vec) gconv_fprop_simt_kernel<float, true><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats);
+    else gconv_fprop_simt_kernel<float, false><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats);
+  }
+  UB_LAUNCH_CHECK("gconv_fprop_simt");
+  return 0;
+}
+
+int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_used) {
+  GconvDev g;
+  int rc = gconv_validate(d, &g);
+  if (rc) return rc;
+  int algo = d->algo;
+  if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_wgrad_supported(d, nullptr, nullptr) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
+  if (algo == UNETB200_ALGO_TC)
+    UB_CHECK_ARG(tc_wgrad_supported(d, nullptr, nullptr), "gconv_wgrad: tcgen05 path requested but shape unsupported");
+  if (algo_used) *algo_used = algo;
+  if (splits) *splits = algo == UNETB200_ALGO_TC ? tc_wgrad_splits(d, g) : simt_wgrad_splits(g);
+  return 0;
+}
+
+int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits,
+                         void* stream) {
+  GconvDev g;
+  int rc = gconv_validate(d, &g);
+  if (rc) return rc;
+  UB_CHECK_ARG(x && gy && partials && splits >= 1, "gconv_wgrad: null pointer / bad splits");
+  cudaStream_t s = (cudaStream_t)stream;
+  int algo = d->algo;
+  if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_wgrad_supported(d, nullptr, nullptr) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
+  if (algo == UNETB200_ALGO_TC) {
+    UB_CHECK_ARG(tc_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path requested but shape/alignment unsupported");
+    return tc_wgrad(d, g, x, gy, partials, splits, s);
+  }
+  long long mper = (g.M + splits - 1) / splits;
+  mper = (mper + WBM - 1) / WBM * WBM;
+  dim3 grid((unsigned)((g.K + WBK - 1) / WBK), (unsigned)((g.N + WBN - 1) / WBN), (unsigned)splits);
+  const size_t esz = d->dtype == UNETB200_BF16 ? 2 : 4;
+  const bool vec = d->Cin % 4 == 0 && g.Cq % 4 == 0 && d->ld_in % 4 == 0 && d->ld_out % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 &&
+                   (reinterpret_cast<uintptr_t>(gy) % (4 * esz)) == 0;
+  if (d->dtype == UNETB200_BF16) {
+    if (vec) gconv_wgrad_simt_kernel<bf16, true><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)gy, partials, mper);
+    else gconv_wgrad_simt_kernel<bf16, false><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)gy, partials, mper);
+  } else {
+    if (vec) gconv_wgrad_simt_kernel<float, true><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)gy, partials, mper);
+    else gconv_wgrad_simt_kernel<float, false><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)gy, partials, mper);
+  }
+  UB_LAUNCH_CHECK("gconv_wgrad_simt");
+  return 0;
+}
+
+int unetb200_wgrad_reduce(const float* partials, int splits, int ntaps, int Cin, int N, int Cq, float* dst,
+                          int64_t st, int64_t sc, int64_t sq, int64_t sn, int accumulate, void* stream) {
+  UB_CHECK_ARG(partials && dst && splits >= 1 && ntaps >= 1 && Cin >= 1 && N >= 1 && Cq >= 1 && N % Cq == 0,
+               "wgrad_reduce: bad args");
+  long long K = (long long)ntaps * Cin;
+  long long total = K * N;
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(partials, splits, Cin, K, N, Cq, dst, st, sc,
+                                                                          sq, sn, accumulate);
+  UB_LAUNCH_CHECK("wgrad_reduce");
+  return 0;
+}
+
+int unetb200_pack_weights(const float* src, void* dst, int dst_dtype, int64_t n0, int64_t n1, int64_t n2,
+                          int64_t s0, int64_t s1, int64_t s2, int64_t off, void* stream) {
+  UB_CHECK_ARG(dst_dtype == UNETB200_F32 || dst_dtype == UNETB200_BF16, "pack_weights: dtype");
+  UB_CHECK_ARG(src && dst && n0 > 0 && n1 > 0 && n2 > 0, "pack_weights: bad args");
+  long long total = n0 * n1 * n2;
+  long long blocks = (total + 255) / 256;
+  long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dst_dtype == UNETB200_BF16)
+    pack_weights_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>(src, (bf16*)dst, n0, n1, n2, s0, s1, s2, off);
+  else
+    pack_weights_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(src, (float*)dst, n0, n1, n2, s0, s1, s2, off);
+  UB_LAUNCH_CHECK("pack_weights");
+  return 0;
+}
+}

@@ -1,0 +1,29 @@
+// Device-side view of unetb200_gconv_t and the dispatch hooks between the SIMT and tcgen05 engines.
+#pragma once
+#include "common.cuh"
+
+namespace ub {
+
+struct GconvDev {
+  int B, Hm, Wm, Cin, ntaps;
+  int tap_dy[9], tap_dx[9];
+  int in_scale, in_off_y, in_off_x, Hin, Win;
+  long long ld_in;
+  int N, nquad, Cq, out_scale, out_off_y, out_off_x, Hout, Wout;
+  long long ld_out;
+  long long M;   // B*Hm*Wm
+  int K;         // ntaps*Cin
+};
+
+int gconv_validate(const unetb200_gconv_t* d, GconvDev* out);
+
+// tcgen05 engine (conv_tc.cu).  *_supported() return 1 when the shape/dtype/alignment fits.
+int tc_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+int tc_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
+             double* stats, cudaStream_t stream);
+int tc_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int tc_wgrad_splits(const unetb200_gconv_t* d, const GconvDev& g);
+int tc_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
+             cudaStream_t stream);
+
+}  // namespace ub

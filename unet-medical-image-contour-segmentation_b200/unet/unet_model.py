@@ -1,0 +1,93 @@
+"""B200-native drop-in for the reference's ``unet/unet_model.py``: ``UNet(n_channels, n_classes,
+bilinear=False)`` with the reference's attributes, sub-module names and ``state_dict`` layout
+(reference unet_model.py:8-50), plus the width variants ``UNet_S`` / ``UNet_T`` that train.py imports.
+
+``forward`` runs the whole network on hand-written sm_100a kernels (see ``unetb200``): activations are
+NHWC in the compute dtype (bf16 under autocast, else fp32), every encoder stage writes its skip
+tensor straight into the first half of the decoder's concat buffer and emits its 2x2 max-pool from
+the same kernel, and the upsampling kernels write the second half -- ``torch.cat`` and
+``nn.MaxPool2d`` never run as separate passes.
+"""
+import logging
+
+import torch
+import torch.nn as nn
+
+from unetb200 import ops
+
+from .unet_parts import DoubleConv, Down, OutConv, Up, _prep
+
+
+class _UNetBase(nn.Module):
+    _BASE = 64
+
+    def __init__(self, n_channels, n_classes, bilinear=False):
+        super().__init__()
+        self.n_channels = n_channels
+        self.n_classes = n_classes
+        self.bilinear = bilinear
+        b = self._BASE
+        factor = 2 if bilinear else 1
+        self.inc = DoubleConv(n_channels, b)
+        self.down1 = Down(b, 2 * b)
+        self.down2 = Down(2 * b, 4 * b)
+        self.down3 = Down(4 * b, 8 * b)
+        self.down4 = Down(8 * b, 16 * b // factor)
+        self.up1 = Up(16 * b, 8 * b // factor, bilinear)
+        self.up2 = Up(8 * b, 4 * b // factor, bilinear)
+        self.up3 = Up(4 * b, 2 * b // factor, bilinear)
+        self.up4 = Up(2 * b, b, bilinear)
+        self.outc = OutConv(b, n_classes)
+
+    def forward(self, x):
+        x = _prep(x, type(self).__name__)
+        B, C, H, W = x.shape
+        if C != self.n_channels:
+            raise ValueError(f"{type(self).__name__} was built for {self.n_channels} input channels, got {C}")
+        if H < 16 or W < 16:
+            raise ValueError(f"{type(self).__name__}: input {H}x{W} is too small for four 2x2 max-pools")
+        b = self._BASE
+        dev, cd = x.device, x.dtype
+        # concat buffers of the four Up stages: [skip | upsampled], at the skip's resolution
+        cats = [ops.empty_nhwc(B, 2 * b * (1 << k), H >> k, W >> k, cd, dev) for k in range(4)]
+        skips = [ops.channel_slice(cats[k], 0, b * (1 << k)) for k in range(4)]
+        x1, p = self.inc.run(x, out=skips[0], want_pool=True)
+        x2, p = self.down1.run(p, out=skips[1], want_pool=True)
+        x3, p = self.down2.run(p, out=skips[2], want_pool=True)
+        x4, p = self.down3.run(p, out=skips[3], want_pool=True)
+        y = self.down4.run(p)
+        y = self.up1.run(y, x4, cat=cats[3])
+        y = self.up2.run(y, x3, cat=cats[2])
+        y = self.up3.run(y, x2, cat=cats[1])
+        y = self.up4.run(y, x1, cat=cats[0])
+        return self.outc.run(y)
+
+    def use_checkpointing(self):
+        """Called by train.py:299 after a CUDA OOM.  The reference's own implementation raises
+        TypeError (it calls checkpoint() without inputs, unet_model.py:40-50); here it is a logged
+        no-op: activations are already bf16 NHWC and the concat copies are fused away."""
+        logging.warning("unetb200: use_checkpointing() requested; activation re-computation is not implemented")
+        self._checkpointing = True
+
+
+class UNet(_UNetBase):
+    """Standard UNet, widths 64-128-256-512-1024 (reference unet_model.py:8-38)."""
+    _BASE = 64
+
+
+class UNet_S(_UNetBase):
+    """Light variant, base width 16 (reference unet_model.py:96-138)."""
+    _BASE = 16
+
+
+class UNet_T(_UNetBase):
+    """Tiny variant, base width 8 (reference unet_model.py:52-94)."""
+    _BASE = 8
+
+
+class UNet_SA(nn.Module):
+    """Spatial-attention variant (reference unet_model.py:140-189): outside the B200 hot path."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        raise NotImplementedError("UNet_SA (spatial attention) is outside the B200 hot path; see SURVEY.md section 2, row 2b")

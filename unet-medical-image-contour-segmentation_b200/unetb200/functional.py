@@ -1,0 +1,350 @@
+"""torch.autograd.Function wrappers of the UNet parts over the C ABI.
+
+One Function per reference part:
+  DoubleConvFn  -- unet_parts.py:7-24   conv3x3+BN+ReLU twice (optionally also emits MaxPool2d(2) of its
+                                        output, and can write its output into a caller-owned NHWC buffer:
+                                        that is how the skip concat of unet_parts.py:95 costs no copy)
+  MaxPoolFn     -- unet_parts.py:32     standalone MaxPool2d(2)
+  UpCatConvTFn  -- unet_parts.py:72-95  ConvTranspose2d(k2,s2)+bias, F.pad placement, cat([x2, x1])
+  UpCatBilinearFn -- unet_parts.py:69-95 bilinear x2 (align_corners=True), F.pad placement, cat
+  OutConvFn     -- unet_parts.py:100-106 1x1 conv + bias
+forward/backward only marshal pointers; all arithmetic happens in libunetb200.so.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib, ops
+from ._lib import ALGO_AUTO, ALGO_PREFER_TC, ALGO_SIMT
+
+
+# ------------------------------------------------------------------------------------------------
+# precision policy
+# ------------------------------------------------------------------------------------------------
+def compute_dtype(x):
+    """bf16 whenever autocast is on (the reference's AMP path, train.py:116; evaluate.py:43;
+    predict.py:22 -- BASELINE's bf16 mode) or the input already is bf16; fp32 otherwise."""
+    if torch.is_autocast_enabled("cuda") or x.dtype == torch.bfloat16:
+        return torch.bfloat16
+    return torch.float32
+
+
+def conv_algo(dtype):
+    """bf16 -> tcgen05 when the layer shape fits.  fp32 -> UNET_B200_PRECISION: 'tf32' runs the
+    tcgen05 kind::tf32 engine (what cuDNN does for the reference with allow_tf32=True), 'fp32'
+    runs exact fp32 FMAs on the CUDA cores."""
+    if dtype == torch.bfloat16:
+        return ALGO_AUTO
+    mode = os.environ.get("UNET_B200_PRECISION", "").lower()
+    if mode == "":
+        mode = "tf32" if torch.backends.cudnn.allow_tf32 else "fp32"
+    if mode == "tf32":
+        return ALGO_PREFER_TC
+    if mode == "fp32":
+        return ALGO_SIMT
+    raise ValueError(f"UNET_B200_PRECISION must be 'tf32' or 'fp32', got {mode!r}")
+
+
+def _w_src(w):
+    """(fp32 tensor, s_out, s_in, s_tap) for a [O, I, kh, kw] parameter whose taps are linear in
+    memory (contiguous or channels_last, cf. train.py:262 `.to(memory_format=channels_last)`)."""
+    w = w.detach()
+    if w.dtype != torch.float32:
+        w = w.float()
+    so, si, skh, skw = w.stride()
+    kh, kw = w.shape[2], w.shape[3]
+    if skh != kw * skw:          # taps must be linear in memory: t = kh*KW + kw -> t * skw
+        w = w.contiguous()
+        so, si, skh, skw = w.stride()
+    return w, so, si, skw
+
+
+def _pack(w, dtype, n0, n1, n2, s0, s1, s2, off=0):
+    dst = torch.empty((n0, n1 * n2), dtype=dtype, device=w.device)
+    _lib.check(ops.lib().unetb200_pack_weights(ops._p(w), ops._p(dst), ops._DT[dtype], n0, n1, n2, s0, s1, s2, off,
+                                               ops._stream()), "pack_weights")
+    return dst
+
+
+def pack3x3_fprop(w, dtype):
+    """OIHW -> Wp[co][(kh,kw)][ci]"""
+    Co, Ci = w.shape[:2]
+    w, so, si, st = _w_src(w)
+    return _pack(w, dtype, Co, 9, Ci, so, st, si)
+
+
+def pack3x3_dgrad(w, dtype):
+    """OIHW -> Wp[ci][(kh',kw')][co] = W[co][ci][2-kh'][2-kw']"""
+    Co, Ci = w.shape[:2]
+    w, so, si, st = _w_src(w)
+    return _pack(w, dtype, Ci, 9, Co, si, -st, so, off=8 * st)
+
+
+def packT_fprop(w, dtype):
+    """IOHW [Ci,Co,2,2] -> Wp[(q,co)][ci]"""
+    Ci, Co = w.shape[:2]
+    w, s_ci, s_co, st = _w_src(w)
+    return _pack(w, dtype, 4, Co, Ci, st, s_co, s_ci).view(4 * Co, Ci)
+
+
+def packT_dgrad(w, dtype):
+    """IOHW -> Wp[ci][(q,co)]"""
+    Ci, Co = w.shape[:2]
+    w, s_ci, s_co, st = _w_src(w)
+    return _pack(w, dtype, Ci, 4, Co, s_ci, st, s_co)
+
+
+def _f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# conv3x3 + BN + ReLU stage
+# ------------------------------------------------------------------------------------------------
+def _gconv3x3(x, Cout, y, dtype):
+    B, Cin, H, W = x.shape
+    return ops.make_gconv(ops._DT[dtype], conv_algo(dtype), B, H, W, Cin, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(x),
+                          Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(y))
+
+
+def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False):
+    """x NHWC -> (y raw conv output, z = relu(bn(y)), pooled or None, coefs[4,C])."""
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    cd, dev = x.dtype, x.device
+    wp = pack3x3_fprop(w, cd)
+    y = ops.empty_nhwc(B, Cout, H, W, cd, dev)
+    use_batch = training or bn.running_mean is None
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if use_batch else None
+    ops.gconv_fprop(_gconv3x3(x, Cout, y, cd), x, wp, None, y, stats)
+    gamma = _f32c(bn.weight) if bn.weight is not None else None
+    beta = _f32c(bn.bias) if bn.bias is not None else None
+    if use_batch:
+        if bn.momentum is None and bn.running_mean is not None and training:
+            raise ValueError("unetb200: BatchNorm2d(momentum=None) (cumulative average) is not supported")
+        update = training and bn.running_mean is not None
+        coefs = ops.bn_finalize(stats, B * H * W, gamma, beta, bn.eps, bn.momentum if update else 0.0,
+                                bn.running_mean if update else None, bn.running_var if update else None, Cout)
+        if update and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    else:
+        coefs = ops.bn_eval_coeffs(gamma, beta, bn.running_mean, bn.running_var, bn.eps, Cout)
+    z = out if out is not None else ops.empty_nhwc(B, Cout, H, W, cd, dev)
+    pooled = ops.empty_nhwc(B, Cout, H // 2, W // 2, cd, dev) if want_pool else None
+    ops.bn_relu_apply(y, coefs, z, pooled)
+    return y, z, pooled, coefs
+
+
+def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx):
+    """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta)."""
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    cd = x.dtype
+    gy, dgamma, dbeta = ops.bn_relu_bwd(gz, y, coefs, batch_stats)
+    dW = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+    ops.gconv_wgrad(_gconv3x3(x, Cout, gy, cd), x, gy, dW, 1, 9, Cin * 9)
+    gx = None
+    if need_gx:
+        gx = ops.empty_nhwc(B, Cin, H, W, cd, x.device)
+        ops.gconv_fprop(_gconv3x3(gy, Cin, gx, cd), gy, pack3x3_dgrad(w, cd), None, gx, None)
+    return gx, dW, dgamma, dbeta
+
+
+class _Cfg:
+    """Non-tensor arguments of a Function call."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class DoubleConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, g1, b1, w2, g2, b2, cfg):
+        y1, z1, _, c1 = conv_bn_relu_fwd(x, w1, cfg.bn1, cfg.training)
+        y2, z2, pooled, c2 = conv_bn_relu_fwd(z1, w2, cfg.bn2, cfg.training, out=cfg.out, want_pool=cfg.want_pool)
+        ctx.batch_stats = (cfg.training or cfg.bn1.running_mean is None, cfg.training or cfg.bn2.running_mean is None)
+        ctx.has_pool = pooled is not None
+        if cfg.save:
+            ctx.save_for_backward(x, y1, z1, y2, z2, c1, c2, w1, w2)
+        if pooled is None:
+            return z2
+        return z2, pooled
+
+    @staticmethod
+    def backward(ctx, gz2, gpooled=None):
+        x, y1, z1, y2, z2, c1, c2, w1, w2 = ctx.saved_tensors
+        cd = x.dtype
+        gz = ops.to_nhwc(gz2, cd) if gz2 is not None else None
+        if ctx.has_pool and gpooled is not None:
+            gp = ops.to_nhwc(gpooled, cd)
+            if gz is None:
+                gz = ops.empty_nhwc(*z2.shape, cd, x.device)
+                ops.maxpool2_bwd(z2, gp, gz, accumulate=False)
+            elif gz is gz2 and ops.nhwc_ld(gz) > gz.shape[1]:
+                # gz2 is the skip half of a concat-gradient buffer produced by our own dgrad: the
+                # pool gradient is accumulated into it in place (skip-gradient sum fused away)
+                ops.maxpool2_bwd(z2, gp, gz, accumulate=True)
+            else:
+                t = ops.empty_nhwc(*z2.shape, cd, x.device)
+                ops.maxpool2_bwd(z2, gp, t, accumulate=False)
+                gz = ops.add_channels_(t, gz)
+        if gz is None:
+            raise RuntimeError("DoubleConvFn.backward called without any output gradient")
+        need = ctx.needs_input_grad
+        gz1, dW2, dg2, db2 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True)
+        gx, dW1, dg1, db1 = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0])
+        return (gx, dW1 if need[1] else None, dg1 if need[2] else None, db1 if need[3] else None,
+                dW2 if need[4] else None, dg2 if need[5] else None, db2 if need[6] else None, None)
+
+
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, Cc, H, W = x.shape
+        p = ops.empty_nhwc(B, Cc, H // 2, W // 2, x.dtype, x.device)
+        ops.maxpool2_fwd(x, p)
+        ctx.save_for_backward(x)
+        return p
+
+    @staticmethod
+    def backward(ctx, gp):
+        (x,) = ctx.saved_tensors
+        gx = ops.empty_nhwc(*x.shape, x.dtype, x.device)
+        ops.maxpool2_bwd(x, ops.to_nhwc(gp, x.dtype), gx, accumulate=False)
+        return gx
+
+
+# ------------------------------------------------------------------------------------------------
+# Up: upsample + pad + concat
+# ------------------------------------------------------------------------------------------------
+def _cat_buffer(x2, Cup, cat):
+    """NHWC [B, C2+Cup, H, W] buffer whose first C2 channels hold x2 (copied unless x2 already
+    lives there, which is the case when UNet.forward pre-allocated the buffer)."""
+    B, C2, H, W = x2.shape
+    if cat is not None and cat.data_ptr() == x2.data_ptr() and ops.nhwc_ld(cat) == ops.nhwc_ld(x2) \
+            and cat.shape == (B, C2 + Cup, H, W):
+        return cat
+    cat = ops.empty_nhwc(B, C2 + Cup, H, W, x2.dtype, x2.device)
+    ops.copy_channels(x2, ops.channel_slice(cat, 0, C2))
+    return cat
+
+
+def _pad_offsets(x1, x2):
+    dy = x2.shape[2] - 2 * x1.shape[2]
+    dx = x2.shape[3] - 2 * x1.shape[3]
+    if dy < 0 or dx < 0:
+        raise ValueError("unetb200.Up: the upsampled tensor is larger than the skip tensor (negative F.pad / "
+                         f"cropping, unet_parts.py:85-88) is not supported: x1 {tuple(x1.shape)}, x2 {tuple(x2.shape)}")
+    return dy, dx, (dy // 2, dx // 2)
+
+
+class UpCatConvTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, wT, bT, cfg):
+        B, C1, h, w = x1.shape
+        Cup = wT.shape[1]
+        C2, H, W = x2.shape[1:]
+        cd = x1.dtype
+        dy, dx, off = _pad_offsets(x1, x2)
+        cat = _cat_buffer(x2, Cup, cfg.cat)
+        up = ops.channel_slice(cat, C2, Cup)
+        if dy or dx:
+            ops.zero_channels(up)
+        d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, C1, ops.TAPS1, 1, (0, 0), h, w, ops.nhwc_ld(x1),
+                           4 * Cup, 4, 2, off, H, W, ops.nhwc_ld(cat))
+        ops.gconv_fprop(d, x1, packT_fprop(wT, cd), _f32c(bT) if bT is not None else None, up, None)
+        ctx.geom = (C2, Cup, off, dy or dx)
+        if cfg.save:
+            ctx.save_for_backward(x1, wT)
+        return cat
+
+    @staticmethod
+    def backward(ctx, gcat):
+        x1, wT = ctx.saved_tensors
+        C2, Cup, off, padded = ctx.geom
+        B, C1, h, w = x1.shape
+        cd = x1.dtype
+        g = ops.to_nhwc(gcat, cd)
+        H, W = g.shape[2:]
+        need = ctx.needs_input_grad
+        g2 = ops.channel_slice(g, 0, C2) if need[1] else None
+        gup = ops.channel_slice(g, C2, Cup)
+        ld = ops.nhwc_ld(g)
+        dW = dB = gx1 = None
+        if need[2]:
+            d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, C1, ops.TAPS1, 1, (0, 0), h, w, ops.nhwc_ld(x1),
+                               4 * Cup, 4, 2, off, H, W, ld)
+            dW = torch.empty((C1, Cup, 2, 2), dtype=torch.float32, device=g.device)
+            ops.gconv_wgrad(d, x1, gup, dW, 0, Cup * 4, 4, sq=1)
+        if need[3]:
+            region = gup if not padded else ops.to_nhwc(
+                gup[:, :, off[0]:off[0] + 2 * h, off[1]:off[1] + 2 * w].contiguous(memory_format=torch.channels_last), cd)
+            dB = ops.channel_sum(region)
+        if need[0]:
+            gx1 = ops.empty_nhwc(B, C1, h, w, cd, g.device)
+            d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, Cup, ops.TAPS_Q, 2, off, H, W, ld,
+                               C1, 1, 1, (0, 0), h, w, ops.nhwc_ld(gx1))
+            ops.gconv_fprop(d, gup, packT_dgrad(wT, cd), None, gx1, None)
+        return gx1, g2, dW, dB, None
+
+
+class UpCatBilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x1, x2, cfg):
+        B, C1, h, w = x1.shape
+        C2 = x2.shape[1]
+        dy, dx, off = _pad_offsets(x1, x2)
+        cat = _cat_buffer(x2, C1, cfg.cat)
+        up = ops.channel_slice(cat, C2, C1)
+        if dy or dx:
+            ops.zero_channels(up)
+        ops.upsample2x_fwd(x1, up, off)
+        ctx.geom = (C2, C1, off, (B, C1, h, w), x1.dtype)
+        return cat
+
+    @staticmethod
+    def backward(ctx, gcat):
+        C2, C1, off, shape, cd = ctx.geom
+        g = ops.to_nhwc(gcat, cd)
+        need = ctx.needs_input_grad
+        g2 = ops.channel_slice(g, 0, C2) if need[1] else None
+        gx1 = None
+        if need[0]:
+            gx1 = ops.empty_nhwc(*shape, g.dtype, g.device)
+            ops.upsample2x_bwd(ops.channel_slice(g, C2, C1), gx1, off)
+        return gx1, g2, None
+
+
+# ------------------------------------------------------------------------------------------------
+# OutConv
+# ------------------------------------------------------------------------------------------------
+class OutConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, cfg):
+        B, Cc, H, W = x.shape
+        K = w.shape[0]
+        logits = torch.empty((B, H, W, K), dtype=x.dtype, device=x.device)
+        w2 = _f32c(w).view(K, Cc)
+        ops.outconv_fwd(x, w2, _f32c(b) if b is not None else None, logits)
+        if cfg.save:
+            ctx.save_for_backward(x, w2)
+        ctx.has_bias = b is not None
+        return logits.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, glogits):
+        x, w2 = ctx.saved_tensors
+        B, Cc, H, W = x.shape
+        K = w2.shape[0]
+        g = ops.to_nhwc(glogits, x.dtype, packed=True)
+        need = ctx.needs_input_grad
+        gx = ops.empty_nhwc(B, Cc, H, W, x.dtype, x.device) if need[0] else None
+        dw = torch.empty((K, Cc, 1, 1), dtype=torch.float32, device=x.device)
+        db = torch.empty(K, dtype=torch.float32, device=x.device)
+        ops.outconv_bwd(x, w2, g, gx, dw, db)
+        return gx, dw if need[1] else None, db if (need[2] and ctx.has_bias) else None, None

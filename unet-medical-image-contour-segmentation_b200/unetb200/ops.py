@@ -1,0 +1,274 @@
+"""Tensor-level wrappers over the C ABI: they only marshal ``data_ptr()``, shapes, strides and the
+current CUDA stream.  PyTorch is used for device memory (``torch.empty`` through the caching
+allocator, so OOM surfaces as ``torch.cuda.OutOfMemoryError``) and streams -- never for arithmetic.
+
+Activation convention: a logical [B, C, H, W] tensor whose strides are (H*W*ld, 1, W*ld, ld) is
+"NHWC with pixel stride ld"; ld > C is a channel slice of a wider NHWC buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, BF16, F32, I64, GConv
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def lib():
+    return _lib.load()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise ValueError(f"unetb200: unsupported dtype {t.dtype}") from None
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"unetb200.{what}: the B200 hot path runs on CUDA tensors only (got a {t.device} tensor); "
+            "there is deliberately no CPU fallback -- move the model and inputs to the GPU.")
+
+
+# ------------------------------------------------------------------------------------------------
+# NHWC views
+# ------------------------------------------------------------------------------------------------
+def nhwc_ld(t):
+    """Pixel stride of a logical [B,C,H,W] tensor if it is NHWC-with-ld, else None."""
+    if t.dim() != 4:
+        return None
+    B, Cc, H, W = t.shape
+    sb, sc, sh, sw = t.stride()
+    if Cc > 1 and sc != 1:
+        return None
+    if W > 1:
+        ld = sw
+    elif H > 1:
+        ld = sh
+    elif B > 1:
+        ld = sb
+    else:
+        ld = Cc
+    if ld < Cc:
+        return None
+    if H > 1 and sh != W * ld:
+        return None
+    if B > 1 and sb != H * W * ld:
+        return None
+    return ld
+
+
+def empty_nhwc(B, Cc, H, W, dtype, device):
+    """Logical [B,C,H,W], physically NHWC contiguous."""
+    return torch.empty((B, H, W, Cc), dtype=dtype, device=device).permute(0, 3, 1, 2)
+
+
+def channel_slice(buf, c0, Cc):
+    """Alias of channels [c0, c0+Cc) of an NHWC buffer, without an autograd view relation."""
+    B, Ct, H, W = buf.shape
+    ld = nhwc_ld(buf)
+    out = buf.new_empty(0)
+    out.set_(buf.untyped_storage(), buf.storage_offset() + c0, (B, Cc, H, W), (H * W * ld, 1, W * ld, ld))
+    return out
+
+
+def to_nhwc(x, dtype, packed=False):
+    """Any-strided logical NCHW tensor -> NHWC of `dtype` (no copy if it already is; with
+    packed=True the pixel stride must equal C)."""
+    ld = nhwc_ld(x)
+    if x.dtype == dtype and ld is not None and (not packed or ld == x.shape[1]):
+        return x
+    if x.dtype not in _DT:
+        x = x.float()
+    B, Cc, H, W = x.shape
+    out = empty_nhwc(B, Cc, H, W, dtype, x.device)
+    sn, sc, sh, sw = x.stride()
+    _lib.check(lib().unetb200_gather_nhwc(_p(x), dt(x), sn, sc, sh, sw, _p(out), _DT[dtype], Cc, B, Cc, H, W,
+                                          _stream()), "gather_nhwc")
+    return out
+
+
+def copy_channels(src, dst):
+    B, Cc, H, W = src.shape
+    _lib.check(lib().unetb200_copy_channels(_p(src), dt(src), nhwc_ld(src), _p(dst), dt(dst), nhwc_ld(dst),
+                                            B * H * W, Cc, _stream()), "copy_channels")
+
+
+def zero_channels(dst):
+    B, Cc, H, W = dst.shape
+    _lib.check(lib().unetb200_zero_channels(_p(dst), dt(dst), nhwc_ld(dst), B * H * W, Cc, _stream()),
+               "zero_channels")
+
+
+def add_channels_(a, b):
+    B, Cc, H, W = a.shape
+    _lib.check(lib().unetb200_add_channels(_p(a), nhwc_ld(a), _p(b), nhwc_ld(b), dt(a), B * H * W, Cc, _stream()),
+               "add_channels")
+    return a
+
+
+def channel_sum(g):
+    B, Cc, H, W = g.shape
+    acc = torch.empty(Cc, dtype=torch.float64, device=g.device)
+    out = torch.empty(Cc, dtype=torch.float32, device=g.device)
+    _lib.check(lib().unetb200_channel_sum(_p(g), dt(g), nhwc_ld(g), B * H * W, Cc, _p(acc), _p(out), _stream()),
+               "channel_sum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# generalised convolution
+# ------------------------------------------------------------------------------------------------
+TAPS3 = [(kh - 1, kw - 1) for kh in range(3) for kw in range(3)]
+TAPS1 = [(0, 0)]
+TAPS_Q = [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+
+def forced_algo():
+    v = os.environ.get("UNETB200_ALGO", "").lower()
+    return {"simt": ALGO_SIMT, "tc": ALGO_TC}.get(v, None)
+
+
+def make_gconv(dtype, algo, B, Hm, Wm, Cin, taps, in_scale, in_off, Hin, Win, ld_in, N, nquad, out_scale, out_off,
+               Hout, Wout, ld_out):
+    d = GConv()
+    d.dtype = dtype
+    fa = forced_algo()
+    d.algo = fa if fa is not None else algo
+    d.B, d.Hm, d.Wm, d.Cin, d.ntaps = B, Hm, Wm, Cin, len(taps)
+    for i, (dy, dx) in enumerate(taps):
+        d.tap_dy[i], d.tap_dx[i] = dy, dx
+    d.in_scale, d.in_off_y, d.in_off_x = in_scale, in_off[0], in_off[1]
+    d.Hin, d.Win, d.ld_in = Hin, Win, ld_in
+    d.N, d.nquad, d.out_scale = N, nquad, out_scale
+    d.out_off_y, d.out_off_x = out_off
+    d.Hout, d.Wout, d.ld_out = Hout, Wout, ld_out
+    return d
+
+
+def gconv_fprop(d, x, wp, bias, y, stats):
+    used = C.c_int(0)
+    _lib.check(lib().unetb200_gconv_fprop(C.byref(d), _p(x), _p(wp), _p(bias), _p(y), _p(stats), C.byref(used),
+                                          _stream()), "gconv_fprop")
+    return used.value
+
+
+def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0):
+    """dst (parameter layout, fp32) = weight gradient; dst[t*st + c*sc + q*sq + co*sn], n = q*Cq + co."""
+    splits, used = C.c_int(0), C.c_int(0)
+    _lib.check(lib().unetb200_gconv_wgrad_plan(C.byref(d), C.byref(splits), C.byref(used)), "gconv_wgrad_plan")
+    K = d.ntaps * d.Cin
+    partials = torch.empty(splits.value * K * d.N, dtype=torch.float32, device=x.device)
+    d2 = GConv.from_buffer_copy(d)
+    d2.algo = used.value
+    _lib.check(lib().unetb200_gconv_wgrad(C.byref(d2), _p(x), _p(gy), _p(partials), splits.value, _stream()),
+               "gconv_wgrad")
+    _lib.check(lib().unetb200_wgrad_reduce(_p(partials), splits.value, d.ntaps, d.Cin, d.N, d.N // d.nquad, _p(dst), st,
+                                           sc, sq, sn, 0, _stream()), "wgrad_reduce")
+    return used.value
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm / ReLU / pooling
+# ------------------------------------------------------------------------------------------------
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, Cc):
+    dev = stats.device
+    coefs = torch.empty((4, Cc), dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
+    _lib.check(lib().unetb200_bn_finalize(_p(stats), count, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
+                                          _p(running_var), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(coefs[3]),
+                                          Cc, _stream()), "bn_finalize")
+    return coefs
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, Cc):
+    coefs = torch.empty((4, Cc), dtype=torch.float32, device=running_mean.device)
+    _lib.check(lib().unetb200_bn_eval_coeffs(_p(gamma), _p(beta), _p(running_mean), _p(running_var), eps,
+                                             _p(coefs[2]), _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), Cc, _stream()),
+               "bn_eval_coeffs")
+    return coefs
+
+
+def bn_relu_apply(y, coefs, z, pooled=None):
+    B, Cc, H, W = y.shape
+    _lib.check(lib().unetb200_bn_relu_apply(_p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]), _p(z), nhwc_ld(z),
+                                            _p(pooled), nhwc_ld(pooled) if pooled is not None else 0, dt(y), B, H, W,
+                                            Cc, _stream()), "bn_relu_apply")
+
+
+def maxpool2_fwd(x, p):
+    B, Cc, H, W = x.shape
+    _lib.check(lib().unetb200_maxpool2_fwd(_p(x), nhwc_ld(x), _p(p), nhwc_ld(p), dt(x), B, H, W, Cc, _stream()),
+               "maxpool2_fwd")
+
+
+def maxpool2_bwd(x, gp, gx, accumulate):
+    B, Cc, H, W = x.shape
+    _lib.check(lib().unetb200_maxpool2_bwd(_p(x), nhwc_ld(x), _p(gp), nhwc_ld(gp), _p(gx), nhwc_ld(gx),
+                                           1 if accumulate else 0, dt(x), B, H, W, Cc, _stream()), "maxpool2_bwd")
+
+
+def bn_relu_bwd(gz, y, coefs, training, want_affine=True):
+    """Returns (gy, dgamma, dbeta) for z = relu(bn(y))."""
+    B, Cc, H, W = y.shape
+    dev = y.device
+    sums = torch.zeros((2, Cc), dtype=torch.float64, device=dev)
+    L = lib()
+    _lib.check(L.unetb200_bn_relu_bwd_reduce(_p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]),
+                                             _p(coefs[0]), _p(coefs[1]), _p(sums), dt(y), B, H, W, Cc, _stream()),
+               "bn_relu_bwd_reduce")
+    dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
+    dbeta = torch.empty(Cc, dtype=torch.float32, device=dev)
+    coef = torch.empty((2, Cc), dtype=torch.float32, device=dev)
+    _lib.check(L.unetb200_bn_bwd_finalize(_p(sums), B * H * W, 1 if training else 0, _p(dgamma), _p(dbeta),
+                                          _p(coef), Cc, _stream()), "bn_bwd_finalize")
+    gy = empty_nhwc(B, Cc, H, W, y.dtype, dev)
+    _lib.check(L.unetb200_bn_relu_bwd_apply(_p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]),
+                                            _p(coefs[0]), _p(coefs[1]), _p(coef), _p(gy), nhwc_ld(gy), dt(y), B, H,
+                                            W, Cc, _stream()), "bn_relu_bwd_apply")
+    return gy, dgamma, dbeta
+
+
+def upsample2x_fwd(x, y, off):
+    B, Cc, h, w = x.shape
+    _lib.check(lib().unetb200_upsample2x_fwd(_p(x), nhwc_ld(x), _p(y), nhwc_ld(y), dt(x), B, h, w, Cc, y.shape[2],
+                                             y.shape[3], off[0], off[1], _stream()), "upsample2x_fwd")
+
+
+def upsample2x_bwd(gy, gx, off):
+    B, Cc, h, w = gx.shape
+    _lib.check(lib().unetb200_upsample2x_bwd(_p(gy), nhwc_ld(gy), _p(gx), nhwc_ld(gx), dt(gx), B, h, w, Cc,
+                                             gy.shape[2], gy.shape[3], off[0], off[1], _stream()), "upsample2x_bwd")
+
+
+# ------------------------------------------------------------------------------------------------
+# OutConv
+# ------------------------------------------------------------------------------------------------
+def outconv_fwd(x, w, bias, logits):
+    B, Cc, H, W = x.shape
+    K = w.shape[0]
+    _lib.check(lib().unetb200_outconv_fwd(_p(x), nhwc_ld(x), _p(w), _p(bias), _p(logits), dt(x), B * H * W, Cc, K,
+                                          _stream()), "outconv_fwd")
+
+
+def outconv_bwd(x, w, glogits, gx, dw, dbias):
+    B, Cc, H, W = x.shape
+    K = w.shape[0]
+    n = lib().unetb200_outconv_bwd_workspace(B * H * W, Cc, K)
+    ws = torch.empty(n, dtype=torch.float32, device=x.device)
+    _lib.check(lib().unetb200_outconv_bwd(_p(x), nhwc_ld(x), _p(w), _p(glogits), _p(gx),
+                                          nhwc_ld(gx) if gx is not None else 0, _p(dw), _p(dbias), _p(ws), dt(x),
+                                          B * H * W, Cc, K, _stream()), "outconv_bwd")
