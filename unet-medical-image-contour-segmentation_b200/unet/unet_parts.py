@@ -15,12 +15,21 @@ from unetb200 import ops
 from unetb200.functional import _Cfg
 
 
+def _to_internal(x, dtype):
+    """NHWC of `dtype`, keeping the autograd graph when the caller's tensor needs a gradient."""
+    if x.dtype == dtype and ops.nhwc_ld(x) is not None:
+        return x
+    if x.requires_grad and torch.is_grad_enabled():
+        return UF.ToNHWCFn.apply(x, dtype)
+    return ops.to_nhwc(x, dtype)
+
+
 def _prep(x, what):
     """Caller tensor (fp32 NCHW-logical, usually channels_last) -> NHWC of the compute dtype."""
     ops.require_cuda(x, what)
     if x.dim() != 4:
         raise ValueError(f"{what}: expected a [B, C, H, W] tensor, got {tuple(x.shape)}")
-    return ops.to_nhwc(x, UF.compute_dtype(x))
+    return _to_internal(x, UF.compute_dtype(x))
 
 
 def _needs_graph(module, *tensors):
@@ -108,8 +117,8 @@ class Up(nn.Module):
 
     def forward(self, x1, x2):
         x1 = _prep(x1, "Up")
-        x2 = ops.to_nhwc(x2, x1.dtype)
-        return self.run(x1, x2)
+        ops.require_cuda(x2, "Up")
+        return self.run(x1, _to_internal(x2, x1.dtype))
 
 
 class OutConv(nn.Module):

@@ -155,6 +155,20 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx):
     return gx, dW, dgamma, dbeta
 
 
+class ToNHWCFn(torch.autograd.Function):
+    """Layout / dtype conversion of a caller tensor into the internal NHWC form (a strided gather)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.in_dtype = x.dtype
+        return ops.to_nhwc(x, dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        dt = ctx.in_dtype if ctx.in_dtype in ops._DT else torch.float32
+        return ops.to_nhwc(g, dt), None
+
+
 class _Cfg:
     """Non-tensor arguments of a Function call."""
 
