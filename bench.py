@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- UNet 512x512 training step on N B200s (BASELINE.json configs[1] / [3]).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm (CUDA path through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # reference arm: the CPU fp32 path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # N > 1
+
+One step = forward (bf16 autocast) + loss (CE + dice + 0.2*boundary_loss, the train.py:137-147 form)
++ backward (+ NCCL gradient all-reduce when N > 1) + clip_grad_norm_ + RMSprop step (train.py:80,153-159)
+on a batch of 16 synthetic 1x512x512 images per GPU.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "unet-medical-image-contour-segmentation_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "unet512_train_images_per_sec"
+UNIT = "img/s"
+# algorithmic conv FLOPs per image, fwd+bwd, UNet(1,2,False) at 512x512 (SURVEY.md section 8d / BASELINE.md section 4)
+GFLOP_PER_IMG = {(False, 512): 1154.004, (True, 512): 957.509}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--bilinear", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            return dict(hbm_gbs=float(d["hbm_gbs"]), tflops_burst=float(d["bf16_tflops"]),
+                        tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+        except Exception:  # noqa: BLE001
+            pass
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (the oracle: torch-CPU fp32 restatement of the reference step)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(size, bilinear, steps, warmup, budget_s):
+    """img/s of the reference's CPU fp32 step on B=1 samples of the workload; bounded by budget_s."""
+    from oracle import unet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    st = O.build_state(1, 2, bilinear, seed=0)
+    img, msk = O.synthetic_batch(1, 1, 2, size, size)
+    times = []
+    t_start = time.perf_counter()
+    done_warm = 0
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.training_step({k: v.clone() for k, v in st.items()}, img, msk, 2, bilinear, boundary_coeff=0.2)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        else:
+            done_warm += 1
+        elapsed = time.perf_counter() - t_start
+        if times and elapsed + dt > budget_s:
+            break
+        if not times and done_warm >= 1 and elapsed + 2 * dt > budget_s:
+            warmup = done_warm          # cut the warm-up short: keep at least one timed step
+    if not times:
+        times = [dt]
+    med = statistics.median(times)
+    return 1.0 / med, len(times), done_warm, med
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, n, nw, med = cpu_reference_rate(args.size, args.bilinear, args.steps, args.warmup, budget_s=150.0)
+    cores = os.cpu_count() or 1
+    sample = (f"oracle port of the reference CPU fp32 step (unet_parts/unet_model/dice/boundary via torch-CPU), "
+              f"B=1 samples of the {args.size}x{args.size} workload, {nw} warm-up + {n} timed steps, median")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": nw, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"UNet(1,2,bilinear={args.bilinear}) training step, {args.size}x{args.size}, "
+                               "CE+dice+0.2*boundary_loss (BASELINE.json configs[1])",
+                   "per_step_sample": "1 image"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [s.strip() for s in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            # "under load": drop the lowest quartile (ramp-up samples)
+            s = sorted(sm)
+            out["sm_mhz"] = statistics.median(s[len(s) // 4:])
+            out["sm_max_mhz"] = max(mx)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import unet
+    from unetb200 import ddp, ops
+    from unetb200 import losses as UL
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the UNet hot path has no CPU fallback (use --impl reference for "
+                         "the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, S = args.batch, args.size
+
+    torch.manual_seed(0)
+    model = unet.UNet(1, 2, args.bilinear).to(dev).to(memory_format=torch.channels_last).train()
+    if world > 1:
+        ddp.broadcast_module_state(model)
+    reducer = ddp.GradAllReducer(model) if world > 1 else None
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True)
+
+    gi = torch.Generator().manual_seed(1 + 1000 * rank)
+    gm = torch.Generator().manual_seed(2 + 1000 * rank)
+    img_h = torch.rand(B, 1, S, S, generator=gi).pin_memory()
+    msk_h = torch.randint(0, 2, (B, S, S), generator=gm, dtype=torch.long).pin_memory()
+    img_d = img_h.to(dev).contiguous(memory_format=torch.channels_last)
+    msk_d = msk_h.to(dev)
+
+    def step(x, t):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", enabled=True):
+            logits = model(x)
+            loss = UL.training_criterion(logits, t, boundary_coeff=0.2, edge_width=51, edge_weight=7)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    def e2e_step():
+        x = img_h.to(device=dev, dtype=torch.float32, non_blocking=True, memory_format=torch.channels_last)
+        t = msk_h.to(device=dev, dtype=torch.long, non_blocking=True)
+        return step(x, t).item()             # D2H read of the loss, as train.py:163
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(args.warmup):
+        step(img_d, msk_d)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.LAUNCHES
+    ms = timed(lambda: step(img_d, msk_d), args.steps)
+    launches = ops.LAUNCHES - l0
+    clocks = sampler.stop() if sampler else {}
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    last_loss = float(step(img_d, msk_d))
+
+    total_imgs = B * world * args.steps
+    value = total_imgs / (ms / 1e3)
+    e2e_value = total_imgs / (ms_e2e / 1e3)
+    peaks = measured_peaks()
+    gf_img = GFLOP_PER_IMG.get((args.bilinear, S))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"UNet(1,2,bilinear={args.bilinear}) bf16 training step, batch {B}/GPU, {S}x{S}, "
+                               "CE+dice+0.2*boundary_loss(51,7), clip_grad_norm, RMSprop "
+                               "(BASELINE.json configs[1]; configs[3] when n_gpus > 1)",
+                   "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": "activations per step (~10 GB) far exceed the 126 MB L2; no flush needed",
+                   "random_init": True},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": img_h.numel() * 4 + msk_h.numel() * 8,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "final_loss": last_loss,
+    }
+    if gf_img:
+        conv_tf = gf_img * 1e9 * value / world / 1e12
+        line["step_conv_tflops_per_gpu"] = conv_tf
+        line["step_frac_of_bf16_peak"] = conv_tf / peaks["tflops_sustained"]
+
+    # ---- per-kernel roofline: instrumented pass (CUDA events around every C-ABI call) ----------
+    if rank == 0 and not args.no_profile:
+        with ops.profile() as rec:
+            for _ in range(2):
+                step(img_d, msk_d)
+        torch.cuda.synchronize()
+        summ = ops.summarize_profile(rec)
+        tot_ms = sum(d["ms"] for d in summ.values()) or 1.0
+        kernels = {}
+        for name, d in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
+            ent = {"ms_per_step": d["ms"] / 2, "share": d["ms"] / tot_ms, "launches_per_step": d["calls"] // 2}
+            if d["flops"] > 0:
+                ent["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12
+                ent["frac_of_peak"] = ent["tflops"] / peaks["tflops_sustained"]
+            elif d["bytes"] > 0:
+                ent["gbs"] = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+                ent["frac_of_peak"] = ent["gbs"] / peaks["hbm_gbs"]
+            kernels[name] = ent
+        line["kernels"] = kernels
+        dom = next(iter(kernels))
+        kd, sd = kernels[dom], summ[dom]
+        if "tflops" in kd:
+            line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": kd["tflops"],
+                                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": kd["frac_of_peak"],
+                                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16 cuBLAS)",
+                                "launches": sd["calls"], "avg_launch_ms": sd["ms"] / sd["calls"]}
+        else:
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": kd.get("gbs"), "peak": peaks["hbm_gbs"],
+                                "unit": "GB/s", "frac": kd.get("frac_of_peak"), "traffic": None,
+                                "peak_source": peaks["source"], "launches": sd["calls"],
+                                "avg_launch_ms": sd["ms"] / sd["calls"]}
+        conv_ms = sum(d["ms"] for n, d in summ.items() if n.startswith("conv_")) / 2
+        conv_fl = sum(d["flops"] for n, d in summ.items() if n.startswith("conv_")) / 2
+        if conv_ms > 0:
+            line["conv_tensor_util"] = {"tflops": conv_fl / (conv_ms * 1e-3) / 1e12,
+                                        "frac_of_sustained_peak": conv_fl / (conv_ms * 1e-3) / 1e12 / peaks["tflops_sustained"],
+                                        "frac_of_burst_peak": conv_fl / (conv_ms * 1e-3) / 1e12 / peaks["tflops_burst"],
+                                        "conv_ms_per_step": conv_ms}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, n, nw, med = cpu_reference_rate(S, args.bilinear, steps=3, warmup=1, budget_s=40.0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": f"oracle port (torch-CPU fp32) of the same step on B=1 {S}x{S} samples, "
+                                          f"{nw} warm-up + {n} timed, median {med:.2f} s/step"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,8 +40,8 @@ def host(t):
 
 
 def rq(x, dtype):
-    """round a CPU fp32 tensor through `dtype` (what the device stores)"""
-    return x.to(dtype).float()
+    """round a CPU fp32 tensor through `dtype` (what the device stores); always a fresh tensor"""
+    return x.detach().to(dtype).float().clone()
 
 
 def rel(a, b):
@@ -420,6 +420,11 @@ def check_conv_simt():
     out += _convT_case(1, 8, 4, 4, 3, (1, 1), FP, S, 17)
     out += _convT_case(2, 32, 16, 4, 5, (1, 2), BF, S, 18)
     out += _convT_case(1, 6, 3, 3, 3, (0, 0), FP, S, 19)
+    # UNet-bottleneck-like shapes: many channels, 2x2 / 4x4 pixels
+    out += _conv3x3_case(2, 256, 512, 2, 2, FP, S, 40)
+    out += _conv3x3_case(2, 512, 256, 4, 4, FP, S, 41)
+    out += _convT_case(2, 256, 128, 2, 2, (0, 0), FP, S, 42)
+    out += _convT_case(2, 128, 64, 4, 4, (0, 0), FP, S, 43)
     return out
 
 
@@ -446,7 +451,7 @@ def check_conv_tc():
 def check_conv_tc_tf32():
     out = []
     T = _lib.ALGO_TC
-    out += _conv3x3_case(2, 32, 64, 10, 12, FP, T, 31)
+    out += _conv3x3_case(2, 64, 64, 10, 12, FP, T, 31)
     out += _conv3x3_case(1, 64, 128, 16, 16, FP, T, 32)
     out += _conv3x3_case(1, 128, 64, 7, 9, FP, T, 33, slice_io=True)
     out += _convT_case(2, 64, 64, 6, 5, (0, 0), FP, T, 34)
@@ -544,11 +549,17 @@ def check_unet(nc, ncls, bilinear, B, H, W, mode, fused=True, boundary_coeff=0.0
             1e-3 if mode != "bf16" else 1e-2)]
     worst, worst_k = 0.0, ""
     l2 = 0.0
+    table = []
     for k, gr in r_grads.items():
         e = rel(grads[k], gr)
-        l2 = max(l2, O.rel_l2(grads[k], gr))
+        e2 = O.rel_l2(grads[k], gr)
+        table.append((e, e2, k))
+        l2 = max(l2, e2)
         if e > worst:
             worst, worst_k = e, k
+    if os.environ.get("UNETB200_TEST_VERBOSE"):
+        for e, e2, k in table:
+            print(f"      grad {k:<50s} max-rel {e:.3e}  l2-rel {e2:.3e}")
     res.append((f"{tag}_grad_worst[{worst_k}]", worst, tol * (1 if mode == "fp32" else 5)))
     res.append((f"{tag}_grad_worst_l2", l2, tol * (1 if mode == "fp32" else 5)))
     sd = model.state_dict()
@@ -576,8 +587,10 @@ GROUPS = {
     "parts_fp32": lambda gd: check_parts(gd, "fp32"),
     "parts_bf16": lambda gd: check_parts(gd, "bf16"),
     "unet_fp32": lambda gd: check_unet(1, 2, False, 2, 32, 32, "fp32") + check_unet(1, 2, True, 2, 32, 32, "fp32", fused=False),
-    "unet_bf16": lambda gd: check_unet(1, 2, False, 2, 32, 32, "bf16", boundary_coeff=0.2) + check_unet(3, 4, False, 1, 48, 48, "bf16"),
-    "unet_tf32": lambda gd: check_unet(1, 2, True, 2, 32, 32, "tf32") + check_unet(1, 2, False, 2, 32, 32, "tf32"),
+    "unet_fp32_b": lambda gd: check_unet(1, 2, False, 2, 32, 32, "fp32", fused=False) + check_unet(1, 2, False, 2, 64, 64, "fp32"),
+    "unet_bf16": lambda gd: check_unet(1, 2, False, 2, 128, 128, "bf16", boundary_coeff=0.2) + check_unet(3, 4, False, 1, 160, 96, "bf16"),
+    "unet_bf16_bil": lambda gd: check_unet(1, 2, True, 2, 128, 128, "bf16"),
+    "unet_tf32": lambda gd: check_unet(1, 2, True, 2, 64, 64, "tf32") + check_unet(1, 2, False, 2, 64, 64, "tf32"),
 }
 
 

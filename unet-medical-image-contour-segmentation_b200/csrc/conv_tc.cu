@@ -130,15 +130,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// Shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor):
-// [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout=2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout type:
+// 2 = SWIZZLE_128B (16-byte atoms, 8-row groups), 1 = SWIZZLE_128B_BASE32B (32-byte atoms, 4-row groups:
+// the only layout tcgen05 accepts for MN-major 32-bit (tf32) operands).
+constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128_32B = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout = kLayoutSW128) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a/b format, majors, N>>3 @17, M>>4 @24
@@ -427,9 +431,12 @@ __global__ void __launch_bounds__(192) tc_wgrad_kernel(const __grid_constant__ T
         const uint32_t sa = smem_u32(smem + s * kStage);
 #pragma unroll
         for (int k = 0; k < MMAS; ++k) {
-          // MN-major: LBO = distance between 128-byte-wide sub-tiles, SBO = 8 pixel rows
-          uint64_t da = make_desc(sa + k * UMMA_K * 128, kWSub, 1024);
-          uint64_t db = make_desc(sa + MSUB * kWSub + k * UMMA_K * 128, kWSub, 1024);
+          // MN-major: LBO = distance between 128-byte-wide sub-tiles, SBO = one swizzle group of
+          // pixel rows (8 rows for 16-bit operands; 4 rows with the 32-byte-atom swizzle for tf32)
+          constexpr uint32_t kLay = TF32 ? kLayoutSW128_32B : kLayoutSW128;
+          constexpr uint32_t kSbo = TF32 ? 512 : 1024;
+          uint64_t da = make_desc(sa + k * UMMA_K * 128, kWSub, kSbo, kLay);
+          uint64_t db = make_desc(sa + MSUB * kWSub + k * UMMA_K * 128, kWSub, kSbo, kLay);
           umma<TF32>(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
@@ -491,7 +498,7 @@ static EncodeTiledFn get_encode() {
 
 // 4-D NHWC view {C, W, H, B} with element strides (sw, sh, sb) and a {128 B, TW, TH, 1} box
 static int encode_act(CUtensorMap* m, int dtype, const void* base, int C, int W, int H, int B, long long sw,
-                      long long sh, long long sb, int TW, int TH) {
+                      long long sh, long long sb, int TW, int TH, bool mn_major = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return UNETB200_E_CUDA; }
   const size_t esz = dtype == UNETB200_BF16 ? 2 : 4;
@@ -501,7 +508,10 @@ static int encode_act(CUtensorMap* m, int dtype, const void* base, int C, int W,
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, dtype == UNETB200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   // MN-major fp32 (tf32 wgrad) operands need the 32-byte-atom flavour of the 128-byte swizzle
+                   (mn_major && dtype == UNETB200_F32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                                       : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation C=%d W=%d H=%d B=%d sw=%lld) failed: %d", C, W, H, B, sw, (int)r);
     return UNETB200_E_CUDA;
@@ -573,7 +583,8 @@ static void tile_shape(int Hm, int Wm, int pixels, int* TW, int* TH) {
   (void)Hm;
 }
 
-static int fill_maps(const unetb200_gconv_t* d, const void* x, const void* y, TcParams* P, int TW, int TH) {
+static int fill_maps(const unetb200_gconv_t* d, const void* x, const void* y, TcParams* P, int TW, int TH,
+                     bool mn_major = false) {
   const size_t esz = d->dtype == UNETB200_BF16 ? 2 : 4;
   const int Cq = d->N / d->nquad;
   int rc;
@@ -581,7 +592,7 @@ static int fill_maps(const unetb200_gconv_t* d, const void* x, const void* y, Tc
     // coordinates carry in_off + tap; the view is the whole source grid so that padding == TMA zero fill
     const char* base = (const char*)x + ((long long)d->in_off_y * d->Win + d->in_off_x) * d->ld_in * (long long)esz;
     rc = encode_act(&P->a_map[0], d->dtype, base, d->Cin, d->Win - d->in_off_x, d->Hin - d->in_off_y, d->B, d->ld_in,
-                    (long long)d->Win * d->ld_in, (long long)d->Hin * d->Win * d->ld_in, TW, TH);
+                    (long long)d->Win * d->ld_in, (long long)d->Hin * d->Win * d->ld_in, TW, TH, mn_major);
     if (rc) return rc;
   } else {
     for (int t = 0; t < 4; ++t) {
@@ -591,7 +602,7 @@ static int fill_maps(const unetb200_gconv_t* d, const void* x, const void* y, Tc
       if (Hq <= 0 || Wq <= 0) { set_error("tc: empty quadrant view"); return UNETB200_E_INVALID; }
       const char* base = (const char*)x + ((long long)oy * d->Win + ox) * d->ld_in * (long long)esz;
       rc = encode_act(&P->a_map[t], d->dtype, base, d->Cin, Wq, Hq, d->B, 2 * d->ld_in,
-                      2LL * d->Win * d->ld_in, (long long)d->Hin * d->Win * d->ld_in, TW, TH);
+                      2LL * d->Win * d->ld_in, (long long)d->Hin * d->Win * d->ld_in, TW, TH, mn_major);
       if (rc) return rc;
     }
   }
@@ -600,7 +611,8 @@ static int fill_maps(const unetb200_gconv_t* d, const void* x, const void* y, Tc
     const int oy = d->out_off_y + (d->out_scale == 2 ? a : 0), ox = d->out_off_x + (d->out_scale == 2 ? c : 0);
     const char* base = (const char*)y + ((long long)oy * d->Wout + ox) * d->ld_out * (long long)esz;
     rc = encode_act(&P->o_map[qd], d->dtype, base, Cq, d->Wm, d->Hm, d->B, (long long)d->out_scale * d->ld_out,
-                    (long long)d->out_scale * d->Wout * d->ld_out, (long long)d->Hout * d->Wout * d->ld_out, TW, TH);
+                    (long long)d->out_scale * d->Wout * d->ld_out, (long long)d->Hout * d->Wout * d->ld_out, TW, TH,
+                    mn_major);
     if (rc) return rc;
   }
   return 0;
@@ -713,7 +725,7 @@ int tc_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const 
   int TW, TH;
   tile_shape(d->Hm, d->Wm, kWPix, &TW, &TH);
   fill_common(d, g, &P, TW, TH);
-  int rc = fill_maps(d, x, gy, &P, TW, TH);
+  int rc = fill_maps(d, x, gy, &P, TW, TH, /*mn_major=*/true);
   if (rc) return rc;
   int mt, nt, pt, BN;
   wgrad_geometry(d, &mt, &nt, &pt, &BN);

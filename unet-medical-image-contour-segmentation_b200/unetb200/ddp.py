@@ -1,0 +1,105 @@
+"""Data-parallel gradient exchange for the UNet step (BASELINE.json configs[3]).
+
+The reference is single-device (train.py:244); this layer has no counterpart there.  Semantics are
+standard DDP: replicated weights (broadcast from rank 0), per-replica BatchNorm batch statistics (the
+reference uses plain nn.BatchNorm2d), gradients mean-reduced over ranks.  The only exchange step of
+the path is that all-reduce, so it is the only collective: NCCL over NVLink 5 / NVSwitch through
+torch.distributed, issued per bucket from autograd hooks *while backward is still running* (buckets
+fill in reverse layer order: outc, up4 ... inc), on NCCL's own stream, joined once before the
+optimizer step.  Works with the gloo backend on CPU tensors too (used by the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def broadcast_module_state(module, src=0):
+    """Replicate parameters and buffers from `src` (rank-0 convention for BN running stats)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src)
+
+
+class GradAllReducer:
+    """Bucketed, backward-overlapped mean all-reduce of ``module``'s gradients.
+
+    Usage per step:  ``loss.backward(); reducer.finish()``  (then clip / optimizer.step()).
+    After ``finish()`` every ``p.grad`` is a view into its bucket holding the rank-averaged gradient.
+    """
+
+    def __init__(self, module, bucket_bytes=32 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        # reverse registration order ~ order in which backward produces the gradients
+        order = list(reversed(self.params))
+        self.buckets = []          # list of dict(params, offsets, numel, buffer, pending, work)
+        cur, cur_bytes = [], 0
+        for p in order:
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                self._close_bucket(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._close_bucket(cur)
+        self._where = {}
+        for bi, b in enumerate(self.buckets):
+            for pi, p in enumerate(b["params"]):
+                self._where[p] = (bi, pi)
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.launched = 0
+
+    def _close_bucket(self, params):
+        offsets, n = [], 0
+        for p in params:
+            offsets.append(n)
+            n += p.numel()
+        dev = params[0].device
+        self.buckets.append(dict(params=list(params), offsets=offsets, numel=n,
+                                 buffer=torch.zeros(n, dtype=torch.float32, device=dev),
+                                 pending=len(params), work=None))
+
+    def _views(self, b):
+        return [b["buffer"][o:o + p.numel()].view_as(p) for p, o in zip(b["params"], b["offsets"])]
+
+    def _on_grad(self, p):
+        if self.world == 1:
+            return
+        bi, _ = self._where[p]
+        b = self.buckets[bi]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b["params"]]
+        torch._foreach_copy_(self._views(b), [g.to(torch.float32) for g in grads])
+        b["buffer"].mul_(1.0 / self.world)
+        b["work"] = dist.all_reduce(b["buffer"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.launched += 1
+
+    def finish(self):
+        """Join the outstanding all-reduces and point every p.grad at its averaged bucket view."""
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if b["work"] is None and b["pending"] != len(b["params"]):
+                self._launch(b)            # a bucket with parameters that received no gradient this step
+        for b in self.buckets:
+            if b["work"] is not None:
+                b["work"].wait()
+                for p, v in zip(b["params"], self._views(b)):
+                    if p.grad is not None:
+                        p.grad = v.to(p.grad.dtype) if p.grad.dtype != torch.float32 else v
+                b["work"] = None
+            b["pending"] = len(b["params"])
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

@@ -63,8 +63,8 @@ def _w_src(w):
 
 def _pack(w, dtype, n0, n1, n2, s0, s1, s2, off=0):
     dst = torch.empty((n0, n1 * n2), dtype=dtype, device=w.device)
-    _lib.check(ops.lib().unetb200_pack_weights(ops._p(w), ops._p(dst), ops._DT[dtype], n0, n1, n2, s0, s1, s2, off,
-                                               ops._stream()), "pack_weights")
+    ops._run("pack_weights", ops.lib().unetb200_pack_weights, ops._p(w), ops._p(dst), ops._DT[dtype], n0, n1, n2, s0,
+             s1, s2, off, ops._stream(), nbytes=dst.numel() * (4 + dst.element_size()))
     return dst
 
 
@@ -151,7 +151,7 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx):
     gx = None
     if need_gx:
         gx = ops.empty_nhwc(B, Cin, H, W, cd, x.device)
-        ops.gconv_fprop(_gconv3x3(gy, Cin, gx, cd), gy, pack3x3_dgrad(w, cd), None, gx, None)
+        ops.gconv_fprop(_gconv3x3(gy, Cin, gx, cd), gy, pack3x3_dgrad(w, cd), None, gx, None, kind="dgrad")
     return gx, dW, dgamma, dbeta
 
 
@@ -271,7 +271,8 @@ class UpCatConvTFn(torch.autograd.Function):
             ops.zero_channels(up)
         d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, C1, ops.TAPS1, 1, (0, 0), h, w, ops.nhwc_ld(x1),
                            4 * Cup, 4, 2, off, H, W, ops.nhwc_ld(cat))
-        ops.gconv_fprop(d, x1, packT_fprop(wT, cd), _f32c(bT) if bT is not None else None, up, None)
+        ops.gconv_fprop(d, x1, packT_fprop(wT, cd), _f32c(bT) if bT is not None else None, up, None,
+                        kind="convT_fprop")
         ctx.geom = (C2, Cup, off, dy or dx)
         if cfg.save:
             ctx.save_for_backward(x1, wT)
@@ -303,7 +304,7 @@ class UpCatConvTFn(torch.autograd.Function):
             gx1 = ops.empty_nhwc(B, C1, h, w, cd, g.device)
             d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, Cup, ops.TAPS_Q, 2, off, H, W, ld,
                                C1, 1, 1, (0, 0), h, w, ops.nhwc_ld(gx1))
-            ops.gconv_fprop(d, gup, packT_dgrad(wT, cd), None, gx1, None)
+            ops.gconv_fprop(d, gup, packT_dgrad(wT, cd), None, gx1, None, kind="convT_dgrad")
         return gx1, g2, dW, dB, None
 
 

@@ -19,8 +19,10 @@ from ._lib import BF16, F32, I64
 # dice
 # ------------------------------------------------------------------------------------------------
 def _dense_same_layout(a, b):
+    def dense(t):
+        return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
     return (a.stride() == b.stride() and a.dtype == torch.float32 and b.dtype == torch.float32 and
-            a.is_non_overlapping_and_dense() and b.is_non_overlapping_and_dense())
+            dense(a) and dense(b))
 
 
 class DiceCoeffFn(torch.autograd.Function):
@@ -33,8 +35,8 @@ class DiceCoeffFn(torch.autograd.Function):
         acc = torch.empty(3 * G, dtype=torch.float64, device=dev)
         out = torch.empty(1, dtype=torch.float32, device=dev)
         saved = torch.empty(2 * G, dtype=torch.float32, device=dev)
-        _lib.check(ops.lib().unetb200_dice_fwd(ops._p(x), ops._p(t), G, L, eps, ops._p(acc), ops._p(out),
-                                               ops._p(saved), ops._stream()), "dice_fwd")
+        ops._run("dice_fwd", ops.lib().unetb200_dice_fwd, ops._p(x), ops._p(t), G, L, eps, ops._p(acc), ops._p(out),
+                 ops._p(saved), ops._stream(), kernels=2, nbytes=8.0 * x.numel())
         ctx.save_for_backward(x, t, saved)
         ctx.G, ctx.eps = G, eps
         return out.reshape(())
@@ -45,8 +47,8 @@ class DiceCoeffFn(torch.autograd.Function):
         G = ctx.G
         gs = g.detach().float().reshape(1).contiguous()
         gx = torch.empty_like(x)
-        _lib.check(ops.lib().unetb200_dice_bwd(ops._p(x), ops._p(t), G, x.numel() // G, ctx.eps, ops._p(saved),
-                                               ops._p(gs), ops._p(gx), ops._stream()), "dice_bwd")
+        ops._run("dice_bwd", ops.lib().unetb200_dice_bwd, ops._p(x), ops._p(t), G, x.numel() // G, ctx.eps,
+                 ops._p(saved), ops._p(gs), ops._p(gx), ops._stream(), nbytes=8.0 * x.numel())
         return gx, None, None, None
 
 
@@ -120,9 +122,10 @@ def boundary_loss(pred_mask, target_mask, edge_width=64, edge_weight=5.0, smooth
     L = ops.lib()
     work = torch.empty(L.unetb200_boundary_work_bytes(), dtype=torch.uint8, device=pred.device)
     out = torch.empty(1, dtype=torch.float32, device=pred.device)
-    _lib.check(L.unetb200_boundary_loss(ops._p(pred), BF16 if pred.dtype == torch.bfloat16 else F32, *pred.stride(),
-                                        ops._p(tgt), tdt, *tgt.stride(), B, H, W, int(edge_width), float(edge_weight),
-                                        float(smooth), ops._p(work), ops._p(out), ops._stream()), "boundary_loss")
+    ops._run("boundary_loss", L.unetb200_boundary_loss, ops._p(pred), BF16 if pred.dtype == torch.bfloat16 else F32,
+             *pred.stride(), ops._p(tgt), tdt, *tgt.stride(), B, H, W, int(edge_width), float(edge_weight),
+             float(smooth), ops._p(work), ops._p(out), ops._stream(), kernels=2,
+             nbytes=float(B * H * W) * (pred.element_size() + tgt.element_size()))
     return out.reshape(())
 
 
@@ -137,9 +140,9 @@ class CeDiceFn(torch.autograd.Function):
         acc = torch.empty(4, dtype=torch.float64, device=dev)
         out = torch.empty(4, dtype=torch.float32, device=dev)
         coefs = torch.empty(4, dtype=torch.float32, device=dev)
-        _lib.check(ops.lib().unetb200_ce_dice_fwd(ops._p(logits), ops.dt(logits), ops._p(target), B * H * W, K, eps,
-                                                  ops._p(acc), ops._p(out), ops._p(coefs), ops._stream()),
-                   "ce_dice_fwd")
+        ops._run("ce_dice_fwd", ops.lib().unetb200_ce_dice_fwd, ops._p(logits), ops.dt(logits), ops._p(target),
+                 B * H * W, K, eps, ops._p(acc), ops._p(out), ops._p(coefs), ops._stream(), kernels=2,
+                 nbytes=float(B * H * W) * (K * logits.element_size() + 8))
         ctx.save_for_backward(logits, target, coefs)
         ctx.mark_non_differentiable(out)
         return out[0].clone().reshape(()), out
@@ -150,9 +153,9 @@ class CeDiceFn(torch.autograd.Function):
         B, K, H, W = logits.shape
         gs = g.detach().float().reshape(1).contiguous()
         gl = torch.empty((B, H, W, K), dtype=logits.dtype, device=logits.device)
-        _lib.check(ops.lib().unetb200_ce_dice_bwd(ops._p(logits), ops.dt(logits), ops._p(target), B * H * W, K,
-                                                  ops._p(coefs), ops._p(gs), ops._p(gl), ops._stream()),
-                   "ce_dice_bwd")
+        ops._run("ce_dice_bwd", ops.lib().unetb200_ce_dice_bwd, ops._p(logits), ops.dt(logits), ops._p(target),
+                 B * H * W, K, ops._p(coefs), ops._p(gs), ops._p(gl), ops._stream(),
+                 nbytes=float(B * H * W) * (2 * K * logits.element_size() + 8))
         return gl.permute(0, 3, 1, 2), None, None
 
 

@@ -4,18 +4,50 @@ allocator, so OOM surfaces as ``torch.cuda.OutOfMemoryError``) and streams -- ne
 
 Activation convention: a logical [B, C, H, W] tensor whose strides are (H*W*ld, 1, W*ld, ld) is
 "NHWC with pixel stride ld"; ld > C is a channel slice of a wider NHWC buffer.
+
+Every wrapper goes through :func:`_run`, which counts kernel launches (``LAUNCHES``, bench.py's
+``gpu_launches``) and, inside ``with profile() as rec:``, brackets the call with CUDA events on the
+launching stream and records its algorithmic FLOPs / bytes (bench.py's ``roofline``).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 
 import torch
 
 from . import _lib
-from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, BF16, F32, I64, GConv
+from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TC, BF16, F32, I64, GConv  # noqa: F401
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
+_ESZ = {torch.float32: 4, torch.bfloat16: 2}
+
+LAUNCHES = 0
+_PROFILE = None
+
+
+@contextlib.contextmanager
+def profile():
+    """Collect (name, start_event, end_event, flops, bytes) per C-ABI call."""
+    global _PROFILE
+    prev, _PROFILE = _PROFILE, []
+    try:
+        yield _PROFILE
+    finally:
+        _PROFILE = prev
+
+
+def summarize_profile(rec):
+    """{name: dict(ms, calls, flops, bytes)} -- call after torch.cuda.synchronize()."""
+    out = {}
+    for name, s, e, flops, nbytes in rec:
+        d = out.setdefault(name, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+        d["ms"] += s.elapsed_time(e)
+        d["calls"] += 1
+        d["flops"] += flops
+        d["bytes"] += nbytes
+    return out
 
 
 def lib():
@@ -24,6 +56,20 @@ def lib():
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _run(name, fn, *args, kernels=1, flops=0.0, nbytes=0.0):
+    global LAUNCHES
+    if _PROFILE is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        _PROFILE.append([name, s, e, flops, nbytes])
+    else:
+        rc = fn(*args)
+    LAUNCHES += kernels
+    _lib.check(rc, name)
 
 
 def _p(t):
@@ -97,27 +143,27 @@ def to_nhwc(x, dtype, packed=False):
     B, Cc, H, W = x.shape
     out = empty_nhwc(B, Cc, H, W, dtype, x.device)
     sn, sc, sh, sw = x.stride()
-    _lib.check(lib().unetb200_gather_nhwc(_p(x), dt(x), sn, sc, sh, sw, _p(out), _DT[dtype], Cc, B, Cc, H, W,
-                                          _stream()), "gather_nhwc")
+    _run("gather_nhwc", lib().unetb200_gather_nhwc, _p(x), dt(x), sn, sc, sh, sw, _p(out), _DT[dtype], Cc, B, Cc, H,
+         W, _stream(), nbytes=x.numel() * (x.element_size() + _ESZ[dtype]))
     return out
 
 
 def copy_channels(src, dst):
     B, Cc, H, W = src.shape
-    _lib.check(lib().unetb200_copy_channels(_p(src), dt(src), nhwc_ld(src), _p(dst), dt(dst), nhwc_ld(dst),
-                                            B * H * W, Cc, _stream()), "copy_channels")
+    _run("copy_channels", lib().unetb200_copy_channels, _p(src), dt(src), nhwc_ld(src), _p(dst), dt(dst),
+         nhwc_ld(dst), B * H * W, Cc, _stream(), nbytes=src.numel() * (src.element_size() + dst.element_size()))
 
 
 def zero_channels(dst):
     B, Cc, H, W = dst.shape
-    _lib.check(lib().unetb200_zero_channels(_p(dst), dt(dst), nhwc_ld(dst), B * H * W, Cc, _stream()),
-               "zero_channels")
+    _run("zero_channels", lib().unetb200_zero_channels, _p(dst), dt(dst), nhwc_ld(dst), B * H * W, Cc, _stream(),
+         nbytes=dst.numel() * dst.element_size())
 
 
 def add_channels_(a, b):
     B, Cc, H, W = a.shape
-    _lib.check(lib().unetb200_add_channels(_p(a), nhwc_ld(a), _p(b), nhwc_ld(b), dt(a), B * H * W, Cc, _stream()),
-               "add_channels")
+    _run("add_channels", lib().unetb200_add_channels, _p(a), nhwc_ld(a), _p(b), nhwc_ld(b), dt(a), B * H * W, Cc,
+         _stream(), nbytes=3 * a.numel() * a.element_size())
     return a
 
 
@@ -125,8 +171,8 @@ def channel_sum(g):
     B, Cc, H, W = g.shape
     acc = torch.empty(Cc, dtype=torch.float64, device=g.device)
     out = torch.empty(Cc, dtype=torch.float32, device=g.device)
-    _lib.check(lib().unetb200_channel_sum(_p(g), dt(g), nhwc_ld(g), B * H * W, Cc, _p(acc), _p(out), _stream()),
-               "channel_sum")
+    _run("channel_sum", lib().unetb200_channel_sum, _p(g), dt(g), nhwc_ld(g), B * H * W, Cc, _p(acc), _p(out),
+         _stream(), kernels=2, nbytes=g.numel() * g.element_size())
     return out
 
 
@@ -136,6 +182,7 @@ def channel_sum(g):
 TAPS3 = [(kh - 1, kw - 1) for kh in range(3) for kw in range(3)]
 TAPS1 = [(0, 0)]
 TAPS_Q = [(0, 0), (0, 1), (1, 0), (1, 1)]
+_ALGO_NAME = {ALGO_SIMT: "simt", ALGO_TC: "tc"}
 
 
 def forced_algo():
@@ -160,10 +207,17 @@ def make_gconv(dtype, algo, B, Hm, Wm, Cin, taps, in_scale, in_off, Hin, Win, ld
     return d
 
 
-def gconv_fprop(d, x, wp, bias, y, stats):
+def gconv_flops(d):
+    """Algorithmic FLOPs of one launch: 2*M*N*K."""
+    return 2.0 * d.B * d.Hm * d.Wm * d.N * d.ntaps * d.Cin
+
+
+def gconv_fprop(d, x, wp, bias, y, stats, kind="fprop"):
     used = C.c_int(0)
-    _lib.check(lib().unetb200_gconv_fprop(C.byref(d), _p(x), _p(wp), _p(bias), _p(y), _p(stats), C.byref(used),
-                                          _stream()), "gconv_fprop")
+    _run(f"conv_{kind}", lib().unetb200_gconv_fprop, C.byref(d), _p(x), _p(wp), _p(bias), _p(y), _p(stats),
+         C.byref(used), _stream(), flops=gconv_flops(d))
+    if _PROFILE is not None:
+        _PROFILE[-1][0] = f"conv_{kind}_{_ALGO_NAME.get(used.value, '?')}"
     return used.value
 
 
@@ -175,10 +229,10 @@ def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0):
     partials = torch.empty(splits.value * K * d.N, dtype=torch.float32, device=x.device)
     d2 = GConv.from_buffer_copy(d)
     d2.algo = used.value
-    _lib.check(lib().unetb200_gconv_wgrad(C.byref(d2), _p(x), _p(gy), _p(partials), splits.value, _stream()),
-               "gconv_wgrad")
-    _lib.check(lib().unetb200_wgrad_reduce(_p(partials), splits.value, d.ntaps, d.Cin, d.N, d.N // d.nquad, _p(dst), st,
-                                           sc, sq, sn, 0, _stream()), "wgrad_reduce")
+    _run(f"conv_wgrad_{_ALGO_NAME.get(used.value, '?')}", lib().unetb200_gconv_wgrad, C.byref(d2), _p(x), _p(gy),
+         _p(partials), splits.value, _stream(), flops=gconv_flops(d))
+    _run("wgrad_reduce", lib().unetb200_wgrad_reduce, _p(partials), splits.value, d.ntaps, d.Cin, d.N,
+         d.N // d.nquad, _p(dst), st, sc, sq, sn, 0, _stream(), nbytes=4.0 * K * d.N * (splits.value + 1))
     return used.value
 
 
@@ -188,70 +242,72 @@ def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0):
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, Cc):
     dev = stats.device
     coefs = torch.empty((4, Cc), dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
-    _lib.check(lib().unetb200_bn_finalize(_p(stats), count, _p(gamma), _p(beta), eps, momentum, _p(running_mean),
-                                          _p(running_var), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(coefs[3]),
-                                          Cc, _stream()), "bn_finalize")
+    _run("bn_finalize", lib().unetb200_bn_finalize, _p(stats), count, _p(gamma), _p(beta), eps, momentum,
+         _p(running_mean), _p(running_var), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(coefs[3]), Cc, _stream())
     return coefs
 
 
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, Cc):
     coefs = torch.empty((4, Cc), dtype=torch.float32, device=running_mean.device)
-    _lib.check(lib().unetb200_bn_eval_coeffs(_p(gamma), _p(beta), _p(running_mean), _p(running_var), eps,
-                                             _p(coefs[2]), _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), Cc, _stream()),
-               "bn_eval_coeffs")
+    _run("bn_eval_coeffs", lib().unetb200_bn_eval_coeffs, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+         eps, _p(coefs[2]), _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), Cc, _stream())
     return coefs
 
 
 def bn_relu_apply(y, coefs, z, pooled=None):
     B, Cc, H, W = y.shape
-    _lib.check(lib().unetb200_bn_relu_apply(_p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]), _p(z), nhwc_ld(z),
-                                            _p(pooled), nhwc_ld(pooled) if pooled is not None else 0, dt(y), B, H, W,
-                                            Cc, _stream()), "bn_relu_apply")
+    es = y.element_size()
+    _run("bn_relu_apply_pool" if pooled is not None else "bn_relu_apply", lib().unetb200_bn_relu_apply, _p(y),
+         nhwc_ld(y), _p(coefs[2]), _p(coefs[3]), _p(z), nhwc_ld(z), _p(pooled),
+         nhwc_ld(pooled) if pooled is not None else 0, dt(y), B, H, W, Cc, _stream(),
+         nbytes=y.numel() * es * (2.25 if pooled is not None else 2.0))
 
 
 def maxpool2_fwd(x, p):
     B, Cc, H, W = x.shape
-    _lib.check(lib().unetb200_maxpool2_fwd(_p(x), nhwc_ld(x), _p(p), nhwc_ld(p), dt(x), B, H, W, Cc, _stream()),
-               "maxpool2_fwd")
+    _run("maxpool2_fwd", lib().unetb200_maxpool2_fwd, _p(x), nhwc_ld(x), _p(p), nhwc_ld(p), dt(x), B, H, W, Cc,
+         _stream(), nbytes=x.numel() * x.element_size() * 1.25)
 
 
 def maxpool2_bwd(x, gp, gx, accumulate):
     B, Cc, H, W = x.shape
-    _lib.check(lib().unetb200_maxpool2_bwd(_p(x), nhwc_ld(x), _p(gp), nhwc_ld(gp), _p(gx), nhwc_ld(gx),
-                                           1 if accumulate else 0, dt(x), B, H, W, Cc, _stream()), "maxpool2_bwd")
+    _run("maxpool2_bwd", lib().unetb200_maxpool2_bwd, _p(x), nhwc_ld(x), _p(gp), nhwc_ld(gp), _p(gx), nhwc_ld(gx),
+         1 if accumulate else 0, dt(x), B, H, W, Cc, _stream(),
+         nbytes=x.numel() * x.element_size() * (3.25 if accumulate else 2.25))
 
 
-def bn_relu_bwd(gz, y, coefs, training, want_affine=True):
+def bn_relu_bwd(gz, y, coefs, training):
     """Returns (gy, dgamma, dbeta) for z = relu(bn(y))."""
     B, Cc, H, W = y.shape
     dev = y.device
+    es = y.element_size()
     sums = torch.zeros((2, Cc), dtype=torch.float64, device=dev)
     L = lib()
-    _lib.check(L.unetb200_bn_relu_bwd_reduce(_p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]),
-                                             _p(coefs[0]), _p(coefs[1]), _p(sums), dt(y), B, H, W, Cc, _stream()),
-               "bn_relu_bwd_reduce")
+    _run("bn_relu_bwd_reduce", L.unetb200_bn_relu_bwd_reduce, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]),
+         _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(sums), dt(y), B, H, W, Cc, _stream(),
+         nbytes=2.0 * y.numel() * es)
     dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
     dbeta = torch.empty(Cc, dtype=torch.float32, device=dev)
     coef = torch.empty((2, Cc), dtype=torch.float32, device=dev)
-    _lib.check(L.unetb200_bn_bwd_finalize(_p(sums), B * H * W, 1 if training else 0, _p(dgamma), _p(dbeta),
-                                          _p(coef), Cc, _stream()), "bn_bwd_finalize")
+    _run("bn_bwd_finalize", L.unetb200_bn_bwd_finalize, _p(sums), B * H * W, 1 if training else 0, _p(dgamma),
+         _p(dbeta), _p(coef), Cc, _stream())
     gy = empty_nhwc(B, Cc, H, W, y.dtype, dev)
-    _lib.check(L.unetb200_bn_relu_bwd_apply(_p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]),
-                                            _p(coefs[0]), _p(coefs[1]), _p(coef), _p(gy), nhwc_ld(gy), dt(y), B, H,
-                                            W, Cc, _stream()), "bn_relu_bwd_apply")
+    _run("bn_relu_bwd_apply", L.unetb200_bn_relu_bwd_apply, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]),
+         _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(coef), _p(gy), nhwc_ld(gy), dt(y), B, H, W, Cc, _stream(),
+         nbytes=3.0 * y.numel() * es)
     return gy, dgamma, dbeta
 
 
 def upsample2x_fwd(x, y, off):
     B, Cc, h, w = x.shape
-    _lib.check(lib().unetb200_upsample2x_fwd(_p(x), nhwc_ld(x), _p(y), nhwc_ld(y), dt(x), B, h, w, Cc, y.shape[2],
-                                             y.shape[3], off[0], off[1], _stream()), "upsample2x_fwd")
+    _run("upsample2x_fwd", lib().unetb200_upsample2x_fwd, _p(x), nhwc_ld(x), _p(y), nhwc_ld(y), dt(x), B, h, w, Cc,
+         y.shape[2], y.shape[3], off[0], off[1], _stream(), nbytes=5.0 * x.numel() * x.element_size())
 
 
 def upsample2x_bwd(gy, gx, off):
     B, Cc, h, w = gx.shape
-    _lib.check(lib().unetb200_upsample2x_bwd(_p(gy), nhwc_ld(gy), _p(gx), nhwc_ld(gx), dt(gx), B, h, w, Cc,
-                                             gy.shape[2], gy.shape[3], off[0], off[1], _stream()), "upsample2x_bwd")
+    _run("upsample2x_bwd", lib().unetb200_upsample2x_bwd, _p(gy), nhwc_ld(gy), _p(gx), nhwc_ld(gx), dt(gx), B, h, w,
+         Cc, gy.shape[2], gy.shape[3], off[0], off[1], _stream(), nbytes=5.0 * gx.numel() * gx.element_size())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -260,8 +316,8 @@ def upsample2x_bwd(gy, gx, off):
 def outconv_fwd(x, w, bias, logits):
     B, Cc, H, W = x.shape
     K = w.shape[0]
-    _lib.check(lib().unetb200_outconv_fwd(_p(x), nhwc_ld(x), _p(w), _p(bias), _p(logits), dt(x), B * H * W, Cc, K,
-                                          _stream()), "outconv_fwd")
+    _run("outconv_fwd", lib().unetb200_outconv_fwd, _p(x), nhwc_ld(x), _p(w), _p(bias), _p(logits), dt(x), B * H * W,
+         Cc, K, _stream(), nbytes=(x.numel() + logits.numel()) * x.element_size())
 
 
 def outconv_bwd(x, w, glogits, gx, dw, dbias):
@@ -269,6 +325,6 @@ def outconv_bwd(x, w, glogits, gx, dw, dbias):
     K = w.shape[0]
     n = lib().unetb200_outconv_bwd_workspace(B * H * W, Cc, K)
     ws = torch.empty(n, dtype=torch.float32, device=x.device)
-    _lib.check(lib().unetb200_outconv_bwd(_p(x), nhwc_ld(x), _p(w), _p(glogits), _p(gx),
-                                          nhwc_ld(gx) if gx is not None else 0, _p(dw), _p(dbias), _p(ws), dt(x),
-                                          B * H * W, Cc, K, _stream()), "outconv_bwd")
+    _run("outconv_bwd", lib().unetb200_outconv_bwd, _p(x), nhwc_ld(x), _p(w), _p(glogits), _p(gx),
+         nhwc_ld(gx) if gx is not None else 0, _p(dw), _p(dbias), _p(ws), dt(x), B * H * W, Cc, K, _stream(),
+         kernels=2, nbytes=(2 * x.numel() + glogits.numel()) * x.element_size())
