@@ -84,12 +84,16 @@ typedef struct unetb200_gconv {
   int64_t ld_out;             /* destination pixel stride, elements                                  */
 } unetb200_gconv_t;           /* HOST struct */
 
-/* y = gconv(x, Wp) (+bias).  `stats` (nullable) = double[2*Cq], accumulated (+=) with the
- * per-channel sum and sum of squares of the values as stored (i.e. after rounding to `dtype`):
- * the BatchNorm batch statistics of unet_parts.py:16,19 fused into the conv epilogue.
+/* y = gconv(x, Wp) (+bias).  `stats` (nullable, nquad == 1 only) = double[2*N], accumulated (+=)
+ * with the per-channel sum and sum of squares of the values as stored (i.e. after rounding to
+ * `dtype`): the BatchNorm batch statistics of unet_parts.py:16,19 fused into the conv epilogue.
+ * Each tile writes its partial sums to `stats_ws` (float[unetb200_gconv_stats_workspace(d)], plain
+ * stores) and a second small kernel reduces them in fp64 -- no global atomics on the hot path.
  * Returns the algorithm actually used through *algo_used (host, nullable). */
+int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d);   /* number of floats */
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp,
-                         const float* bias, void* y, double* stats, int* algo_used, void* stream);
+                         const float* bias, void* y, double* stats, float* stats_ws, int* algo_used,
+                         void* stream);
 
 /* Weight gradient of the same generalised conv:
  *   dWp[(t,c)][n] = sum_m A[m][(t,c)] * G[m][n],  G[m][n] = gy at the destination of (m,n).

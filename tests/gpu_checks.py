@@ -411,6 +411,10 @@ def check_conv_simt():
     out = []
     S = _lib.ALGO_SIMT
     out += _conv3x3_case(2, 1, 8, 9, 11, FP, S, 10)
+    out += _conv3x3_case(2, 1, 64, 16, 20, FP, S, 50)      # first-layer kernels (C_in = 1, 64 channels)
+    out += _conv3x3_case(2, 1, 64, 16, 20, BF, S, 51)
+    out += _conv3x3_case(1, 3, 64, 12, 12, BF, S, 52)      # RGB first layer (fprop special, wgrad generic)
+    out += _conv3x3_case(1, 4, 32, 7, 9, FP, S, 53)
     out += _conv3x3_case(1, 3, 20, 8, 8, FP, S, 11)
     out += _conv3x3_case(2, 16, 24, 10, 12, FP, S, 12)
     out += _conv3x3_case(2, 32, 64, 7, 9, BF, S, 13)
@@ -570,6 +574,59 @@ def check_unet(nc, ncls, bilinear, B, H, W, mode, fused=True, boundary_coeff=0.0
     return res
 
 
+def torch_gpu_step(st, img, msk, ncls, bilinear, mode):
+    """The reference's own GPU path (PyTorch ATen/cuDNN through the oracle's functional restatement) --
+    used ONLY to calibrate how far a reduced-precision GPU run sits from the CPU fp32 oracle."""
+    names = O.param_names(st)
+    leaves = {k: st[k].detach().clone().to(DEV).requires_grad_(True) for k in names}
+    work = {k: (leaves[k] if k in leaves else v.clone().to(DEV)) for k, v in st.items()}
+    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    t = msk.to(DEV)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = (mode == "tf32")
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+            logits = O.unet_forward(work, x, bilinear, True)
+            loss = O.train_loss(logits, t, ncls)
+        grads = torch.autograd.grad(loss, [leaves[k] for k in names])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return host(logits), float(loss), {k: host(g) for k, g in zip(names, grads)}
+
+
+def calibrate(nc, ncls, bilinear, B, H, W, mode):
+    """Errors vs the CPU fp32 oracle of (a) torch's GPU path and (b) ours, and (c) ours vs torch-GPU."""
+    import statistics
+    import unet
+    tag = f"calib{nc}_{ncls}_{'bil' if bilinear else 'convT'}_{B}x{H}x{W}_{mode}"
+    st = O.build_state(nc, ncls, bilinear, seed=0)
+    img, msk = O.synthetic_batch(B, nc, ncls, H, W)
+    r_logits, r_loss, r_grads = O.training_step({k: v.clone() for k, v in st.items()}, img, msk, ncls, bilinear)
+    t_logits, t_loss, t_grads = torch_gpu_step(st, img, msk, ncls, bilinear, mode)
+    model = unet.UNet(nc, ncls, bilinear)
+    model.load_state_dict(st)
+    model = model.to(DEV).to(memory_format=torch.channels_last).train()
+    os.environ["UNET_B200_PRECISION"] = "tf32" if mode == "tf32" else "fp32"
+    m_logits, m_loss, m_grads = unet_step_gpu(model, img, msk, amp=(mode == "bf16"))
+    inf = float("inf")
+    res = []
+    for who, lg, ls, gr in (("torch_gpu", t_logits, t_loss, t_grads), ("ours", m_logits, m_loss, m_grads)):
+        l2 = [O.rel_l2(gr[k], r_grads[k]) for k in r_grads]
+        mx = [rel(gr[k], r_grads[k]) for k in r_grads]
+        res += [(f"{tag}_{who}_logits_maxrel", rel(lg, r_logits), inf),
+                (f"{tag}_{who}_loss_rel", abs(ls - float(r_loss)) / abs(float(r_loss)), inf),
+                (f"{tag}_{who}_argmax_mismatch", (lg.argmax(1) != r_logits.argmax(1)).float().mean().item(), inf),
+                (f"{tag}_{who}_grad_l2_median", statistics.median(l2), inf),
+                (f"{tag}_{who}_grad_l2_worst", max(l2), inf),
+                (f"{tag}_{who}_grad_maxrel_median", statistics.median(mx), inf),
+                (f"{tag}_{who}_grad_maxrel_worst", max(mx), inf)]
+    l2 = [O.rel_l2(m_grads[k], t_grads[k]) for k in r_grads]
+    res += [(f"{tag}_ours_vs_torch_gpu_logits_maxrel", rel(m_logits, t_logits), inf),
+            (f"{tag}_ours_vs_torch_gpu_grad_l2_median", statistics.median(l2), inf),
+            (f"{tag}_ours_vs_torch_gpu_grad_l2_worst", max(l2), inf)]
+    return res
+
+
 GROUPS = {
     "layout": lambda gd: check_layout_ops(),
     "bn_fwd": lambda gd: check_bn_forward(),
@@ -591,6 +648,9 @@ GROUPS = {
     "unet_bf16": lambda gd: check_unet(1, 2, False, 2, 128, 128, "bf16", boundary_coeff=0.2) + check_unet(3, 4, False, 1, 160, 96, "bf16"),
     "unet_bf16_bil": lambda gd: check_unet(1, 2, True, 2, 128, 128, "bf16"),
     "unet_tf32": lambda gd: check_unet(1, 2, True, 2, 64, 64, "tf32") + check_unet(1, 2, False, 2, 64, 64, "tf32"),
+    "calib_small": lambda gd: sum((calibrate(1, 2, False, 2, 128, 128, m) for m in ("fp32", "tf32", "bf16")), []),
+    "calib_large": lambda gd: sum((calibrate(1, 2, False, 4, 256, 256, m) for m in ("fp32", "tf32", "bf16")), []),
+    "calib_bil": lambda gd: sum((calibrate(1, 2, True, 2, 256, 256, m) for m in ("tf32", "bf16")), []),
 }
 
 

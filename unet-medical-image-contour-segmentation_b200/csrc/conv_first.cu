@@ -1,0 +1,227 @@
+// First-layer convolution: 3x3, C_in = 1..4 (grayscale / RGB input, unet_model.py:15), K = 9*C_in <= 36.
+// With so little reduction depth the layer is HBM-bound (it writes / reads the full-resolution 64-channel
+// activation once), so it stays on the CUDA cores with a channel-stationary mapping: a thread owns 8
+// output channels (one 16-byte NHWC store) and streams over pixels; the 8 threads of a pixel cover
+// 128 contiguous bytes.  fprop keeps its 72 weights in registers (C_in = 1) and also produces the
+// BatchNorm partial sums; wgrad keeps its 72 accumulators in registers and reads dY exactly once.
+#include "gconv.cuh"
+
+namespace ub {
+
+__device__ __forceinline__ void first_decode(const GconvDev& d, long long m, int& b, int& i, int& j) {
+  j = (int)(m % d.Wm);
+  long long r = m / d.Wm;
+  i = (int)(r % d.Hm);
+  b = (int)(r / d.Hm);
+}
+
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256)
+first_conv_fprop_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ wp, T* __restrict__ y,
+                        float* __restrict__ stats_ws) {
+  constexpr int K = 9 * CIN;
+  __shared__ float sstat[2][256];
+  __shared__ float sw[CIN == 1 ? 1 : K * 256];          // [k][n], only for C_in > 1
+  const int G = d.N >> 3, lanes = 256 / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  const bool active = lane < lanes;
+  for (int i = threadIdx.x; i < 2 * 256; i += 256) (&sstat[0][0])[i] = 0.f;
+  float wr[CIN == 1 ? K : 1][8];
+  if constexpr (CIN == 1) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wr[k][i] = Elem<T>::ld(wp + (long long)(g * 8 + i) * K + k);
+  } else {
+    for (int e = threadIdx.x; e < K * d.N; e += 256) {
+      const int n = e / K, k = e - n * K;
+      sw[k * d.N + n] = Elem<T>::ld(wp + e);
+    }
+  }
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (active) {
+    for (long long m = (long long)blockIdx.x * lanes + lane; m < d.M; m += (long long)gridDim.x * lanes) {
+      int b, pi, pj;
+      first_decode(d, m, b, pi, pj);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int si = pi + d.tap_dy[t], sj = pj + d.tap_dx[t];
+        if (si < 0 || si >= d.Hin || sj < 0 || sj >= d.Win) continue;
+        const T* src = x + (((long long)b * d.Hin + si) * d.Win + sj) * d.ld_in;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float xv = Elem<T>::ld(src + c);
+          if constexpr (CIN == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wr[t][i], acc[i]);
+          } else {
+            const float4 w0 = *reinterpret_cast<const float4*>(&sw[(t * CIN + c) * d.N + g * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&sw[(t * CIN + c) * d.N + g * 8 + 4]);
+            acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+            acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+            acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] = Elem<T>::round(acc[i]);
+        s[i] += acc[i];
+        q[i] += acc[i] * acc[i];
+      }
+      store8(y + m * d.ld_out + g * 8, acc);
+    }
+  }
+  if (stats_ws) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&sstat[0][g * 8 + i], s[i]); atomicAdd(&sstat[1][g * 8 + i], q[i]); }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * d.N; e += 256) {
+      const int which = e / d.N, c = e - which * d.N;
+      stats_ws[((long long)blockIdx.x * 2 + which) * d.N + c] = sstat[which][c];
+    }
+  }
+}
+
+// dWp[(t)][n] partial per block (C_in == 1): partials[block][9][N]
+template <typename T>
+__global__ void __launch_bounds__(256)
+first_conv_wgrad_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ partials) {
+  __shared__ float red[8][9 * 128];
+  const int G = d.N >> 3, lanes = 256 / G;              // G is a power of two <= 16 (checked on the host)
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  for (long long m = (long long)blockIdx.x * lanes + lane; m < d.M; m += (long long)gridDim.x * lanes) {
+    int b, pi, pj;
+    first_decode(d, m, b, pi, pj);
+    float gv[8];
+    load8(gy + m * d.ld_out + g * 8, gv);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int si = pi + d.tap_dy[t], sj = pj + d.tap_dx[t];
+      float xv = 0.f;
+      if (si >= 0 && si < d.Hin && sj >= 0 && sj < d.Win)
+        xv = Elem<T>::ld(x + (((long long)b * d.Hin + si) * d.Win + sj) * d.ld_in);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(xv, gv[i], acc[t][i]);
+    }
+  }
+  // lanes of one warp that share a channel group: xor-shuffle over the lane bits above log2(G)
+  const int warp = threadIdx.x >> 5;
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = acc[t][i];
+      for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[t][i] = v;
+    }
+  if ((threadIdx.x & 31) < G) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][t * d.N + g * 8 + i] = acc[t][i];
+  }
+  __syncthreads();
+  float* out = partials + (long long)blockIdx.x * 9 * d.N;
+  for (int e = threadIdx.x; e < 9 * d.N; e += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][e];
+    out[e] = v;
+  }
+}
+
+static bool first_common(const unetb200_gconv_t* d) {
+  if (d->ntaps != 9 || d->in_scale != 1 || d->out_scale != 1 || d->nquad != 1) return false;
+  if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) return false;
+  if (d->Hm != d->Hout || d->Wm != d->Wout) return false;
+  if (d->N % 8 || d->N > 256 || d->ld_out % 8) return false;
+  return true;
+}
+
+int first_fprop_supported(const unetb200_gconv_t* d, const void* y) {
+  if (!first_common(d) || d->Cin < 1 || d->Cin > 4) return 0;
+  const int G = d->N / 8;
+  if (256 % G) return 0;
+  return aligned16(y) ? 1 : 0;
+}
+
+static int first_blocks(long long M, int lanes) {
+  long long b = (M + (long long)lanes * 16 - 1) / ((long long)lanes * 16);
+  long long cap = (long long)sm_count() * 6;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+long long first_fprop_tiles(const unetb200_gconv_t* d) {
+  if (!first_common(d)) return 0;
+  return first_blocks((long long)d->B * d->Hm * d->Wm, 256 / (d->N / 8));
+}
+
+int first_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
+                float* stats_ws, cudaStream_t s) {
+  const int blocks = first_blocks(g.M, 256 / (d->N / 8));
+#define GO(T, CIN) \
+  first_conv_fprop_kernel<T, CIN><<<blocks, 256, 0, s>>>(g, (const T*)x, (const T*)wp, (T*)y, stats ? stats_ws : nullptr)
+  if (d->dtype == UNETB200_BF16) {
+    switch (d->Cin) {
+      case 1: GO(__nv_bfloat16, 1); break;
+      case 2: GO(__nv_bfloat16, 2); break;
+      case 3: GO(__nv_bfloat16, 3); break;
+      default: GO(__nv_bfloat16, 4); break;
+    }
+  } else {
+    switch (d->Cin) {
+      case 1: GO(float, 1); break;
+      case 2: GO(float, 2); break;
+      case 3: GO(float, 3); break;
+      default: GO(float, 4); break;
+    }
+  }
+#undef GO
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "first_conv_fprop");
+  if (stats) return launch_stats_reduce(stats_ws, blocks, 2 * d->N, stats, s);
+  return 0;
+}
+
+int first_wgrad_supported(const unetb200_gconv_t* d, const void* gy) {
+  if (!first_common(d) || d->Cin != 1 || d->N > 128) return 0;
+  const int G = d->N / 8;
+  if (G & (G - 1)) return 0;
+  return (!gy || aligned16(gy)) ? 1 : 0;
+}
+
+int first_wgrad_splits(const unetb200_gconv_t* d) {
+  return first_blocks((long long)d->B * d->Hm * d->Wm, 256 / (d->N / 8));
+}
+
+int first_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials,
+                int splits, cudaStream_t s) {
+  if (d->dtype == UNETB200_BF16)
+    first_conv_wgrad_kernel<__nv_bfloat16><<<splits, 256, 0, s>>>(g, (const __nv_bfloat16*)x,
+                                                                  (const __nv_bfloat16*)gy, partials);
+  else
+    first_conv_wgrad_kernel<float><<<splits, 256, 0, s>>>(g, (const float*)x, (const float*)gy, partials);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "first_conv_wgrad");
+  return 0;
+}
+
+}  // namespace ub

@@ -85,7 +85,7 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
 gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
-                        T* __restrict__ y, double* __restrict__ stats) {
+                        T* __restrict__ y, float* __restrict__ stats_ws) {
   __shared__ __align__(16) float As[FBK][FBM + 4];
   __shared__ __align__(16) float Bs[FBK][FBN + 4];
   __shared__ int pb[FBM], pi[FBM], pj[FBM];
@@ -201,7 +201,7 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
         if (nb + c < d.N) Elem<T>::st(y + dst_offset(d, pb[ml], pi[ml], pj[ml], qq[c]) + cc[c], v[c]);
     }
   }
-  if (stats) {
+  if (stats_ws) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       // the two ty rows of a warp first, then shared-memory atomics across the 8 warps
@@ -210,12 +210,41 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
       if ((tid & 16) == 0) { atomicAdd(&sstat[0][tx * 4 + c], a); atomicAdd(&sstat[1][tx * 4 + c], b); }
     }
     __syncthreads();
-    if (tid < FBN && n0 + tid < d.N) {
-      int co = (n0 + tid) % d.Cq;
-      atomicAdd(stats + co, (double)sstat[0][tid]);
-      atomicAdd(stats + d.Cq + co, (double)sstat[1][tid]);
+    // per-tile partials [tile][2][N]: plain stores, reduced by stats_reduce_kernel (no global atomics)
+    if (tid < 2 * FBN) {
+      const int which = tid / FBN, c = tid % FBN;
+      if (n0 + c < d.N) stats_ws[((long long)blockIdx.x * 2 + which) * d.N + n0 + c] = sstat[which][c];
     }
   }
+}
+
+// stats[col] += sum over tiles of ws[tile][col]; ws rows have C2 = 2*C columns laid out like stats
+__global__ void stats_reduce_kernel(const float* __restrict__ ws, long long ntiles, int C2, double* __restrict__ stats) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (col < C2)
+    for (long long t = (long long)blockIdx.y * 8 + ry; t < ntiles; t += (long long)gridDim.y * 8)
+      acc += (double)ws[t * C2 + col];
+  red[ry][lane] = acc;
+  __syncthreads();
+  if (ry == 0 && col < C2) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][lane];
+    atomicAdd(stats + col, s);
+  }
+}
+
+int launch_stats_reduce(const float* ws, long long ntiles, int C2, double* stats, cudaStream_t s) {
+  long long sy = ntiles / 32;
+  if (sy < 1) sy = 1;
+  if (sy > 256) sy = 256;
+  stats_reduce_kernel<<<dim3((unsigned)((C2 + 31) / 32), (unsigned)sy), 256, 0, s>>>(ws, ntiles, C2, stats);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "stats_reduce");
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -369,31 +398,46 @@ typedef __nv_bfloat16 bf16;
 
 extern "C" {
 
+int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
+  GconvDev g;
+  if (gconv_validate(d, &g)) return -1;
+  long long simt_tiles = (g.M + FBM - 1) / FBM;
+  long long tc_tiles = tc_fprop_tiles(d);
+  long long tiles = simt_tiles > tc_tiles ? simt_tiles : tc_tiles;
+  long long ft = first_fprop_tiles(d);
+  if (ft > tiles) tiles = ft;
+  return tiles * 2 * g.N;
+}
+
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
-                         double* stats, int* algo_used, void* stream) {
+                         double* stats, float* stats_ws, int* algo_used, void* stream) {
   GconvDev g;
   int rc = gconv_validate(d, &g);
   if (rc) return rc;
   UB_CHECK_ARG(x && wp && y, "gconv_fprop: null pointer");
+  UB_CHECK_ARG(!stats || (stats_ws && d->nquad == 1), "gconv_fprop: stats need a workspace and nquad == 1");
+  if (!stats) stats_ws = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   int algo = d->algo;
   if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_fprop_supported(d, x, wp, y) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
   if (algo_used) *algo_used = algo;
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_fprop_supported(d, x, wp, y), "gconv_fprop: tcgen05 path requested but shape/alignment unsupported");
-    return tc_fprop(d, g, x, wp, bias, y, stats, s);
+    return tc_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
   }
   UB_CHECK_ARG(algo == UNETB200_ALGO_SIMT, "gconv_fprop: unknown algo %d", algo);
+  if (!bias && first_fprop_supported(d, y)) return first_fprop(d, g, x, wp, y, stats, stats_ws, s);
   dim3 grid((unsigned)((g.M + FBM - 1) / FBM), (unsigned)((g.N + FBN - 1) / FBN));
   const bool vec = simt_vec_ok(d, x, wp, y) && (g.K % 4 == 0);
   if (d->dtype == UNETB200_BF16) {
-    if (vec) gconv_fprop_simt_kernel<bf16, true><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats);
-    else gconv_fprop_simt_kernel<bf16, false><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats);
+    if (vec) gconv_fprop_simt_kernel<bf16, true><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats_ws);
+    else gconv_fprop_simt_kernel<bf16, false><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats_ws);
   } else {
-    if (vec) gconv_fprop_simt_kernel<float, true><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats);
-    else gconv_fprop_simt_kernel<float, false><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats);
+    if (vec) gconv_fprop_simt_kernel<float, true><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats_ws);
+    else gconv_fprop_simt_kernel<float, false><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats_ws);
   }
   UB_LAUNCH_CHECK("gconv_fprop_simt");
+  if (stats) return launch_stats_reduce(stats_ws, (g.M + FBM - 1) / FBM, 2 * g.N, stats, s);
   return 0;
 }
 
@@ -406,7 +450,11 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
   if (algo == UNETB200_ALGO_TC)
     UB_CHECK_ARG(tc_wgrad_supported(d, nullptr, nullptr), "gconv_wgrad: tcgen05 path requested but shape unsupported");
   if (algo_used) *algo_used = algo;
-  if (splits) *splits = algo == UNETB200_ALGO_TC ? tc_wgrad_splits(d, g) : simt_wgrad_splits(g);
+  if (splits) {
+    if (algo == UNETB200_ALGO_TC) *splits = tc_wgrad_splits(d, g);
+    else if (first_wgrad_supported(d, nullptr)) *splits = first_wgrad_splits(d);
+    else *splits = simt_wgrad_splits(g);
+  }
   return 0;
 }
 
@@ -422,6 +470,11 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path requested but shape/alignment unsupported");
     return tc_wgrad(d, g, x, gy, partials, splits, s);
+  }
+  if (first_wgrad_supported(d, nullptr)) {
+    UB_CHECK_ARG(first_wgrad_supported(d, gy) && splits == first_wgrad_splits(d),
+                 "gconv_wgrad: first-layer kernel needs 16-byte aligned dY and the planned split count");
+    return first_wgrad(d, g, x, gy, partials, splits, s);
   }
   long long mper = (g.M + splits - 1) / splits;
   mper = (mper + WBM - 1) / WBM * WBM;

@@ -163,7 +163,7 @@ struct alignas(64) TcParams {
   int tiles_w, tiles_h, TW, TH, tw_shift;
   int Hm, Wm, Cq, N, K;
   const float* bias;
-  double* stats;
+  float* stats_ws;          // per-tile BN partials [tile][2][Cq] (nullptr: no statistics)
   float* partials;          // wgrad
   int nsub;                 // wgrad: number of (tap, chunk) sub-tiles
   int ptiles, ptiles_per_split;
@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(192) tc_fprop_kernel(const __grid_constant__ T
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     uint8_t* stage_out = smem;                        // pipeline buffers are free now
+    float* sstat = reinterpret_cast<float*>(smem + STAGES * kStage + 256);   // [2][BLOCK_N]
+    if (p.stats_ws)
+      for (int i = et; i < 2 * BLOCK_N; i += 128) sstat[i] = 0.f;          // ordered by the barrier below
 #pragma unroll 1
     for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
       uint32_t v[32];
@@ -299,45 +302,41 @@ __global__ void __launch_bounds__(192) tc_fprop_kernel(const __grid_constant__ T
         tma_store_4d(&p.o_map[q], stage_out + sub * kABytes, co0 + sub * EPR, j0, i0, b);
       tma_store_commit();
     }
-    if (p.stats) {
+    if (p.stats_ws) {
       // per-channel sum / sum of squares of the rounded tile, rows outside the M grid masked out.
       // words of a sub-tile row: bf16 -> 32 words of 2 channels; fp32 -> 32 words of 1 channel.
-      constexpr int WORDS = NSUB * 32;                 // 32-bit words per tile row
-      constexpr int RSPLIT = 128 / WORDS > 0 ? 128 / WORDS : 1;
-      constexpr int WPT = WORDS > 128 ? WORDS / 128 : 1;   // words per thread
-#pragma unroll 1
-      for (int wi = 0; wi < WPT; ++wi) {
-        const int word = (WORDS > 128) ? et + wi * 128 : et % WORDS;
-        const int rs = (WORDS > 128) ? 0 : et / WORDS;
-        if (rs >= RSPLIT) break;
-        const int sub = word >> 5, w32 = word & 31;
-        const int r0 = rs * (128 / RSPLIT), r1 = r0 + 128 / RSPLIT;
-        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-        for (int r = r0; r < r1; ++r) {
-          const int pi = i0 + (r >> p.tw_shift), pj = j0 + (r & (p.TW - 1));
-          if (pi >= p.Hm || pj >= p.Wm) continue;
-          const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_out + sub * kABytes + r * 128 +
-                                                                ((((w32 >> 2) ^ (r & 7)) << 4) | ((w32 & 3) << 2)));
-          if constexpr (TF32) {
-            float a = __uint_as_float(u);
-            s0 += a; q0 += a * a;
-          } else {
-            float a = __uint_as_float(u << 16), c = __uint_as_float(u & 0xffff0000u);
-            s0 += a; q0 += a * a; s1 += c; q1 += c * c;
-          }
-        }
+      // Row splits are combined in shared memory; the tile's partial goes to the workspace with plain
+      // stores (no global atomics: 16M fp64 atomics on 128 addresses cost more than the MMAs).
+      constexpr int WORDS = NSUB * 32;                 // 32-bit words per tile row (<= 128)
+      constexpr int RSPLIT = 128 / WORDS;
+      const int word = et % WORDS, rs = et / WORDS;
+      const int sub = word >> 5, w32 = word & 31;
+      const int r0 = rs * (128 / RSPLIT), r1 = r0 + 128 / RSPLIT;
+      float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+      for (int r = r0; r < r1; ++r) {
+        const int pi = i0 + (r >> p.tw_shift), pj = j0 + (r & (p.TW - 1));
+        if (pi >= p.Hm || pj >= p.Wm) continue;
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_out + sub * kABytes + r * 128 +
+                                                              ((((w32 >> 2) ^ (r & 7)) << 4) | ((w32 & 3) << 2)));
         if constexpr (TF32) {
-          const int co = co0 + sub * 32 + w32;
-          atomicAdd(p.stats + co, (double)s0);
-          atomicAdd(p.stats + p.Cq + co, (double)q0);
+          float a = __uint_as_float(u);
+          s0 += a; q0 += a * a;
         } else {
-          const int co = co0 + sub * 64 + w32 * 2;
-          atomicAdd(p.stats + co, (double)s0);
-          atomicAdd(p.stats + p.Cq + co, (double)q0);
-          atomicAdd(p.stats + co + 1, (double)s1);
-          atomicAdd(p.stats + p.Cq + co + 1, (double)q1);
+          float a = __uint_as_float(u << 16), c = __uint_as_float(u & 0xffff0000u);
+          s0 += a; q0 += a * a; s1 += c; q1 += c * c;
         }
       }
+      const int lc = TF32 ? sub * 32 + w32 : sub * 64 + w32 * 2;      // channel within the N block
+      if constexpr (RSPLIT == 1) {
+        sstat[lc] = s0; sstat[BLOCK_N + lc] = q0;
+        if constexpr (!TF32) { sstat[lc + 1] = s1; sstat[BLOCK_N + lc + 1] = q1; }
+      } else {
+        atomicAdd(&sstat[lc], s0); atomicAdd(&sstat[BLOCK_N + lc], q0);
+        if constexpr (!TF32) { atomicAdd(&sstat[lc + 1], s1); atomicAdd(&sstat[BLOCK_N + lc + 1], q1); }
+      }
+      epi_bar_sync();
+      float* dst = p.stats_ws + (long long)blockIdx.x * 2 * p.Cq + co0;
+      for (int i = et; i < 2 * BLOCK_N; i += 128) dst[(i / BLOCK_N) * p.Cq + (i % BLOCK_N)] = sstat[i];
     }
     if (et == 0) tma_store_wait_all();
   }
@@ -632,7 +631,7 @@ static void fill_common(const unetb200_gconv_t* d, const GconvDev& g, TcParams* 
   P->tiles_w = (d->Wm + TW - 1) / TW;
   P->tiles_h = (d->Hm + TH - 1) / TH;
   P->Hm = d->Hm; P->Wm = d->Wm; P->Cq = g.Cq; P->N = d->N; P->K = g.K;
-  P->bias = nullptr; P->stats = nullptr; P->partials = nullptr;
+  P->bias = nullptr; P->stats_ws = nullptr; P->partials = nullptr;
   P->nsub = d->ntaps * P->cchunks;
   P->ptiles = d->B * P->tiles_w * P->tiles_h;
   P->ptiles_per_split = P->ptiles;
@@ -640,7 +639,7 @@ static void fill_common(const unetb200_gconv_t* d, const GconvDev& g, TcParams* 
 
 template <typename T, int BN, int ST>
 static int launch_fprop(const TcParams& P, dim3 grid, cudaStream_t s) {
-  constexpr int smem = ST * (kABytes + BN * 128) + 1024 + 256;
+  constexpr int smem = ST * (kABytes + BN * 128) + 1024 + 256 + 2 * BN * 4;   // + barriers + BN-stat scratch
   static bool configured = false;   // benign race: attribute set is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_fprop_kernel<T, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -653,8 +652,17 @@ static int launch_fprop(const TcParams& P, dim3 grid, cudaStream_t s) {
   return 0;
 }
 
+long long tc_fprop_tiles(const unetb200_gconv_t* d) {
+  int TW, TH;
+  tile_shape(d->Hm, d->Wm, 128, &TW, &TH);
+  return (long long)d->B * ((d->Wm + TW - 1) / TW) * ((d->Hm + TH - 1) / TH);
+}
+
+template <typename T, int BN, int ST>
+static int launch_fprop(const TcParams& P, dim3 grid, cudaStream_t s);
+
 int tc_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
-             double* stats, cudaStream_t stream) {
+             double* stats, float* stats_ws, cudaStream_t stream) {
   TcParams P;
   int TW, TH;
   tile_shape(d->Hm, d->Wm, 128, &TW, &TH);
@@ -665,15 +673,19 @@ int tc_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const 
   rc = encode_weights(&P.b_map, d->dtype, wp, g.K, d->N, BN);
   if (rc) return rc;
   P.bias = bias;
-  P.stats = stats;
+  P.stats_ws = stats ? stats_ws : nullptr;
   dim3 grid((unsigned)P.ptiles, (unsigned)(d->N / BN));
   if (d->dtype == UNETB200_BF16) {
-    if (BN == 256) return launch_fprop<__nv_bfloat16, 256, 2>(P, grid, stream);
-    if (BN == 128) return launch_fprop<__nv_bfloat16, 128, 3>(P, grid, stream);
-    return launch_fprop<__nv_bfloat16, 64, 4>(P, grid, stream);
+    if (BN == 256) rc = launch_fprop<__nv_bfloat16, 256, 2>(P, grid, stream);
+    else if (BN == 128) rc = launch_fprop<__nv_bfloat16, 128, 3>(P, grid, stream);
+    else rc = launch_fprop<__nv_bfloat16, 64, 4>(P, grid, stream);
+  } else {
+    if (BN == 128) rc = launch_fprop<float, 128, 3>(P, grid, stream);
+    else rc = launch_fprop<float, 64, 4>(P, grid, stream);
   }
-  if (BN == 128) return launch_fprop<float, 128, 3>(P, grid, stream);
-  return launch_fprop<float, 64, 4>(P, grid, stream);
+  if (rc) return rc;
+  if (stats) return launch_stats_reduce(stats_ws, P.ptiles, 2 * g.Cq, stats, stream);
+  return 0;
 }
 
 static int wgrad_geometry(const unetb200_gconv_t* d, int* mtiles, int* ntiles, int* ptiles, int* BN) {

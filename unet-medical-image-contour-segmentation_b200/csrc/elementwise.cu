@@ -41,6 +41,24 @@ static inline int grid_for(int64_t work, int threads, int per_sm = 8) {
   return (int)b;
 }
 
+struct CsGeom {
+  int CVB, gy;
+  unsigned gx;
+};
+static CsGeom cs_geom(int CV, int64_t items, int per_thread) {
+  CsGeom g;
+  g.CVB = CV < 256 ? CV : 256;
+  const int lanes = 256 / g.CVB;
+  g.gy = (CV + g.CVB - 1) / g.CVB;
+  int64_t gx = (items + (int64_t)lanes * per_thread - 1) / ((int64_t)lanes * per_thread);
+  int64_t cap = (int64_t)sm_count() * 8 / g.gy;
+  if (cap < 1) cap = 1;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  g.gx = (unsigned)gx;
+  return g;
+}
+
 template <typename T>
 static bool vec_ok(int C, std::initializer_list<int64_t> lds, std::initializer_list<const void*> ptrs) {
   if (C % 8) return false;
@@ -91,19 +109,50 @@ __global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const flo
 // ------------------------------------------------------------------------------------------
 // BN apply + ReLU (+ 2x2 max-pool)
 // ------------------------------------------------------------------------------------------
+// Channel-stationary mapping used by the BN kernels: a block of 256 threads = CVB channel vectors x
+// LANES pixel lanes (blockIdx.y selects the channel-vector block when C is wide).  Each thread keeps
+// its per-channel coefficients in registers and streams over pixels with 4 independent 16-byte loads
+// in flight; a warp touches LANES consecutive pixels x CVB vectors = one contiguous run of NHWC.
+struct CsThread {
+  int cv, lane, lanes;
+  bool active;
+};
+__device__ __forceinline__ CsThread cs_thread(int CV, int CVB) {
+  CsThread t;
+  t.lanes = blockDim.x / CVB;
+  t.lane = threadIdx.x / CVB;
+  t.cv = blockIdx.y * CVB + threadIdx.x % CVB;
+  t.active = t.cv < CV && t.lane < t.lanes;
+  return t;
+}
+
 template <typename T, int V>
-__global__ void bn_relu_apply_kernel(const T* __restrict__ y, int64_t ld_y, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, T* __restrict__ z, int64_t ld_z,
-                                     int64_t npix, int CV) {
-  const int64_t total = npix * CV;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = idx / CV;
-    int c = (int)(idx - p * CV) * V;
-    float v[V], sc[V], sh[V];
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(const T* __restrict__ y, int64_t ld_y, const float* __restrict__ scale,
+                     const float* __restrict__ shift, T* __restrict__ z, int64_t ld_z, int64_t npix, int CV,
+                     int CVB) {
+  const CsThread t = cs_thread(CV, CVB);
+  if (!t.active) return;
+  const int c = t.cv * V;
+  float sc[V], sh[V];
+  ldf<V>(scale + c, sc);
+  ldf<V>(shift + c, sh);
+  const int64_t stride = (int64_t)gridDim.x * t.lanes;
+  int64_t p = (int64_t)blockIdx.x * t.lanes + t.lane;
+  for (; p + 3 * stride < npix; p += 4 * stride) {
+    float v[4][V];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ldv<T, V>(y + (p + u * stride) * ld_y + c, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[u][i] = fmaxf(fmaf(v[u][i], sc[i], sh[i]), 0.f);
+      stv<T, V>(z + (p + u * stride) * ld_z + c, v[u]);
+    }
+  }
+  for (; p < npix; p += stride) {
+    float v[V];
     ldv<T, V>(y + p * ld_y + c, v);
-    ldf<V>(scale + c, sc);
-    ldf<V>(shift + c, sh);
 #pragma unroll
     for (int i = 0; i < V; ++i) v[i] = fmaxf(fmaf(v[i], sc[i], sh[i]), 0.f);
     stv<T, V>(z + p * ld_z + c, v);
@@ -114,43 +163,58 @@ __device__ __forceinline__ float pool_max(float m, float v) { return (v > m || v
 
 // one thread = one 2x2 window (ceil grid, so odd rows/cols still get their z written) x V channels
 template <typename T, int V>
-__global__ void bn_relu_apply_pool_kernel(const T* __restrict__ y, int64_t ld_y, const float* __restrict__ scale,
-                                          const float* __restrict__ shift, T* __restrict__ z, int64_t ld_z,
-                                          T* __restrict__ pooled, int64_t ld_p, int B, int H, int W, int CV) {
+__global__ void __launch_bounds__(256)
+bn_relu_apply_pool_kernel(const T* __restrict__ y, int64_t ld_y, const float* __restrict__ scale,
+                          const float* __restrict__ shift, T* __restrict__ z, int64_t ld_z, T* __restrict__ pooled,
+                          int64_t ld_p, int B, int H, int W, int CV, int CVB) {
+  const CsThread t = cs_thread(CV, CVB);
+  if (!t.active) return;
+  const int c = t.cv * V;
+  float sc[V], sh[V];
+  ldf<V>(scale + c, sc);
+  ldf<V>(shift + c, sh);
   const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
-  const int64_t total = (int64_t)B * Hc * Wc * CV;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    int64_t r = idx / CV;
-    int j = (int)(r % Wc);
-    r /= Wc;
-    int i = (int)(r % Hc);
-    int n = (int)(r / Hc);
-    int c = cv * V;
-    float sc[V], sh[V], m[V];
-    ldf<V>(scale + c, sc);
-    ldf<V>(shift + c, sh);
+  const int64_t nwin = (int64_t)B * Hc * Wc;
+  const int64_t stride = (int64_t)gridDim.x * t.lanes;
+  for (int64_t wdx = (int64_t)blockIdx.x * t.lanes + t.lane; wdx < nwin; wdx += stride) {
+    const int j = (int)(wdx % Wc);
+    int64_t r = wdx / Wc;
+    const int i = (int)(r % Hc);
+    const int n = (int)(r / Hc);
+    const bool full = (2 * i + 1 < H) && (2 * j + 1 < W);
+    float v[4][V], m[V];
+    if (full) {
+      const int64_t p00 = ((int64_t)n * H + 2 * i) * W + 2 * j;
+      ldv<T, V>(y + p00 * ld_y + c, v[0]);
+      ldv<T, V>(y + (p00 + 1) * ld_y + c, v[1]);
+      ldv<T, V>(y + (p00 + W) * ld_y + c, v[2]);
+      ldv<T, V>(y + (p00 + W + 1) * ld_y + c, v[3]);
 #pragma unroll
-    for (int k = 0; k < V; ++k) m[k] = -INFINITY;
+      for (int k = 0; k < V; ++k) m[k] = -INFINITY;
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+      for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        int h = 2 * i + a, w = 2 * j + b;
+        for (int k = 0; k < V; ++k) {
+          v[q][k] = Elem<T>::round(fmaxf(fmaf(v[q][k], sc[k], sh[k]), 0.f));
+          m[k] = pool_max(m[k], v[q][k]);
+        }
+      stv<T, V>(z + p00 * ld_z + c, v[0]);
+      stv<T, V>(z + (p00 + 1) * ld_z + c, v[1]);
+      stv<T, V>(z + (p00 + W) * ld_z + c, v[2]);
+      stv<T, V>(z + (p00 + W + 1) * ld_z + c, v[3]);
+      stv<T, V>(pooled + (((int64_t)n * Hp + i) * Wp + j) * ld_p + c, m);
+    } else {
+      for (int q = 0; q < 4; ++q) {
+        const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
         if (h < H && w < W) {
-          int64_t p = ((int64_t)n * H + h) * W + w;
-          float v[V];
-          ldv<T, V>(y + p * ld_y + c, v);
+          const int64_t p = ((int64_t)n * H + h) * W + w;
+          ldv<T, V>(y + p * ld_y + c, v[0]);
 #pragma unroll
-          for (int k = 0; k < V; ++k) {
-            v[k] = Elem<T>::round(fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f));
-            m[k] = pool_max(m[k], v[k]);
-          }
-          stv<T, V>(z + p * ld_z + c, v);
+          for (int k = 0; k < V; ++k) v[0][k] = fmaxf(fmaf(v[0][k], sc[k], sh[k]), 0.f);
+          stv<T, V>(z + p * ld_z + c, v[0]);
         }
       }
-    if (i < Hp && j < Wp) stv<T, V>(pooled + (((int64_t)n * Hp + i) * Wp + j) * ld_p + c, m);
+    }
   }
 }
 
@@ -238,29 +302,44 @@ __global__ void maxpool2_bwd_kernel(const T* __restrict__ x, int64_t ld_x, const
 // ------------------------------------------------------------------------------------------
 // block = 256 threads = CVB channel-vectors x LANES pixel lanes; blockIdx.y = channel-vector block.
 template <typename T, int V>
-__global__ void bn_relu_bwd_reduce_kernel(const T* __restrict__ gz, int64_t ld_gz, const T* __restrict__ y,
-                                          int64_t ld_y, const float* __restrict__ scale,
-                                          const float* __restrict__ shift, const float* __restrict__ mean,
-                                          const float* __restrict__ invstd, double* __restrict__ sums, int64_t npix,
-                                          int C, int CV, int CVB) {
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_reduce_kernel(const T* __restrict__ gz, int64_t ld_gz, const T* __restrict__ y, int64_t ld_y,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          double* __restrict__ sums, int64_t npix, int C, int CV, int CVB) {
   constexpr int RED = (V == 8) ? 2048 : 256;
   __shared__ float red[2][RED];
-  const int lanes = blockDim.x / CVB;
-  const int cvl = threadIdx.x % CVB, lane = threadIdx.x / CVB;
-  const int cv = blockIdx.y * CVB + cvl;
-  const bool active = (cv < CV) && (lane < lanes);
+  const CsThread t = cs_thread(CV, CVB);
+  const int cvl = threadIdx.x % CVB;
   float s0[V], s1[V];
 #pragma unroll
   for (int k = 0; k < V; ++k) s0[k] = s1[k] = 0.f;
-  if (active) {
-    const int c = cv * V;
+  if (t.active) {
+    const int c = t.cv * V;
     float sc[V], sh[V], mu[V], is[V];
     ldf<V>(scale + c, sc);
     ldf<V>(shift + c, sh);
     ldf<V>(mean + c, mu);
     ldf<V>(invstd + c, is);
-#pragma unroll 2
-    for (int64_t p = (int64_t)blockIdx.x * lanes + lane; p < npix; p += (int64_t)gridDim.x * lanes) {
+    const int64_t stride = (int64_t)gridDim.x * t.lanes;
+    int64_t p = (int64_t)blockIdx.x * t.lanes + t.lane;
+    for (; p + stride < npix; p += 2 * stride) {
+      float g[2][V], v[2][V];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        ldv<T, V>(gz + (p + u * stride) * ld_gz + c, g[u]);
+        ldv<T, V>(y + (p + u * stride) * ld_y + c, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          float gg = (fmaf(v[u][k], sc[k], sh[k]) > 0.f) ? g[u][k] : 0.f;
+          s0[k] += gg;
+          s1[k] += gg * ((v[u][k] - mu[k]) * is[k]);
+        }
+    }
+    for (; p < npix; p += stride) {
       float g[V], v[V];
       ldv<T, V>(gz + p * ld_gz + c, g);
       ldv<T, V>(y + p * ld_y + c, v);
@@ -273,11 +352,12 @@ __global__ void bn_relu_bwd_reduce_kernel(const T* __restrict__ gz, int64_t ld_g
     }
   }
   // reduce over pixel lanes through shared memory, `chunk` lanes at a time: red[.][lane][cvl*V + k]
+  const int lanes = t.lanes, lane = t.lane;
   const int row = CVB * V;
   const int chunk = RED / row;   // >= 1 by construction (row <= RED)
   for (int base = 0; base < lanes; base += chunk) {
     __syncthreads();
-    if (active && lane >= base && lane < base + chunk) {
+    if (t.active && lane >= base && lane < base + chunk) {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         red[0][(lane - base) * row + cvl * V + k] = s0[k];
@@ -309,20 +389,20 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double i
   coef[C + c] = training ? (float)(sgx * inv_count) : 0.f;
 }
 
+// gy = sc*g*mask + A*(y - mu) + B0 with A = -sc*c1*invstd, B0 = -sc*c0 (per channel, in registers)
 template <typename T, int V>
-__global__ void bn_relu_bwd_apply_kernel(const T* __restrict__ gz, int64_t ld_gz, const T* __restrict__ y,
-                                         int64_t ld_y, const float* __restrict__ scale,
-                                         const float* __restrict__ shift, const float* __restrict__ mean,
-                                         const float* __restrict__ invstd, const float* __restrict__ coef,
-                                         T* __restrict__ gy, int64_t ld_gy, int64_t npix, int C, int CV) {
-  const int64_t total = npix * CV;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int64_t p = idx / CV;
-    int c = (int)(idx - p * CV) * V;
-    float g[V], v[V], sc[V], sh[V], mu[V], is[V], c0[V], c1[V], o[V];
-    ldv<T, V>(gz + p * ld_gz + c, g);
-    ldv<T, V>(y + p * ld_y + c, v);
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_kernel(const T* __restrict__ gz, int64_t ld_gz, const T* __restrict__ y, int64_t ld_y,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ coef, T* __restrict__ gy, int64_t ld_gy, int64_t npix, int C,
+                         int CV, int CVB) {
+  const CsThread t = cs_thread(CV, CVB);
+  if (!t.active) return;
+  const int c = t.cv * V;
+  float sc[V], sh[V], mu[V], A[V], B0[V];
+  {
+    float is[V], c0[V], c1[V];
     ldf<V>(scale + c, sc);
     ldf<V>(shift + c, sh);
     ldf<V>(mean + c, mu);
@@ -330,12 +410,37 @@ __global__ void bn_relu_bwd_apply_kernel(const T* __restrict__ gz, int64_t ld_gz
     ldf<V>(coef + c, c0);
     ldf<V>(coef + C + c, c1);
 #pragma unroll
+    for (int k = 0; k < V; ++k) { A[k] = -sc[k] * c1[k] * is[k]; B0[k] = -sc[k] * c0[k]; }
+  }
+  const int64_t stride = (int64_t)gridDim.x * t.lanes;
+  int64_t p = (int64_t)blockIdx.x * t.lanes + t.lane;
+  for (; p + stride < npix; p += 2 * stride) {
+    float g[2][V], v[2][V];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ldv<T, V>(gz + (p + u * stride) * ld_gz + c, g[u]);
+      ldv<T, V>(y + (p + u * stride) * ld_y + c, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float gg = (fmaf(v[u][k], sc[k], sh[k]) > 0.f) ? g[u][k] : 0.f;
+        g[u][k] = fmaf(sc[k], gg, fmaf(A[k], v[u][k] - mu[k], B0[k]));
+      }
+      stv<T, V>(gy + (p + u * stride) * ld_gy + c, g[u]);
+    }
+  }
+  for (; p < npix; p += stride) {
+    float g[V], v[V];
+    ldv<T, V>(gz + p * ld_gz + c, g);
+    ldv<T, V>(y + p * ld_y + c, v);
+#pragma unroll
     for (int k = 0; k < V; ++k) {
       float gg = (fmaf(v[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
-      float xh = (v[k] - mu[k]) * is[k];
-      o[k] = sc[k] * (gg - c0[k] - xh * c1[k]);
+      g[k] = fmaf(sc[k], gg, fmaf(A[k], v[k] - mu[k], B0[k]));
     }
-    stv<T, V>(gy + p * ld_gy + c, o);
+    stv<T, V>(gy + p * ld_gy + c, g);
   }
 }
 
@@ -564,12 +669,13 @@ int unetb200_bn_relu_apply(const void* y, int64_t ld_y, const float* scale, cons
   do {                                                                                                        \
     int CV = C / V;                                                                                           \
     if (pooled) {                                                                                             \
-      int64_t work = (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2) * CV;                                         \
-      bn_relu_apply_pool_kernel<T, V><<<grid_for(work, 256, 16), 256, 0, s>>>(                                \
-          (const T*)y, ld_y, scale, shift, (T*)z, ld_z, (T*)pooled, ld_p, B, H, W, CV);                       \
+      CsGeom g_ = cs_geom(CV, (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2), 2);                                 \
+      bn_relu_apply_pool_kernel<T, V><<<dim3(g_.gx, g_.gy), 256, 0, s>>>(                                     \
+          (const T*)y, ld_y, scale, shift, (T*)z, ld_z, (T*)pooled, ld_p, B, H, W, CV, g_.CVB);               \
     } else {                                                                                                  \
-      bn_relu_apply_kernel<T, V><<<grid_for(npix * CV, 256, 16), 256, 0, s>>>((const T*)y, ld_y, scale,       \
-                                                                              shift, (T*)z, ld_z, npix, CV);  \
+      CsGeom g_ = cs_geom(CV, npix, 8);                                                                       \
+      bn_relu_apply_kernel<T, V><<<dim3(g_.gx, g_.gy), 256, 0, s>>>((const T*)y, ld_y, scale, shift, (T*)z,   \
+                                                                   ld_z, npix, CV, g_.CVB);                   \
     }                                                                                                         \
   } while (0)
   if (dtype == UNETB200_BF16) {
@@ -640,16 +746,9 @@ int unetb200_bn_relu_bwd_reduce(const void* gz, int64_t ld_gz, const void* y, in
 #define GO(T, V)                                                                                              \
   do {                                                                                                        \
     int CV = C / V;                                                                                           \
-    int CVB = CV < 256 ? CV : 256;                                                                            \
-    int lanes = 256 / CVB;                                                                                    \
-    int gy_ = (CV + CVB - 1) / CVB;                                                                           \
-    int64_t gx_ = (npix + (int64_t)lanes * 8 - 1) / ((int64_t)lanes * 8);                                     \
-    int64_t cap = (int64_t)sm_count() * 8 / gy_;                                                              \
-    if (cap < 1) cap = 1;                                                                                     \
-    if (gx_ > cap) gx_ = cap;                                                                                 \
-    if (gx_ < 1) gx_ = 1;                                                                                     \
-    bn_relu_bwd_reduce_kernel<T, V><<<dim3((unsigned)gx_, gy_), 256, 0, s>>>(                                 \
-        (const T*)gz, ld_gz, (const T*)y, ld_y, scale, shift, mean, invstd, sums, npix, C, CV, CVB);          \
+    CsGeom g_ = cs_geom(CV, npix, 8);                                                                         \
+    bn_relu_bwd_reduce_kernel<T, V><<<dim3(g_.gx, g_.gy), 256, 0, s>>>(                                       \
+        (const T*)gz, ld_gz, (const T*)y, ld_y, scale, shift, mean, invstd, sums, npix, C, CV, g_.CVB);       \
   } while (0)
   if (dtype == UNETB200_BF16) {
     if (vec_ok<bf16>(C, {ld_gz, ld_y}, {gz, y})) GO(bf16, 8); else GO(bf16, 1);
@@ -680,8 +779,10 @@ int unetb200_bn_relu_bwd_apply(const void* gz, int64_t ld_gz, const void* y, int
 #define GO(T, V)                                                                                             \
   do {                                                                                                       \
     int CV = C / V;                                                                                          \
-    bn_relu_bwd_apply_kernel<T, V><<<grid_for(npix * CV, 256, 16), 256, 0, s>>>(                             \
-        (const T*)gz, ld_gz, (const T*)y, ld_y, scale, shift, mean, invstd, coef, (T*)gy, ld_gy, npix, C, CV); \
+    CsGeom g_ = cs_geom(CV, npix, 8);                                                                        \
+    bn_relu_bwd_apply_kernel<T, V><<<dim3(g_.gx, g_.gy), 256, 0, s>>>(                                       \
+        (const T*)gz, ld_gz, (const T*)y, ld_y, scale, shift, mean, invstd, coef, (T*)gy, ld_gy, npix, C, CV,  \
+        g_.CVB);                                                                                             \
   } while (0)
   if (dtype == UNETB200_BF16) {
     if (vec_ok<bf16>(C, {ld_gz, ld_y, ld_gy}, {gz, y, gy})) GO(bf16, 8); else GO(bf16, 1);

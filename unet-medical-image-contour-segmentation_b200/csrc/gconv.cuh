@@ -19,11 +19,23 @@ int gconv_validate(const unetb200_gconv_t* d, GconvDev* out);
 
 // tcgen05 engine (conv_tc.cu).  *_supported() return 1 when the shape/dtype/alignment fits.
 int tc_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+long long tc_fprop_tiles(const unetb200_gconv_t* d);
 int tc_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
-             double* stats, cudaStream_t stream);
+             double* stats, float* stats_ws, cudaStream_t stream);
+int launch_stats_reduce(const float* ws, long long ntiles, int C2, double* stats, cudaStream_t s);
 int tc_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int tc_wgrad_splits(const unetb200_gconv_t* d, const GconvDev& g);
 int tc_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
              cudaStream_t stream);
+
+// first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)
+int first_fprop_supported(const unetb200_gconv_t* d, const void* y);
+long long first_fprop_tiles(const unetb200_gconv_t* d);
+int first_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
+                float* stats_ws, cudaStream_t s);
+int first_wgrad_supported(const unetb200_gconv_t* d, const void* gy);
+int first_wgrad_splits(const unetb200_gconv_t* d);
+int first_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials,
+                int splits, cudaStream_t s);
 
 }  // namespace ub

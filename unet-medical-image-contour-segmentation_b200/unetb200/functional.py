@@ -199,7 +199,7 @@ class DoubleConvFn(torch.autograd.Function):
             if gz is None:
                 gz = ops.empty_nhwc(*z2.shape, cd, x.device)
                 ops.maxpool2_bwd(z2, gp, gz, accumulate=False)
-            elif gz is gz2 and ops.nhwc_ld(gz) > gz.shape[1]:
+            elif gz is gz2 and ops.nhwc_ld(gz) > gz.shape[1] and not os.environ.get("UNETB200_NO_INPLACE_SKIP"):
                 # gz2 is the skip half of a concat-gradient buffer produced by our own dgrad: the
                 # pool gradient is accumulated into it in place (skip-gradient sum fused away)
                 ops.maxpool2_bwd(z2, gp, gz, accumulate=True)

@@ -214,8 +214,14 @@ def gconv_flops(d):
 
 def gconv_fprop(d, x, wp, bias, y, stats, kind="fprop"):
     used = C.c_int(0)
-    _run(f"conv_{kind}", lib().unetb200_gconv_fprop, C.byref(d), _p(x), _p(wp), _p(bias), _p(y), _p(stats),
-         C.byref(used), _stream(), flops=gconv_flops(d))
+    ws = None
+    if stats is not None:
+        n = lib().unetb200_gconv_stats_workspace(C.byref(d))
+        if n < 0:
+            _lib.check(-1, "gconv_stats_workspace")
+        ws = torch.empty(n, dtype=torch.float32, device=x.device)
+    _run(f"conv_{kind}", lib().unetb200_gconv_fprop, C.byref(d), _p(x), _p(wp), _p(bias), _p(y), _p(stats), _p(ws),
+         C.byref(used), _stream(), kernels=2 if stats is not None else 1, flops=gconv_flops(d))
     if _PROFILE is not None:
         _PROFILE[-1][0] = f"conv_{kind}_{_ALGO_NAME.get(used.value, '?')}"
     return used.value
