@@ -30,32 +30,32 @@ def test_library_is_the_one_in_tree(G):
 
 @pytest.mark.parametrize("group", ["layout", "bn_fwd", "maxpool", "bn_bwd", "upsample"])
 def test_memory_bound_kernels(G, golden, group):
-    _assert_all(G.GROUPS[group](golden))
+    _assert_all(G.all_groups()[group](golden))
 
 
 @pytest.mark.parametrize("group", ["ce_dice", "dice", "boundary"])
 def test_losses(G, golden, group):
-    _assert_all(G.GROUPS[group](golden))
+    _assert_all(G.all_groups()[group](golden))
 
 
 def test_outconv(G, golden):
-    _assert_all(G.GROUPS["outconv"](golden))
+    _assert_all(G.all_groups()["outconv"](golden))
 
 
 def test_conv_simt(G, golden):
-    _assert_all(G.GROUPS["conv_simt"](golden))
+    _assert_all(G.all_groups()["conv_simt"](golden))
 
 
 @pytest.mark.parametrize("group", ["conv_tc_first", "conv_tc", "conv_tc_tf32"])
 def test_conv_tcgen05(G, golden, group):
-    _assert_all(G.GROUPS[group](golden))
+    _assert_all(G.all_groups()[group](golden))
 
 
 @pytest.mark.parametrize("group", ["parts_fp32", "parts_bf16"])
 def test_parts_against_reference_fixtures(G, golden, group):
-    _assert_all(G.GROUPS[group](golden))
+    _assert_all(G.all_groups()[group](golden))
 
 
 @pytest.mark.parametrize("group", ["unet_fp32", "unet_fp32_b", "unet_tf32", "unet_bf16", "unet_bf16_bil"])
 def test_unet_training_step(G, golden, group):
-    _assert_all(G.GROUPS[group](golden))
+    _assert_all(G.all_groups()[group](golden))

@@ -8,11 +8,11 @@
 
 namespace ub {
 
-__device__ __forceinline__ void first_decode(const GconvDev& d, long long m, int& b, int& i, int& j) {
-  j = (int)(m % d.Wm);
-  long long r = m / d.Wm;
-  i = (int)(r % d.Hm);
-  b = (int)(r / d.Hm);
+__device__ __forceinline__ void first_decode(const GconvDev& d, int m, int& b, int& i, int& j) {
+  j = m % d.Wm;                 // 32-bit: M < 2^31 is checked on the host (64-bit div costs ~100 instr)
+  const int r = m / d.Wm;
+  i = r % d.Hm;
+  b = r / d.Hm;
 }
 
 template <typename T, int CIN>
@@ -43,7 +43,8 @@ first_conv_fprop_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (active) {
-    for (long long m = (long long)blockIdx.x * lanes + lane; m < d.M; m += (long long)gridDim.x * lanes) {
+    const int M = (int)d.M, mstride = gridDim.x * lanes;
+    for (int m = blockIdx.x * lanes + lane; m < M; m += mstride) {
       int b, pi, pj;
       first_decode(d, m, b, pi, pj);
       float acc[8];
@@ -76,7 +77,7 @@ first_conv_fprop_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
         s[i] += acc[i];
         q[i] += acc[i] * acc[i];
       }
-      store8(y + m * d.ld_out + g * 8, acc);
+      store8(y + (long long)m * d.ld_out + g * 8, acc);
     }
   }
   if (stats_ws) {
@@ -104,11 +105,12 @@ first_conv_wgrad_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
-  for (long long m = (long long)blockIdx.x * lanes + lane; m < d.M; m += (long long)gridDim.x * lanes) {
+  const int M = (int)d.M, mstride = gridDim.x * lanes;
+  for (int m = blockIdx.x * lanes + lane; m < M; m += mstride) {
     int b, pi, pj;
     first_decode(d, m, b, pi, pj);
     float gv[8];
-    load8(gy + m * d.ld_out + g * 8, gv);
+    load8(gy + (long long)m * d.ld_out + g * 8, gv);
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int si = pi + d.tap_dy[t], sj = pj + d.tap_dx[t];
@@ -151,6 +153,7 @@ static bool first_common(const unetb200_gconv_t* d) {
   if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) return false;
   if (d->Hm != d->Hout || d->Wm != d->Wout) return false;
   if (d->N % 8 || d->N > 256 || d->ld_out % 8) return false;
+  if ((long long)d->B * d->Hm * d->Wm >= (1LL << 31) - (1 << 20)) return false;
   return true;
 }
 

@@ -207,6 +207,13 @@ def make_gconv(dtype, algo, B, Hm, Wm, Cin, taps, in_scale, in_off, Hin, Win, ld
     return d
 
 
+def _shape_tag(d):
+    """Per-layer profile names when UNETB200_PROFILE_SHAPES is set (bench.py --per-layer)."""
+    if not os.environ.get("UNETB200_PROFILE_SHAPES"):
+        return ""
+    return f"[M={d.B * d.Hm * d.Wm},N={d.N},K={d.ntaps * d.Cin}]"
+
+
 def gconv_flops(d):
     """Algorithmic FLOPs of one launch: 2*M*N*K."""
     return 2.0 * d.B * d.Hm * d.Wm * d.N * d.ntaps * d.Cin
@@ -223,7 +230,7 @@ def gconv_fprop(d, x, wp, bias, y, stats, kind="fprop"):
     _run(f"conv_{kind}", lib().unetb200_gconv_fprop, C.byref(d), _p(x), _p(wp), _p(bias), _p(y), _p(stats), _p(ws),
          C.byref(used), _stream(), kernels=2 if stats is not None else 1, flops=gconv_flops(d))
     if _PROFILE is not None:
-        _PROFILE[-1][0] = f"conv_{kind}_{_ALGO_NAME.get(used.value, '?')}"
+        _PROFILE[-1][0] = f"conv_{kind}_{_ALGO_NAME.get(used.value, '?')}" + _shape_tag(d)
     return used.value
 
 
@@ -235,7 +242,7 @@ def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0):
     partials = torch.empty(splits.value * K * d.N, dtype=torch.float32, device=x.device)
     d2 = GConv.from_buffer_copy(d)
     d2.algo = used.value
-    _run(f"conv_wgrad_{_ALGO_NAME.get(used.value, '?')}", lib().unetb200_gconv_wgrad, C.byref(d2), _p(x), _p(gy),
+    _run(f"conv_wgrad_{_ALGO_NAME.get(used.value, '?')}" + _shape_tag(d), lib().unetb200_gconv_wgrad, C.byref(d2), _p(x), _p(gy),
          _p(partials), splits.value, _stream(), flops=gconv_flops(d))
     _run("wgrad_reduce", lib().unetb200_wgrad_reduce, _p(partials), splits.value, d.ntaps, d.Cin, d.N,
          d.N // d.nquad, _p(dst), st, sc, sq, sn, 0, _stream(), nbytes=4.0 * K * d.N * (splits.value + 1))
