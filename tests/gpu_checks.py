@@ -446,6 +446,10 @@ def check_conv_tc():
     out += _conv3x3_case(1, 256, 512, 6, 6, BF, T, 24)
     out += _conv3x3_case(2, 64, 128, 2, 2, BF, T, 25)
     out += _conv3x3_case(2, 64, 64, 16, 16, BF, T, 26, slice_io=True)
+    out += _conv3x3_case(2, 64, 64, 40, 36, BF, T, 60)          # several 16x16 tiles, ragged edges
+    out += _conv3x3_case(1, 128, 256, 33, 17, BF, T, 61)
+    out += _conv3x3_case(3, 64, 128, 20, 8, BF, T, 62)          # W <= 8: stacked sub-tile geometry
+    out += _conv3x3_case(1, 192, 64, 48, 48, BF, T, 63)         # 3 channel chunks, odd unit count
     out += _convT_case(2, 128, 64, 6, 10, (0, 0), BF, T, 27)
     out += _convT_case(1, 256, 128, 5, 4, (1, 1), BF, T, 28)
     out += _convT_case(1, 512, 256, 4, 4, (0, 0), BF, T, 29)

@@ -2,6 +2,8 @@
 // It handles every shape (C_in = 1 or 3 first layer, widths that do not fill a UMMA tile, unaligned
 // channel slices) and is the arithmetic of the fp32 "exactness" mode.  Large bf16 layers are
 // dispatched to the tcgen05 engine in conv_tc.cu instead.
+#include <cstdlib>
+
 #include "gconv.cuh"
 
 namespace ub {
@@ -406,7 +408,9 @@ int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
   long long tiles = simt_tiles > tc_tiles ? simt_tiles : tc_tiles;
   long long ft = first_fprop_tiles(d);
   if (ft > tiles) tiles = ft;
-  return tiles * 2 * g.N;
+  long long n = tiles * 2 * g.N;
+  long long n2 = tc2_stats_workspace(d);
+  return n > n2 ? n : n2;
 }
 
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
@@ -423,6 +427,8 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (algo_used) *algo_used = algo;
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_fprop_supported(d, x, wp, y), "gconv_fprop: tcgen05 path requested but shape/alignment unsupported");
+    static const bool use_v1 = getenv("UNETB200_TC_V1") != nullptr;      // first-generation kernel, for A/B runs
+    if (!use_v1 && tc2_fprop_supported(d, x, wp, y)) return tc2_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
     return tc_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
   }
   UB_CHECK_ARG(algo == UNETB200_ALGO_SIMT, "gconv_fprop: unknown algo %d", algo);
@@ -451,7 +457,9 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
     UB_CHECK_ARG(tc_wgrad_supported(d, nullptr, nullptr), "gconv_wgrad: tcgen05 path requested but shape unsupported");
   if (algo_used) *algo_used = algo;
   if (splits) {
-    if (algo == UNETB200_ALGO_TC) *splits = tc_wgrad_splits(d, g);
+    if (algo == UNETB200_ALGO_TC)
+      *splits = (!getenv("UNETB200_TC_V1") && tc2_wgrad_supported(d, nullptr, nullptr)) ? tc2_wgrad_splits(d)
+                                                                                        : tc_wgrad_splits(d, g);
     else if (first_wgrad_supported(d, nullptr)) *splits = first_wgrad_splits(d);
     else *splits = simt_wgrad_splits(g);
   }
@@ -469,6 +477,10 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_wgrad_supported(d, nullptr, nullptr) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path requested but shape/alignment unsupported");
+    if (!getenv("UNETB200_TC_V1") && tc2_wgrad_supported(d, nullptr, nullptr)) {
+      UB_CHECK_ARG(tc2_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path needs 16-byte aligned operands");
+      return tc2_wgrad(d, g, x, gy, partials, splits, s);
+    }
     return tc_wgrad(d, g, x, gy, partials, splits, s);
   }
   if (first_wgrad_supported(d, nullptr)) {

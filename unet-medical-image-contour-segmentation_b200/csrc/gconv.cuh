@@ -28,6 +28,17 @@ int tc_wgrad_splits(const unetb200_gconv_t* d, const GconvDev& g);
 int tc_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
              cudaStream_t stream);
 
+// persistent tcgen05 engine, second generation (conv_tc2.cu)
+int tc2_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+long long tc2_stats_workspace(const unetb200_gconv_t* d);
+int tc2_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
+              double* stats, float* stats_ws, cudaStream_t stream);
+
+int tc2_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int tc2_wgrad_splits(const unetb200_gconv_t* d);
+int tc2_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
+              cudaStream_t stream);
+
 // first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)
 int first_fprop_supported(const unetb200_gconv_t* d, const void* y);
 long long first_fprop_tiles(const unetb200_gconv_t* d);
