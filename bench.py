@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--bilinear", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--per-layer", action="store_true", help="add a per-layer conv table (`layers`) to the JSON line")
     return ap.parse_args()
 
 
@@ -278,11 +279,22 @@ def run_ours(args):
 
     # ---- per-kernel roofline: instrumented pass (CUDA events around every C-ABI call) ----------
     if rank == 0 and not args.no_profile:
+        os.environ["UNETB200_PROFILE_SHAPES"] = "1"
         with ops.profile() as rec:
             for _ in range(2):
                 step(img_d, msk_d)
         torch.cuda.synchronize()
-        summ = ops.summarize_profile(rec)
+        os.environ.pop("UNETB200_PROFILE_SHAPES", None)
+        per_layer = ops.summarize_profile(rec)
+        summ = {}
+        for name, d in per_layer.items():                 # class = name without the [M=..,N=..,K=..] tag
+            cls = name.split("[")[0]
+            e = summ.setdefault(cls, dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+            for k in e:
+                e[k] += d[k]
+        if args.per_layer:
+            line["layers"] = {n: {"ms": d["ms"] / 2, "tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12}
+                              for n, d in sorted(per_layer.items(), key=lambda kv: -kv[1]["ms"]) if "[" in n}
         tot_ms = sum(d["ms"] for d in summ.values()) or 1.0
         kernels = {}
         for name, d in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
