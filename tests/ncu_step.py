@@ -1,0 +1,41 @@
+"""One profiled UNet training step (BASELINE.json configs[1]) for Nsight Compute:
+    ncu --profile-from-start off ... python tests/ncu_step.py [batch] [size]
+Two warm-up steps run outside the capture range; cudaProfilerStart/Stop bracket the third."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "unet-medical-image-contour-segmentation_b200"))
+import unet  # noqa: E402
+from unetb200 import losses as UL  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+model = unet.UNet(1, 2, False).to(dev).to(memory_format=torch.channels_last).train()
+opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True)
+x = torch.rand(B, 1, S, S, device=dev).contiguous(memory_format=torch.channels_last)
+t = torch.randint(0, 2, (B, S, S), device=dev)
+
+
+def step():
+    opt.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", enabled=True):
+        loss = UL.training_criterion(model(x), t, boundary_coeff=0.2, edge_width=51, edge_weight=7)
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    opt.step()
+    return loss
+
+
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+loss = step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("loss", float(loss))

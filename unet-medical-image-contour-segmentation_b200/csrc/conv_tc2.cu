@@ -131,20 +131,22 @@ __global__ void __launch_bounds__(192, 1) tc2_fprop_kernel(const __grid_constant
           for (int g = 0; g < p.ngroups; ++g) {
             const uint32_t sa = ia % SA;
             mbar_wait(&a_full[sa], (ia / SA) & 1);
-            const uint32_t a_addr = smem_u32(a_ring + sa * kAStage);
+            // descriptors differ only in their 14-bit start-address field: build one per stage and add
+            // byte offsets >> 4 (the single issuing thread must sustain one MMA per 32 cycles at N = 64)
+            const uint64_t a_desc0 = make_desc(smem_u32(a_ring + sa * kAStage), 16, p.row_bytes);
             for (int k = 0; k < p.g_ntaps[g]; ++k) {
               const uint32_t sb = ib % SB;
               mbar_wait(&b_full[sb], (ib / SB) & 1);
               tc_fence_after();
-              const uint32_t b_addr = smem_u32(b_ring + sb * kBStage);
+              const uint64_t b_desc0 = make_desc(smem_u32(b_ring + sb * kBStage), 16, 1024);
+              const uint64_t a_desc1 = a_desc0 + ((k * p.row_bytes) >> 4);
 #pragma unroll
               for (int s = 0; s < 2; ++s) {
+                const uint64_t a_desc2 = a_desc1 + (p.sub_off[s] >> 4);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint64_t da = make_desc(a_addr + k * p.row_bytes + p.sub_off[s] + kk * 32, 16, p.row_bytes);
-                  const uint64_t db = make_desc(b_addr + kk * 32, 16, 1024);
-                  umma<TF32>(d_tmem + s * BLOCK_N, da, db, idesc, (first && kk == 0) ? 0u : 1u);
-                }
+                for (int kk = 0; kk < 4; ++kk)
+                  umma<TF32>(d_tmem + s * BLOCK_N, a_desc2 + 2 * kk, b_desc0 + 2 * kk, idesc,
+                             (first && kk == 0) ? 0u : 1u);
               }
               first = false;
               umma_commit(&b_empty[sb]);
