@@ -43,31 +43,43 @@ first_conv_fprop_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (active) {
+    // source grid == M grid (checked on the host): the source pixel of tap t is simply m + dy*W + dx
+    int toff[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) toff[t] = d.tap_dy[t] * d.Win + d.tap_dx[t];
     const int M = (int)d.M, mstride = gridDim.x * lanes;
     for (int m = blockIdx.x * lanes + lane; m < M; m += mstride) {
       int b, pi, pj;
       first_decode(d, m, b, pi, pj);
+      // all loads first, branch-free (out-of-range taps read pixel m itself and are zeroed by a select)
+      float xv[9][CIN];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const bool ok = (unsigned)(pi + d.tap_dy[t]) < (unsigned)d.Hin && (unsigned)(pj + d.tap_dx[t]) < (unsigned)d.Win;
+        const T* src = x + (long long)(ok ? m + toff[t] : m) * d.ld_in;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float v = Elem<T>::ld(src + c);
+          xv[t][c] = ok ? v : 0.f;
+        }
+      }
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const int si = pi + d.tap_dy[t], sj = pj + d.tap_dx[t];
-        if (si < 0 || si >= d.Hin || sj < 0 || sj >= d.Win) continue;
-        const T* src = x + (((long long)b * d.Hin + si) * d.Win + sj) * d.ld_in;
 #pragma unroll
         for (int c = 0; c < CIN; ++c) {
-          const float xv = Elem<T>::ld(src + c);
           if constexpr (CIN == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, wr[t][i], acc[i]);
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv[t][c], wr[t][i], acc[i]);
           } else {
             const float4 w0 = *reinterpret_cast<const float4*>(&sw[(t * CIN + c) * d.N + g * 8]);
             const float4 w1 = *reinterpret_cast<const float4*>(&sw[(t * CIN + c) * d.N + g * 8 + 4]);
-            acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-            acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-            acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+            acc[0] = fmaf(xv[t][c], w0.x, acc[0]); acc[1] = fmaf(xv[t][c], w0.y, acc[1]);
+            acc[2] = fmaf(xv[t][c], w0.z, acc[2]); acc[3] = fmaf(xv[t][c], w0.w, acc[3]);
+            acc[4] = fmaf(xv[t][c], w1.x, acc[4]); acc[5] = fmaf(xv[t][c], w1.y, acc[5]);
+            acc[6] = fmaf(xv[t][c], w1.z, acc[6]); acc[7] = fmaf(xv[t][c], w1.w, acc[7]);
           }
         }
       }
@@ -105,21 +117,25 @@ first_conv_wgrad_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
   for (int t = 0; t < 9; ++t)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  int toff[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) toff[t] = d.tap_dy[t] * d.Win + d.tap_dx[t];
   const int M = (int)d.M, mstride = gridDim.x * lanes;
   for (int m = blockIdx.x * lanes + lane; m < M; m += mstride) {
     int b, pi, pj;
     first_decode(d, m, b, pi, pj);
-    float gv[8];
+    float gv[8], xv[9];
     load8(gy + (long long)m * d.ld_out + g * 8, gv);
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int si = pi + d.tap_dy[t], sj = pj + d.tap_dx[t];
-      float xv = 0.f;
-      if (si >= 0 && si < d.Hin && sj >= 0 && sj < d.Win)
-        xv = Elem<T>::ld(x + (((long long)b * d.Hin + si) * d.Win + sj) * d.ld_in);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(xv, gv[i], acc[t][i]);
+    for (int t = 0; t < 9; ++t) {            // branch-free: all loads in flight together
+      const bool ok = (unsigned)(pi + d.tap_dy[t]) < (unsigned)d.Hin && (unsigned)(pj + d.tap_dx[t]) < (unsigned)d.Win;
+      const float v = Elem<T>::ld(x + (long long)(ok ? m + toff[t] : m) * d.ld_in);
+      xv[t] = ok ? v : 0.f;
     }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(xv[t], gv[i], acc[t][i]);
   }
   // lanes of one warp that share a channel group: xor-shuffle over the lane bits above log2(G)
   const int warp = threadIdx.x >> 5;
@@ -151,7 +167,7 @@ first_conv_wgrad_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
 static bool first_common(const unetb200_gconv_t* d) {
   if (d->ntaps != 9 || d->in_scale != 1 || d->out_scale != 1 || d->nquad != 1) return false;
   if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) return false;
-  if (d->Hm != d->Hout || d->Wm != d->Wout) return false;
+  if (d->Hm != d->Hout || d->Wm != d->Wout || d->Hm != d->Hin || d->Wm != d->Win) return false;
   if (d->N % 8 || d->N > 256 || d->ld_out % 8) return false;
   if ((long long)d->B * d->Hm * d->Wm >= (1LL << 31) - (1 << 20)) return false;
   return true;

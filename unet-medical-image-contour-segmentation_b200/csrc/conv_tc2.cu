@@ -29,6 +29,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 struct alignas(64) Tc2Params {
   CUtensorMap a_map[4];      // source view per tap group, box {128 B, box_w, box_h(g), 1}
   CUtensorMap b_map;         // packed weights [N][K], box {128 B, BLOCK_N}
@@ -44,14 +58,16 @@ struct alignas(64) Tc2Params {
   int m_tiles, total_tiles;
   int Hm, Wm, Cq;
   const float* bias;
-  float* stats_ws;           // [n_block][cta][4 warps][2][BLOCK_N]
+  float* stats_ws;           // [n_block][cta][8 epilogue warps][2][BLOCK_N]
 };
 
 constexpr uint32_t kAStage = 36864;     // max box: 18 rows x 16 px (or 34 x 8) x 128 B
-constexpr int kEpiStage = 4096;         // 32 rows x 128 B per epilogue warp and buffer
+constexpr int kEpiStage = 4096;         // 32 rows x 128 B per epilogue warp
+constexpr int kEpiWarps = 8;            // two per TMEM lane quadrant: one per 128-row sub-tile
+constexpr int kTc2Threads = 64 + 32 * kEpiWarps;
 
 template <typename T, int BLOCK_N, int SA, int SB, int ACC>
-__global__ void __launch_bounds__(192, 1) tc2_fprop_kernel(const __grid_constant__ Tc2Params p) {
+__global__ void __launch_bounds__(kTc2Threads, 1) tc2_fprop_kernel(const __grid_constant__ Tc2Params p) {
   constexpr bool TF32 = sizeof(T) == 4;
   constexpr int EPR = 128 / sizeof(T);
   constexpr uint32_t kBStage = BLOCK_N * 128;
@@ -61,8 +77,8 @@ __global__ void __launch_bounds__(192, 1) tc2_fprop_kernel(const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + SA * kAStage;
-  uint8_t* epi = b_ring + SB * kBStage;                // 4 warps x 2 buffers x 4 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 8 * kEpiStage);
+  uint8_t* epi = b_ring + SB * kBStage;                // 8 warps x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpiWarps * kEpiStage);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + SA;
   uint64_t* b_full = a_empty + SA;
@@ -77,7 +93,7 @@ __global__ void __launch_bounds__(192, 1) tc2_fprop_kernel(const __grid_constant
     tma_prefetch_desc(&p.b_map);
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+    for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -161,9 +177,12 @@ __global__ void __launch_bounds__(192, 1) tc2_fprop_kernel(const __grid_constant
     }
   } else {
     // ------------------------------------ epilogue -----------------------------------------
+    // 8 warps: warp handles TMEM lane quadrant (warp % 4) of sub-tile (warp - 2) / 4.
     const int quad = warp & 3;
-    uint8_t* stg = epi + quad * 2 * kEpiStage;
-    uint32_t it = 0, sbuf = 0;
+    const int s = (warp - 2) >> 2;
+    const int ew = s * 4 + quad;                                      // 0..7
+    uint8_t* buf = epi + ew * kEpiStage;
+    uint32_t it = 0;
     int cur_nb = -1;
     float st[NCB][TF32 ? 2 : 4];
 #pragma unroll
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(192, 1) tc2_fprop_kernel(const __grid_constant
       for (int j = 0; j < (TF32 ? 2 : 4); ++j) st[i][j] = 0.f;
     auto flush = [&](int nb) {
       if (!p.stats_ws || nb < 0) return;
-      float* dst = p.stats_ws + (((long long)nb * gridDim.x + blockIdx.x) * 4 + quad) * 2 * BLOCK_N;
+      float* dst = p.stats_ws + (((long long)nb * gridDim.x + blockIdx.x) * kEpiWarps + ew) * 2 * BLOCK_N;
 #pragma unroll
       for (int cb = 0; cb < NCB; ++cb) {
         if constexpr (TF32) {
@@ -199,81 +218,91 @@ __global__ void __launch_bounds__(192, 1) tc2_fprop_kernel(const __grid_constant
       const int q = n0 / p.Cq, co0 = n0 - q * p.Cq;
       if (nb != cur_nb) { flush(cur_nb); cur_nb = nb; }
       const uint32_t acc = it % ACC;
+      const int pi0 = ti * p.tile_h + p.sub_di[s] + 4 * quad;        // first image row of this warp's 4 x 8 patch
+      const int pj0 = tj * p.tile_w + p.sub_dj[s];
+      // rows of this warp: r = lane -> pixel (pi0 + r / 8, pj0 + r % 8); bit r of valid_rows: inside the M grid
+      const uint32_t valid_rows =
+          __ballot_sync(0xffffffffu, (pi0 + (lane >> 3) < p.Hm) && (pj0 + (lane & 7) < p.Wm));
       mbar_wait(&t_full[acc], (it / ACC) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int s = 0; s < 2; ++s) {
-        const int pi0 = ti * p.tile_h + p.sub_di[s] + 4 * quad;      // first image row of this warp's 4 x 8 patch
-        const int pj0 = tj * p.tile_w + p.sub_dj[s];
-        // rows of this warp: r = lane -> pixel (pi0 + r / 8, pj0 + r % 8)
-        uint32_t valid_rows = 0;                                     // bit r: pixel inside the M grid
-        if (p.stats_ws) {
-          const bool ok = (pi0 + (lane >> 3) < p.Hm) && (pj0 + (lane & 7) < p.Wm);
-          valid_rows = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+      for (int cb = 0; cb < NCB; ++cb) {                              // unrolled: st[cb] must stay in registers
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BLOCK_N + s * BLOCK_N + cb * EPR;
+        uint32_t v[EPR];
+#pragma unroll
+        for (int h = 0; h < EPR / 32; ++h) tmem_ld32_nowait(taddr + h * 32, v + h * 32);
+        if (lane == 0) tma_store_wait_read0();                        // the previous store has finished reading `buf`
+        tmem_ld_wait();
+        __syncwarp();
+        uint8_t* dst = buf + lane * 128;
+#pragma unroll
+        for (int h = 0; h < EPR / 32; ++h) {
+          float f[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            f[e] = __uint_as_float(v[h * 32 + e]);
+            if (p.bias) f[e] += Elem<T>::round(__ldg(p.bias + co0 + cb * EPR + h * 32 + e));
+          }
+          if constexpr (TF32) {
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16)
+              *reinterpret_cast<float4*>(dst + ((c16 ^ (lane & 7)) << 4)) =
+                  make_float4(f[4 * c16], f[4 * c16 + 1], f[4 * c16 + 2], f[4 * c16 + 3]);
+          } else {
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) {
+              uint4 r;
+              r.x = pack_bf16x2(f[8 * c16 + 0], f[8 * c16 + 1]);
+              r.y = pack_bf16x2(f[8 * c16 + 2], f[8 * c16 + 3]);
+              r.z = pack_bf16x2(f[8 * c16 + 4], f[8 * c16 + 5]);
+              r.w = pack_bf16x2(f[8 * c16 + 6], f[8 * c16 + 7]);
+              *reinterpret_cast<uint4*>(dst + (((h * 4 + c16) ^ (lane & 7)) << 4)) = r;
+            }
+          }
         }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&p.o_map[q], buf, co0 + cb * EPR, pj0, pi0, b);
+          tma_store_commit();
+        }
+        if (p.stats_ws) {
+          // lane = 32-bit word of the 128-byte row: sum the rounded values over the 32 rows (branch-free,
+          // all loads issued up front; rows outside the M grid are multiplied by 0)
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+          uint32_t u[32];
 #pragma unroll
-        for (int cb = 0; cb < NCB; ++cb) {                            // unrolled: st[cb] must stay in registers
-          uint8_t* buf = stg + sbuf * kEpiStage;
-          if (lane == 0) tma_store_wait_read1();                     // the store that last read `buf` is done
-          __syncwarp();
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BLOCK_N + s * BLOCK_N + cb * EPR;
+          for (int r = 0; r < 32; ++r)
+            u[r] = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+          if (valid_rows == 0xffffffffu) {
 #pragma unroll
-          for (int h = 0; h < EPR / 32; ++h) {
-            uint32_t v[32];
-            tmem_ld32(taddr + h * 32, v);
-            float f[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              f[e] = __uint_as_float(v[e]);
-              if (p.bias) f[e] += Elem<T>::round(__ldg(p.bias + co0 + cb * EPR + h * 32 + e));
-            }
-            uint8_t* dst = buf + lane * 128;
-            if constexpr (TF32) {
-#pragma unroll
-              for (int c16 = 0; c16 < 8; ++c16)
-                *reinterpret_cast<float4*>(dst + ((c16 ^ (lane & 7)) << 4)) =
-                    make_float4(f[4 * c16], f[4 * c16 + 1], f[4 * c16 + 2], f[4 * c16 + 3]);
-            } else {
-#pragma unroll
-              for (int c16 = 0; c16 < 4; ++c16) {
-                uint4 r;
-                r.x = pack_bf16x2(f[8 * c16 + 0], f[8 * c16 + 1]);
-                r.y = pack_bf16x2(f[8 * c16 + 2], f[8 * c16 + 3]);
-                r.z = pack_bf16x2(f[8 * c16 + 4], f[8 * c16 + 5]);
-                r.w = pack_bf16x2(f[8 * c16 + 6], f[8 * c16 + 7]);
-                *reinterpret_cast<uint4*>(dst + (((h * 4 + c16) ^ (lane & 7)) << 4)) = r;
-              }
-            }
-          }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_4d(&p.o_map[q], buf, co0 + cb * EPR, pj0, pi0, b);
-            tma_store_commit();
-          }
-          if (p.stats_ws) {
-            // lane = 32-bit word of the 128-byte row; sum the rounded values of the valid rows
-            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-              if (!((valid_rows >> r) & 1u)) continue;
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(buf + r * 128 +
-                                                                    ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
               if constexpr (TF32) {
-                const float a = __uint_as_float(u);
-                s0 += a; q0 += a * a;
+                const float a = __uint_as_float(u[r]);
+                s0 += a; q0 = fmaf(a, a, q0);
               } else {
-                const float a = __uint_as_float(u << 16), c2 = __uint_as_float(u & 0xffff0000u);
-                s0 += a; q0 += a * a; s1 += c2; q1 += c2 * c2;
+                const float a = __uint_as_float(u[r] << 16), c2 = __uint_as_float(u[r] & 0xffff0000u);
+                s0 += a; q0 = fmaf(a, a, q0); s1 += c2; q1 = fmaf(c2, c2, q1);
               }
             }
-            st[cb][0] += s0; st[cb][1] += q0;
-            if constexpr (!TF32) { st[cb][2] += s1; st[cb][3] += q1; }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const float m = ((valid_rows >> r) & 1u) ? 1.f : 0.f;
+              if constexpr (TF32) {
+                const float a = __uint_as_float(u[r]) * m;
+                s0 += a; q0 = fmaf(a, a, q0);
+              } else {
+                const float a = __uint_as_float(u[r] << 16) * m, c2 = __uint_as_float(u[r] & 0xffff0000u) * m;
+                s0 += a; q0 = fmaf(a, a, q0); s1 += c2; q1 = fmaf(c2, c2, q1);
+              }
+            }
           }
-          sbuf ^= 1;
+          st[cb][0] += s0; st[cb][1] += q0;
+          if constexpr (!TF32) { st[cb][2] += s1; st[cb][3] += q1; }
         }
       }
-      // this warp has drained its 32 lanes of accumulator set `acc`
+      // this warp has drained its 32 lanes of its sub-tile of accumulator set `acc`
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
@@ -383,12 +412,12 @@ int tc2_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp
 long long tc2_stats_workspace(const unetb200_gconv_t* d) {
   Tc2Plan pl;
   if (!tc2_plan(d, &pl)) return 0;
-  return (long long)pl.n_blocks * pl.grid * 4 * 2 * pl.BN;
+  return (long long)pl.n_blocks * pl.grid * kEpiWarps * 2 * pl.BN;
 }
 
 template <typename T, int BN, int SA, int SB, int ACC>
 static int tc2_launch(const Tc2Params& P, int grid, cudaStream_t s) {
-  constexpr int smem = SA * kAStage + SB * BN * 128 + 8 * kEpiStage + 1024 + 256;
+  constexpr int smem = SA * kAStage + SB * BN * 128 + kEpiWarps * kEpiStage + 1024 + 256;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
@@ -397,7 +426,7 @@ static int tc2_launch(const Tc2Params& P, int grid, cudaStream_t s) {
     if (e != cudaSuccess) return cuda_fail(e, "tc2_fprop smem attribute");
     configured = true;
   }
-  tc2_fprop_kernel<T, BN, SA, SB, ACC><<<grid, 192, smem, s>>>(P);
+  tc2_fprop_kernel<T, BN, SA, SB, ACC><<<grid, kTc2Threads, smem, s>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "tc2_fprop launch");
   return 0;
@@ -475,7 +504,7 @@ int tc2_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   }
   if (rc) return rc;
   if (stats) {
-    const int rows = pl.grid * 4;
+    const int rows = pl.grid * kEpiWarps;
     tc2_stats_reduce_kernel<<<dim3((2 * pl.BN + 31) / 32, pl.n_blocks), 256, 0, stream>>>(stats_ws, rows, pl.BN, g.Cq,
                                                                                          stats);
     cudaError_t e = cudaGetLastError();
