@@ -1,0 +1,373 @@
+// umma_probe: microbenchmarks and known-answer checks of tcgen05 behaviour the conv kernels depend on.
+// Not part of the product library; built by `make -C tools` and run on the GPU box by hand:
+//   tools/build/umma_probe rate          cycles per tcgen05.mma (1-CTA and 2-CTA, N = 64/128/256), operands
+//                                        resident in shared memory, with and without concurrent bulk-copy fills
+//   tools/build/umma_probe check         (a) cta_group::2 GEMM against a host reference,
+//                                        (b) descriptors whose start address / SBO are not 1024-byte aligned
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../unet-medical-image-contour-segmentation_b200/csrc/tc_common.cuh"
+
+using namespace ub;
+
+#define CK(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) {                                                                    \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);           \
+      exit(1);                                                                                  \
+    }                                                                                           \
+  } while (0)
+
+// ---------------------------------------------------------------- cta_group::2 wrappers
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* g, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem)), "l"(g), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------- rate
+// One CTA (or CTA pair) per SM.  The issuing thread loops over `iters` steps of 8 MMAs (4 K-slices x 2
+// accumulators, like one (tap, channel-chunk) step of tc2_fprop), rotating over 4 operand stages and
+// committing each step to a ring of 4 mbarriers it waits on 4 steps later (a bounded pipeline).  A
+// second warp optionally streams `fill_bytes` per step from global memory into scratch shared memory
+// with bulk copies, paced by the same ring.
+constexpr int kRing = 4;
+template <int CG>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int fill_bytes, const uint8_t* gsrc,
+                                                      long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;                    // 4 x 16 KB
+  uint8_t* b_ring = smem + 4 * 16384;        // 4 x 16 KB (32 KB for N = 256 at CG = 1 -> 2 stages alias; values unused)
+  uint8_t* scratch = smem + 8 * 16384;           // 64 KB fill target
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + 65536);
+  uint64_t* done = bars;                     // kRing
+  uint64_t* fbar = bars + kRing;             // kRing
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRing);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  for (int i = threadIdx.x; i < (8 * 16384 + 65536) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kRing; ++i) { mbar_init(&done[i], 1); mbar_init(&fbar[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { if (CG == 2) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc(false, false, false, 128 * CG, N);
+    const uint64_t a_t = make_desc(smem_u32(a_ring), 16, 1024), b_t = make_desc(smem_u32(b_ring), 16, 1024);
+    const uint32_t dcol2 = N <= 256 ? (uint32_t)N : 0u;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kRing;
+      if (it >= kRing) mbar_wait(&done[s], ((it / kRing) - 1) & 1);
+      if (fill_bytes > 0) mbar_wait(&fbar[s], (it / kRing) & 1);      // like a consumer waiting for its stage
+      tc_fence_after();
+      const uint64_t a0 = a_t + s * (16384 >> 4), b0 = b_t + (s & (N > 128 && CG == 1 ? 1 : 3)) * ((N > 128 && CG == 1 ? 32768 : 16384) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (CG == 2) {
+            umma2(tmem_base, a0 + 2 * kk, b0 + 2 * kk, idesc, 1);
+            umma2(tmem_base + dcol2, a0 + 512 + 2 * kk, b0 + 2 * kk, idesc, 1);
+          } else {
+            umma<false>(tmem_base, a0 + 2 * kk, b0 + 2 * kk, idesc, 1);
+            umma<false>(tmem_base + dcol2, a0 + 512 + 2 * kk, b0 + 2 * kk, idesc, 1);
+          }
+        }
+        if (CG == 2) umma_commit2(&done[s], 3); else umma_commit(&done[s]);
+      }
+      __syncwarp();
+    }
+    for (int it = iters > kRing ? iters - kRing : 0; it < iters; ++it) mbar_wait(&done[it % kRing], (it / kRing) & 1);
+    long long t1 = clock64();
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
+  } else if (warp == 0) {
+    // follower CTA of a pair: its `done` barriers receive the multicast commits; just wait for the end
+    for (int it = 0; it < iters; ++it) mbar_wait(&done[it % kRing], (it / kRing) & 1);
+    if (lane == 0) out[blockIdx.x] = 0;
+  } else if (warp == 2 && fill_bytes > 0) {
+    const uint8_t* src = gsrc + (size_t)blockIdx.x * (1 << 20);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kRing;
+      if (it >= kRing) {
+        mbar_wait(&done[s], ((it / kRing) - 1) & 1);      // MMAs of step it-4 are done
+        mbar_wait(&fbar[s], ((it / kRing) - 1) & 1);      // and so is the fill that used this slot
+      }
+      if (elect_one()) {
+        mbar_expect_tx(&fbar[s], fill_bytes);
+        bulk_g2s(scratch + s * 16384, src + ((it * 16384) & ((1 << 20) - 1)), fill_bytes, &fbar[s]);
+      }
+      __syncwarp();
+    }
+    for (int it = iters > kRing ? iters - kRing : 0; it < iters; ++it) mbar_wait(&fbar[it % kRing], (it / kRing) & 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 1) { if (CG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+}
+
+static void run_rate() {
+  const int smem = 8 * 16384 + 65536 + 1024 + 256;
+  CK(cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  uint8_t* gsrc;
+  CK(cudaMalloc(&gsrc, 148u << 20));
+  CK(cudaMemset(gsrc, 0, 148u << 20));
+  long long* out;
+  CK(cudaMalloc(&out, 148 * sizeof(long long)));
+  const int iters = 4000;
+  for (int cg = 1; cg <= 2; ++cg)
+    for (int N : {64, 128, 256})
+      for (int fill : {0, 4096, 8192, 16384}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(148);
+        cfg.blockDim = dim3(128);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        for (int rep = 0; rep < 2; ++rep) {
+          if (cg == 1) CK(cudaLaunchKernelEx(&cfg, rate_kernel<1>, N, iters, fill, (const uint8_t*)gsrc, out));
+          else CK(cudaLaunchKernelEx(&cfg, rate_kernel<2>, N, iters, fill, (const uint8_t*)gsrc, out));
+          CK(cudaDeviceSynchronize());
+        }
+        std::vector<long long> h(148);
+        CK(cudaMemcpy(h.data(), out, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+        double sum = 0; int n = 0; long long mx = 0;
+        for (auto v : h) if (v > 0) { sum += v; ++n; if (v > mx) mx = v; }
+        const double per = sum / n / (iters * 8.0);
+        const double floor = 128.0 * N / 256.0 / 2.0;      // cycles per 128 x N x 16 MMA per SM at 8192 FLOP/cycle/SM
+        printf("cta_group::%d N=%3d fill=%5d B/step: %.1f cycles/MMA (max CTA %.1f), floor %.0f -> %.0f%% of tensor peak\n", cg, N,
+               fill, per, mx / (iters * 8.0), floor, 100.0 * floor / per);
+      }
+}
+
+// ---------------------------------------------------------------- check (a): cta_group::2 GEMM
+// D[256][N] = A[256][64] * B[N][64]^T, bf16 in, fp32 out.  CTA r of the pair holds A rows [128r, 128r+128) and
+// B rows [N/2 r, N/2 r + N/2), both K-major SWIZZLE_128B at the same shared-memory offsets.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+pair_gemm_kernel(const __nv_bfloat16* A, const __nv_bfloat16* B, float* D, int N) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sa = smem;            // 128 rows x 128 B
+  uint8_t* sb = smem + 16384;    // N/2 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 16384);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  // swizzled store: row r, 16-byte chunk c -> r * 128 + ((c ^ (r & 7)) << 4)
+  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) =
+        *reinterpret_cast<const uint4*>(A + (size_t)(rank * 128 + r) * 64 + c * 8);
+  }
+  for (int i = threadIdx.x; i < (N / 2) * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sb + r * 128 + ((c ^ (r & 7)) << 4)) =
+        *reinterpret_cast<const uint4*>(B + (size_t)(rank * (N / 2) + r) * 64 + c * 8);
+  }
+  if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc2(tmem_slot, 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc(false, false, false, 256, N);
+    const uint64_t a0 = make_desc(smem_u32(sa), 16, 1024), b0 = make_desc(smem_u32(sb), 16, 1024);
+    if (elect_one()) {
+      for (int kk = 0; kk < 4; ++kk) umma2(tmem_base, a0 + 2 * kk, b0 + 2 * kk, idesc, kk > 0);
+      umma_commit2(bar, 3);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int ch = 0; ch < N / 32; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
+    for (int e = 0; e < 32; ++e) D[(size_t)(rank * 128 + warp * 32 + lane) * N + ch * 32 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------- check (b): unaligned descriptor starts
+// Shared memory holds `rows` pixel rows of 128 B written with the swizzle TMA applies (16-byte chunk index XOR
+// bits [7,10) of the absolute shared address).  A = 128 rows addressed as start + (m / 8) * sbo + (m % 8) * 128
+// with start = base + start_row * 128; B = 64 x 64 identity-like known matrix; D is compared on the host.
+__global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* X, const __nv_bfloat16* B, float* D, int rows,
+                                                        int start_row, int sbo, int use_base_offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sx = smem;                 // rows x 128 B (up to 48 KB)
+  uint8_t* sb = smem + 49152;         // 64 rows x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 49152 + 8192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    const uint32_t addr = smem_u32(sx) + r * 128;
+    *reinterpret_cast<uint4*>(sx + r * 128 + ((c ^ ((addr >> 7) & 7)) << 4)) =
+        *reinterpret_cast<const uint4*>(X + (size_t)r * 64 + c * 8);
+  }
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sb + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(B + (size_t)r * 64 + c * 8);
+  }
+  if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(false, false, false, 128, 64);
+    const uint32_t start = smem_u32(sx) + start_row * 128;
+    uint64_t a0 = make_desc(start, 16, sbo);
+    if (use_base_offset) a0 |= (uint64_t)((start >> 7) & 7) << 49;
+    const uint64_t b0 = make_desc(smem_u32(sb), 16, 1024);
+    if (elect_one()) {
+      for (int kk = 0; kk < 4; ++kk) umma<false>(tmem_base, a0 + 2 * kk, b0 + 2 * kk, idesc, kk > 0);
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
+    for (int e = 0; e < 32; ++e) D[(size_t)(warp * 32 + lane) * 64 + ch * 32 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+static void run_check() {
+  // (a)
+  for (int N : {64, 128, 256}) {
+    std::vector<__nv_bfloat16> hA(256 * 64), hB(N * 64);
+    std::vector<float> fA(256 * 64), fB(N * 64);
+    srand(1);
+    for (size_t i = 0; i < hA.size(); ++i) { fA[i] = bf((rand() % 17 - 8) / 8.f); hA[i] = __float2bfloat16(fA[i]); }
+    for (size_t i = 0; i < hB.size(); ++i) { fB[i] = bf((rand() % 13 - 6) / 4.f); hB[i] = __float2bfloat16(fB[i]); }
+    __nv_bfloat16 *dA, *dB; float* dD;
+    CK(cudaMalloc(&dA, hA.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 256 * N * 4));
+    CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, 256 * N * 4));
+    const int smem = 16384 + 16384 + 1024 + 256;
+    CK(cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pair_gemm_kernel<<<2, 128, smem>>>(dA, dB, dD, N);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> hD(256 * N);
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    for (int m = 0; m < 256; ++m)
+      for (int n = 0; n < N; ++n) {
+        double ref = 0;
+        for (int k = 0; k < 64; ++k) ref += (double)fA[m * 64 + k] * fB[n * 64 + k];
+        double e = fabs(ref - hD[m * N + n]);
+        if (!(e <= maxerr)) maxerr = e;
+      }
+    printf("check(a) cta_group::2 M=256 N=%d K=64: max abs err %.3g %s\n", N, maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
+    cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  }
+  // (b)
+  const int rows = 384;
+  std::vector<__nv_bfloat16> hX(rows * 64), hB(64 * 64);
+  std::vector<float> fX(rows * 64), fB(64 * 64);
+  srand(2);
+  for (size_t i = 0; i < hX.size(); ++i) { fX[i] = bf((rand() % 31 - 15) / 8.f); hX[i] = __float2bfloat16(fX[i]); }
+  for (size_t i = 0; i < hB.size(); ++i) { fB[i] = bf((rand() % 9 - 4) / 4.f); hB[i] = __float2bfloat16(fB[i]); }
+  __nv_bfloat16 *dX, *dB; float* dD;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 128 * 64 * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  const int smem = 49152 + 8192 + 1024 + 256;
+  CK(cudaFuncSetAttribute(shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int sbo : {1024, 1280, 2304}) {
+    for (int start_row : {0, 1, 3, 8, 9, 19}) {
+      for (int ubo = 0; ubo < 2; ++ubo) {
+        CK(cudaMemset(dD, 0xff, 128 * 64 * 4));
+        shift_kernel<<<1, 128, smem>>>(dX, dB, dD, rows, start_row, sbo, ubo);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("check(b) sbo=%d start=%d base_offset=%d: CUDA error %s\n", sbo, start_row, ubo, cudaGetErrorString(e)); exit(1); }
+        std::vector<float> hD(128 * 64);
+        CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+        double maxerr = 0;
+        for (int m = 0; m < 128; ++m) {
+          const int r = start_row + (m / 8) * (sbo / 128) + (m % 8);
+          for (int n = 0; n < 64; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 64; ++k) ref += (double)fX[r * 64 + k] * fB[n * 64 + k];
+            double er = fabs(ref - hD[m * 64 + n]);
+            if (!(er <= maxerr)) maxerr = er;
+          }
+        }
+        printf("check(b) sbo=%4d start_row=%2d base_offset_field=%d: max abs err %.3g %s\n", sbo, start_row, ubo, maxerr,
+               maxerr < 1e-3 ? "OK" : "MISMATCH");
+      }
+    }
+  }
+}
+
+int main(int argc, char** argv) {
+  const char* mode = argc > 1 ? argv[1] : "all";
+  if (!strcmp(mode, "check") || !strcmp(mode, "all")) run_check();
+  if (!strcmp(mode, "rate") || !strcmp(mode, "all")) run_rate();
+  return 0;
+}

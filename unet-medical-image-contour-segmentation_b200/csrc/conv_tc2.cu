@@ -104,76 +104,81 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_fprop_kernel(const __grid_
 
   if (warp == 0) {
     // ------------------------------------ TMA producer ------------------------------------
-    if (lane == 0) {
-      uint32_t ia = 0, ib = 0;                         // running stage counters
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int nb = t / p.m_tiles;
-        int mt = t - nb * p.m_tiles;
-        const int tj = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int ti = mt % p.tiles_h;
-        const int b = mt / p.tiles_h;
-        const int i0 = ti * p.tile_h, j0 = tj * p.tile_w, n0 = nb * BLOCK_N;
-        for (int c = 0; c < p.cchunks; ++c) {
-          for (int g = 0; g < p.ngroups; ++g) {
-            const uint32_t sa = ia % SA;
-            mbar_wait(&a_empty[sa], ((ia / SA) & 1) ^ 1);
+    // The whole warp runs the loop convergently and one elected lane issues: values stay in uniform
+    // registers, so a TMA issue is a handful of instructions (a lane-0-only branch makes the compiler
+    // wrap every UTMALDG / UTCHMMA in an elect + broadcast loop).
+    uint32_t sa = 0, pa = 1, sb = 0, pb = 1;             // stage index, parity to wait for on *_empty
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int nb = t / p.m_tiles;
+      int mt = t - nb * p.m_tiles;
+      const int tj = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int ti = mt % p.tiles_h;
+      const int b = mt / p.tiles_h;
+      const int i0 = ti * p.tile_h, j0 = tj * p.tile_w, n0 = nb * BLOCK_N;
+      for (int c = 0; c < p.cchunks; ++c) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          mbar_wait(&a_empty[sa], pa);
+          if (elect_one()) {
             mbar_expect_tx(&a_full[sa], p.g_box_bytes[g]);
             tma_load_4d(a_ring + sa * kAStage, &p.a_map[g], &a_full[sa], c * EPR, j0 + p.g_dx[g], i0 + p.g_dy0[g], b);
-            ++ia;
-            for (int k = 0; k < p.g_ntaps[g]; ++k) {
-              const uint32_t sb = ib % SB;
-              mbar_wait(&b_empty[sb], ((ib / SB) & 1) ^ 1);
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+          const int nt = p.g_ntaps[g];
+          for (int k = 0; k < nt; ++k) {
+            mbar_wait(&b_empty[sb], pb);
+            if (elect_one()) {
               mbar_expect_tx(&b_full[sb], kBStage);
               tma_load_2d(b_ring + sb * kBStage, &p.b_map, &b_full[sb], p.g_tap[g][k] * p.Cin + c * EPR, n0);
-              ++ib;
             }
+            if (++sb == SB) { sb = 0; pb ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------ MMA issuer ---------------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32, false, false, 128, BLOCK_N);
-      uint32_t ia = 0, ib = 0, it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const uint32_t acc = it % ACC;
-        mbar_wait(&t_empty[acc], ((it / ACC) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 2 * BLOCK_N;
-        bool first = true;
-        for (int c = 0; c < p.cchunks; ++c) {
-          for (int g = 0; g < p.ngroups; ++g) {
-            const uint32_t sa = ia % SA;
-            mbar_wait(&a_full[sa], (ia / SA) & 1);
-            // descriptors differ only in their 14-bit start-address field: build one per stage and add
-            // byte offsets >> 4 (the single issuing thread must sustain one MMA per 32 cycles at N = 64)
-            const uint64_t a_desc0 = make_desc(smem_u32(a_ring + sa * kAStage), 16, p.row_bytes);
-            for (int k = 0; k < p.g_ntaps[g]; ++k) {
-              const uint32_t sb = ib % SB;
-              mbar_wait(&b_full[sb], (ib / SB) & 1);
-              tc_fence_after();
-              const uint64_t b_desc0 = make_desc(smem_u32(b_ring + sb * kBStage), 16, 1024);
-              const uint64_t a_desc1 = a_desc0 + ((k * p.row_bytes) >> 4);
+    // Convergent warp, one elected lane issues.  Descriptors differ only in their 14-bit start-address
+    // field: one template per operand, plus byte offsets >> 4.
+    constexpr uint32_t idesc = make_idesc(TF32, false, false, 128, BLOCK_N);
+    const uint64_t a_desc_t = make_desc(smem_u32(a_ring), 16, p.row_bytes);
+    const uint64_t b_desc_t = make_desc(smem_u32(b_ring), 16, 1024);
+    const uint32_t sub1 = p.sub_off[1] >> 4, rowq = p.row_bytes >> 4;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 1;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(&t_empty[acc], pacc);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 2 * BLOCK_N;
+      uint32_t accum = 0;
+      for (int c = 0; c < p.cchunks; ++c) {
+        for (int g = 0; g < p.ngroups; ++g) {
+          mbar_wait(&a_full[sa], pa);
+          const uint64_t a_desc0 = a_desc_t + sa * (kAStage >> 4);
+          const int nt = p.g_ntaps[g];
+          for (int k = 0; k < nt; ++k) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t b_desc0 = b_desc_t + sb * (kBStage >> 4);
+            const uint64_t a_desc1 = a_desc0 + k * rowq;
+            if (elect_one()) {
 #pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                const uint64_t a_desc2 = a_desc1 + (p.sub_off[s] >> 4);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                  umma<TF32>(d_tmem + s * BLOCK_N, a_desc2 + 2 * kk, b_desc0 + 2 * kk, idesc,
-                             (first && kk == 0) ? 0u : 1u);
+              for (int kk = 0; kk < 4; ++kk) {
+                umma<TF32>(d_tmem, a_desc1 + 2 * kk, b_desc0 + 2 * kk, idesc, accum | (uint32_t)kk);
+                umma<TF32>(d_tmem + BLOCK_N, a_desc1 + sub1 + 2 * kk, b_desc0 + 2 * kk, idesc, accum | (uint32_t)kk);
               }
-              first = false;
               umma_commit(&b_empty[sb]);
-              ++ib;
+              if (k == nt - 1) umma_commit(&a_empty[sa]);
             }
-            umma_commit(&a_empty[sa]);
-            ++ia;
+            __syncwarp();
+            accum = 1;
+            if (++sb == SB) { sb = 0; pb ^= 1; }
           }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
         }
-        umma_commit(&t_full[acc]);
       }
+      if (elect_one()) umma_commit(&t_full[acc]);
+      __syncwarp();
+      if (++acc == ACC) { acc = 0; pacc ^= 1; }
     }
   } else {
     // ------------------------------------ epilogue -----------------------------------------
@@ -581,52 +586,63 @@ __global__ void __launch_bounds__(192, 1) tc2_wgrad_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t stage_bytes = MSUB * p.a_box_bytes + NSUBT * kGSub;
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+    // convergent warp, one elected lane issues (see tc2_fprop_kernel)
+    const uint32_t stage_bytes = MSUB * p.a_box_bytes + NSUBT * kGSub;
+    int pt = pt_begin;
+    int tj = pt % p.tiles_w;
+    int rest = pt / p.tiles_w;
+    int ti = rest % p.tiles_h;
+    int b = rest / p.tiles_h;
+    // the MSUB units of this M tile are fixed for the whole kernel
+    int uc[MSUB], ug[MSUB];
+#pragma unroll
+    for (int h = 0; h < MSUB; ++h) {
+      int u = mt * MSUB + h;
+      if (u >= p.nunits) u = p.nunits - 1;              // padding rows: valid data, results discarded
+      uc[h] = u / p.ngroups;
+      ug[h] = u - uc[h] * p.ngroups;
+    }
+    uint32_t s = 0, ph = 1;
+    for (int kb = 0; kb < num_k; ++kb) {
+      mbar_wait(&empty_bar[s], ph);
+      if (elect_one()) {
         mbar_expect_tx(&full_bar[s], stage_bytes);
-        int pt = pt_begin + kb;
-        const int tj = pt % p.tiles_w;
-        pt /= p.tiles_w;
-        const int ti = pt % p.tiles_h;
-        const int b = pt / p.tiles_h;
         const int i0 = ti * 8, j0 = tj * 8;
         uint8_t* sa = smem + s * kStage;
 #pragma unroll
-        for (int h = 0; h < MSUB; ++h) {
-          int u = mt * MSUB + h;
-          if (u >= p.nunits) u = p.nunits - 1;          // padding rows: valid data, results discarded
-          const int c = u / p.ngroups, g = u - c * p.ngroups;
-          tma_load_4d(sa + h * kABox, &p.a_map[g], &full_bar[s], c * EPR, j0 + p.g_dx[g], i0 + p.g_dy0[g], b);
-        }
+        for (int h = 0; h < MSUB; ++h)
+          tma_load_4d(sa + h * kABox, &p.a_map[ug[h]], &full_bar[s], uc[h] * EPR, j0 + p.g_dx[ug[h]], i0 + p.g_dy0[ug[h]], b);
 #pragma unroll
         for (int h = 0; h < NSUBT; ++h)
           tma_load_4d(sa + MSUB * kABox + h * kGSub, &p.o_map[q], &full_bar[s], co0 + h * EPR, j0, i0, b);
       }
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (++tj == p.tiles_w) { tj = 0; if (++ti == p.tiles_h) { ti = 0; ++b; } }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TF32, true, true, 128, BLOCK_N);
-      for (int kb = 0; kb < num_k; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * kStage);
+    constexpr uint32_t idesc = make_idesc(TF32, true, true, 128, BLOCK_N);
+    // MN-major: LBO = distance between 128-byte-wide sub-tiles, SBO = one swizzle group of pixel rows
+    const uint64_t da_t = make_desc(smem_u32(smem), kABox, kSbo, kLay);
+    const uint64_t db_t = make_desc(smem_u32(smem) + MSUB * kABox, kGSub, kSbo, kLay);
+    uint32_t s = 0, ph = 0;
+    for (int kb = 0; kb < num_k; ++kb) {
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint64_t da0 = da_t + s * (kStage >> 4), db0 = db_t + s * (kStage >> 4);
+      if (elect_one()) {
         for (int a = 0; a < p.ndy; ++a) {
 #pragma unroll
-          for (int k = 0; k < MMAS; ++k) {
-            // MN-major: LBO = distance between 128-byte-wide sub-tiles, SBO = one swizzle group of pixel rows
-            const uint64_t da = make_desc(sa + a * 1024 + k * UMMA_K * 128, kABox, kSbo, kLay);
-            const uint64_t db = make_desc(sa + MSUB * kABox + k * UMMA_K * 128, kGSub, kSbo, kLay);
-            umma<TF32>(tmem_base + a * BLOCK_N, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < MMAS; ++k)
+            umma<TF32>(tmem_base + a * BLOCK_N, da0 + ((a * 1024 + k * UMMA_K * 128) >> 4), db0 + ((k * UMMA_K * 128) >> 4),
+                       idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);
       }
-      umma_commit(tmem_full);
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int row = quad * 32 + lane;                  // D row = (unit row / EPR, channel row % EPR)
