@@ -410,7 +410,9 @@ int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
   if (ft > tiles) tiles = ft;
   long long n = tiles * 2 * g.N;
   long long n2 = tc2_stats_workspace(d);
-  return n > n2 ? n : n2;
+  if (n2 > n) n = n2;
+  long long n3 = tc3_stats_workspace(d);
+  return n > n3 ? n : n3;
 }
 
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
@@ -428,6 +430,7 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_fprop_supported(d, x, wp, y), "gconv_fprop: tcgen05 path requested but shape/alignment unsupported");
     static const bool use_v1 = getenv("UNETB200_TC_V1") != nullptr;      // first-generation kernel, for A/B runs
+    if (!use_v1 && tc3_fprop_supported(d, x, wp, y)) return tc3_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
     if (!use_v1 && tc2_fprop_supported(d, x, wp, y)) return tc2_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
     return tc_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
   }

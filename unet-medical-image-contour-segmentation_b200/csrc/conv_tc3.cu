@@ -1,0 +1,597 @@
+// Third-generation tcgen05 engine for the 3x3 convolutions (fprop and dgrad of nn.Conv2d(k=3, padding=1),
+// unet_parts.py:15,18 and their autograd dgrad): CTA pairs (cta_group::2) + full 3x3 tap reuse.
+//
+// What bounded the second generation (conv_tc2.cu), measured with tools/umma_probe.cu and ncu:
+//   * a 1-CTA tcgen05.mma of M=128 runs at 77 / 87 / 128 cycles for N = 64 / 128 / 256 (floor 32 / 64 / 128):
+//     the A operand is re-read from shared memory for every MMA.  As a CTA pair (M = 256, each SM reads its
+//     own A and HALF of B) the same instructions take 49 / 64 / 128 cycles;
+//   * the L2 -> shared-memory fill stream ran at 7-8 TB/s chip-wide, its ceiling.  Per 64-channel chunk and
+//     256-pixel tile the old kernel fetched 3 activation boxes (one per column shift, 108 KB) + 9 weight
+//     tiles; here ONE halo box {128 B, tile_w + 2, tile_h + 2} (41.5 KB) serves all nine taps -- the UMMA
+//     descriptor of tap (dy, dx) starts ((dy+1) * box_w + (dx+1)) * 128 B into the box, its 8-row groups are
+//     box_w * 128 B apart (SBO), and the 128-byte swizzle is a function of the absolute shared-memory
+//     address, so neither needs 1024-byte alignment (tools/umma_probe.cu check (b)) -- and each CTA of the
+//     pair fetches half of every weight tile.
+//
+// Structure per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner,
+// warps 2..9 = epilogue (as in conv_tc2.cu: tcgen05.ld -> +bias -> round -> swizzled staging -> TMA store,
+// BatchNorm partial sums in registers).  Each CTA of a pair owns one 256-pixel tile (two 128-row
+// accumulators); the pair shares the n-block.  Barriers: the `full` barriers live in the leader and count
+// the bytes of both CTAs' TMA loads (the peer's loads signal the leader's barrier); MMA completion is
+// multicast to the `empty` barriers of both CTAs; the epilogue warps of both CTAs arrive on the leader's
+// `t_empty`.
+#include <cstring>
+
+#include "tc_common.cuh"
+
+namespace ub {
+
+// ---------------------------------------------------------------------------- cluster / cta_group::2 PTX
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_4d_cg(void* smem, const void* desc, uint32_t bar_addr, int c0, int c1, int c2,
+                                               int c3) {
+  if constexpr (CG == 2) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(void* smem, const void* desc, uint32_t bar_addr, int c0, int c1) {
+  if constexpr (CG == 2) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* dst_smem, uint32_t ncols) {
+  if constexpr (CG == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    tmem_alloc(dst_smem, ncols);
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+  if constexpr (CG == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  } else {
+    tmem_dealloc(taddr, ncols);
+  }
+}
+template <int CG, bool KIND_TF32>
+__device__ __forceinline__ void umma_cg(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if constexpr (CG == 2) {
+    if constexpr (KIND_TF32) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+          : "memory");
+    }
+  } else {
+    umma<KIND_TF32>(d_tmem, a_desc, b_desc, idesc, acc);
+  }
+}
+// MMA completion -> mbarrier at the same shared-memory offset in every CTA of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+  if constexpr (CG == 2) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_fence() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+struct alignas(64) Tc3Params {
+  CUtensorMap a_map;         // source view, box {128 B, box_w, box_h, 1}
+  CUtensorMap b_map;         // packed weights [N][K], box {128 B, BLOCK_N / CG}
+  CUtensorMap o_map;         // destination view, box {128 B, 8, 4, 1}
+  uint32_t tap_aoff[9];      // (((dy + 1) * box_w + (dx + 1)) * 128) >> 4
+  uint32_t a_box_bytes;
+  uint32_t sub1_off;         // byte offset >> 4 of sub-tile 1's first pixel inside the box
+  uint32_t row_bytes;        // box_w * 128 = SBO
+  int cchunks, Cin;
+  int tiles_w, tiles_h, tile_w, tile_h;
+  int sub1_di, sub1_dj;
+  int m_tiles, m_groups, total_groups;   // m_groups = ceil(m_tiles / CG); one "group" = CG tiles of one n-block
+  int Hm, Wm, B;
+  const float* bias;
+  float* stats_ws;           // [n_block][cta][8 epilogue warps][2][BLOCK_N]
+};
+
+constexpr uint32_t kA3Stage = 44032;    // 43 KB >= the largest halo box: 34 rows x 10 px x 128 B
+constexpr int kEpi3Stage = 4096;        // 32 rows x 128 B per epilogue warp
+constexpr int kEpi3Warps = 8;           // two per TMEM lane quadrant: one per 128-row sub-tile
+constexpr int kTc3Threads = 64 + 32 * kEpi3Warps;
+
+template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG>
+__global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_constant__ Tc3Params p) {
+  constexpr bool TF32 = sizeof(T) == 4;
+  constexpr int EPR = 128 / sizeof(T);
+  constexpr uint32_t kBStage = (BLOCK_N / CG) * 128;
+  constexpr int NCB = BLOCK_N / EPR;                   // 128-byte channel blocks per accumulator row
+  static_assert(2 * BLOCK_N * ACC <= 512, "TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + SA * kA3Stage;
+  uint8_t* epi = b_ring + SB * kBStage;                // 8 warps x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpi3Warps * kEpi3Stage);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + SA;
+  uint64_t* b_full = a_empty + SA;
+  uint64_t* b_empty = b_full + SB;
+  uint64_t* t_full = b_empty + SB;
+  uint64_t* t_empty = t_full + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int group0 = blockIdx.x / CG, ngroups = gridDim.x / CG;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.o_map);
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kEpi3Warps * CG); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_cg<CG>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();           // barrier inits + TMEM allocation of both CTAs are in place
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------ TMA producer (both CTAs) ------------------------
+    uint32_t sa = 0, pa = 1, sb = 0, pb = 1;             // stage index, parity to wait for on *_empty
+    for (int gt = group0; gt < p.total_groups; gt += ngroups) {
+      const int nb = gt / p.m_groups;
+      int mt = (gt - nb * p.m_groups) * CG + (int)rank;
+      const bool valid = mt < p.m_tiles;
+      const int tj = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int ti = mt % p.tiles_h;
+      const int b = valid ? mt / p.tiles_h : p.B;       // a tile past the end reads zeros (TMA out-of-bounds fill)
+      const int i0 = ti * p.tile_h - 1, j0 = tj * p.tile_w - 1;
+      const int n0 = nb * BLOCK_N + (int)rank * (BLOCK_N / CG);
+      for (int c = 0; c < p.cchunks; ++c) {
+        mbar_wait(&a_empty[sa], pa);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&a_full[sa], CG * p.a_box_bytes);
+          tma_load_4d_cg<CG>(a_ring + sa * kA3Stage, &p.a_map, mapa_u32(smem_u32(&a_full[sa]), 0), c * EPR, j0, i0, b);
+        }
+        if (++sa == SA) { sa = 0; pa ^= 1; }
+        for (int t = 0; t < 9; ++t) {
+          mbar_wait(&b_empty[sb], pb);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&b_full[sb], CG * kBStage);
+            tma_load_2d_cg<CG>(b_ring + sb * kBStage, &p.b_map, mapa_u32(smem_u32(&b_full[sb]), 0), t * p.Cin + c * EPR, n0);
+          }
+          if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------ MMA issuer (leader CTA) --------------------------
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(TF32, false, false, 128 * CG, BLOCK_N);
+      const uint64_t a_desc_t = make_desc(smem_u32(a_ring), 16, p.row_bytes);
+      const uint64_t b_desc_t = make_desc(smem_u32(b_ring), 16, 1024);
+      const uint32_t sub1 = p.sub1_off;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 1;
+      for (int gt = group0; gt < p.total_groups; gt += ngroups) {
+        mbar_wait(&t_empty[acc], pacc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 2 * BLOCK_N;
+        uint32_t accum = 0;
+        for (int c = 0; c < p.cchunks; ++c) {
+          mbar_wait(&a_full[sa], pa);
+          const uint64_t a_desc0 = a_desc_t + sa * (kA3Stage >> 4);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t b_desc0 = b_desc_t + sb * (kBStage >> 4);
+            const uint64_t a_desc1 = a_desc0 + p.tap_aoff[t];
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                umma_cg<CG, TF32>(d_tmem, a_desc1 + 2 * kk, b_desc0 + 2 * kk, idesc, accum | (uint32_t)kk);
+                umma_cg<CG, TF32>(d_tmem + BLOCK_N, a_desc1 + sub1 + 2 * kk, b_desc0 + 2 * kk, idesc, accum | (uint32_t)kk);
+              }
+              umma_commit_cg<CG>(&b_empty[sb]);
+              if (t == 8) umma_commit_cg<CG>(&a_empty[sa]);
+            }
+            __syncwarp();
+            accum = 1;
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+          }
+          if (++sa == SA) { sa = 0; pa ^= 1; }
+        }
+        if (elect_one()) umma_commit_cg<CG>(&t_full[acc]);
+        __syncwarp();
+        if (++acc == ACC) { acc = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------ epilogue (both CTAs) -----------------------------
+    // 8 warps: warp handles TMEM lane quadrant (warp % 4) of sub-tile (warp - 2) / 4.
+    const int quad = warp & 3;
+    const int s = (warp - 2) >> 2;
+    const int ew = s * 4 + quad;                                      // 0..7
+    uint8_t* buf = epi + ew * kEpi3Stage;
+    uint32_t acc = 0, pacc = 0;
+    int cur_nb = -1;
+    float st[NCB][TF32 ? 2 : 4];
+#pragma unroll
+    for (int i = 0; i < NCB; ++i)
+#pragma unroll
+      for (int j = 0; j < (TF32 ? 2 : 4); ++j) st[i][j] = 0.f;
+    auto flush = [&](int nb) {
+      if (!p.stats_ws || nb < 0) return;
+      float* dst = p.stats_ws + (((long long)nb * gridDim.x + blockIdx.x) * kEpi3Warps + ew) * 2 * BLOCK_N;
+#pragma unroll
+      for (int cb = 0; cb < NCB; ++cb) {
+        if constexpr (TF32) {
+          dst[cb * 32 + lane] = st[cb][0];
+          dst[BLOCK_N + cb * 32 + lane] = st[cb][1];
+          st[cb][0] = st[cb][1] = 0.f;
+        } else {
+          dst[cb * 64 + 2 * lane] = st[cb][0];
+          dst[BLOCK_N + cb * 64 + 2 * lane] = st[cb][1];
+          dst[cb * 64 + 2 * lane + 1] = st[cb][2];
+          dst[BLOCK_N + cb * 64 + 2 * lane + 1] = st[cb][3];
+          st[cb][0] = st[cb][1] = st[cb][2] = st[cb][3] = 0.f;
+        }
+      }
+    };
+    const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&t_empty[0]), 0);
+    for (int gt = group0; gt < p.total_groups; gt += ngroups) {
+      const int nb = gt / p.m_groups;
+      int mt = (gt - nb * p.m_groups) * CG + (int)rank;
+      const bool valid = mt < p.m_tiles;
+      const int tj = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int ti = mt % p.tiles_h;
+      const int b = mt / p.tiles_h;
+      const int n0 = nb * BLOCK_N;
+      if (nb != cur_nb) { flush(cur_nb); cur_nb = nb; }
+      const int pi0 = ti * p.tile_h + s * p.sub1_di + 4 * quad;       // first image row of this warp's 4 x 8 patch
+      const int pj0 = tj * p.tile_w + s * p.sub1_dj;
+      // rows of this warp: r = lane -> pixel (pi0 + r / 8, pj0 + r % 8); bit r of valid_rows: inside the M grid
+      const uint32_t valid_rows =
+          __ballot_sync(0xffffffffu, valid && (pi0 + (lane >> 3) < p.Hm) && (pj0 + (lane & 7) < p.Wm));
+      mbar_wait(&t_full[acc], pacc);
+      tc_fence_after();
+      if (valid_rows != 0u) {
+#pragma unroll
+        for (int cb = 0; cb < NCB; ++cb) {                            // unrolled: st[cb] must stay in registers
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BLOCK_N + s * BLOCK_N + cb * EPR;
+          uint32_t v[EPR];
+#pragma unroll
+          for (int h = 0; h < EPR / 32; ++h) tmem_ld32_issue(taddr + h * 32, v + h * 32);
+          if (lane == 0) tma_store_wait_read_all();                   // the previous store has finished reading `buf`
+          tmem_ld_fence();
+          __syncwarp();
+          uint8_t* dst = buf + lane * 128;
+#pragma unroll
+          for (int h = 0; h < EPR / 32; ++h) {
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              f[e] = __uint_as_float(v[h * 32 + e]);
+              if (p.bias) f[e] += Elem<T>::round(__ldg(p.bias + n0 + cb * EPR + h * 32 + e));
+            }
+            if constexpr (TF32) {
+#pragma unroll
+              for (int c16 = 0; c16 < 8; ++c16)
+                *reinterpret_cast<float4*>(dst + ((c16 ^ (lane & 7)) << 4)) =
+                    make_float4(f[4 * c16], f[4 * c16 + 1], f[4 * c16 + 2], f[4 * c16 + 3]);
+            } else {
+#pragma unroll
+              for (int c16 = 0; c16 < 4; ++c16) {
+                uint4 r;
+                r.x = pack_bf16x2(f[8 * c16 + 0], f[8 * c16 + 1]);
+                r.y = pack_bf16x2(f[8 * c16 + 2], f[8 * c16 + 3]);
+                r.z = pack_bf16x2(f[8 * c16 + 4], f[8 * c16 + 5]);
+                r.w = pack_bf16x2(f[8 * c16 + 6], f[8 * c16 + 7]);
+                *reinterpret_cast<uint4*>(dst + (((h * 4 + c16) ^ (lane & 7)) << 4)) = r;
+              }
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&p.o_map, buf, n0 + cb * EPR, pj0, pi0, b);
+            tma_store_commit();
+          }
+          if (p.stats_ws) {
+            // lane = 32-bit word of the 128-byte row: sum the rounded values over the 32 rows (branch-free,
+            // all loads issued up front; rows outside the M grid are multiplied by 0)
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+            uint32_t u[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              u[r] = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            if (valid_rows == 0xffffffffu) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                if constexpr (TF32) {
+                  const float a = __uint_as_float(u[r]);
+                  s0 += a; q0 = fmaf(a, a, q0);
+                } else {
+                  const float a = __uint_as_float(u[r] << 16), c2 = __uint_as_float(u[r] & 0xffff0000u);
+                  s0 += a; q0 = fmaf(a, a, q0); s1 += c2; q1 = fmaf(c2, c2, q1);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float m = ((valid_rows >> r) & 1u) ? 1.f : 0.f;
+                if constexpr (TF32) {
+                  const float a = __uint_as_float(u[r]) * m;
+                  s0 += a; q0 = fmaf(a, a, q0);
+                } else {
+                  const float a = __uint_as_float(u[r] << 16) * m, c2 = __uint_as_float(u[r] & 0xffff0000u) * m;
+                  s0 += a; q0 = fmaf(a, a, q0); s1 += c2; q1 = fmaf(c2, c2, q1);
+                }
+              }
+            }
+            st[cb][0] += s0; st[cb][1] += q0;
+            if constexpr (!TF32) { st[cb][2] += s1; st[cb][3] += q1; }
+          }
+        }
+      }
+      // this warp has drained its 32 lanes of its sub-tile of accumulator set `acc`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(t_empty_leader0 + acc * 8);
+        else mbar_arrive_local(&t_empty[acc]);
+      }
+      if (++acc == ACC) { acc = 0; pacc ^= 1; }
+    }
+    flush(cur_nb);
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();           // no CTA exits (or frees TMEM) while its peer still signals it
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_cg<CG>(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct Tc3Plan {
+  int BN, CG, tile_w, tile_h, box_w, box_h;
+  int m_tiles, m_groups, n_blocks, grid;
+};
+
+static int tc3_cluster_size() {
+  static const int cg = getenv("UNETB200_TC3_CG1") ? 1 : 2;        // 1-CTA variant of the same kernel, for A/B runs
+  return cg;
+}
+
+static bool tc3_plan(const unetb200_gconv_t* d, Tc3Plan* pl) {
+  const int esz = d->dtype == UNETB200_BF16 ? 2 : 4;
+  const int epr = 128 / esz;
+  if (d->dtype != UNETB200_BF16 && d->dtype != UNETB200_F32) return false;
+  if (d->nquad != 1 || d->in_scale != 1 || d->out_scale != 1 || d->ntaps != 9) return false;
+  if (d->in_off_y || d->in_off_x) return false;
+  if (d->Cin % epr || d->N % 64) return false;
+  if ((d->ld_in * esz) % 16 || (d->ld_out * esz) % 16) return false;
+  bool seen[9] = {false};
+  for (int t = 0; t < 9; ++t) {
+    const int dy = d->tap_dy[t], dx = d->tap_dx[t];
+    if (dy < -1 || dy > 1 || dx < -1 || dx > 1) return false;
+    if (seen[(dy + 1) * 3 + dx + 1]) return false;
+    seen[(dy + 1) * 3 + dx + 1] = true;
+  }
+  pl->CG = tc3_cluster_size();
+  pl->BN = (d->dtype == UNETB200_BF16 && d->N % 256 == 0) ? 256 : (d->N % 128 == 0 ? 128 : 64);
+  if (d->Wm > 8) { pl->tile_w = 16; pl->tile_h = 16; }
+  else { pl->tile_w = 8; pl->tile_h = 32; }
+  pl->box_w = pl->tile_w + 2;
+  pl->box_h = pl->tile_h + 2;
+  const int tiles_w = (d->Wm + pl->tile_w - 1) / pl->tile_w, tiles_h = (d->Hm + pl->tile_h - 1) / pl->tile_h;
+  pl->m_tiles = d->B * tiles_w * tiles_h;
+  pl->m_groups = (pl->m_tiles + pl->CG - 1) / pl->CG;
+  pl->n_blocks = d->N / pl->BN;
+  const long long total = (long long)pl->m_groups * pl->n_blocks;
+  const int slots = sm_count() / pl->CG;
+  pl->grid = (int)(total < slots ? total : slots) * pl->CG;
+  return true;
+}
+
+int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y) {
+  if (getenv("UNETB200_NO_TC3")) return 0;
+  if (d->dtype == UNETB200_F32 && d->algo != UNETB200_ALGO_TC && d->algo != UNETB200_ALGO_PREFER_TC) return 0;
+  Tc3Plan pl;
+  if (!tc3_plan(d, &pl)) return 0;
+  if (!aligned16(x) || !aligned16(wp) || !aligned16(y)) return 0;
+  return 1;
+}
+
+long long tc3_stats_workspace(const unetb200_gconv_t* d) {
+  Tc3Plan pl;
+  if (!tc3_plan(d, &pl)) return 0;
+  return (long long)pl.n_blocks * pl.grid * kEpi3Warps * 2 * pl.BN;
+}
+
+template <typename T, int BN, int SA, int SB, int ACC, int CG>
+static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
+  constexpr int smem = SA * kA3Stage + SB * (BN / CG) * 128 + kEpi3Warps * kEpi3Stage + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc3_conv_kernel<T, BN, SA, SB, ACC, CG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "tc3_conv smem attribute");
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kTc3Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_conv_kernel<T, BN, SA, SB, ACC, CG>, P);
+  if (e != cudaSuccess) return cuda_fail(e, "tc3_conv launch");
+  return 0;
+}
+
+__global__ void tc3_stats_reduce_kernel(const float* __restrict__ ws, int rows, int BN, int N, double* __restrict__ stats) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int nb = blockIdx.y;
+  const int col = blockIdx.x * 32 + lane;              // 0 .. 2*BN
+  double acc = 0.0;
+  if (col < 2 * BN)
+    for (int r = ry; r < rows; r += 8) acc += (double)ws[((long long)nb * rows + r) * 2 * BN + col];
+  red[ry][lane] = acc;
+  __syncthreads();
+  if (ry == 0 && col < 2 * BN) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][lane];
+    const int which = col / BN, c = col - which * BN;
+    atomicAdd(stats + which * N + nb * BN + c, s);
+  }
+}
+
+int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
+              double* stats, float* stats_ws, cudaStream_t stream) {
+  Tc3Plan pl;
+  if (!tc3_plan(d, &pl)) { set_error("tc3_fprop: unsupported shape"); return UNETB200_E_INVALID; }
+  const int esz = d->dtype == UNETB200_BF16 ? 2 : 4;
+  Tc3Params P;
+  memset(&P, 0, sizeof(P));
+  int rc = encode_act_box(&P.a_map, d->dtype, x, d->Cin, d->Win, d->Hin, d->B, d->ld_in, (long long)d->Win * d->ld_in,
+                          (long long)d->Hin * d->Win * d->ld_in, pl.box_w, pl.box_h, false);
+  if (rc) return rc;
+  const char* obase = (const char*)y + ((long long)d->out_off_y * d->Wout + d->out_off_x) * d->ld_out * (long long)esz;
+  rc = encode_act_box(&P.o_map, d->dtype, obase, d->N, d->Wm, d->Hm, d->B, d->ld_out, (long long)d->Wout * d->ld_out,
+                      (long long)d->Hout * d->Wout * d->ld_out, 8, 4, false);
+  if (rc) return rc;
+  rc = encode_weights(&P.b_map, d->dtype, wp, g.K, d->N, pl.BN / pl.CG);
+  if (rc) return rc;
+  for (int t = 0; t < 9; ++t)
+    P.tap_aoff[t] = (uint32_t)(((d->tap_dy[t] + 1) * pl.box_w + (d->tap_dx[t] + 1)) * 128) >> 4;
+  P.a_box_bytes = (uint32_t)(pl.box_w * pl.box_h * 128);
+  P.row_bytes = (uint32_t)pl.box_w * 128;
+  if (pl.tile_w == 16) { P.sub1_di = 0; P.sub1_dj = 8; P.sub1_off = (8 * 128) >> 4; }       // two 8-wide sub-tiles side by side
+  else { P.sub1_di = 16; P.sub1_dj = 0; P.sub1_off = (uint32_t)(16 * pl.box_w * 128) >> 4; }  // two 16-row sub-tiles stacked
+  P.cchunks = d->Cin / (128 / esz);
+  P.Cin = d->Cin;
+  P.tile_w = pl.tile_w; P.tile_h = pl.tile_h;
+  P.tiles_w = (d->Wm + pl.tile_w - 1) / pl.tile_w;
+  P.tiles_h = (d->Hm + pl.tile_h - 1) / pl.tile_h;
+  P.m_tiles = pl.m_tiles; P.m_groups = pl.m_groups;
+  P.total_groups = pl.m_groups * pl.n_blocks;
+  P.Hm = d->Hm; P.Wm = d->Wm; P.B = d->B;
+  P.bias = bias;
+  P.stats_ws = stats ? stats_ws : nullptr;
+  if (stats) {
+    cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * (size_t)tc3_stats_workspace(d), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "tc3 stats workspace memset");
+  }
+  if (d->dtype == UNETB200_BF16) {
+    if (pl.CG == 2) {
+      if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 6, 1, 2>(P, pl.grid, stream);
+      else if (pl.BN == 128) rc = tc3_launch<__nv_bfloat16, 128, 2, 9, 2, 2>(P, pl.grid, stream);
+      else rc = tc3_launch<__nv_bfloat16, 64, 3, 9, 2, 2>(P, pl.grid, stream);
+    } else {
+      if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 3, 1, 1>(P, pl.grid, stream);
+      else if (pl.BN == 128) rc = tc3_launch<__nv_bfloat16, 128, 2, 6, 2, 1>(P, pl.grid, stream);
+      else rc = tc3_launch<__nv_bfloat16, 64, 3, 6, 2, 1>(P, pl.grid, stream);
+    }
+  } else {
+    if (pl.CG == 2) {
+      if (pl.BN == 128) rc = tc3_launch<float, 128, 2, 9, 2, 2>(P, pl.grid, stream);
+      else rc = tc3_launch<float, 64, 3, 9, 2, 2>(P, pl.grid, stream);
+    } else {
+      if (pl.BN == 128) rc = tc3_launch<float, 128, 2, 6, 2, 1>(P, pl.grid, stream);
+      else rc = tc3_launch<float, 64, 3, 6, 2, 1>(P, pl.grid, stream);
+    }
+  }
+  if (rc) return rc;
+  if (stats) {
+    const int rows = pl.grid * kEpi3Warps;
+    tc3_stats_reduce_kernel<<<dim3((2 * pl.BN + 31) / 32, pl.n_blocks), 256, 0, stream>>>(stats_ws, rows, pl.BN, d->N, stats);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "tc3_stats_reduce");
+  }
+  return 0;
+}
+
+}  // namespace ub
