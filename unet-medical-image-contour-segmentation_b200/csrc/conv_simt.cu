@@ -430,7 +430,7 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_fprop_supported(d, x, wp, y), "gconv_fprop: tcgen05 path requested but shape/alignment unsupported");
     static const bool use_v1 = getenv("UNETB200_TC_V1") != nullptr;      // first-generation kernel, for A/B runs
-    if (!use_v1 && tc3_fprop_supported(d, x, wp, y)) return tc3_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
+    if (!use_v1 && tc3_fprop_supported(d, x, wp, bias, y)) return tc3_fprop(d, g, x, wp, y, stats, stats_ws, s);
     if (!use_v1 && tc2_fprop_supported(d, x, wp, y)) return tc2_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
     return tc_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
   }

@@ -244,9 +244,15 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_fprop_kernel(const __grid_
         for (int h = 0; h < EPR / 32; ++h) {
           float f[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            f[e] = __uint_as_float(v[h * 32 + e]);
-            if (p.bias) f[e] += Elem<T>::round(__ldg(p.bias + co0 + cb * EPR + h * 32 + e));
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[h * 32 + e]);
+          if (p.bias) {                                                 // one warp-uniform branch, not 32 predicated loads
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + co0 + cb * EPR + h * 32);
+#pragma unroll
+            for (int e4 = 0; e4 < 8; ++e4) {
+              const float4 b4 = __ldg(bp + e4);
+              f[4 * e4 + 0] += Elem<T>::round(b4.x); f[4 * e4 + 1] += Elem<T>::round(b4.y);
+              f[4 * e4 + 2] += Elem<T>::round(b4.z); f[4 * e4 + 3] += Elem<T>::round(b4.w);
+            }
           }
           if constexpr (TF32) {
 #pragma unroll

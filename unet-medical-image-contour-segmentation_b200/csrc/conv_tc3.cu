@@ -137,6 +137,14 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t v[32]) 
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_fence() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
@@ -153,7 +161,6 @@ struct alignas(64) Tc3Params {
   int sub1_di, sub1_dj;
   int m_tiles, m_groups, total_groups;   // m_groups = ceil(m_tiles / CG); one "group" = CG tiles of one n-block
   int Hm, Wm, B;
-  const float* bias;
   float* stats_ws;           // [n_block][cta][8 epilogue warps][2][BLOCK_N]
 };
 
@@ -162,11 +169,13 @@ constexpr int kEpi3Stage = 4096;        // 32 rows x 128 B per epilogue warp
 constexpr int kEpi3Warps = 8;           // two per TMEM lane quadrant: one per 128-row sub-tile
 constexpr int kTc3Threads = 64 + 32 * kEpi3Warps;
 
-template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG>
+template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG, int TPS>
 __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_constant__ Tc3Params p) {
   constexpr bool TF32 = sizeof(T) == 4;
   constexpr int EPR = 128 / sizeof(T);
-  constexpr uint32_t kBStage = (BLOCK_N / CG) * 128;
+  constexpr uint32_t kBTap = (BLOCK_N / CG) * 128;     // one tap's weight tile (this CTA's half of it)
+  constexpr uint32_t kBStage = TPS * kBTap;            // a B stage holds TPS taps: one barrier round trip per TPS * 8 MMAs
+  static_assert(9 % TPS == 0, "taps per stage");
   constexpr int NCB = BLOCK_N / EPR;                   // 128-byte channel blocks per accumulator row
   static_assert(2 * BLOCK_N * ACC <= 512, "TMEM columns");
   extern __shared__ uint8_t smem_raw[];
@@ -222,11 +231,14 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
           tma_load_4d_cg<CG>(a_ring + sa * kA3Stage, &p.a_map, mapa_u32(smem_u32(&a_full[sa]), 0), c * EPR, j0, i0, b);
         }
         if (++sa == SA) { sa = 0; pa ^= 1; }
-        for (int t = 0; t < 9; ++t) {
+        for (int t = 0; t < 9; t += TPS) {
           mbar_wait(&b_empty[sb], pb);
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(&b_full[sb], CG * kBStage);
-            tma_load_2d_cg<CG>(b_ring + sb * kBStage, &p.b_map, mapa_u32(smem_u32(&b_full[sb]), 0), t * p.Cin + c * EPR, n0);
+            const uint32_t bar = mapa_u32(smem_u32(&b_full[sb]), 0);
+#pragma unroll
+            for (int j = 0; j < TPS; ++j)
+              tma_load_2d_cg<CG>(b_ring + sb * kBStage + j * kBTap, &p.b_map, bar, (t + j) * p.Cin + c * EPR, n0);
           }
           if (++sb == SB) { sb = 0; pb ^= 1; }
         }
@@ -248,19 +260,24 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
         for (int c = 0; c < p.cchunks; ++c) {
           mbar_wait(&a_full[sa], pa);
           const uint64_t a_desc0 = a_desc_t + sa * (kA3Stage >> 4);
-          for (int t = 0; t < 9; ++t) {
+          for (int t = 0; t < 9; t += TPS) {
             mbar_wait(&b_full[sb], pb);
             tc_fence_after();
             const uint64_t b_desc0 = b_desc_t + sb * (kBStage >> 4);
-            const uint64_t a_desc1 = a_desc0 + p.tap_aoff[t];
             if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                umma_cg<CG, TF32>(d_tmem, a_desc1 + 2 * kk, b_desc0 + 2 * kk, idesc, accum | (uint32_t)kk);
-                umma_cg<CG, TF32>(d_tmem + BLOCK_N, a_desc1 + sub1 + 2 * kk, b_desc0 + 2 * kk, idesc, accum | (uint32_t)kk);
+              for (int j = 0; j < TPS; ++j) {
+                const uint64_t a_desc1 = a_desc0 + p.tap_aoff[t + j];
+                const uint64_t b_desc1 = b_desc0 + j * (kBTap >> 4);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint32_t on = accum | (uint32_t)(j | kk);
+                  umma_cg<CG, TF32>(d_tmem, a_desc1 + 2 * kk, b_desc1 + 2 * kk, idesc, on);
+                  umma_cg<CG, TF32>(d_tmem + BLOCK_N, a_desc1 + sub1 + 2 * kk, b_desc1 + 2 * kk, idesc, on);
+                }
               }
               umma_commit_cg<CG>(&b_empty[sb]);
-              if (t == 8) umma_commit_cg<CG>(&a_empty[sa]);
+              if (t + TPS == 9) umma_commit_cg<CG>(&a_empty[sa]);
             }
             __syncwarp();
             accum = 1;
@@ -280,6 +297,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
     const int s = (warp - 2) >> 2;
     const int ew = s * 4 + quad;                                      // 0..7
     uint8_t* buf = epi + ew * kEpi3Stage;
+    const uint32_t buf_s = smem_u32(buf);
     uint32_t acc = 0, pacc = 0;
     int cur_nb = -1;
     float st[NCB][TF32 ? 2 : 4];
@@ -333,29 +351,22 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
           if (lane == 0) tma_store_wait_read_all();                   // the previous store has finished reading `buf`
           tmem_ld_fence();
           __syncwarp();
-          uint8_t* dst = buf + lane * 128;
+          const uint32_t dst = buf_s + lane * 128;
 #pragma unroll
           for (int h = 0; h < EPR / 32; ++h) {
-            float f[32];
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              f[e] = __uint_as_float(v[h * 32 + e]);
-              if (p.bias) f[e] += Elem<T>::round(__ldg(p.bias + n0 + cb * EPR + h * 32 + e));
-            }
             if constexpr (TF32) {
 #pragma unroll
               for (int c16 = 0; c16 < 8; ++c16)
-                *reinterpret_cast<float4*>(dst + ((c16 ^ (lane & 7)) << 4)) =
-                    make_float4(f[4 * c16], f[4 * c16 + 1], f[4 * c16 + 2], f[4 * c16 + 3]);
+                sts_v4(dst + ((c16 ^ (lane & 7)) << 4), v[4 * c16], v[4 * c16 + 1], v[4 * c16 + 2], v[4 * c16 + 3]);
             } else {
 #pragma unroll
               for (int c16 = 0; c16 < 4; ++c16) {
-                uint4 r;
-                r.x = pack_bf16x2(f[8 * c16 + 0], f[8 * c16 + 1]);
-                r.y = pack_bf16x2(f[8 * c16 + 2], f[8 * c16 + 3]);
-                r.z = pack_bf16x2(f[8 * c16 + 4], f[8 * c16 + 5]);
-                r.w = pack_bf16x2(f[8 * c16 + 6], f[8 * c16 + 7]);
-                *reinterpret_cast<uint4*>(dst + (((h * 4 + c16) ^ (lane & 7)) << 4)) = r;
+                const uint32_t* w = v + h * 32 + 8 * c16;
+                sts_v4(dst + (((h * 4 + c16) ^ (lane & 7)) << 4),
+                       pack_bf16x2(__uint_as_float(w[0]), __uint_as_float(w[1])),
+                       pack_bf16x2(__uint_as_float(w[2]), __uint_as_float(w[3])),
+                       pack_bf16x2(__uint_as_float(w[4]), __uint_as_float(w[5])),
+                       pack_bf16x2(__uint_as_float(w[6]), __uint_as_float(w[7])));
               }
             }
           }
@@ -372,7 +383,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
             uint32_t u[32];
 #pragma unroll
             for (int r = 0; r < 32; ++r)
-              u[r] = *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+              u[r] = lds_u32(buf_s + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
             if (valid_rows == 0xffffffffu) {
 #pragma unroll
               for (int r = 0; r < 32; ++r) {
@@ -467,8 +478,8 @@ static bool tc3_plan(const unetb200_gconv_t* d, Tc3Plan* pl) {
   return true;
 }
 
-int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y) {
-  if (getenv("UNETB200_NO_TC3")) return 0;
+int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, const void* y) {
+  if (getenv("UNETB200_NO_TC3") || bias) return 0;      // the 3x3 convolutions of the path are bias-free (unet_parts.py:15,18)
   if (d->dtype == UNETB200_F32 && d->algo != UNETB200_ALGO_TC && d->algo != UNETB200_ALGO_PREFER_TC) return 0;
   Tc3Plan pl;
   if (!tc3_plan(d, &pl)) return 0;
@@ -482,13 +493,13 @@ long long tc3_stats_workspace(const unetb200_gconv_t* d) {
   return (long long)pl.n_blocks * pl.grid * kEpi3Warps * 2 * pl.BN;
 }
 
-template <typename T, int BN, int SA, int SB, int ACC, int CG>
+template <typename T, int BN, int SA, int SB, int ACC, int CG, int TPS>
 static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
-  constexpr int smem = SA * kA3Stage + SB * (BN / CG) * 128 + kEpi3Warps * kEpi3Stage + 1024 + 256;
+  constexpr int smem = SA * kA3Stage + SB * TPS * (BN / CG) * 128 + kEpi3Warps * kEpi3Stage + 1024 + 256;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc3_conv_kernel<T, BN, SA, SB, ACC, CG>,
+    cudaError_t e = cudaFuncSetAttribute(tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "tc3_conv smem attribute");
     configured = true;
@@ -505,7 +516,7 @@ static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_conv_kernel<T, BN, SA, SB, ACC, CG>, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS>, P);
   if (e != cudaSuccess) return cuda_fail(e, "tc3_conv launch");
   return 0;
 }
@@ -529,8 +540,8 @@ __global__ void tc3_stats_reduce_kernel(const float* __restrict__ ws, int rows, 
   }
 }
 
-int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
-              double* stats, float* stats_ws, cudaStream_t stream) {
+int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
+              float* stats_ws, cudaStream_t stream) {
   Tc3Plan pl;
   if (!tc3_plan(d, &pl)) { set_error("tc3_fprop: unsupported shape"); return UNETB200_E_INVALID; }
   const int esz = d->dtype == UNETB200_BF16 ? 2 : 4;
@@ -559,7 +570,6 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   P.m_tiles = pl.m_tiles; P.m_groups = pl.m_groups;
   P.total_groups = pl.m_groups * pl.n_blocks;
   P.Hm = d->Hm; P.Wm = d->Wm; P.B = d->B;
-  P.bias = bias;
   P.stats_ws = stats ? stats_ws : nullptr;
   if (stats) {
     cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * (size_t)tc3_stats_workspace(d), stream);
@@ -567,21 +577,21 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   }
   if (d->dtype == UNETB200_BF16) {
     if (pl.CG == 2) {
-      if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 6, 1, 2>(P, pl.grid, stream);
-      else if (pl.BN == 128) rc = tc3_launch<__nv_bfloat16, 128, 2, 9, 2, 2>(P, pl.grid, stream);
-      else rc = tc3_launch<__nv_bfloat16, 64, 3, 9, 2, 2>(P, pl.grid, stream);
+      if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 2, 1, 2, 3>(P, pl.grid, stream);
+      else if (pl.BN == 128) rc = tc3_launch<__nv_bfloat16, 128, 2, 3, 2, 2, 3>(P, pl.grid, stream);
+      else rc = tc3_launch<__nv_bfloat16, 64, 3, 3, 2, 2, 3>(P, pl.grid, stream);
     } else {
-      if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 3, 1, 1>(P, pl.grid, stream);
-      else if (pl.BN == 128) rc = tc3_launch<__nv_bfloat16, 128, 2, 6, 2, 1>(P, pl.grid, stream);
-      else rc = tc3_launch<__nv_bfloat16, 64, 3, 6, 2, 1>(P, pl.grid, stream);
+      if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 3, 1, 1, 1>(P, pl.grid, stream);
+      else if (pl.BN == 128) rc = tc3_launch<__nv_bfloat16, 128, 2, 6, 2, 1, 1>(P, pl.grid, stream);
+      else rc = tc3_launch<__nv_bfloat16, 64, 3, 6, 2, 1, 1>(P, pl.grid, stream);
     }
   } else {
     if (pl.CG == 2) {
-      if (pl.BN == 128) rc = tc3_launch<float, 128, 2, 9, 2, 2>(P, pl.grid, stream);
-      else rc = tc3_launch<float, 64, 3, 9, 2, 2>(P, pl.grid, stream);
+      if (pl.BN == 128) rc = tc3_launch<float, 128, 2, 3, 2, 2, 3>(P, pl.grid, stream);
+      else rc = tc3_launch<float, 64, 3, 3, 2, 2, 3>(P, pl.grid, stream);
     } else {
-      if (pl.BN == 128) rc = tc3_launch<float, 128, 2, 6, 2, 1>(P, pl.grid, stream);
-      else rc = tc3_launch<float, 64, 3, 6, 2, 1>(P, pl.grid, stream);
+      if (pl.BN == 128) rc = tc3_launch<float, 128, 2, 6, 2, 1, 1>(P, pl.grid, stream);
+      else rc = tc3_launch<float, 64, 3, 6, 2, 1, 1>(P, pl.grid, stream);
     }
   }
   if (rc) return rc;

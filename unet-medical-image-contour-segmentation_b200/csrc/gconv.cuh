@@ -40,10 +40,10 @@ int tc2_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
               cudaStream_t stream);
 
 // CTA-pair tcgen05 engine for the 3x3 convolutions, third generation (conv_tc3.cu)
-int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, const void* y);
 long long tc3_stats_workspace(const unetb200_gconv_t* d);
-int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
-              double* stats, float* stats_ws, cudaStream_t stream);
+int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
+              float* stats_ws, cudaStream_t stream);
 
 // first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)
 int first_fprop_supported(const unetb200_gconv_t* d, const void* y);
