@@ -375,6 +375,112 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, D* __restrict
   }
 }
 
+// Split reduction + transpose for the case dst[co * sn + k] (k = t*Cin + c linear in the parameter: a
+// channels_last weight gradient): partial rows [k][n] are read coalesced along n, summed over the splits in a
+// fixed order (deterministic), transposed through shared memory and written coalesced along k.
+__global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __restrict__ partials, int splits, long long K,
+                                                              int N, float* __restrict__ dst, long long sn, int accumulate) {
+  // thread (tx, ty): column n0 + tx, splits ty, ty + 8, ...; 32 row sums in registers (32 loads in flight)
+  __shared__ float red[8][32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long k0 = (long long)blockIdx.x * 32;
+  const int n0 = blockIdx.y * 32;
+  const long long total = K * N;
+  const int n = n0 + tx;
+  float acc[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+  if (n < N) {
+    for (int sp = ty; sp < splits; sp += 8) {
+      const float* p = partials + (long long)sp * total + k0 * N + n;
+      if (k0 + 32 <= K) {
+        float v[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = p[(long long)r * N];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) acc[r] += v[r];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (k0 + r < K) acc[r] += p[(long long)r * N];
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 32; ++r) red[ty][r][tx] = acc[r];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int nn = n0 + ty + 8 * r;
+    const long long k = k0 + tx;
+    float v = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v += red[j][tx][ty + 8 * r];          // fixed order: deterministic
+    if (k < K && nn < N) {
+      float* o = dst + (long long)nn * sn + k;
+      *o = accumulate ? *o + v : v;
+    }
+  }
+}
+
+// few splits: threads over the tile (4 rows each), loop over the splits
+__global__ void __launch_bounds__(256) wgrad_reduce_t4_kernel(const float* __restrict__ partials, int splits, long long K,
+                                                               int N, float* __restrict__ dst, long long sn, int accumulate) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  const long long k0 = (long long)blockIdx.x * 32;
+  const int n0 = blockIdx.y * 32;
+  const long long total = K * N;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const int n = n0 + tx;
+  if (n < N) {
+    for (int sp = 0; sp < splits; ++sp) {
+      float v[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const long long k = k0 + ty + 8 * r;
+        v[r] = k < K ? partials[(long long)sp * total + k * N + n] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[r] += v[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = s[r];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int nn = n0 + ty + 8 * r;
+    const long long k = k0 + tx;
+    if (k < K && nn < N) {
+      float* o = dst + (long long)nn * sn + k;
+      const float v = tile[tx][ty + 8 * r];
+      *o = accumulate ? *o + v : v;
+    }
+  }
+}
+
+// dst[i0][i1][i2] = cast(src[off + i0 + i1*s1 + i2*s2]) (source contiguous along i0): 32 x 32 transpose tiles
+// of (i0, i2) per i1, reads coalesced along i0, writes coalesced along i2.
+template <typename D>
+__global__ void __launch_bounds__(256) pack_weights_t_kernel(const float* __restrict__ src, D* __restrict__ dst, int n0,
+                                                              int n1, int n2, long long s1, long long s2, long long off) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int a0 = blockIdx.x * 32, c0 = blockIdx.y * 32, i1 = blockIdx.z;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i2 = c0 + ty + 8 * r, i0 = a0 + tx;
+    tile[ty + 8 * r][tx] = (i0 < n0 && i2 < n2) ? src[off + i0 + i1 * s1 + (long long)i2 * s2] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i0 = a0 + ty + 8 * r, i2 = c0 + tx;
+    if (i0 < n0 && i2 < n2) Elem<D>::st(dst + ((long long)i0 * n1 + i1) * n2 + i2, tile[tx][ty + 8 * r]);
+  }
+}
+
 static bool simt_vec_ok(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y) {
   const size_t esz = d->dtype == UNETB200_BF16 ? 2 : 4;
   const int Cq = d->N / d->nquad;
@@ -461,8 +567,9 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
   if (algo_used) *algo_used = algo;
   if (splits) {
     if (algo == UNETB200_ALGO_TC)
-      *splits = (!getenv("UNETB200_TC_V1") && tc2_wgrad_supported(d, nullptr, nullptr)) ? tc2_wgrad_splits(d)
-                                                                                        : tc_wgrad_splits(d, g);
+      *splits = (!getenv("UNETB200_TC_V1") && tc3_wgrad_supported(d, nullptr, nullptr)) ? tc3_wgrad_splits(d)
+                : (!getenv("UNETB200_TC_V1") && tc2_wgrad_supported(d, nullptr, nullptr)) ? tc2_wgrad_splits(d)
+                                                                                          : tc_wgrad_splits(d, g);
     else if (first_wgrad_supported(d, nullptr)) *splits = first_wgrad_splits(d);
     else *splits = simt_wgrad_splits(g);
   }
@@ -480,6 +587,10 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_wgrad_supported(d, nullptr, nullptr) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path requested but shape/alignment unsupported");
+    if (!getenv("UNETB200_TC_V1") && tc3_wgrad_supported(d, nullptr, nullptr)) {
+      UB_CHECK_ARG(tc3_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path needs 16-byte aligned operands");
+      return tc3_wgrad(d, g, x, gy, partials, splits, s);
+    }
     if (!getenv("UNETB200_TC_V1") && tc2_wgrad_supported(d, nullptr, nullptr)) {
       UB_CHECK_ARG(tc2_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path needs 16-byte aligned operands");
       return tc2_wgrad(d, g, x, gy, partials, splits, s);
@@ -515,6 +626,14 @@ int unetb200_wgrad_reduce(const float* partials, int splits, int ntaps, int Cin,
                "wgrad_reduce: bad args");
   long long K = (long long)ntaps * Cin;
   long long total = K * N;
+  if (Cq == N && sc == 1 && (ntaps == 1 || st == Cin) && sn != 1) {
+    // the parameter is k-linear (channels_last Conv2d weight): coalesced transpose
+    dim3 grid((unsigned)((K + 31) / 32), (unsigned)((N + 31) / 32));
+    if (splits >= 8) wgrad_reduce_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, splits, K, N, dst, sn, accumulate);
+    else wgrad_reduce_t4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, splits, K, N, dst, sn, accumulate);
+    UB_LAUNCH_CHECK("wgrad_reduce_t");
+    return 0;
+  }
   long long blocks = (total + 255) / 256;
   long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
@@ -533,6 +652,16 @@ int unetb200_pack_weights(const float* src, void* dst, int dst_dtype, int64_t n0
   long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t s = (cudaStream_t)stream;
+  if (s0 == 1 && s2 != 1 && n0 >= 32 && n2 >= 32 && n1 <= 65535) {
+    // source contiguous along the OUTER destination index (e.g. the dgrad operand of a channels_last weight)
+    dim3 grid((unsigned)((n0 + 31) / 32), (unsigned)((n2 + 31) / 32), (unsigned)n1);
+    if (dst_dtype == UNETB200_BF16)
+      pack_weights_t_kernel<bf16><<<grid, 256, 0, s>>>(src, (bf16*)dst, (int)n0, (int)n1, (int)n2, s1, s2, off);
+    else
+      pack_weights_t_kernel<float><<<grid, 256, 0, s>>>(src, (float*)dst, (int)n0, (int)n1, (int)n2, s1, s2, off);
+    UB_LAUNCH_CHECK("pack_weights_t");
+    return 0;
+  }
   if (dst_dtype == UNETB200_BF16)
     pack_weights_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>(src, (bf16*)dst, n0, n1, n2, s0, s1, s2, off);
   else

@@ -604,4 +604,255 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// wgrad as CTA pairs:  dWp[(t,c)][n] = sum_pixels A[pixel][(t,c)] * G[pixel][n]   (both operands MN-major, K = pixels)
+// Same decomposition as tc2_wgrad_kernel (a "unit" = (column shift dx, 128-byte channel chunk); its x box
+// {128 B, 8, 8 + 2, 1} serves the three row shifts, one accumulator each), but one tcgen05.mma.cta_group::2
+// covers FOUR units (M = 256: two per CTA) against one dY tile of 128 output channels of which each CTA loads
+// half -- per 64-pixel step a CTA fills 20 KB + 8 KB instead of 20 KB + 16 KB and the MMA runs at its N = 128
+// pair rate (64 cycles instead of 87).  Used when the unit count is a multiple of 4 (C_in >= 256).
+// ------------------------------------------------------------------------------------------
+struct alignas(64) Tc3WParams {
+  CUtensorMap a_map;         // x view, box {128 B, 8, 10, 1}
+  CUtensorMap o_map;         // dY view, box {128 B, 8, 8, 1}
+  int g_dx[3], g_dy0, g_tap[3][3];
+  int Cin, nunits;
+  int tiles_w, tiles_h;
+  int ptiles, ptiles_per_split;
+  int N, K;
+  float* partials;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1) tc3_wgrad_kernel(const __grid_constant__ Tc3WParams p) {
+  constexpr int EPR = 64, BLOCK_N = 128;
+  constexpr uint32_t kGSub = 64 * 128;                 // one 8x8-pixel x 128-byte dY sub-tile (this CTA's 64 channels)
+  constexpr uint32_t kABox = 10 * 8 * 128;             // x box
+  constexpr uint32_t kStage = 2 * kABox + kGSub;       // 28 KB
+  constexpr int UMMA_K = 16, MMAS = 64 / UMMA_K;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int mt = blockIdx.x >> 1;                      // pair index along M: units 4*mt .. 4*mt + 3
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int split = blockIdx.z;
+  const int pt_begin = split * p.ptiles_per_split;
+  int pt_end = pt_begin + p.ptiles_per_split;
+  if (pt_end > p.ptiles) pt_end = p.ptiles;
+  const int num_k = pt_end - pt_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map);
+    tma_prefetch_desc(&p.o_map);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_cg<2>(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    int pt = pt_begin;
+    int tj = pt % p.tiles_w;
+    int rest = pt / p.tiles_w;
+    int ti = rest % p.tiles_h;
+    int b = rest / p.tiles_h;
+    int uc[2], ug[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int u = mt * 4 + (int)rank * 2 + h;         // < nunits (nunits % 4 == 0)
+      uc[h] = u / 3;
+      ug[h] = u - uc[h] * 3;
+    }
+    uint32_t s = 0, ph = 1;
+    for (int kb = 0; kb < num_k; ++kb) {
+      mbar_wait(&empty_bar[s], ph);
+      if (elect_one()) {
+        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * kStage);
+        const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+        const int i0 = ti * 8, j0 = tj * 8;
+        uint8_t* sa = smem + s * kStage;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d_cg<2>(sa + h * kABox, &p.a_map, bar, uc[h] * EPR, j0 + p.g_dx[ug[h]], i0 + p.g_dy0, b);
+        tma_load_4d_cg<2>(sa + 2 * kABox, &p.o_map, bar, n0 + (int)rank * 64, j0, i0, b);
+      }
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+      if (++tj == p.tiles_w) { tj = 0; if (++ti == p.tiles_h) { ti = 0; ++b; } }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(false, true, true, 256, BLOCK_N);
+      // MN-major: LBO = distance between 128-byte-wide sub-tiles, SBO = one swizzle group of pixel rows
+      const uint64_t da_t = make_desc(smem_u32(smem), kABox, 1024, kLayoutSW128);
+      const uint64_t db_t = make_desc(smem_u32(smem) + 2 * kABox, kGSub, 1024, kLayoutSW128);
+      uint32_t s = 0, ph = 0;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t da0 = da_t + s * (kStage >> 4), db0 = db_t + s * (kStage >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int k = 0; k < MMAS; ++k)
+              umma_cg<2, false>(tmem_base + a * BLOCK_N, da0 + ((a * 1024 + k * UMMA_K * 128) >> 4),
+                                db0 + ((k * UMMA_K * 128) >> 4), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_cg<2>(&empty_bar[s]);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (elect_one()) umma_commit_cg<2>(tmem_full);
+      __syncwarp();
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                  // D row of this CTA = (unit row / 64, channel row % 64)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int u = mt * 4 + (int)rank * 2 + row / EPR;
+    const int c = u / 3, g = u - c * 3;
+    for (int a = 0; a < 3; ++a) {
+      const long long k = (long long)p.g_tap[g][a] * p.Cin + c * EPR + (row % EPR);
+      float* out = p.partials + (long long)split * p.K * p.N + k * p.N + n0;
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + a * BLOCK_N + ch * 32, v);
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          float4 o4 = num_k > 0 ? make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                              __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(out + ch * 32 + e) = o4;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_cg<2>(tmem_base, 512);
+  }
+}
+
+struct Tc3WPlan {
+  int nunits, mpairs, ntiles, ptiles, tiles_w, tiles_h;
+  int g_dx[3], g_dy0, g_tap[3][3];
+};
+
+static bool tc3_wgrad_plan(const unetb200_gconv_t* d, Tc3WPlan* w) {
+  if (getenv("UNETB200_NO_TC3") || getenv("UNETB200_NO_TC3W")) return false;
+  if (d->dtype != UNETB200_BF16) return false;
+  if (d->nquad != 1 || d->in_scale != 1 || d->out_scale != 1 || d->ntaps != 9) return false;
+  if (d->in_off_y || d->in_off_x) return false;
+  if (d->Cin % 64 || d->N % 128) return false;
+  if ((d->ld_in * 2) % 16 || (d->ld_out * 2) % 16) return false;
+  const int cchunks = d->Cin / 64;
+  if ((3 * cchunks) % 4) return false;                   // a pair owns four units
+  // groups: column shift dx = -1, 0, 1, each with the row shifts dy = -1, 0, 1
+  for (int g = 0; g < 3; ++g) {
+    w->g_dx[g] = g - 1;
+    for (int a = 0; a < 3; ++a) {
+      int found = -1;
+      for (int t = 0; t < 9; ++t)
+        if (d->tap_dx[t] == g - 1 && d->tap_dy[t] == a - 1) found = t;
+      if (found < 0) return false;
+      w->g_tap[g][a] = found;
+    }
+  }
+  w->g_dy0 = -1;
+  w->nunits = 3 * cchunks;
+  w->mpairs = w->nunits / 4;
+  w->ntiles = d->N / 128;
+  w->tiles_w = (d->Wm + 7) / 8;
+  w->tiles_h = (d->Hm + 7) / 8;
+  w->ptiles = d->B * w->tiles_w * w->tiles_h;
+  return true;
+}
+
+int tc3_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy) {
+  Tc3WPlan w;
+  if (!tc3_wgrad_plan(d, &w)) return 0;
+  if ((x && !aligned16(x)) || (gy && !aligned16(gy))) return 0;
+  return 1;
+}
+
+int tc3_wgrad_splits(const unetb200_gconv_t* d) {
+  Tc3WPlan w;
+  if (!tc3_wgrad_plan(d, &w)) return 1;
+  const long long pairs = (long long)w.mpairs * w.ntiles;
+  long long want = ((long long)(sm_count() / 2) * 2 + pairs - 1) / pairs;   // about two waves of CTA pairs
+  long long max_by_k = (w.ptiles + 15) / 16;            // at least 16 pixel tiles (1024 pixels) per split
+  if (want > max_by_k) want = max_by_k;
+  if (want > 512) want = 512;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+int tc3_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
+              cudaStream_t stream) {
+  Tc3WPlan w;
+  if (!tc3_wgrad_plan(d, &w)) { set_error("tc3_wgrad: unsupported shape"); return UNETB200_E_INVALID; }
+  Tc3WParams P;
+  memset(&P, 0, sizeof(P));
+  int rc = encode_act_box(&P.a_map, d->dtype, x, d->Cin, d->Win, d->Hin, d->B, d->ld_in, (long long)d->Win * d->ld_in,
+                          (long long)d->Hin * d->Win * d->ld_in, 8, 10, true);
+  if (rc) return rc;
+  const char* obase = (const char*)gy + ((long long)d->out_off_y * d->Wout + d->out_off_x) * d->ld_out * 2LL;
+  rc = encode_act_box(&P.o_map, d->dtype, obase, d->N, d->Wm, d->Hm, d->B, d->ld_out, (long long)d->Wout * d->ld_out,
+                      (long long)d->Hout * d->Wout * d->ld_out, 8, 8, true);
+  if (rc) return rc;
+  for (int gi = 0; gi < 3; ++gi) {
+    P.g_dx[gi] = w.g_dx[gi];
+    for (int a = 0; a < 3; ++a) P.g_tap[gi][a] = w.g_tap[gi][a];
+  }
+  P.g_dy0 = w.g_dy0;
+  P.Cin = d->Cin; P.nunits = w.nunits;
+  P.tiles_w = w.tiles_w; P.tiles_h = w.tiles_h;
+  P.ptiles = w.ptiles;
+  P.ptiles_per_split = (w.ptiles + splits - 1) / splits;
+  P.N = d->N; P.K = g.K;
+  P.partials = partials;
+  constexpr int ST = 7;
+  constexpr int smem = ST * (2 * 10240 + 8192) + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc3_wgrad_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cuda_fail(e, "tc3_wgrad smem attribute");
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)w.mpairs * 2, (unsigned)w.ntiles, (unsigned)splits);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_wgrad_kernel<ST>, P);
+  if (e != cudaSuccess) return cuda_fail(e, "tc3_wgrad launch");
+  return 0;
+}
+
 }  // namespace ub

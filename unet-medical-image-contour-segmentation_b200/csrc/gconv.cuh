@@ -45,6 +45,11 @@ long long tc3_stats_workspace(const unetb200_gconv_t* d);
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
               float* stats_ws, cudaStream_t stream);
 
+int tc3_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int tc3_wgrad_splits(const unetb200_gconv_t* d);
+int tc3_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
+              cudaStream_t stream);
+
 // first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)
 int first_fprop_supported(const unetb200_gconv_t* d, const void* y);
 long long first_fprop_tiles(const unetb200_gconv_t* d);

@@ -9,10 +9,13 @@ namespace ub {
 
 constexpr int kMaxK = 8;
 
-template <typename T>
-__global__ void outconv_fwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
-                                       const float* __restrict__ bias, T* __restrict__ out, int64_t npix, int C,
-                                       int K, int LPP) {
+// K (= n_classes) is a template parameter so that the class loops carry no predicated-off iterations, and every
+// thread keeps UNR pixels' 16-byte loads in flight (the kernel is a pure stream over the last activation).
+constexpr int kOutUnr = 4;
+template <typename T, int K>
+__global__ void __launch_bounds__(256) outconv_fwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, T* __restrict__ out,
+                                                              int64_t npix, int C, int LPP) {
   extern __shared__ float sw[];   // [K][C] rounded to T, then bias[K]
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = Elem<T>::round(w[i]);
   for (int i = threadIdx.x; i < K; i += blockDim.x) sw[K * C + i] = bias ? Elem<T>::round(bias[i]) : 0.f;
@@ -20,34 +23,42 @@ __global__ void outconv_fwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, co
   const int sub = threadIdx.x % LPP;
   const int ppb = blockDim.x / LPP;
   const int c0 = sub * 8;
+  float wr[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wr[k][i] = sw[k * C + c0 + i];
   // the trip count is block-uniform so that the shuffles below are executed by full warps
-  for (int64_t base = (int64_t)blockIdx.x * ppb; base < npix; base += (int64_t)gridDim.x * ppb) {
-    const int64_t p = base + threadIdx.x / LPP;
-    float v[8];
-    if (p < npix) {
-      load8(x + p * ld_x + c0, v);
-    } else {
+  for (int64_t base = (int64_t)blockIdx.x * ppb * kOutUnr; base < npix; base += (int64_t)gridDim.x * ppb * kOutUnr) {
+    float v[kOutUnr][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    }
-    float acc[kMaxK];
+    for (int u = 0; u < kOutUnr; ++u) {
+      const int64_t p = base + u * ppb + threadIdx.x / LPP;
+      if (p < npix) {
+        load8(x + p * ld_x + c0, v[u]);
+      } else {
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k) {
-      acc[k] = 0.f;
-      if (k < K) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[k] = fmaf(v[i], sw[k * C + c0 + i], acc[k]);
+        for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
       }
     }
-    for (int o = LPP >> 1; o > 0; o >>= 1) {
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        if (k < K) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    }
-    if (sub == 0 && p < npix) {
+    for (int u = 0; u < kOutUnr; ++u) {
+      const int64_t p = base + u * ppb + threadIdx.x / LPP;
+      float acc[K];
 #pragma unroll
-      for (int k = 0; k < kMaxK; ++k)
-        if (k < K) Elem<T>::st(out + p * K + k, acc[k] + sw[K * C + k]);
+      for (int k = 0; k < K; ++k) {
+        acc[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k] = fmaf(v[u][i], wr[k][i], acc[k]);
+      }
+      for (int o = LPP >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      }
+      if (sub == 0 && p < npix) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) Elem<T>::st(out + p * K + k, acc[k] + sw[K * C + k]);
+      }
     }
   }
 }
@@ -66,10 +77,10 @@ __global__ void outconv_fwd_scalar_kernel(const T* __restrict__ x, int64_t ld_x,
 }
 
 // backward, vector path.  partial layout per block: float[K*C] dW then float[K] dbias.
-template <typename T>
-__global__ void outconv_bwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
-                                       const T* __restrict__ g, T* __restrict__ gx, int64_t ld_gx,
-                                       float* __restrict__ partial, int64_t npix, int C, int K, int LPP) {
+template <typename T, int K>
+__global__ void __launch_bounds__(256) outconv_bwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
+                                                              const T* __restrict__ g, T* __restrict__ gx, int64_t ld_gx,
+                                                              float* __restrict__ partial, int64_t npix, int C, int LPP) {
   extern __shared__ float sm[];   // [K][C] weights; then reduction scratch [K][C] + [K]
   float* sw = sm;
   float* red = sm + K * C;
@@ -79,39 +90,53 @@ __global__ void outconv_bwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, co
   const int sub = threadIdx.x % LPP;
   const int ppb = blockDim.x / LPP;
   const int c0 = sub * 8;
-  float dw[kMaxK][8];
-  float db[kMaxK];
+  float wr[K][8], dw[K][8], db[K];
 #pragma unroll
-  for (int k = 0; k < kMaxK; ++k) {
+  for (int k = 0; k < K; ++k) {
     db[k] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dw[k][i] = 0.f;
+    for (int i = 0; i < 8; ++i) { dw[k][i] = 0.f; wr[k][i] = sw[k * C + c0 + i]; }
   }
-  for (int64_t p = (int64_t)blockIdx.x * ppb + threadIdx.x / LPP; p < npix; p += (int64_t)gridDim.x * ppb) {
-    float v[8], o[8], gk[kMaxK];
-    load8(x + p * ld_x + c0, v);
+  for (int64_t base = (int64_t)blockIdx.x * ppb * kOutUnr; base < npix; base += (int64_t)gridDim.x * ppb * kOutUnr) {
+    float v[kOutUnr][8], gk[kOutUnr][K];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    for (int u = 0; u < kOutUnr; ++u) {
+      const int64_t p = base + u * ppb + threadIdx.x / LPP;
+      if (p < npix) {
+        load8(x + p * ld_x + c0, v[u]);
 #pragma unroll
-    for (int k = 0; k < kMaxK; ++k)
-      if (k < K) {
-        gk[k] = Elem<T>::ld(g + p * K + k);
-        db[k] += gk[k];
+        for (int k = 0; k < K; ++k) gk[u][k] = Elem<T>::ld(g + p * K + k);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) gk[u][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kOutUnr; ++u) {
+      const int64_t p = base + u * ppb + threadIdx.x / LPP;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        db[k] += gk[u][k];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          o[i] = fmaf(gk[k], sw[k * C + c0 + i], o[i]);
-          dw[k][i] = fmaf(gk[k], v[i], dw[k][i]);
+          o[i] = fmaf(gk[u][k], wr[k][i], o[i]);
+          dw[k][i] = fmaf(gk[u][k], v[u][i], dw[k][i]);
         }
       }
-    if (gx) store8(gx + p * ld_gx + c0, o);
+      if (gx && p < npix) store8(gx + p * ld_gx + c0, o);
+    }
   }
 #pragma unroll
-  for (int k = 0; k < kMaxK; ++k)
-    if (k < K) {
+  for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&red[k * C + c0 + i], dw[k][i]);
-      if (sub == 0) atomicAdd(&red[K * C + k], db[k]);
-    }
+    for (int i = 0; i < 8; ++i) atomicAdd(&red[k * C + c0 + i], dw[k][i]);
+    if (sub == 0) atomicAdd(&red[K * C + k], db[k]);
+  }
   __syncthreads();
   float* dst = partial + (int64_t)blockIdx.x * (K * C + K);
   for (int i = threadIdx.x; i < K * C + K; i += blockDim.x) dst[i] = red[i];
@@ -184,12 +209,18 @@ int unetb200_outconv_fwd(const void* x, int64_t ld_x, const float* w, const floa
   size_t esz = dtype == UNETB200_BF16 ? 2 : 4;
   size_t smem = sizeof(float) * ((size_t)ncls * C + ncls);
   if (outconv_vec(C, ld_x, x, esz) && smem <= 48 * 1024) {
-    if (dtype == UNETB200_BF16)
-      outconv_fwd_vec_kernel<bf16><<<blocks, 256, smem, s>>>((const bf16*)x, ld_x, w, bias, (bf16*)logits, npix, C,
-                                                             ncls, C / 8);
-    else
-      outconv_fwd_vec_kernel<float><<<blocks, 256, smem, s>>>((const float*)x, ld_x, w, bias, (float*)logits, npix,
-                                                              C, ncls, C / 8);
+#define UB_OUTCONV_FWD(KK)                                                                                           \
+  case KK:                                                                                                           \
+    if (dtype == UNETB200_BF16)                                                                                      \
+      outconv_fwd_vec_kernel<bf16, KK><<<blocks, 256, smem, s>>>((const bf16*)x, ld_x, w, bias, (bf16*)logits, npix, C, C / 8); \
+    else                                                                                                             \
+      outconv_fwd_vec_kernel<float, KK><<<blocks, 256, smem, s>>>((const float*)x, ld_x, w, bias, (float*)logits, npix, C, C / 8); \
+    break;
+    switch (ncls) {
+      UB_OUTCONV_FWD(1) UB_OUTCONV_FWD(2) UB_OUTCONV_FWD(3) UB_OUTCONV_FWD(4)
+      UB_OUTCONV_FWD(5) UB_OUTCONV_FWD(6) UB_OUTCONV_FWD(7) UB_OUTCONV_FWD(8)
+    }
+#undef UB_OUTCONV_FWD
   } else {
     if (dtype == UNETB200_BF16)
       outconv_fwd_scalar_kernel<bf16><<<blocks, 256, 0, s>>>((const bf16*)x, ld_x, w, bias, (bf16*)logits, npix, C,
@@ -221,12 +252,20 @@ int unetb200_outconv_bwd(const void* x, int64_t ld_x, const float* w, const void
   UB_CHECK_ARG(smem_s <= 48 * 1024, "outconv_bwd: n_classes*C too large (%d)", KC);
   bool vec = outconv_vec(C, ld_x, x, esz) && (!gx || outconv_vec(C, ld_gx, gx, esz)) && smem_v <= 48 * 1024;
   if (vec) {
-    if (dtype == UNETB200_BF16)
-      outconv_bwd_vec_kernel<bf16><<<blocks, 256, smem_v, s>>>((const bf16*)x, ld_x, w, (const bf16*)glogits,
-                                                               (bf16*)gx, ld_gx, workspace, npix, C, ncls, C / 8);
-    else
-      outconv_bwd_vec_kernel<float><<<blocks, 256, smem_v, s>>>((const float*)x, ld_x, w, (const float*)glogits,
-                                                                (float*)gx, ld_gx, workspace, npix, C, ncls, C / 8);
+#define UB_OUTCONV_BWD(KK)                                                                                           \
+  case KK:                                                                                                           \
+    if (dtype == UNETB200_BF16)                                                                                      \
+      outconv_bwd_vec_kernel<bf16, KK><<<blocks, 256, smem_v, s>>>((const bf16*)x, ld_x, w, (const bf16*)glogits, (bf16*)gx, \
+                                                                   ld_gx, workspace, npix, C, C / 8);                 \
+    else                                                                                                             \
+      outconv_bwd_vec_kernel<float, KK><<<blocks, 256, smem_v, s>>>((const float*)x, ld_x, w, (const float*)glogits,  \
+                                                                    (float*)gx, ld_gx, workspace, npix, C, C / 8);    \
+    break;
+    switch (ncls) {
+      UB_OUTCONV_BWD(1) UB_OUTCONV_BWD(2) UB_OUTCONV_BWD(3) UB_OUTCONV_BWD(4)
+      UB_OUTCONV_BWD(5) UB_OUTCONV_BWD(6) UB_OUTCONV_BWD(7) UB_OUTCONV_BWD(8)
+    }
+#undef UB_OUTCONV_BWD
   } else {
     if (dtype == UNETB200_BF16)
       outconv_bwd_scalar_kernel<bf16><<<blocks, 256, smem_s, s>>>((const bf16*)x, ld_x, w, (const bf16*)glogits,

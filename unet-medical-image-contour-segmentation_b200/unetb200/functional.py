@@ -146,8 +146,14 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx):
     Cout = w.shape[0]
     cd = x.dtype
     gy, dgamma, dbeta = ops.bn_relu_bwd(gz, y, coefs, batch_stats)
-    dW = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
-    ops.gconv_wgrad(_gconv3x3(x, Cout, gy, cd), x, gy, dW, 1, 9, Cin * 9)
+    # the gradient takes the parameter's own memory layout (OIHW or channels_last): AccumulateGrad then keeps it
+    # without a copy, and for channels_last the split reduction writes it coalesced
+    dW = torch.empty_like(w, dtype=torch.float32)
+    so, si, skh, skw = dW.stride()
+    if skh != 3 * skw or dW.shape != (Cout, Cin, 3, 3):
+        dW = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
+        so, si, skh, skw = dW.stride()
+    ops.gconv_wgrad(_gconv3x3(x, Cout, gy, cd), x, gy, dW, skw, si, so)
     gx = None
     if need_gx:
         gx = ops.empty_nhwc(B, Cin, H, W, cd, x.device)
