@@ -183,7 +183,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev, timeout=__import__("datetime").timedelta(seconds=180))
     B, S = args.batch, args.size
 
     torch.manual_seed(0)
@@ -249,7 +249,7 @@ def run_ours(args):
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
-    last_loss = float(step(img_d, msk_d))
+    last_loss = float(step(img_d, msk_d).detach())
 
     total_imgs = B * world * args.steps
     value = total_imgs / (ms / 1e3)
@@ -278,6 +278,12 @@ def run_ours(args):
         line["step_frac_of_bf16_peak"] = conv_tf / peaks["tflops_sustained"]
 
     # ---- per-kernel roofline: instrumented pass (CUDA events around every C-ABI call) ----------
+    if world > 1 and not args.no_profile:
+        # every rank must take part in the instrumented steps (they all-reduce); only rank 0 records
+        if rank != 0:
+            for _ in range(2):
+                step(img_d, msk_d)
+            torch.cuda.synchronize()
     if rank == 0 and not args.no_profile:
         os.environ["UNETB200_PROFILE_SHAPES"] = "1"
         with ops.profile() as rec:

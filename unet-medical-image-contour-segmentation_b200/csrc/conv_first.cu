@@ -164,6 +164,202 @@ first_conv_wgrad_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled variants for the layer the path actually has (C_in = 1, 64 output channels): a block owns an
+// 8 x 32 pixel tile, stages its 10 x 34 input halo in shared memory once (no per-pixel index division, no
+// global-load latency in the inner loop) and walks down the 8 rows with a 3 x 3 register window.
+// Thread = (pixel column of the tile, 8-channel group): the 8 threads of a pixel write / read 128 contiguous bytes.
+// ------------------------------------------------------------------------------------------
+constexpr int kFT_H = 8, kFT_W = 32, kFT_LD = 36;
+
+template <typename T>
+__device__ __forceinline__ void first_load_halo(const GconvDev& d, const T* __restrict__ x, float (*halo)[kFT_LD], int b,
+                                                int i0, int j0) {
+  for (int e = threadIdx.x; e < (kFT_H + 2) * (kFT_W + 2); e += 256) {
+    const int r = e / (kFT_W + 2), c = e - r * (kFT_W + 2);
+    const int gi = i0 - 1 + r, gj = j0 - 1 + c;
+    float v = 0.f;
+    if ((unsigned)gi < (unsigned)d.Hin && (unsigned)gj < (unsigned)d.Win)
+      v = Elem<T>::ld(x + ((long long)(b * d.Hin + gi) * d.Win + gj) * d.ld_in);
+    halo[r][c] = v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+first_conv_fprop_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ wp, T* __restrict__ y,
+                              float* __restrict__ stats_ws, int tiles_w, int tiles_h, int ntiles) {
+  __shared__ float halo[kFT_H + 2][kFT_LD];
+  __shared__ float sstat[2][64];
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  if (threadIdx.x < 128) (&sstat[0][0])[threadIdx.x] = 0.f;
+  // weights by window position (row a = dy + 1, column c = dx + 1)
+  float wr[3][3][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int a = d.tap_dy[t] + 1, c = d.tap_dx[t] + 1;
+#pragma unroll
+    for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+        if (aa == a && cc == c) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wr[aa][cc][i] = Elem<T>::ld(wp + (long long)(g * 8 + i) * 9 + t);
+        }
+  }
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tj = tile % tiles_w;
+    const int rest = tile / tiles_w;
+    const int ti = rest % tiles_h, b = rest / tiles_h;
+    const int i0 = ti * kFT_H, j0 = tj * kFT_W;
+    __syncthreads();
+    first_load_halo<T>(d, x, halo, b, i0, j0);
+    __syncthreads();
+    const int j = j0 + pl;
+    float win[3][3];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) win[a][c] = halo[a][pl + c];
+#pragma unroll
+    for (int r = 0; r < kFT_H; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) win[2][c] = halo[r + 2][pl + c];
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(win[a][c], wr[a][c][i], acc[i]);
+      const int i = i0 + r;
+      if (i < d.Hm && j < d.Wm) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[k] = Elem<T>::round(acc[k]);
+          s[k] += acc[k];
+          q[k] = fmaf(acc[k], acc[k], q[k]);
+        }
+        store8(y + ((long long)(b * d.Hm + i) * d.Wm + j) * d.ld_out + g * 8, acc);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { win[0][c] = win[1][c]; win[1][c] = win[2][c]; }
+    }
+  }
+  if (stats_ws) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      // the 4 pixel columns of a warp share a channel group: combine them first (lanes g, g+8, g+16, g+24)
+      float a = s[i], c = q[i];
+      a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+      c += __shfl_xor_sync(0xffffffffu, c, 8); c += __shfl_xor_sync(0xffffffffu, c, 16);
+      if ((threadIdx.x & 31) < 8) { atomicAdd(&sstat[0][g * 8 + i], a); atomicAdd(&sstat[1][g * 8 + i], c); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
+      stats_ws[((long long)blockIdx.x * 2 + which) * 64 + c] = sstat[which][c];
+    }
+  }
+}
+
+// dWp[t][n] partial per block: partials[block][9][64]
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+first_conv_wgrad_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ partials,
+                              int tiles_w, int tiles_h, int ntiles) {
+  __shared__ float halo[kFT_H + 2][kFT_LD];
+  __shared__ float red[9 * 64];
+  const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  for (int e = threadIdx.x; e < 9 * 64; e += 256) red[e] = 0.f;
+  float acc[3][3][8];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[a][c][i] = 0.f;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tj = tile % tiles_w;
+    const int rest = tile / tiles_w;
+    const int ti = rest % tiles_h, b = rest / tiles_h;
+    const int i0 = ti * kFT_H, j0 = tj * kFT_W;
+    __syncthreads();
+    first_load_halo<T>(d, x, halo, b, i0, j0);
+    __syncthreads();
+    const int j = j0 + pl;
+    float win[3][3];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) win[a][c] = halo[a][pl + c];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      // four 16-byte loads of dY in flight, then the FMAs
+      float gv[4][8];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int i = i0 + half * 4 + rr;
+        if (i < d.Hm && j < d.Wm) {
+          load8(gy + ((long long)(b * d.Hm + i) * d.Wm + j) * d.ld_out + g * 8, gv[rr]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gv[rr][k] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = half * 4 + rr;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) win[2][c] = halo[r + 2][pl + c];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[a][c][k] = fmaf(win[a][c], gv[rr][k], acc[a][c][k]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { win[0][c] = win[1][c]; win[1][c] = win[2][c]; }
+      }
+    }
+  }
+  __syncthreads();
+  // window position (a, c) -> tap index t
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int ta = d.tap_dy[t] + 1, tc = d.tap_dx[t] + 1;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (a == ta && c == tc) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float v = acc[a][c][k];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((threadIdx.x & 31) < 8) atomicAdd(&red[t * 64 + g * 8 + k], v);
+          }
+        }
+  }
+  __syncthreads();
+  float* out = partials + (long long)blockIdx.x * 9 * 64;
+  for (int e = threadIdx.x; e < 9 * 64; e += 256) out[e] = red[e];
+}
+
+static bool first_tiled_ok(const unetb200_gconv_t* d) {
+  if (getenv("UNETB200_FIRST_V1")) return false;
+  if (d->Cin != 1 || d->N != 64 || d->ld_out % 8) return false;
+  for (int t = 0; t < 9; ++t)
+    if (d->tap_dy[t] < -1 || d->tap_dy[t] > 1 || d->tap_dx[t] < -1 || d->tap_dx[t] > 1) return false;
+  return (long long)d->B * d->Hin * d->Win < (1LL << 31);
+}
+
 static bool first_common(const unetb200_gconv_t* d) {
   if (d->ntaps != 9 || d->in_scale != 1 || d->out_scale != 1 || d->nquad != 1) return false;
   if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) return false;
@@ -196,6 +392,21 @@ long long first_fprop_tiles(const unetb200_gconv_t* d) {
 int first_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
                 float* stats_ws, cudaStream_t s) {
   const int blocks = first_blocks(g.M, 256 / (d->N / 8));
+  if (first_tiled_ok(d)) {
+    const int tiles_w = (d->Wm + kFT_W - 1) / kFT_W, tiles_h = (d->Hm + kFT_H - 1) / kFT_H;
+    const int ntiles = d->B * tiles_w * tiles_h;
+    if (d->dtype == UNETB200_BF16)
+      first_conv_fprop_tiled_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)wp,
+                                                                          (__nv_bfloat16*)y, stats ? stats_ws : nullptr,
+                                                                          tiles_w, tiles_h, ntiles);
+    else
+      first_conv_fprop_tiled_kernel<float><<<blocks, 256, 0, s>>>(g, (const float*)x, (const float*)wp, (float*)y,
+                                                                  stats ? stats_ws : nullptr, tiles_w, tiles_h, ntiles);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "first_conv_fprop_tiled");
+    if (stats) return launch_stats_reduce(stats_ws, blocks, 2 * d->N, stats, s);
+    return 0;
+  }
 #define GO(T, CIN) \
   first_conv_fprop_kernel<T, CIN><<<blocks, 256, 0, s>>>(g, (const T*)x, (const T*)wp, (T*)y, stats ? stats_ws : nullptr)
   if (d->dtype == UNETB200_BF16) {
@@ -233,6 +444,19 @@ int first_wgrad_splits(const unetb200_gconv_t* d) {
 
 int first_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials,
                 int splits, cudaStream_t s) {
+  if (first_tiled_ok(d)) {
+    const int tiles_w = (d->Wm + kFT_W - 1) / kFT_W, tiles_h = (d->Hm + kFT_H - 1) / kFT_H;
+    const int ntiles = d->B * tiles_w * tiles_h;
+    if (d->dtype == UNETB200_BF16)
+      first_conv_wgrad_tiled_kernel<__nv_bfloat16><<<splits, 256, 0, s>>>(g, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gy,
+                                                                          partials, tiles_w, tiles_h, ntiles);
+    else
+      first_conv_wgrad_tiled_kernel<float><<<splits, 256, 0, s>>>(g, (const float*)x, (const float*)gy, partials, tiles_w,
+                                                                  tiles_h, ntiles);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "first_conv_wgrad_tiled");
+    return 0;
+  }
   if (d->dtype == UNETB200_BF16)
     first_conv_wgrad_kernel<__nv_bfloat16><<<splits, 256, 0, s>>>(g, (const __nv_bfloat16*)x,
                                                                   (const __nv_bfloat16*)gy, partials);

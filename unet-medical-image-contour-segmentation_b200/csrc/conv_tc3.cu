@@ -527,8 +527,19 @@ __global__ void tc3_stats_reduce_kernel(const float* __restrict__ ws, int rows, 
   const int nb = blockIdx.y;
   const int col = blockIdx.x * 32 + lane;              // 0 .. 2*BN
   double acc = 0.0;
-  if (col < 2 * BN)
-    for (int r = ry; r < rows; r += 8) acc += (double)ws[((long long)nb * rows + r) * 2 * BN + col];
+  // blockIdx.z takes a contiguous slice of the rows; 4 loads in flight per thread
+  const int per = (rows + gridDim.z - 1) / gridDim.z;
+  const int r0 = blockIdx.z * per, r1 = min(rows, r0 + per);
+  if (col < 2 * BN) {
+    const float* base = ws + (long long)nb * rows * 2 * BN + col;
+    int r = r0 + ry;
+    for (; r + 24 < r1; r += 32) {
+      const float a = base[(long long)r * 2 * BN], b = base[(long long)(r + 8) * 2 * BN],
+                  c = base[(long long)(r + 16) * 2 * BN], d = base[(long long)(r + 24) * 2 * BN];
+      acc += (double)a + (double)b + (double)c + (double)d;
+    }
+    for (; r < r1; r += 8) acc += (double)base[(long long)r * 2 * BN];
+  }
   red[ry][lane] = acc;
   __syncthreads();
   if (ry == 0 && col < 2 * BN) {
@@ -597,7 +608,7 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   if (rc) return rc;
   if (stats) {
     const int rows = pl.grid * kEpi3Warps;
-    tc3_stats_reduce_kernel<<<dim3((2 * pl.BN + 31) / 32, pl.n_blocks), 256, 0, stream>>>(stats_ws, rows, pl.BN, d->N, stats);
+    tc3_stats_reduce_kernel<<<dim3((2 * pl.BN + 31) / 32, pl.n_blocks, 16), 256, 0, stream>>>(stats_ws, rows, pl.BN, d->N, stats);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "tc3_stats_reduce");
   }
