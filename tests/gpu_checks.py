@@ -456,6 +456,54 @@ def check_conv_tc():
     return out
 
 
+def _conv3x3_cl_case(B, Ci, Co, H, W, dt_, seed):
+    """3x3 conv with a channels_last parameter (what `model.to(memory_format=channels_last)` gives train.py:262):
+    the dgrad operand is packed by the transposing kernel and the weight gradient is written in the parameter's
+    own layout by the coalesced split reduction (few / >= 8 / >= 32 splits depending on the shape)."""
+    res = []
+    g = gen(seed)
+    x = rq(torch.randn(B, Ci, H, W, generator=g), dt_).requires_grad_(True)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) / ((Ci * 9) ** 0.5)
+    wq = rq(w, dt_).requires_grad_(True)
+    ref = F.conv2d(x, wq, padding=1)
+    gy = rq(torch.randn(ref.shape, generator=g), dt_)
+    ref.backward(gy)
+    tol = 2e-3 if dt_ == FP else 1.2e-2
+    tag = f"cl_{Ci}to{Co}_{B}x{H}x{W}_{str(dt_)[6:]}"
+    algo = _lib.ALGO_TC
+    xd, gyd = dev_nhwc(x.detach(), dt_), dev_nhwc(gy, dt_)
+    wcl = w.to(DEV).contiguous(memory_format=torch.channels_last)
+    assert wcl.stride(1) == 1
+
+    def desc(xin, Cout, yout):
+        d = ops.make_gconv(ops._DT[dt_], algo, B, H, W, xin.shape[1], ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(xin),
+                           Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(yout))
+        d.algo = algo
+        return d
+    y = ops.empty_nhwc(B, Co, H, W, dt_, DEV)
+    ops.gconv_fprop(desc(xd, Co, y), xd, UF.pack3x3_fprop(wcl, dt_), None, y, None)
+    res.append((f"fprop_{tag}", rel(host(y), ref.detach()), tol))
+    gx = ops.empty_nhwc(B, Ci, H, W, dt_, DEV)
+    ops.gconv_fprop(desc(gyd, Ci, gx), gyd, UF.pack3x3_dgrad(wcl, dt_), None, gx, None)
+    res.append((f"dgrad_{tag}", rel(host(gx), x.grad), tol))
+    dW = torch.empty_like(wcl)
+    so, si, skh, skw = dW.stride()
+    assert skh == 3 * skw and si == 1
+    ops.gconv_wgrad(desc(xd, Co, gyd), xd, gyd, dW, skw, si, so)
+    res.append((f"wgrad_{tag}", rel(host(dW), wq.grad), 5e-3))
+    return res
+
+
+def check_conv_layouts():
+    out = []
+    out += _conv3x3_cl_case(2, 64, 64, 64, 64, BF, 70)        # 2 wgrad tiles -> >= 32 splits
+    out += _conv3x3_cl_case(2, 128, 128, 32, 48, BF, 71)      # 8 <= splits < 32
+    out += _conv3x3_cl_case(1, 256, 512, 16, 16, BF, 72)      # CTA-pair wgrad, few splits
+    out += _conv3x3_cl_case(3, 512, 256, 16, 8, BF, 73)       # CTA-pair wgrad, W <= 8, odd batch (a pair with one tile)
+    out += _conv3x3_cl_case(1, 64, 128, 24, 40, FP, 74)       # tf32
+    return out
+
+
 def check_conv_tc_tf32():
     out = []
     T = _lib.ALGO_TC
@@ -649,6 +697,7 @@ GROUPS = {
     "conv_tc_first": lambda gd: check_conv_tc_fprop_small(),
     "conv_tc": lambda gd: check_conv_tc(),
     "conv_tc_tf32": lambda gd: check_conv_tc_tf32(),
+    "conv_layouts": lambda gd: check_conv_layouts(),
     "parts_fp32": lambda gd: check_parts(gd, "fp32"),
     "parts_bf16": lambda gd: check_parts(gd, "bf16"),
     "calib_small": lambda gd: sum((calibrate(1, 2, False, 2, 128, 128, m) for m in ("fp32", "tf32", "bf16")), []),

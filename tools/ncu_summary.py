@@ -56,7 +56,10 @@ def launches(path):
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     print(f"# ncu --set full --clock-control none: raw metrics per launch ({path.split('/')[-1]})\n")
@@ -78,5 +81,44 @@ def full(path):
         print()
 
 
+def metrics(path):
+    """Long-format CSV of a few metrics for every launch of a step -> per-kernel table + per-launch list."""
+    lines = [ln for ln in open(path) if ln.startswith('"')]
+    rows = list(csv.reader(lines))
+    hdr = rows[0]
+    iid, ik, im, iu, iv, ig = (hdr.index(x) for x in ("ID", "Kernel Name", "Metric Name", "Metric Unit", "Metric Value", "Grid Size"))
+    per = collections.OrderedDict()
+    mul = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "%": 1.0, "cycle": 1.0}
+    for r in rows[1:]:
+        if len(r) <= iv:
+            continue
+        e = per.setdefault(r[iid], {"name": short(r[ik]), "grid": r[ig]})
+        e[r[im]] = float(r[iv].replace(",", "")) * mul.get(r[iu], 1.0)
+    T, RD, WR, TP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
+    agg = collections.OrderedDict()
+    for e in per.values():
+        a = agg.setdefault(e["name"], dict(n=0, us=0.0, rd=0.0, wr=0.0, tp=0.0))
+        a["n"] += 1
+        a["us"] += e.get(T, 0.0)
+        a["rd"] += e.get(RD, 0.0)
+        a["wr"] += e.get(WR, 0.0)
+        a["tp"] += e.get(TP, 0.0) * e.get(T, 0.0)
+    tot = sum(a["us"] for a in agg.values())
+    print(f"# One training step (UNet(1,2) bf16, B=16, 512x512) under ncu: {len(per)} launches, {tot / 1e3:.2f} ms of kernel time")
+    print("# ncu --metrics gpu__time_duration.sum,dram__bytes_{read,write}.sum,sm__pipe_tensor_cycles_active... --clock-control none")
+    print("# (serialised, cold-cache replays: compare SHARES; traffic = DRAM bytes read + written, summed over the launches)\n")
+    print("| kernel | launches | total us | share | DRAM read MB | DRAM write MB | traffic MB / launch | achieved DRAM GB/s | tensor pipe active % (time-weighted) |")
+    print("|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        gbs = (a["rd"] + a["wr"]) / (a["us"] * 1e-6) / 1e9 if a["us"] else 0.0
+        print(f"| `{k}` | {a['n']} | {a['us']:.1f} | {100 * a['us'] / tot:.1f}% | {a['rd'] / 1e6:.1f} | {a['wr'] / 1e6:.1f} | "
+              f"{(a['rd'] + a['wr']) / 1e6 / a['n']:.1f} | {gbs:.0f} | {a['tp'] / a['us'] if a['us'] else 0:.1f} |")
+    print("\n## Every launch, in order\n")
+    print("| # | kernel | grid | us | DRAM read MB | DRAM write MB | tensor % |\n|---:|---|---|---:|---:|---:|---:|")
+    for i, e in per.items():
+        print(f"| {i} | `{e['name'][:70]}` | {e['grid']} | {e.get(T, 0):.1f} | {e.get(RD, 0) / 1e6:.1f} | {e.get(WR, 0) / 1e6:.1f} | {e.get(TP, 0):.1f} |")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "metrics": metrics}[sys.argv[1]](sys.argv[2])

@@ -378,44 +378,41 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, D* __restrict
 // Split reduction + transpose for the case dst[co * sn + k] (k = t*Cin + c linear in the parameter: a
 // channels_last weight gradient): partial rows [k][n] are read coalesced along n, summed over the splits in a
 // fixed order (deterministic), transposed through shared memory and written coalesced along k.
-__global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __restrict__ partials, int splits, long long K,
-                                                              int N, float* __restrict__ dst, long long sn, int accumulate) {
-  // thread (tx, ty): column n0 + tx, splits ty, ty + 8, ...; 32 row sums in registers (32 loads in flight)
-  __shared__ float red[8][32][33];
+template <int SL>
+__global__ void __launch_bounds__(32 * SL) wgrad_reduce_t_kernel(const float* __restrict__ partials, int splits, long long K,
+                                                                 int N, float* __restrict__ dst, long long sn, int accumulate) {
+  // many splits: a block owns an 8 (k) x 32 (n) tile; thread (tx, ty) sums column n0 + tx over the splits
+  // ty, ty + SL, ... with its 8 row sums in registers (8 loads in flight), then the SL lanes are combined in
+  // a fixed order through shared memory (deterministic)
+  __shared__ float red[SL][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const long long k0 = (long long)blockIdx.x * 32;
+  const long long k0 = (long long)blockIdx.x * 8;
   const int n0 = blockIdx.y * 32;
   const long long total = K * N;
   const int n = n0 + tx;
-  float acc[32];
+  float acc[8];
 #pragma unroll
-  for (int r = 0; r < 32; ++r) acc[r] = 0.f;
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
   if (n < N) {
-    for (int sp = ty; sp < splits; sp += 8) {
+    for (int sp = ty; sp < splits; sp += SL) {
       const float* p = partials + (long long)sp * total + k0 * N + n;
-      if (k0 + 32 <= K) {
-        float v[32];
+      float v[8];
 #pragma unroll
-        for (int r = 0; r < 32; ++r) v[r] = p[(long long)r * N];
+      for (int r = 0; r < 8; ++r) v[r] = (k0 + r < K) ? p[(long long)r * N] : 0.f;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) acc[r] += v[r];
-      } else {
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-          if (k0 + r < K) acc[r] += p[(long long)r * N];
-      }
+      for (int r = 0; r < 8; ++r) acc[r] += v[r];
     }
   }
 #pragma unroll
-  for (int r = 0; r < 32; ++r) red[ty][r][tx] = acc[r];
+  for (int r = 0; r < 8; ++r) red[ty][r][tx] = acc[r];
   __syncthreads();
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int nn = n0 + ty + 8 * r;
-    const long long k = k0 + tx;
+  if (threadIdx.x < 256) {
+    const int kl = threadIdx.x & 7, nl = threadIdx.x >> 3;
     float v = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v += red[j][tx][ty + 8 * r];          // fixed order: deterministic
+#pragma unroll 4
+    for (int j = 0; j < SL; ++j) v += red[j][kl][nl];
+    const long long k = k0 + kl;
+    const int nn = n0 + nl;
     if (k < K && nn < N) {
       float* o = dst + (long long)nn * sn + k;
       *o = accumulate ? *o + v : v;
@@ -629,7 +626,9 @@ int unetb200_wgrad_reduce(const float* partials, int splits, int ntaps, int Cin,
   if (Cq == N && sc == 1 && (ntaps == 1 || st == Cin) && sn != 1) {
     // the parameter is k-linear (channels_last Conv2d weight): coalesced transpose
     dim3 grid((unsigned)((K + 31) / 32), (unsigned)((N + 31) / 32));
-    if (splits >= 8) wgrad_reduce_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, splits, K, N, dst, sn, accumulate);
+    dim3 grid8((unsigned)((K + 7) / 8), (unsigned)((N + 31) / 32));
+    if (splits >= 32) wgrad_reduce_t_kernel<32><<<grid8, 1024, 0, (cudaStream_t)stream>>>(partials, splits, K, N, dst, sn, accumulate);
+    else if (splits >= 8) wgrad_reduce_t_kernel<8><<<grid8, 256, 0, (cudaStream_t)stream>>>(partials, splits, K, N, dst, sn, accumulate);
     else wgrad_reduce_t4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, splits, K, N, dst, sn, accumulate);
     UB_LAUNCH_CHECK("wgrad_reduce_t");
     return 0;

@@ -463,7 +463,8 @@ static bool tc3_plan(const unetb200_gconv_t* d, Tc3Plan* pl) {
     seen[(dy + 1) * 3 + dx + 1] = true;
   }
   pl->CG = tc3_cluster_size();
-  pl->BN = (d->dtype == UNETB200_BF16 && d->N % 256 == 0) ? 256 : (d->N % 128 == 0 ? 128 : 64);
+  static const int max_bn = getenv("UNETB200_TC3_MAXBN") ? atoi(getenv("UNETB200_TC3_MAXBN")) : 256;   // A/B runs
+  pl->BN = (d->dtype == UNETB200_BF16 && d->N % 256 == 0 && max_bn >= 256) ? 256 : (d->N % 128 == 0 ? 128 : 64);
   if (d->Wm > 8) { pl->tile_w = 16; pl->tile_h = 16; }
   else { pl->tile_w = 8; pl->tile_h = 32; }
   pl->box_w = pl->tile_w + 2;
