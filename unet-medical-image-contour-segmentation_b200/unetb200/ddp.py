@@ -30,7 +30,15 @@ class GradAllReducer:
     After ``finish()`` every ``p.grad`` is a view into its bucket holding the rank-averaged gradient.
     """
 
-    def __init__(self, module, bucket_bytes=32 << 20, group=None):
+    def __init__(self, module, bucket_bytes=32 << 20, group=None, overlap=None):
+        # overlap=True launches each bucket's all-reduce from the autograd hook that completes it (while backward
+        # is still running); overlap=False launches them all from finish().  The conv kernels are persistent
+        # grids of one CTA (pair) per SM, so an NCCL kernel that holds SMs during backward delays whole CTA
+        # pairs -- measured on 2 GPUs, see DESIGN.md section 5.  Default: UNETB200_DDP_OVERLAP (0/1), else on.
+        if overlap is None:
+            import os
+            overlap = os.environ.get("UNETB200_DDP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap)
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.params = [p for p in module.parameters() if p.requires_grad]
@@ -73,14 +81,17 @@ class GradAllReducer:
         bi, _ = self._where[p]
         b = self.buckets[bi]
         b["pending"] -= 1
-        if b["pending"] == 0:
+        if b["pending"] == 0 and self.overlap:
             self._launch(b)
 
     def _launch(self, b):
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b["params"]]
         torch._foreach_copy_(self._views(b), [g.to(torch.float32) for g in grads])
-        b["buffer"].mul_(1.0 / self.world)
-        b["work"] = dist.all_reduce(b["buffer"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        if dist.get_backend(self.group) == "nccl":       # NCCL averages inside the collective
+            b["work"] = dist.all_reduce(b["buffer"], op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:
+            b["buffer"].mul_(1.0 / self.world)
+            b["work"] = dist.all_reduce(b["buffer"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self.launched += 1
 
     def finish(self):
@@ -89,7 +100,7 @@ class GradAllReducer:
             return
         for b in self.buckets:
             if b["work"] is None and b["pending"] != len(b["params"]):
-                self._launch(b)            # a bucket with parameters that received no gradient this step
+                self._launch(b)            # not launched from a hook: overlap off, or parameters without a gradient
         for b in self.buckets:
             if b["work"] is not None:
                 b["work"].wait()
