@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--per-layer", action="store_true", help="add a per-layer conv table (`layers`) to the JSON line")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the whole step as one CUDA graph (auto: try, fall back to eager launches)")
     return ap.parse_args()
 
 
@@ -191,7 +193,8 @@ def run_ours(args):
     if world > 1:
         ddp.broadcast_module_state(model)
     reducer = ddp.GradAllReducer(model) if world > 1 else None
-    opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True)
+    opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True,
+                              capturable=(args.graph != "off"))
 
     gi = torch.Generator().manual_seed(1 + 1000 * rank)
     gm = torch.Generator().manual_seed(2 + 1000 * rank)
@@ -263,14 +266,44 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(img_d, msk_d)
     sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- whole-step CUDA graph (falls back to eager launches if capture is not possible) -------
+    eager_step = step
+    graphed, graph_note = None, "off"
     l0 = ops.LAUNCHES
+    eager_step(img_d, msk_d)
+    launches_per_step = ops.LAUNCHES - l0
+    if args.graph != "off":
+        try:
+            from unetb200.graph import GraphedStep
+            graphed = GraphedStep(eager_step, (img_d, msk_d), warmup=2)
+            graph_note = "on"
+        except Exception as exc:  # noqa: BLE001
+            if args.graph == "on":
+                raise
+            graphed, graph_note = None, f"capture failed, eager launches: {type(exc).__name__}: {exc}"[:200]
+            torch.cuda.synchronize()
+        if world > 1:                                     # every rank must take the same path
+            flag = torch.tensor([1 if graphed is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if flag.item() == 0:
+                graphed = None
+    if graphed is not None:
+        def step(x, t):                                   # noqa: F811  (x, t are already in the static buffers when equal)
+            if x is not graphed.static_inputs[0]:
+                graphed.load(x, t)
+            return graphed.replay()
+        img_d, msk_d = graphed.static_inputs
+        for _ in range(2):
+            step(img_d, msk_d)
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
     ms = timed(lambda: step(img_d, msk_d), args.steps)
-    launches = ops.LAUNCHES - l0
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if sampler else {}
     e2e_steps(2)
     ms_e2e = timed(lambda: e2e_steps(args.steps), 1)
     last_loss = float(step(img_d, msk_d).detach())
+    step = eager_step                                     # the instrumented pass below times individual launches
 
     total_imgs = B * world * args.steps
     value = total_imgs / (ms / 1e3)
@@ -290,6 +323,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": img_h.numel() * 4 + msk_h.numel() * 8,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "cuda_graph": graph_note,
         "clocks": clocks,
         "final_loss": last_loss,
     }

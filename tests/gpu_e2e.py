@@ -78,7 +78,40 @@ def gate(nc, ncls, bilinear, B, H, W, mode, boundary_coeff=0.0, fused=True):
     return res
 
 
+def infer_gate(nc, ncls, bilinear, B, H, W, mode):
+    """predict.py / evaluate.py style forward (BASELINE.json configs[4] shape class): eval-mode BatchNorm (running
+    statistics), torch.inference_mode, optional bf16 autocast; logits and argmax mask against the oracle."""
+    import unet
+    tag = f"infer{nc}_{ncls}_{'bil' if bilinear else 'convT'}_{B}x{H}x{W}_{mode}"
+    st = O.build_state(nc, ncls, bilinear, seed=0)
+    g = torch.Generator().manual_seed(123)
+    for k in st:                                  # non-trivial running statistics
+        if k.endswith("running_mean"):
+            st[k] = 0.1 * torch.randn(st[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            st[k] = 0.5 + torch.rand(st[k].shape, generator=g)
+    img, _ = O.synthetic_batch(B, nc, ncls, H, W)
+    r_logits = O.unet_forward({k: v.clone() for k, v in st.items()}, img, bilinear, training=False)
+    model = unet.UNet(nc, ncls, bilinear)
+    model.load_state_dict(st)
+    model = model.to(DEV).to(memory_format=torch.channels_last).eval()
+    os.environ["UNET_B200_PRECISION"] = "tf32" if mode == "tf32" else "fp32"
+    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    with torch.inference_mode(), torch.autocast("cuda", enabled=(mode == "bf16")):
+        logits = model(x)
+    logits = host(logits.float())
+    agree = (logits.argmax(1) == r_logits.argmax(1)).float().mean().item()
+    res = [(f"{tag}_logits", rel(logits, r_logits), {"fp32": 1e-3, "tf32": 2e-2, "bf16": 1e-1}[mode]),
+           (f"{tag}_argmax_mismatch", 1.0 - agree, {"fp32": 1e-3, "tf32": 5e-3, "bf16": 2e-2}[mode])]
+    sd = model.state_dict()
+    unchanged = all(torch.equal(host(sd[k]), st[k]) for k in sd if "running" in k or "tracked" in k)
+    res.append((f"{tag}_buffers_untouched", 0.0 if unchanged else 1.0, 0.0))
+    return res
+
+
 GROUPS = {
+    "unet_infer": lambda gd: infer_gate(3, 4, False, 2, 128, 160, "fp32") + infer_gate(3, 4, False, 2, 128, 160, "bf16")
+                  + infer_gate(1, 2, True, 1, 96, 96, "tf32"),
     "unet_fp32": lambda gd: gate(1, 2, False, 2, 64, 64, "fp32") + gate(1, 2, True, 2, 64, 64, "fp32", fused=False),
     "unet_fp32_b": lambda gd: gate(3, 4, False, 1, 96, 80, "fp32") + gate(1, 2, False, 2, 128, 128, "fp32", boundary_coeff=0.2),
     "unet_tf32": lambda gd: gate(1, 2, True, 2, 128, 128, "tf32") + gate(1, 2, False, 2, 128, 128, "tf32"),
