@@ -272,11 +272,37 @@ def run_ours(args):
     l0 = ops.LAUNCHES
     eager_step(img_d, msk_d)
     launches_per_step = ops.LAUNCHES - l0
+    graphed_b = None
     if args.graph != "off":
         try:
             from unetb200.graph import GraphedStep
-            graphed = GraphedStep(eager_step, (img_d, msk_d), warmup=2)
-            graph_note = "on"
+            if world == 1:
+                graphed = GraphedStep(eager_step, (img_d, msk_d), warmup=2)
+            else:
+                # the NCCL all-reduce stays outside the captured regions:
+                #   graph A = forward + loss + backward + gradients packed into the buckets
+                #   eager   = mean all-reduce of the buckets
+                #   graph B = clip_grad_norm_ + RMSprop step on the bucket views
+                reducer.manual = True
+
+                def part_a(x, t):
+                    opt.zero_grad(set_to_none=True)
+                    with torch.autocast("cuda", enabled=True):
+                        loss = UL.training_criterion(model(x), t, boundary_coeff=0.2, edge_width=51, edge_weight=7)
+                    loss.backward()
+                    reducer.pack_all()
+                    return loss
+
+                def part_b():
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+                    opt.step()
+                    return None
+
+                graphed = GraphedStep(part_a, (img_d, msk_d), warmup=2)
+                reducer.allreduce_all()
+                reducer.point_grads()
+                graphed_b = GraphedStep(part_b, (), warmup=1)
+            graph_note = "on" if world == 1 else "on (backward graph | eager NCCL all-reduce | optimizer graph)"
         except Exception as exc:  # noqa: BLE001
             if args.graph == "on":
                 raise
@@ -287,11 +313,16 @@ def run_ours(args):
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if flag.item() == 0:
                 graphed = None
+                reducer.manual = False
     if graphed is not None:
         def step(x, t):                                   # noqa: F811  (x, t are already in the static buffers when equal)
             if x is not graphed.static_inputs[0]:
                 graphed.load(x, t)
-            return graphed.replay()
+            loss = graphed.replay()
+            if graphed_b is not None:
+                reducer.allreduce_all()
+                graphed_b.replay()
+            return loss
         img_d, msk_d = graphed.static_inputs
         for _ in range(2):
             step(img_d, msk_d)
@@ -304,6 +335,8 @@ def run_ours(args):
     ms_e2e = timed(lambda: e2e_steps(args.steps), 1)
     last_loss = float(step(img_d, msk_d).detach())
     step = eager_step                                     # the instrumented pass below times individual launches
+    if reducer is not None:
+        reducer.manual = False
 
     total_imgs = B * world * args.steps
     value = total_imgs / (ms / 1e3)

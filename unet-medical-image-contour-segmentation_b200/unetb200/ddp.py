@@ -39,6 +39,7 @@ class GradAllReducer:
             import os
             overlap = os.environ.get("UNETB200_DDP_OVERLAP", "1") != "0"
         self.overlap = bool(overlap)
+        self.manual = False          # True: hooks are inert, the caller drives pack_all / allreduce_all / point_grads
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.params = [p for p in module.parameters() if p.requires_grad]
@@ -75,8 +76,36 @@ class GradAllReducer:
     def _views(self, b):
         return [b["buffer"][o:o + p.numel()].view_as(p) for p, o in zip(b["params"], b["offsets"])]
 
-    def _on_grad(self, p):
+    # ---- explicit three-phase form (used when the step is replayed as CUDA graphs: the collective stays outside
+    # the captured regions) -- pack_all() inside the backward graph, allreduce_all() eagerly, then point_grads()
+    def pack_all(self):
+        """Copy every gradient into its bucket (no communication)."""
+        for b in self.buckets:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b["params"]]
+            torch._foreach_copy_(self._views(b), [g.to(torch.float32) for g in grads])
+
+    def allreduce_all(self):
+        """Mean all-reduce of every bucket; returns when the results are ordered on the current stream."""
         if self.world == 1:
+            return
+        works = []
+        for b in self.buckets:
+            if dist.get_backend(self.group) == "nccl":
+                works.append(dist.all_reduce(b["buffer"], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            else:
+                b["buffer"].mul_(1.0 / self.world)
+                works.append(dist.all_reduce(b["buffer"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for w in works:
+            w.wait()
+
+    def point_grads(self):
+        """p.grad = its (averaged) bucket view."""
+        for b in self.buckets:
+            for p, v in zip(b["params"], self._views(b)):
+                p.grad = v
+
+    def _on_grad(self, p):
+        if self.world == 1 or self.manual:
             return
         bi, _ = self._where[p]
         b = self.buckets[bi]
