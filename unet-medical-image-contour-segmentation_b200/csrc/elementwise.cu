@@ -45,9 +45,9 @@ struct CsGeom {
   int CVB, gy;
   unsigned gx;
 };
-static CsGeom cs_geom(int CV, int64_t items, int per_thread) {
+static CsGeom cs_geom(int CV, int64_t items, int per_thread, int max_cvb = 256) {
   CsGeom g;
-  g.CVB = CV < 256 ? CV : 256;
+  g.CVB = CV < max_cvb ? CV : max_cvb;
   const int lanes = 256 / g.CVB;
   g.gy = (CV + g.CVB - 1) / g.CVB;
   int64_t gx = (items + (int64_t)lanes * per_thread - 1) / ((int64_t)lanes * per_thread);
@@ -307,7 +307,7 @@ bn_relu_bwd_reduce_kernel(const T* __restrict__ gz, int64_t ld_gz, const T* __re
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           double* __restrict__ sums, int64_t npix, int C, int CV, int CVB) {
-  constexpr int RED = (V == 8) ? 2048 : 256;
+  constexpr int RED = (V == 8) ? 512 : 256;      // 4 KB: small enough to co-reside with a tensor kernel that holds ~200 KB
   __shared__ float red[2][RED];
   const CsThread t = cs_thread(CV, CVB);
   const int cvl = threadIdx.x % CVB;
@@ -783,7 +783,7 @@ int unetb200_bn_relu_bwd_reduce(const void* gz, int64_t ld_gz, const void* y, in
 #define GO(T, V)                                                                                              \
   do {                                                                                                        \
     int CV = C / V;                                                                                           \
-    CsGeom g_ = cs_geom(CV, npix, 8);                                                                         \
+    CsGeom g_ = cs_geom(CV, npix, 8, V == 8 ? 64 : 256);   /* CVB * V <= the kernel's shared reduction row */   \
     bn_relu_bwd_reduce_kernel<T, V><<<dim3(g_.gx, g_.gy), 256, 0, s>>>(                                       \
         (const T*)gz, ld_gz, (const T*)y, ld_y, scale, shift, mean, invstd, sums, npix, C, CV, g_.CVB);       \
   } while (0)

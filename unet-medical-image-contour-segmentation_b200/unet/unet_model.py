@@ -48,6 +48,8 @@ class _UNetBase(nn.Module):
             raise ValueError(f"{type(self).__name__}: input {H}x{W} is too small for four 2x2 max-pools")
         b = self._BASE
         dev, cd = x.device, x.dtype
+        from unetb200 import functional as UF
+        forked = UF.prepack(self, cd, need_dgrad=torch.is_grad_enabled())
         # concat buffers of the four Up stages: [skip | upsampled], at the skip's resolution
         cats = [ops.empty_nhwc(B, 2 * b * (1 << k), H >> k, W >> k, cd, dev) for k in range(4)]
         skips = [ops.channel_slice(cats[k], 0, b * (1 << k)) for k in range(4)]
@@ -60,7 +62,10 @@ class _UNetBase(nn.Module):
         y = self.up2.run(y, x3, cat=cats[2])
         y = self.up3.run(y, x2, cat=cats[1])
         y = self.up4.run(y, x1, cat=cats[0])
-        return self.outc.run(y)
+        out = self.outc.run(y)
+        if forked and not torch.is_grad_enabled():
+            ops.side_stream_sync()        # no backward will join the side stream: do it here (it finished long ago)
+        return out
 
     def use_checkpointing(self):
         """Called by train.py:299 after a CUDA OOM.  The reference's own implementation raises

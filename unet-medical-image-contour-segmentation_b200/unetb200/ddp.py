@@ -14,6 +14,15 @@ import torch
 import torch.distributed as dist
 
 
+def _side_stream_sync():
+    try:
+        from . import ops
+    except Exception:  # noqa: BLE001  (CPU-only use of this module in the gloo tests)
+        return
+    if torch.cuda.is_available():
+        ops.side_stream_sync()
+
+
 def broadcast_module_state(module, src=0):
     """Replicate parameters and buffers from `src` (rank-0 convention for BN running stats)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -80,6 +89,7 @@ class GradAllReducer:
     # the captured regions) -- pack_all() inside the backward graph, allreduce_all() eagerly, then point_grads()
     def pack_all(self):
         """Copy every gradient into its bucket (no communication)."""
+        _side_stream_sync()
         for b in self.buckets:
             grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b["params"]]
             torch._foreach_copy_(self._views(b), [g.to(torch.float32) for g in grads])
@@ -114,6 +124,7 @@ class GradAllReducer:
             self._launch(b)
 
     def _launch(self, b):
+        _side_stream_sync()          # weight gradients are produced on the library's side stream
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in b["params"]]
         torch._foreach_copy_(self._views(b), [g.to(torch.float32) for g in grads])
         if dist.get_backend(self.group) == "nccl":       # NCCL averages inside the collective

@@ -68,32 +68,92 @@ def _pack(w, dtype, n0, n1, n2, s0, s1, s2, off=0):
     return dst
 
 
-def pack3x3_fprop(w, dtype):
-    """OIHW -> Wp[co][(kh,kw)][ci]"""
+def _pack3x3_fprop(w, dtype):
     Co, Ci = w.shape[:2]
     w, so, si, st = _w_src(w)
     return _pack(w, dtype, Co, 9, Ci, so, st, si)
 
 
-def pack3x3_dgrad(w, dtype):
-    """OIHW -> Wp[ci][(kh',kw')][co] = W[co][ci][2-kh'][2-kw']"""
+def _pack3x3_dgrad(w, dtype):
     Co, Ci = w.shape[:2]
     w, so, si, st = _w_src(w)
     return _pack(w, dtype, Ci, 9, Co, si, -st, so, off=8 * st)
 
 
-def packT_fprop(w, dtype):
-    """IOHW [Ci,Co,2,2] -> Wp[(q,co)][ci]"""
+def _packT_fprop(w, dtype):
     Ci, Co = w.shape[:2]
     w, s_ci, s_co, st = _w_src(w)
     return _pack(w, dtype, 4, Co, Ci, st, s_co, s_ci).view(4 * Co, Ci)
 
 
-def packT_dgrad(w, dtype):
-    """IOHW -> Wp[ci][(q,co)]"""
+def _packT_dgrad(w, dtype):
     Ci, Co = w.shape[:2]
     w, s_ci, s_co, st = _w_src(w)
     return _pack(w, dtype, Ci, 4, Co, s_ci, st, s_co)
+
+
+# GEMM operands packed ahead of their use, on the side stream, at the start of a whole-network forward
+# (`prepack`): the ~40 small pack kernels of a step then run in the shadow of the first convolutions instead of
+# in front of each one.  Entries are valid for one forward/backward pass of the same parameter version.
+_PRE = {}          # (id(w), kind) -> (packed, ready event, dtype, parameter version)
+_PACKERS = {"f3": _pack3x3_fprop, "d3": _pack3x3_dgrad, "fT": _packT_fprop, "dT": _packT_dgrad}
+
+
+def _packed(w, dtype, kind):
+    ent = _PRE.get((id(w), kind))
+    if ent is not None and ent[2] == dtype and ent[3] == w._version and ent[0].device == w.device:
+        torch.cuda.current_stream().wait_event(ent[1])
+        return ent[0]
+    return _PACKERS[kind](w, dtype)
+
+
+def prepack(model, dtype, need_dgrad):
+    """Pack every 3x3 / transposed conv weight of `model` on the side stream (see ops.on_side_stream)."""
+    _PRE.clear()
+    if not ops.side_enabled():
+        return False
+    jobs = []
+    for m in model.modules():
+        if isinstance(m, torch.nn.ConvTranspose2d) and m.kernel_size == (2, 2):
+            jobs.append((m.weight, "fT"))
+            if need_dgrad:
+                jobs.append((m.weight, "dT"))
+        elif isinstance(m, torch.nn.Conv2d) and m.kernel_size == (3, 3):
+            jobs.append((m.weight, "f3"))
+            if need_dgrad and m.in_channels >= 16:       # the first layer has no data gradient
+                jobs.append((m.weight, "d3"))
+    if not jobs or not all(w.is_cuda for w, _ in jobs):
+        return False
+
+    def run():
+        for w, kind in jobs:
+            packed = _PACKERS[kind](w, dtype)
+            ev = torch.cuda.Event()
+            ev.record()
+            _PRE[(id(w), kind)] = (packed, ev, dtype, w._version)
+
+    ops.on_side_stream(run, join=False)
+    return True
+
+
+def pack3x3_fprop(w, dtype):
+    """OIHW -> Wp[co][(kh,kw)][ci]"""
+    return _packed(w, dtype, "f3")
+
+
+def pack3x3_dgrad(w, dtype):
+    """OIHW -> Wp[ci][(kh',kw')][co] = W[co][ci][2-kh'][2-kw']"""
+    return _packed(w, dtype, "d3")
+
+
+def packT_fprop(w, dtype):
+    """IOHW [Ci,Co,2,2] -> Wp[(q,co)][ci]"""
+    return _packed(w, dtype, "fT")
+
+
+def packT_dgrad(w, dtype):
+    """IOHW -> Wp[ci][(q,co)]"""
+    return _packed(w, dtype, "dT")
 
 
 def _f32c(t):
@@ -140,8 +200,9 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False):
     return y, z, pooled, coefs
 
 
-def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx):
-    """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta)."""
+def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None):
+    """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta).  `param`: the Parameter object behind `w`."""
+    param = w if param is None else param
     B, Cin, H, W = x.shape
     Cout = w.shape[0]
     cd = x.dtype
@@ -153,11 +214,17 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx):
     if skh != 3 * skw or dW.shape != (Cout, Cin, 3, 3):
         dW = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
         so, si, skh, skw = dW.stride()
-    ops.gconv_wgrad(_gconv3x3(x, Cout, gy, cd), x, gy, dW, skw, si, so)
     gx = None
     if need_gx:
         gx = ops.empty_nhwc(B, Cin, H, W, cd, x.device)
         ops.gconv_fprop(_gconv3x3(gy, Cin, gx, cd), gy, pack3x3_dgrad(w, cd), None, gx, None, kind="dgrad")
+    # after the dgrad, on the side stream: overlaps the (memory-bound) BatchNorm backward of the previous layer
+    # (only when AccumulateGrad will simply keep dW: an existing .grad would be accumulated into on the main stream)
+    run = lambda: ops.gconv_wgrad(_gconv3x3(x, Cout, gy, cd), x, gy, dW, skw, si, so)  # noqa: E731
+    if getattr(param, "grad", None) is None and dW.stride() == param.stride() and param.dtype == torch.float32:
+        ops.on_side_stream(run, x, gy)      # AccumulateGrad keeps dW as it is (same layout, no other owner)
+    else:
+        run()                               # it would accumulate / re-layout dW on the main stream right away
     return gx, dW, dgamma, dbeta
 
 
@@ -191,6 +258,7 @@ class DoubleConvFn(torch.autograd.Function):
         ctx.has_pool = pooled is not None
         if cfg.save:
             ctx.save_for_backward(x, y1, z1, y2, z2, c1, c2, w1, w2)
+            ctx.param_objs = (w1, w2)            # the Parameter objects themselves (their .grad decides the wgrad stream)
         if pooled is None:
             return z2
         return z2, pooled
@@ -216,8 +284,9 @@ class DoubleConvFn(torch.autograd.Function):
         if gz is None:
             raise RuntimeError("DoubleConvFn.backward called without any output gradient")
         need = ctx.needs_input_grad
-        gz1, dW2, dg2, db2 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True)
-        gx, dW1, dg1, db1 = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0])
+        p1, p2 = getattr(ctx, "param_objs", (w1, w2))
+        gz1, dW2, dg2, db2 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True, param=p2)
+        gx, dW1, dg1, db1 = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0], param=p1)
         return (gx, dW1 if need[1] else None, dg1 if need[2] else None, db1 if need[3] else None,
                 dW2 if need[4] else None, dg2 if need[5] else None, db2 if need[6] else None, None)
 
@@ -282,6 +351,7 @@ class UpCatConvTFn(torch.autograd.Function):
         ctx.geom = (C2, Cup, off, dy or dx)
         if cfg.save:
             ctx.save_for_backward(x1, wT)
+            ctx.param_obj = wT
         return cat
 
     @staticmethod
@@ -300,17 +370,28 @@ class UpCatConvTFn(torch.autograd.Function):
         if need[2]:
             d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, C1, ops.TAPS1, 1, (0, 0), h, w, ops.nhwc_ld(x1),
                                4 * Cup, 4, 2, off, H, W, ld)
-            dW = torch.empty((C1, Cup, 2, 2), dtype=torch.float32, device=g.device)
-            ops.gconv_wgrad(d, x1, gup, dW, 0, Cup * 4, 4, sq=1)
+            # gradient in the parameter's own layout (see conv_bn_relu_bwd); quadrant q = kh*2 + kw must stay linear
+            dW = torch.empty_like(wT, dtype=torch.float32)
+            if dW.shape != (C1, Cup, 2, 2) or dW.stride(2) != 2 * dW.stride(3):
+                dW = torch.empty((C1, Cup, 2, 2), dtype=torch.float32, device=g.device)
+            s_ci, s_co, _, s_q = dW.stride()
+        if need[0]:
+            gx1 = ops.empty_nhwc(B, C1, h, w, cd, g.device)
+            dd = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, Cup, ops.TAPS_Q, 2, off, H, W, ld,
+                                C1, 1, 1, (0, 0), h, w, ops.nhwc_ld(gx1))
+            ops.gconv_fprop(dd, gup, packT_dgrad(wT, cd), None, gx1, None, kind="convT_dgrad")
+        if need[2]:
+            # after the dgrad, on the side stream (see conv_bn_relu_bwd)
+            run = lambda: ops.gconv_wgrad(d, x1, gup, dW, 0, s_ci, s_co, sq=s_q)  # noqa: E731
+            pT = getattr(ctx, "param_obj", wT)
+            if getattr(pT, "grad", None) is None and dW.stride() == pT.stride() and pT.dtype == torch.float32:
+                ops.on_side_stream(run, x1, g)
+            else:
+                run()
         if need[3]:
             region = gup if not padded else ops.to_nhwc(
                 gup[:, :, off[0]:off[0] + 2 * h, off[1]:off[1] + 2 * w].contiguous(memory_format=torch.channels_last), cd)
             dB = ops.channel_sum(region)
-        if need[0]:
-            gx1 = ops.empty_nhwc(B, C1, h, w, cd, g.device)
-            d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, Cup, ops.TAPS_Q, 2, off, H, W, ld,
-                               C1, 1, 1, (0, 0), h, w, ops.nhwc_ld(gx1))
-            ops.gconv_fprop(d, gup, packT_dgrad(wT, cd), None, gx1, None, kind="convT_dgrad")
         return gx1, g2, dW, dB, None
 
 

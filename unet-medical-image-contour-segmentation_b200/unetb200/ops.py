@@ -72,6 +72,64 @@ def _run(name, fn, *args, kernels=1, flops=0.0, nbytes=0.0):
     _lib.check(rc, name)
 
 
+# ------------------------------------------------------------------------------------------------
+# side stream for weight gradients
+# ------------------------------------------------------------------------------------------------
+# A weight gradient is needed only by the optimizer, while the BatchNorm backward of the previous layer (HBM bound,
+# few registers, no shared memory) needs the data gradient and is what autograd runs next.  Issuing the wgrad GEMM
+# on a second stream -- ordered after the dgrad of the same layer -- lets the memory-bound kernels of the next
+# layer run on the SM resources the tensor kernel leaves idle.  The streams are joined by an autograd-engine
+# callback at the end of the backward pass (so callers such as the reference train.py need no change), and the
+# operands are kept alive until then.  UNETB200_WGRAD_STREAM=0 turns this off.
+import os as _os
+
+_SIDE = {}            # device index -> torch.cuda.Stream
+_SIDE_KEEP = []       # tensors the side stream still reads
+_SIDE_PENDING = [False]
+_SIDE_ON = _os.environ.get("UNETB200_WGRAD_STREAM", "1") != "0"
+
+
+def _side_join():
+    _SIDE_PENDING[0] = False
+    for s in _SIDE.values():
+        torch.cuda.current_stream(s.device).wait_stream(s)
+    _SIDE_KEEP.clear()
+
+
+def side_stream_sync():
+    """Order the current stream after the side stream (for code that reads weight gradients DURING backward)."""
+    for s in _SIDE.values():
+        torch.cuda.current_stream(s.device).wait_stream(s)
+
+
+def side_enabled():
+    return _SIDE_ON and _PROFILE is None
+
+
+def on_side_stream(fn, *keep, join=True):
+    """Run fn() on the side stream, ordered after everything enqueued so far on the current stream.  join=True
+    queues the end-of-backward join; join=False leaves ordering to events recorded by fn (see functional.prepack)."""
+    if not _SIDE_ON or _PROFILE is not None:
+        return fn()
+    dev = torch.cuda.current_device()
+    side = _SIDE.get(dev)
+    if side is None:
+        side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    _SIDE_KEEP.extend(keep)
+    with torch.cuda.stream(side):
+        side.wait_event(ev)
+        out = fn()
+    if join and not _SIDE_PENDING[0]:
+        _SIDE_PENDING[0] = True
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(_side_join)
+        except RuntimeError:          # not inside a backward pass: join right away
+            _side_join()
+    return out
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
