@@ -109,7 +109,57 @@ def infer_gate(nc, ncls, bilinear, B, H, W, mode):
     return res
 
 
+def graph_gate():
+    """The whole-step CUDA graph and the side-stream weight gradients change scheduling, not arithmetic: three
+    optimizer steps replayed from a graph must follow the eager, single-stream trajectory."""
+    import unet
+    from unetb200 import losses as UL
+    from unetb200 import ops
+    from unetb200.graph import GraphedStep
+    st = O.build_state(1, 2, False, seed=0)
+    img, msk = O.synthetic_batch(2, 1, 2, 64, 64)
+    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    t = msk.to(DEV)
+
+    def make():
+        m = unet.UNet(1, 2, False)
+        m.load_state_dict(st)
+        m = m.to(DEV).to(memory_format=torch.channels_last).train()
+        o = torch.optim.RMSprop(m.parameters(), lr=1e-4, momentum=0.9, foreach=True, capturable=True)
+
+        def step(xx, tt):
+            o.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", enabled=True):
+                loss = UL.training_criterion(m(xx), tt, boundary_coeff=0.2)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            o.step()
+            return loss
+        return m, step
+
+    # eager, everything on one stream
+    side_was = ops._SIDE_ON
+    ops._SIDE_ON = False
+    m1, step1 = make()
+    l1 = [float(step1(x, t).detach()) for _ in range(5)]
+    ops._SIDE_ON = side_was
+    # graph (2 eager warm-up steps + 1 captured... the capture itself does not execute), then replays
+    m2, step2 = make()
+    g = GraphedStep(step2, (x, t), warmup=2)
+    l2 = [float(g.replay().detach()) for _ in range(3)]
+    torch.cuda.synchronize()
+    res = [("graph_loss_step3", abs(l2[0] - l1[2]) / abs(l1[2]), 5e-3),
+           ("graph_loss_step5", abs(l2[2] - l1[4]) / abs(l1[4]), 1e-2)]
+    w1 = {k: host(v) for k, v in m1.state_dict().items() if v.dtype.is_floating_point}
+    w2 = {k: host(v) for k, v in m2.state_dict().items() if v.dtype.is_floating_point}
+    worst = max(O.rel_l2(w2[k], w1[k]) for k in w1 if "running" not in k)
+    res.append(("graph_weights_after_5_steps_rel_l2", worst, 2e-2))
+    res.append(("graph_losses_finite", 0.0 if all(v == v and abs(v) < 1e3 for v in l1 + l2) else 1.0, 0.0))
+    return res
+
+
 GROUPS = {
+    "graph_side_stream": lambda gd: graph_gate(),
     "unet_infer": lambda gd: infer_gate(3, 4, False, 2, 128, 160, "fp32") + infer_gate(3, 4, False, 2, 128, 160, "bf16")
                   + infer_gate(1, 2, True, 1, 96, 96, "tf32"),
     "unet_fp32": lambda gd: gate(1, 2, False, 2, 64, 64, "fp32") + gate(1, 2, True, 2, 64, 64, "fp32", fused=False),
