@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--per-layer", action="store_true", help="add a per-layer conv table (`layers`) to the JSON line")
+    ap.add_argument("--torch-optim", action="store_true",
+                    help="torch.optim.RMSprop + clip_grad_norm_ instead of the fused multi-tensor kernels (A/B)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the whole step as one CUDA graph (auto: try, fall back to eager launches)")
     return ap.parse_args()
@@ -193,8 +195,19 @@ def run_ours(args):
     if world > 1:
         ddp.broadcast_module_state(model)
     reducer = ddp.GradAllReducer(model) if world > 1 else None
-    opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True,
-                              capturable=(args.graph != "off"))
+    if args.torch_optim:
+        opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True,
+                                  capturable=(args.graph != "off"))
+
+        def clip_and_step():
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+    else:
+        from unetb200.optim import FusedRMSprop      # same arithmetic (tests: optim group), two launches
+        opt = FusedRMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999)
+
+        def clip_and_step():
+            opt.step(clip_max_norm=1.0)
 
     gi = torch.Generator().manual_seed(1 + 1000 * rank)
     gm = torch.Generator().manual_seed(2 + 1000 * rank)
@@ -211,8 +224,7 @@ def run_ours(args):
         loss.backward()
         if reducer is not None:
             reducer.finish()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
+        clip_and_step()
         return loss
 
     copy_stream = torch.cuda.Stream(device=dev)
@@ -294,8 +306,7 @@ def run_ours(args):
                     return loss
 
                 def part_b():
-                    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-                    opt.step()
+                    clip_and_step()
                     return None
 
                 graphed = GraphedStep(part_a, (img_d, msk_d), warmup=2)

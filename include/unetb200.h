@@ -235,6 +235,21 @@ int unetb200_boundary_loss(const void* pred, int pred_dtype, int64_t sb, int64_t
                            void* work, float* out, void* stream);
 int64_t unetb200_boundary_work_bytes(void);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer side of the step -- train.py:80-84 (RMSprop with momentum), :157 (clip_grad_norm_), :158.
+ * Multi-tensor: `w`, `g`, `sq`, `mom` are HOST arrays of `ntensors` DEVICE pointers (fp32, contiguous storage of
+ * `numel[i]` elements each; any dense layout, all four of a tensor in the same element order).
+ * ------------------------------------------------------------------------------------------- */
+/* *out (device double) = sum_i sum(g_i^2): the squared total 2-norm clip_grad_norm_ computes. */
+int unetb200_grad_sqnorm(float* const* grads, const int64_t* numel, int ntensors, double* out, void* stream);
+/* torch.optim.RMSprop (centered=False) update of every tensor in one pass.  sumsq != NULL: gradients are first
+ * scaled by min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (clip_grad_norm_), and written back when
+ * write_clipped_grad != 0.  mom == NULL iff momentum == 0. */
+int unetb200_rmsprop_step(float* const* w, float* const* g, float* const* sq, float* const* mom,
+                          const int64_t* numel, int ntensors, const double* sumsq, float max_norm, float lr,
+                          float alpha, float eps, float weight_decay, float momentum, int write_clipped_grad,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -683,6 +683,51 @@ def calibrate(nc, ncls, bilinear, B, H, W, mode):
     return res
 
 
+def check_optim():
+    """FusedRMSprop (+ folded clip_grad_norm_) against torch.optim.RMSprop + torch.nn.utils.clip_grad_norm_."""
+    from unetb200.optim import FusedRMSprop
+    out = []
+    g = gen(90)
+    shapes = [(64, 1, 3, 3), (128, 64, 3, 3), (64,), (7,), (2, 64, 1, 1), (256, 128, 2, 2), (3, 5, 3, 3), (1024, 17)]
+    for mom, wd, clip in ((0.999, 1e-8, 1.0), (0.0, 0.0, None), (0.9, 1e-2, 0.05)):
+        ps_a, ps_b = [], []
+        for i, sh in enumerate(shapes):
+            w = torch.randn(sh, generator=g)
+            if len(sh) == 4 and i % 2 == 1:
+                w = w.contiguous(memory_format=torch.channels_last)
+            ps_a.append(torch.nn.Parameter(w.clone().to(DEV)))
+            ps_b.append(torch.nn.Parameter(w.clone().to(DEV)))
+            if len(sh) == 4 and i % 2 == 1:
+                ps_a[-1].data = ps_a[-1].data.contiguous(memory_format=torch.channels_last)
+                ps_b[-1].data = ps_b[-1].data.contiguous(memory_format=torch.channels_last)
+        oa = torch.optim.RMSprop(ps_a, lr=1e-3, alpha=0.99, eps=1e-8, weight_decay=wd, momentum=mom, foreach=True)
+        ob = FusedRMSprop(ps_b, lr=1e-3, alpha=0.99, eps=1e-8, weight_decay=wd, momentum=mom)
+        norms = []
+        for it in range(3):
+            for pa, pb in zip(ps_a, ps_b):
+                gr = torch.randn(pa.shape, generator=g).to(DEV) * (10.0 if it == 1 else 0.1)
+                pa.grad = torch.empty_like(pa).copy_(gr)
+                pb.grad = torch.empty_like(pb).copy_(gr)
+            if clip is not None:
+                na = torch.nn.utils.clip_grad_norm_(ps_a, clip)
+                oa.step()
+                nb = ob.step(clip_max_norm=clip)
+                norms.append(abs(float(na) - float(nb)) / float(na))
+            else:
+                oa.step()
+                ob.step()
+        tag = f"mom{mom}_wd{wd}_clip{clip}"
+        out.append((f"rmsprop_w_{tag}", max(rel(host(b), host(a)) for a, b in zip(ps_a, ps_b)), 1e-5))
+        out.append((f"rmsprop_sq_{tag}", max(rel(host(ob.state[b]["square_avg"]), host(oa.state[a]["square_avg"]))
+                                             for a, b in zip(ps_a, ps_b)), 1e-5))
+        if mom > 0:
+            out.append((f"rmsprop_buf_{tag}", max(rel(host(ob.state[b]["momentum_buffer"]), host(oa.state[a]["momentum_buffer"]))
+                                                  for a, b in zip(ps_a, ps_b)), 1e-5))
+        if norms:
+            out.append((f"clip_total_norm_{tag}", max(norms), 1e-6))
+    return out
+
+
 GROUPS = {
     "layout": lambda gd: check_layout_ops(),
     "bn_fwd": lambda gd: check_bn_forward(),
@@ -698,6 +743,7 @@ GROUPS = {
     "conv_tc": lambda gd: check_conv_tc(),
     "conv_tc_tf32": lambda gd: check_conv_tc_tf32(),
     "conv_layouts": lambda gd: check_conv_layouts(),
+    "optim": lambda gd: check_optim(),
     "parts_fp32": lambda gd: check_parts(gd, "fp32"),
     "parts_bf16": lambda gd: check_parts(gd, "bf16"),
     "calib_small": lambda gd: sum((calibrate(1, 2, False, 2, 128, 128, m) for m in ("fp32", "tf32", "bf16")), []),

@@ -38,6 +38,10 @@ def test_losses(G, golden, group):
     _assert_all(G.all_groups()[group](golden))
 
 
+def test_fused_optimizer(G, golden):
+    _assert_all(G.all_groups()["optim"](golden))
+
+
 def test_outconv(G, golden):
     _assert_all(G.all_groups()["outconv"](golden))
 

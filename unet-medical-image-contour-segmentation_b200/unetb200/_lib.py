@@ -72,6 +72,9 @@ PROTOTYPES = {
     "unetb200_boundary_loss": (C.c_int, [c_p, C.c_int, c_i64, c_i64, c_i64, c_p, C.c_int, c_i64, c_i64, c_i64,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, c_p, c_p, c_p]),
     "unetb200_boundary_work_bytes": (c_i64, []),
+    "unetb200_grad_sqnorm": (C.c_int, [c_p, c_p, C.c_int, c_p, c_p]),
+    "unetb200_rmsprop_step": (C.c_int, [c_p, c_p, c_p, c_p, c_p, C.c_int, c_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_float, C.c_int, c_p]),
 }
 
 _lib = None
