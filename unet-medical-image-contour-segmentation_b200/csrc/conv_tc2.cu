@@ -220,7 +220,6 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_fprop_kernel(const __grid_
       const int ti = mt % p.tiles_h;
       const int b = mt / p.tiles_h;
       const int n0 = nb * BLOCK_N;
-      const int q = n0 / p.Cq, co0 = n0 - q * p.Cq;
       if (nb != cur_nb) { flush(cur_nb); cur_nb = nb; }
       const uint32_t acc = it % ACC;
       const int pi0 = ti * p.tile_h + p.sub_di[s] + 4 * quad;        // first image row of this warp's 4 x 8 patch
@@ -232,6 +231,9 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_fprop_kernel(const __grid_
       tc_fence_after();
 #pragma unroll
       for (int cb = 0; cb < NCB; ++cb) {                              // unrolled: st[cb] must stay in registers
+        // an n-block may span output quadrants (ConvTranspose: n = q * Cq + co): one quadrant per 128-byte block
+        const int n_cb = n0 + cb * EPR;
+        const int q = n_cb / p.Cq, co_cb = n_cb - q * p.Cq;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BLOCK_N + s * BLOCK_N + cb * EPR;
         uint32_t v[EPR];
 #pragma unroll
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_fprop_kernel(const __grid_
 #pragma unroll
           for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[h * 32 + e]);
           if (p.bias) {                                                 // one warp-uniform branch, not 32 predicated loads
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + co0 + cb * EPR + h * 32);
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + co_cb + h * 32);
 #pragma unroll
             for (int e4 = 0; e4 < 8; ++e4) {
               const float4 b4 = __ldg(bp + e4);
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kTc2Threads, 1) tc2_fprop_kernel(const __grid_
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&p.o_map[q], buf, co0 + cb * EPR, pj0, pi0, b);
+          tma_store_4d(&p.o_map[q], buf, co_cb, pj0, pi0, b);
           tma_store_commit();
         }
         if (p.stats_ws) {
@@ -411,7 +413,13 @@ static bool tc2_plan(const unetb200_gconv_t* d, Tc2Plan* pl) {
     for (int t = 0; t < d->ntaps; ++t)
       if (!used[t]) return false;
   }
-  pl->BN = (d->dtype == UNETB200_BF16 && Cq % 256 == 0) ? 256 : (Cq % 128 == 0 ? 128 : 64);
+  static const int max_bn = getenv("UNETB200_TC2_MAXBN") ? atoi(getenv("UNETB200_TC2_MAXBN")) : 256;   // A/B runs
+  // the N block may span quadrants (the epilogue resolves the quadrant per 128-byte channel block), so the block
+  // width follows N = nquad * Cq: a 64-channel ConvTranspose reads its input once (N = 256) instead of 4 times
+  const int epr_n = 128 / esz;
+  const int Nall = (Cq % epr_n == 0) ? d->N : Cq;
+  const bool wide = d->dtype == UNETB200_BF16 && max_bn >= 256 && (Cq % 256 == 0 || (Cq == 64 && Nall == 256));
+  pl->BN = wide ? 256 : (Cq % 128 == 0 ? 128 : (Nall % 128 == 0 && Cq == 64 && d->nquad == 4 ? 128 : 64));
   if (d->Wm > 8) { pl->tile_w = 16; pl->tile_h = 16; pl->box_w = 16; }
   else { pl->tile_w = 8; pl->tile_h = 32; pl->box_w = 8; }
   const int tiles_w = (d->Wm + pl->tile_w - 1) / pl->tile_w, tiles_h = (d->Hm + pl->tile_h - 1) / pl->tile_h;
