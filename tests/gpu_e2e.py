@@ -125,7 +125,9 @@ def graph_gate():
         m = unet.UNet(1, 2, False)
         m.load_state_dict(st)
         m = m.to(DEV).to(memory_format=torch.channels_last).train()
-        o = torch.optim.RMSprop(m.parameters(), lr=1e-4, momentum=0.9, foreach=True, capturable=True)
+        # plain SGD: RMSprop's first steps are sign-like (g / sqrt((1-alpha) g^2)), which turns rounding-level
+        # gradient noise into O(lr) weight differences and makes a trajectory comparison meaningless
+        o = torch.optim.SGD(m.parameters(), lr=1e-3, foreach=True)
 
         def step(xx, tt):
             o.zero_grad(set_to_none=True)
@@ -148,16 +150,32 @@ def graph_gate():
     g = GraphedStep(step2, (x, t), warmup=2)
     l2 = [float(g.replay().detach()) for _ in range(3)]
     torch.cuda.synchronize()
-    res = [("graph_loss_step3", abs(l2[0] - l1[2]) / abs(l1[2]), 5e-3),
-           ("graph_loss_step5", abs(l2[2] - l1[4]) / abs(l1[4]), 1e-2)]
+    # bf16 training from random init is chaotic (a ReLU-mask flip changes later steps), so the multi-step comparison
+    # only has to catch gross errors (a race gives NaN or errors >> 1); the tight check is the single-step one below
+    res = [("graph_loss_step3", abs(l2[0] - l1[2]) / abs(l1[2]), 2e-3),
+           ("graph_loss_step5", abs(l2[2] - l1[4]) / abs(l1[4]), 5e-3)]
     w1 = {k: host(v) for k, v in m1.state_dict().items() if v.dtype.is_floating_point}
     w2 = {k: host(v) for k, v in m2.state_dict().items() if v.dtype.is_floating_point}
     # (zero-initialised biases are pure accumulated gradient after 5 steps: a bf16 ReLU flip moves them by tens of
     # per cent in relative terms, so they are compared on the scale of the weights they sit next to)
     worst = max(O.rel_l2(w2[k], w1[k]) for k in w1 if "running" not in k and not k.endswith(".bias"))
     worst_b = max(float((w2[k] - w1[k]).abs().max()) for k in w1 if k.endswith(".bias"))
-    res.append(("graph_biases_after_5_steps_abs", worst_b, 2e-3))
-    res.append(("graph_weights_after_5_steps_rel_l2", worst, 2e-2))
+    res.append(("graph_biases_after_5_steps_abs", worst_b, 1e-3))
+    res.append(("graph_weights_after_5_steps_rel_l2", worst, 1e-2))
+    # one backward from identical weights: side-stream weight gradients == single-stream weight gradients
+    def grads_of(side):
+        ops._SIDE_ON = side
+        m = unet.UNet(1, 2, False)
+        m.load_state_dict(st)
+        m = m.to(DEV).to(memory_format=torch.channels_last).train()
+        with torch.autocast("cuda", enabled=True):
+            loss = UL.training_criterion(m(x), t, boundary_coeff=0.2)
+        loss.backward()
+        torch.cuda.synchronize()
+        return {k: host(p.grad) for k, p in m.named_parameters()}
+    ga, gb = grads_of(False), grads_of(True)
+    ops._SIDE_ON = side_was
+    res.append(("side_stream_grads_vs_single_stream_rel_l2", max(O.rel_l2(gb[k], ga[k]) for k in ga), 1e-3))
     res.append(("graph_losses_finite", 0.0 if all(v == v and abs(v) < 1e3 for v in l1 + l2) else 1.0, 0.0))
     return res
 

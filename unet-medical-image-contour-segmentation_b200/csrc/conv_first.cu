@@ -190,23 +190,20 @@ __global__ void __launch_bounds__(256, 2)
 first_conv_fprop_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ wp, T* __restrict__ y,
                               float* __restrict__ stats_ws, int tiles_w, int tiles_h, int ntiles) {
   __shared__ float halo[kFT_H + 2][kFT_LD];
-  __shared__ float sstat[2][64];
   const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  if (threadIdx.x < 128) (&sstat[0][0])[threadIdx.x] = 0.f;
   // weights by window position (row a = dy + 1, column c = dx + 1)
+  __shared__ int tmap[9];
+  if (threadIdx.x < 9) tmap[(d.tap_dy[threadIdx.x] + 1) * 3 + d.tap_dx[threadIdx.x] + 1] = threadIdx.x;
+  __syncthreads();
   float wr[3][3][8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int a = d.tap_dy[t] + 1, c = d.tap_dx[t] + 1;
+  for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int aa = 0; aa < 3; ++aa)
+    for (int c = 0; c < 3; ++c) {
+      const int t = tmap[a * 3 + c];
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc)
-        if (aa == a && cc == c) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) wr[aa][cc][i] = Elem<T>::ld(wp + (long long)(g * 8 + i) * 9 + t);
-        }
-  }
+      for (int i = 0; i < 8; ++i) wr[a][c][i] = Elem<T>::ld(wp + (long long)(g * 8 + i) * 9 + t);
+    }
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
@@ -252,31 +249,47 @@ first_conv_fprop_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __re
     }
   }
   if (stats_ws) {
+    // deterministic: per-warp partials in shared memory, summed in a fixed order (float atomics would make the
+    // BatchNorm statistics -- and through ReLU flips the whole step -- differ from run to run)
+    __shared__ float wstat[8][2][64];
+    const int warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       // the 4 pixel columns of a warp share a channel group: combine them first (lanes g, g+8, g+16, g+24)
       float a = s[i], c = q[i];
       a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
       c += __shfl_xor_sync(0xffffffffu, c, 8); c += __shfl_xor_sync(0xffffffffu, c, 16);
-      if ((threadIdx.x & 31) < 8) { atomicAdd(&sstat[0][g * 8 + i], a); atomicAdd(&sstat[1][g * 8 + i], c); }
+      if ((threadIdx.x & 31) < 8) { wstat[warp][0][g * 8 + i] = a; wstat[warp][1][g * 8 + i] = c; }
     }
     __syncthreads();
     if (threadIdx.x < 128) {
       const int which = threadIdx.x >> 6, c = threadIdx.x & 63;
-      stats_ws[((long long)blockIdx.x * 2 + which) * 64 + c] = sstat[which][c];
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += wstat[w][which][c];
+      stats_ws[((long long)blockIdx.x * 2 + which) * 64 + c] = v;
     }
   }
 }
 
 // dWp[t][n] partial per block: partials[block][9][64]
+// Software-pipelined: the halo of the NEXT tile and the dY rows of the next row pair are loaded (into registers)
+// before the FMAs of the current ones, so global-load latency hides behind the 72 FMAs per pixel.
+template <typename T>
+__device__ __forceinline__ float first_halo_elem(const GconvDev& d, const T* __restrict__ x, int b, int i0, int j0, int e) {
+  const int r = e / (kFT_W + 2), c = e - r * (kFT_W + 2);
+  const int gi = i0 - 1 + r, gj = j0 - 1 + c;
+  if (e < (kFT_H + 2) * (kFT_W + 2) && (unsigned)gi < (unsigned)d.Hin && (unsigned)gj < (unsigned)d.Win)
+    return Elem<T>::ld(x + ((long long)(b * d.Hin + gi) * d.Win + gj) * d.ld_in);
+  return 0.f;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 2)
 first_conv_wgrad_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ partials,
                               int tiles_w, int tiles_h, int ntiles) {
   __shared__ float halo[kFT_H + 2][kFT_LD];
-  __shared__ float red[9 * 64];
   const int g = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  for (int e = threadIdx.x; e < 9 * 64; e += 256) red[e] = 0.f;
   float acc[3][3][8];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
@@ -284,15 +297,65 @@ first_conv_wgrad_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __re
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[a][c][i] = 0.f;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto decode = [&](int tile, int& b, int& i0, int& j0) {
     const int tj = tile % tiles_w;
     const int rest = tile / tiles_w;
-    const int ti = rest % tiles_h, b = rest / tiles_h;
-    const int i0 = ti * kFT_H, j0 = tj * kFT_W;
-    __syncthreads();
-    first_load_halo<T>(d, x, halo, b, i0, j0);
-    __syncthreads();
+    b = rest / tiles_h;
+    i0 = (rest % tiles_h) * kFT_H;
+    j0 = tj * kFT_W;
+  };
+  // dY rows travel packed (16 bytes per pixel and channel group for bf16) and are unpacked at use; the four rows of
+  // the NEXT half tile are requested before the FMAs of the current half (prefetch distance ~4 x 72 FMAs)
+  struct Row { uint4 a, b; };
+  auto load_half = [&](int tile, int half, Row* dst) {
+    int b, i0, j0;
+    decode(tile, b, i0, j0);
     const int j = j0 + pl;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int i = i0 + half * 4 + rr;
+      dst[rr].a = make_uint4(0u, 0u, 0u, 0u);
+      dst[rr].b = make_uint4(0u, 0u, 0u, 0u);
+      if (tile < ntiles && i < d.Hm && j < d.Wm) {
+        const T* src = gy + ((long long)(b * d.Hm + i) * d.Wm + j) * d.ld_out + g * 8;
+        dst[rr].a = *reinterpret_cast<const uint4*>(src);
+        if constexpr (sizeof(T) == 4) dst[rr].b = *reinterpret_cast<const uint4*>(src + 4);
+      }
+    }
+  };
+  auto unpack = [&](const Row& r, float v[8]) {
+    if constexpr (sizeof(T) == 4) {
+      v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+      v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+    } else {
+      const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+  };
+  int tile = blockIdx.x;
+  float h0 = 0.f, h1 = 0.f;                       // this thread's two halo elements of the tile about to be staged
+  Row cur[4], nxt[4];
+  if (tile < ntiles) {
+    int b, i0, j0;
+    decode(tile, b, i0, j0);
+    h0 = first_halo_elem<T>(d, x, b, i0, j0, threadIdx.x);
+    h1 = first_halo_elem<T>(d, x, b, i0, j0, threadIdx.x + 256);
+  }
+  load_half(tile, 0, cur);
+  for (; tile < ntiles; tile += gridDim.x) {
+    __syncthreads();                              // everyone is done with the previous halo
+    (&halo[0][0])[(threadIdx.x / (kFT_W + 2)) * kFT_LD + threadIdx.x % (kFT_W + 2)] = h0;
+    if (threadIdx.x + 256 < (kFT_H + 2) * (kFT_W + 2))
+      (&halo[0][0])[((threadIdx.x + 256) / (kFT_W + 2)) * kFT_LD + (threadIdx.x + 256) % (kFT_W + 2)] = h1;
+    __syncthreads();
+    const int nxt_tile = tile + gridDim.x;
+    if (nxt_tile < ntiles) {                      // prefetch the next tile's halo
+      int nb, ni0, nj0;
+      decode(nxt_tile, nb, ni0, nj0);
+      h0 = first_halo_elem<T>(d, x, nb, ni0, nj0, threadIdx.x);
+      h1 = first_halo_elem<T>(d, x, nb, ni0, nj0, threadIdx.x + 256);
+    }
     float win[3][3];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
@@ -300,21 +363,12 @@ first_conv_wgrad_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __re
       for (int c = 0; c < 3; ++c) win[a][c] = halo[a][pl + c];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      // four 16-byte loads of dY in flight, then the FMAs
-      float gv[4][8];
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int i = i0 + half * 4 + rr;
-        if (i < d.Hm && j < d.Wm) {
-          load8(gy + ((long long)(b * d.Hm + i) * d.Wm + j) * d.ld_out + g * 8, gv[rr]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) gv[rr][k] = 0.f;
-        }
-      }
+      if (half == 0) load_half(tile, 1, nxt); else load_half(nxt_tile, 0, nxt);
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         const int r = half * 4 + rr;
+        float gv[8];
+        unpack(cur[rr], gv);
 #pragma unroll
         for (int c = 0; c < 3; ++c) win[2][c] = halo[r + 2][pl + c];
 #pragma unroll
@@ -322,34 +376,42 @@ first_conv_wgrad_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __re
 #pragma unroll
           for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[a][c][k] = fmaf(win[a][c], gv[rr][k], acc[a][c][k]);
+            for (int k = 0; k < 8; ++k) acc[a][c][k] = fmaf(win[a][c], gv[k], acc[a][c][k]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) { win[0][c] = win[1][c]; win[1][c] = win[2][c]; }
       }
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) cur[rr] = nxt[rr];
     }
   }
   __syncthreads();
-  // window position (a, c) -> tap index t
+  // window position (a, c) -> tap index t (a 9-entry table in shared memory), then per-warp partials without atomics
+  __shared__ int tmap[9];
+  __shared__ float wred[8][9 * 64];
+  if (threadIdx.x < 9) tmap[(d.tap_dy[threadIdx.x] + 1) * 3 + d.tap_dx[threadIdx.x] + 1] = threadIdx.x;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const int ta = d.tap_dy[t] + 1, tc = d.tap_dx[t] + 1;
+  for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) {
+      const int t = tmap[a * 3 + c];
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        if (a == ta && c == tc) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            float v = acc[a][c][k];
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if ((threadIdx.x & 31) < 8) atomicAdd(&red[t * 64 + g * 8 + k], v);
-          }
-        }
-  }
+      for (int k = 0; k < 8; ++k) {
+        float v = acc[a][c][k];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);      // the 4 pixel columns of a warp share the channel group
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if ((threadIdx.x & 31) < 8) wred[warp][t * 64 + g * 8 + k] = v;
+      }
+    }
   __syncthreads();
   float* out = partials + (long long)blockIdx.x * 9 * 64;
-  for (int e = threadIdx.x; e < 9 * 64; e += 256) out[e] = red[e];
+  for (int e = threadIdx.x; e < 9 * 64; e += 256) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += wred[w][e];
+    out[e] = v;
+  }
 }
 
 static bool first_tiled_ok(const unetb200_gconv_t* d) {

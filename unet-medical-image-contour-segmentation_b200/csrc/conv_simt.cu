@@ -91,7 +91,7 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
   __shared__ __align__(16) float As[FBK][FBM + 4];
   __shared__ __align__(16) float Bs[FBK][FBN + 4];
   __shared__ int pb[FBM], pi[FBM], pj[FBM];
-  __shared__ float sstat[2][FBN];
+  __shared__ float wstat[8][2][FBN];      // per-warp BatchNorm partials (256 threads = 8 warps)
   const int tid = threadIdx.x;
   const long long m0 = (long long)blockIdx.x * FBM;
   const int n0 = blockIdx.y * FBN;
@@ -101,7 +101,6 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
     if (m < d.M) decode_m(d, m, b, i, j);
     pb[t] = b; pi[t] = i; pj[t] = j;
   }
-  if (tid < FBN) { sstat[0][tid] = 0.f; sstat[1][tid] = 0.f; }
   __syncthreads();
   const int tx = tid & 15, ty = tid >> 4;
   float acc[8][4];
@@ -209,13 +208,17 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
       // the two ty rows of a warp first, then shared-memory atomics across the 8 warps
       float a = s1[c] + __shfl_xor_sync(0xffffffffu, s1[c], 16);
       float b = s2[c] + __shfl_xor_sync(0xffffffffu, s2[c], 16);
-      if ((tid & 16) == 0) { atomicAdd(&sstat[0][tx * 4 + c], a); atomicAdd(&sstat[1][tx * 4 + c], b); }
+      // per-warp partials, summed in a fixed order below (float atomics would make the statistics run-dependent)
+      if ((tid & 16) == 0) { wstat[tid >> 5][0][tx * 4 + c] = a; wstat[tid >> 5][1][tx * 4 + c] = b; }
     }
     __syncthreads();
     // per-tile partials [tile][2][N]: plain stores, reduced by stats_reduce_kernel (no global atomics)
     if (tid < 2 * FBN) {
       const int which = tid / FBN, c = tid % FBN;
-      if (n0 + c < d.N) stats_ws[((long long)blockIdx.x * 2 + which) * d.N + n0 + c] = sstat[which][c];
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += wstat[w][which][c];
+      if (n0 + c < d.N) stats_ws[((long long)blockIdx.x * 2 + which) * d.N + n0 + c] = v;
     }
   }
 }

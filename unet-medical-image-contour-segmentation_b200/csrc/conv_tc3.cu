@@ -525,33 +525,32 @@ static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
   return 0;
 }
 
-__global__ void tc3_stats_reduce_kernel(const float* __restrict__ ws, int rows, int BN, int N, double* __restrict__ stats) {
-  __shared__ double red[8][33];
+__global__ void __launch_bounds__(1024) tc3_stats_reduce_kernel(const float* __restrict__ ws, int rows, int BN, int N, double* __restrict__ stats) {
+  // one block per (32 columns, n-block): 32 row lanes x 32 columns, fixed assignment of rows to lanes and a fixed
+  // order of the final sum -> bit-reproducible statistics (no atomics between blocks; `stats` is += by this block only)
+  __shared__ double red[32][33];
   const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int nb = blockIdx.y;
   const int col = blockIdx.x * 32 + lane;              // 0 .. 2*BN
   double acc = 0.0;
-  // blockIdx.z takes a contiguous slice of the rows; 4 loads in flight per thread
-  const int per = (rows + gridDim.z - 1) / gridDim.z;
-  const int r0 = blockIdx.z * per, r1 = min(rows, r0 + per);
   if (col < 2 * BN) {
     const float* base = ws + (long long)nb * rows * 2 * BN + col;
-    int r = r0 + ry;
-    for (; r + 24 < r1; r += 32) {
-      const float a = base[(long long)r * 2 * BN], b = base[(long long)(r + 8) * 2 * BN],
-                  c = base[(long long)(r + 16) * 2 * BN], d = base[(long long)(r + 24) * 2 * BN];
-      acc += (double)a + (double)b + (double)c + (double)d;
+    int r = ry;
+    for (; r + 96 < rows; r += 128) {
+      const float a = base[(long long)r * 2 * BN], b = base[(long long)(r + 32) * 2 * BN],
+                  c = base[(long long)(r + 64) * 2 * BN], d = base[(long long)(r + 96) * 2 * BN];
+      acc += (double)a; acc += (double)b; acc += (double)c; acc += (double)d;
     }
-    for (; r < r1; r += 8) acc += (double)base[(long long)r * 2 * BN];
+    for (; r < rows; r += 32) acc += (double)base[(long long)r * 2 * BN];
   }
   red[ry][lane] = acc;
   __syncthreads();
   if (ry == 0 && col < 2 * BN) {
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][lane];
+    for (int i = 0; i < 32; ++i) s += red[i][lane];
     const int which = col / BN, c = col - which * BN;
-    atomicAdd(stats + which * N + nb * BN + c, s);
+    stats[which * N + nb * BN + c] += s;
   }
 }
 
@@ -612,7 +611,7 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   if (rc) return rc;
   if (stats) {
     const int rows = pl.grid * kEpi3Warps;
-    tc3_stats_reduce_kernel<<<dim3((2 * pl.BN + 31) / 32, pl.n_blocks, 16), 256, 0, stream>>>(stats_ws, rows, pl.BN, d->N, stats);
+    tc3_stats_reduce_kernel<<<dim3((2 * pl.BN + 31) / 32, pl.n_blocks), 1024, 0, stream>>>(stats_ws, rows, pl.BN, d->N, stats);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "tc3_stats_reduce");
   }
