@@ -355,6 +355,9 @@ bn_relu_bwd_reduce_kernel(const T* __restrict__ gz, int64_t ld_gz, const T* __re
   const int lanes = t.lanes, lane = t.lane;
   const int row = CVB * V;
   const int chunk = RED / row;   // >= 1 by construction (row <= RED)
+  // (row <= RED = 2 * blockDim: a thread owns at most two columns; it carries their sums over the chunks and
+  // issues ONE pair of fp64 atomics per column per block)
+  float fa[2] = {0.f, 0.f}, fb[2] = {0.f, 0.f};
   for (int base = 0; base < lanes; base += chunk) {
     __syncthreads();
     if (t.active && lane >= base && lane < base + chunk) {
@@ -366,14 +369,20 @@ bn_relu_bwd_reduce_kernel(const T* __restrict__ gz, int64_t ld_gz, const T* __re
     }
     __syncthreads();
     const int nl = lanes - base < chunk ? lanes - base : chunk;
-    for (int e = threadIdx.x; e < row; e += blockDim.x) {
-      int ch = blockIdx.y * CVB * V + e;
-      if (ch < C) {
-        float a = 0.f, b = 0.f;
-        for (int l = 0; l < nl; ++l) { a += red[0][l * row + e]; b += red[1][l * row + e]; }
-        atomicAdd(sums + ch, (double)a);
-        atomicAdd(sums + C + ch, (double)b);
-      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = threadIdx.x + u * blockDim.x;
+      if (e < row)
+        for (int l = 0; l < nl; ++l) { fa[u] += red[0][l * row + e]; fb[u] += red[1][l * row + e]; }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int e = threadIdx.x + u * blockDim.x;
+    const int ch = blockIdx.y * CVB * V + e;
+    if (e < row && ch < C) {
+      atomicAdd(sums + ch, (double)fa[u]);
+      atomicAdd(sums + C + ch, (double)fb[u]);
     }
   }
 }
