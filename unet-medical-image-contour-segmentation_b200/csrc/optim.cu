@@ -83,21 +83,51 @@ __global__ void __launch_bounds__(256) rmsprop_step_kernel(const __grid_constant
   float* sq = t.sq[ti];
   float* mom = t.mom[ti];
   const float one_m_alpha = 1.f - alpha;
-  for (long long i = begin + threadIdx.x; i < end; i += 256) {
-    float gi = g[i] * coef;
-    if (write_clipped_grad) g[i] = gi;
-    const float wi = w[i];
+  auto update = [&](float gi, float wi, float si, float mi, float& w_out, float& s_out, float& m_out, float& g_out) {
+    gi *= coef;
+    g_out = gi;
     if (weight_decay != 0.f) gi = fmaf(weight_decay, wi, gi);
-    const float s = fmaf(one_m_alpha * gi, gi, sq[i] * alpha);   // square_avg.mul_(alpha).addcmul_(g, g, value=1-alpha)
-    sq[i] = s;
+    const float s = fmaf(one_m_alpha * gi, gi, si * alpha);       // square_avg.mul_(alpha).addcmul_(g, g, value=1-alpha)
+    s_out = s;
     const float avg = sqrtf(s) + eps;
     if (mom) {
-      const float b = fmaf(momentum, mom[i], gi / avg);          // buf.mul_(momentum).addcdiv_(g, avg)
-      mom[i] = b;
-      w[i] = fmaf(-lr, b, wi);
+      const float b = fmaf(momentum, mi, gi / avg);               // buf.mul_(momentum).addcdiv_(g, avg)
+      m_out = b;
+      w_out = fmaf(-lr, b, wi);
     } else {
-      w[i] = fmaf(-lr, gi / avg, wi);
+      m_out = 0.f;
+      w_out = fmaf(-lr, gi / avg, wi);
     }
+  };
+  const bool vec = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(sq) |
+                     reinterpret_cast<uintptr_t>(mom)) & 15) == 0;
+  long long i0 = begin;
+  if (vec) {
+    const long long nvec = (end - begin) >> 2;
+    for (long long v = threadIdx.x; v < nvec; v += 256) {
+      const long long i = begin + 4 * v;
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i), w4 = *reinterpret_cast<const float4*>(w + i),
+                   s4 = *reinterpret_cast<const float4*>(sq + i);
+      const float4 m4 = mom ? *reinterpret_cast<const float4*>(mom + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 wo, so, mo, go;
+      update(g4.x, w4.x, s4.x, m4.x, wo.x, so.x, mo.x, go.x);
+      update(g4.y, w4.y, s4.y, m4.y, wo.y, so.y, mo.y, go.y);
+      update(g4.z, w4.z, s4.z, m4.z, wo.z, so.z, mo.z, go.z);
+      update(g4.w, w4.w, s4.w, m4.w, wo.w, so.w, mo.w, go.w);
+      *reinterpret_cast<float4*>(w + i) = wo;
+      *reinterpret_cast<float4*>(sq + i) = so;
+      if (mom) *reinterpret_cast<float4*>(mom + i) = mo;
+      if (write_clipped_grad) *reinterpret_cast<float4*>(g + i) = go;
+    }
+    i0 = begin + 4 * nvec;
+  }
+  for (long long i = i0 + threadIdx.x; i < end; i += 256) {
+    float wo, so, mo, go;
+    update(g[i], w[i], sq[i], mom ? mom[i] : 0.f, wo, so, mo, go);
+    w[i] = wo;
+    sq[i] = so;
+    if (mom) mom[i] = mo;
+    if (write_clipped_grad) g[i] = go;
   }
 }
 
