@@ -16,7 +16,8 @@ S = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = unet.UNet(1, 2, False).to(dev).to(memory_format=torch.channels_last).train()
-opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True)
+from unetb200.optim import FusedRMSprop  # noqa: E402
+opt = FusedRMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999)
 x = torch.rand(B, 1, S, S, device=dev).contiguous(memory_format=torch.channels_last)
 t = torch.randint(0, 2, (B, S, S), device=dev)
 
@@ -26,8 +27,7 @@ def step():
     with torch.autocast("cuda", enabled=True):
         loss = UL.training_criterion(model(x), t, boundary_coeff=0.2, edge_width=51, edge_weight=7)
     loss.backward()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-    opt.step()
+    opt.step(clip_max_norm=1.0)
     return loss
 
 
