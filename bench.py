@@ -275,8 +275,11 @@ def run_ours(args):
             ms = t.item()
         return ms
 
+    first_loss = None
     for _ in range(args.warmup):
-        step(img_d, msk_d)
+        lw = step(img_d, msk_d)
+        if first_loss is None:
+            first_loss = float(lw.detach())
     sync_all()
     # ---- whole-step CUDA graph (falls back to eager launches if capture is not possible) -------
     eager_step = step
@@ -318,6 +321,9 @@ def run_ours(args):
             if args.graph == "on":
                 raise
             graphed, graph_note = None, f"capture failed, eager launches: {type(exc).__name__}: {exc}"[:200]
+            graphed_b = None
+            if reducer is not None:
+                reducer.manual = False
             torch.cuda.synchronize()
         if world > 1:                                     # every rank must take the same path
             flag = torch.tensor([1 if graphed is not None else 0], device=dev)
@@ -369,7 +375,10 @@ def run_ours(args):
         "gpu_launches": launches,
         "cuda_graph": graph_note,
         "clocks": clocks,
-        "final_loss": last_loss,
+        "first_loss": first_loss, "final_loss": last_loss,
+        # the step really trains: same synthetic batch every step, so the loss must not blow up (a scheduling bug
+        # that feeds the optimizer stale gradients shows here)
+        "loss_sane": bool(first_loss is not None and last_loss == last_loss and last_loss < 1.2 * first_loss),
     }
     if gf_img:
         conv_tf = gf_img * 1e9 * value / world / 1e12

@@ -58,7 +58,29 @@ def _worker(rank, world, port, out):
             red.finish()
             for p, e in zip(model.parameters(), expect):
                 ok_steps &= torch.allclose(p.grad, e, rtol=1e-5, atol=1e-6)
-        out[rank] = (same_weights, nb, bool(ok_steps), red.launched)
+        launched_hooks = red.launched
+        # explicit three-phase form (the CUDA-graph step): channels_last parameters, gradients keep their layout,
+        # and p.grad stays a live view of the bucket (a later pack_all + allreduce_all must show through it)
+        model = model.to(memory_format=torch.channels_last)
+        red.remove()
+        red2 = ddp.GradAllReducer(model, bucket_bytes=256)
+        red2.manual = True
+        ok_manual = True
+        for it in range(2):
+            model.zero_grad(set_to_none=True)
+            model(x).square().sum().backward()
+            red2.pack_all()
+            red2.allreduce_all()
+            if it == 0:
+                red2.point_grads()
+                views = [p.grad for p in model.parameters()]
+            else:                                           # second round: read through the views taken in round one
+                for p, v in zip(model.parameters(), views):
+                    p.grad = v
+            for p, e in zip(model.parameters(), expect):
+                ok_manual &= torch.allclose(p.grad, e, rtol=1e-5, atol=1e-6)
+                ok_manual &= p.grad.stride() == p.stride()
+        out[rank] = (same_weights, nb, bool(ok_steps) and bool(ok_manual), launched_hooks)
     finally:
         dist.destroy_process_group()
 

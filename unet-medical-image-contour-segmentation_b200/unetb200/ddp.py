@@ -83,7 +83,18 @@ class GradAllReducer:
                                  pending=len(params), work=None))
 
     def _views(self, b):
-        return [b["buffer"][o:o + p.numel()].view_as(p) for p, o in zip(b["params"], b["offsets"])]
+        """Bucket slices shaped AND strided like their parameters (a channels_last parameter gets a channels_last
+        gradient view), so that optimizers and AccumulateGrad see the layout they expect and nothing re-copies."""
+        out = []
+        for p, o in zip(b["params"], b["offsets"]):
+            flat = b["buffer"][o:o + p.numel()]
+            dense = sorted((st, sz) for sz, st in zip(p.shape, p.stride()) if sz > 1)
+            expect, ok = 1, True
+            for st, sz in dense:
+                ok = ok and st == expect
+                expect *= sz
+            out.append(flat.as_strided(p.shape, p.stride()) if ok and p.dim() > 0 else flat.view_as(p))
+        return out
 
     # ---- explicit three-phase form (used when the step is replayed as CUDA graphs: the collective stays outside
     # the captured regions) -- pack_all() inside the backward graph, allreduce_all() eagerly, then point_grads()

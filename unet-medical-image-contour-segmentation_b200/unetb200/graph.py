@@ -27,7 +27,9 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads of the process (NCCL's watchdog polls CUDA events) must not invalidate the
+        # capture -- with 8 ranks per box the default "global" mode failed with cudaErrorStreamCaptureInvalidated
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.static_loss = step_fn(*self.static_inputs)
         torch.cuda.synchronize()
 

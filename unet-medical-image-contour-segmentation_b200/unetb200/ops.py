@@ -89,17 +89,28 @@ _SIDE_PENDING = [False]
 _SIDE_ON = _os.environ.get("UNETB200_WGRAD_STREAM", "1") != "0"
 
 
+def _wait_side(s):
+    """current stream waits for side stream `s` -- unless a CUDA-graph capture is in progress that `s` is not part
+    of (a captured stream may not wait on work outside its capture; there is then nothing pending on `s` either)."""
+    cur = torch.cuda.current_stream(s.device)
+    if torch.cuda.is_current_stream_capturing():
+        with torch.cuda.stream(s):
+            if not torch.cuda.is_current_stream_capturing():
+                return
+    cur.wait_stream(s)
+
+
 def _side_join():
     _SIDE_PENDING[0] = False
     for s in _SIDE.values():
-        torch.cuda.current_stream(s.device).wait_stream(s)
+        _wait_side(s)
     _SIDE_KEEP.clear()
 
 
 def side_stream_sync():
     """Order the current stream after the side stream (for code that reads weight gradients DURING backward)."""
     for s in _SIDE.values():
-        torch.cuda.current_stream(s.device).wait_stream(s)
+        _wait_side(s)
 
 
 def side_enabled():

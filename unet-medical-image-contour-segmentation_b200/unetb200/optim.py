@@ -75,9 +75,8 @@ class FusedRMSprop(torch.optim.Optimizer):
                         st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 g = p.grad
                 # the kernel walks raw storage: all four tensors must share one dense element order
-                if g.stride() != p.stride():
+                if g.stride() != p.stride():          # re-layout into a temporary; p.grad itself is left alone
                     g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
-                    p.grad = g
                 if st["square_avg"].stride() != p.stride() or not _dense(p):
                     raise ValueError("FusedRMSprop: parameters must be dense and state must share their layout")
                 st["step"] += 1
