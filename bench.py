@@ -280,12 +280,14 @@ def run_ours(args):
         lw = step(img_d, msk_d)
         if first_loss is None:
             first_loss = float(lw.detach())
+        del lw      # a live loss tensor keeps its autograd graph (and default-stream AccumulateGrad nodes) alive,
+        #             which breaks the CUDA-graph capture below (cudaErrorStreamCaptureImplicit)
     sync_all()
     # ---- whole-step CUDA graph (falls back to eager launches if capture is not possible) -------
     eager_step = step
     graphed, graph_note = None, "off"
     l0 = ops.LAUNCHES
-    eager_step(img_d, msk_d)
+    eager_step(img_d, msk_d)             # (result dropped at once, see above)
     launches_per_step = ops.LAUNCHES - l0
     graphed_b = None
     if args.graph != "off":
@@ -298,7 +300,11 @@ def run_ours(args):
                 #   graph A = forward + loss + backward + gradients packed into the buckets
                 #   eager   = mean all-reduce of the buckets
                 #   graph B = clip_grad_norm_ + RMSprop step on the bucket views
+                # no autograd hooks in this mode: a hook keeps the parameter's AccumulateGrad node (created on the
+                # default stream by the eager warm-up) alive, and autograd would then make the legacy stream depend
+                # on the capturing stream (cudaErrorStreamCaptureImplicit)
                 reducer.manual = True
+                reducer.remove()
 
                 def part_a(x, t):
                     opt.zero_grad(set_to_none=True)
@@ -320,17 +326,21 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             if args.graph == "on":
                 raise
+            import traceback
+            sys.stderr.write(f"[rank {rank}] CUDA graph capture failed:\n" + traceback.format_exc())
             graphed, graph_note = None, f"capture failed, eager launches: {type(exc).__name__}: {exc}"[:200]
             graphed_b = None
             if reducer is not None:
-                reducer.manual = False
+                reducer.remove()
+                reducer = ddp.GradAllReducer(model)       # back to hook-driven eager mode
             torch.cuda.synchronize()
         if world > 1:                                     # every rank must take the same path
             flag = torch.tensor([1 if graphed is not None else 0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if flag.item() == 0:
-                graphed = None
-                reducer.manual = False
+            if flag.item() == 0 and graphed is not None:
+                graphed = graphed_b = None
+                reducer.remove()
+                reducer = ddp.GradAllReducer(model)
     if graphed is not None:
         def step(x, t):                                   # noqa: F811  (x, t are already in the static buffers when equal)
             if x is not graphed.static_inputs[0]:
@@ -352,8 +362,9 @@ def run_ours(args):
     ms_e2e = timed(lambda: e2e_steps(args.steps), 1)
     last_loss = float(step(img_d, msk_d).detach())
     step = eager_step                                     # the instrumented pass below times individual launches
-    if reducer is not None:
-        reducer.manual = False
+    if reducer is not None and reducer.manual:
+        reducer.remove()
+        reducer = ddp.GradAllReducer(model)
 
     total_imgs = B * world * args.steps
     value = total_imgs / (ms / 1e3)
