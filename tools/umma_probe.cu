@@ -180,7 +180,7 @@ static void run_rate() {
         double sum = 0; int n = 0; long long mx = 0;
         for (auto v : h) if (v > 0) { sum += v; ++n; if (v > mx) mx = v; }
         const double per = sum / n / (iters * 8.0);
-        const double floor = 128.0 * N / 256.0 / 2.0;      // cycles per 128 x N x 16 MMA per SM at 8192 FLOP/cycle/SM
+        const double floor = 128.0 * N / 256.0;            // cycles per 128 x N x 16 MMA per SM at 8192 FLOP/cycle/SM
         printf("cta_group::%d N=%3d fill=%5d B/step: %.1f cycles/MMA (max CTA %.1f), floor %.0f -> %.0f%% of tensor peak\n", cg, N,
                fill, per, mx / (iters * 8.0), floor, 100.0 * floor / per);
       }

@@ -132,12 +132,22 @@ def on_side_stream(fn, *keep, join=True):
     with torch.cuda.stream(side):
         side.wait_event(ev)
         out = fn()
-    if join and not _SIDE_PENDING[0]:
-        _SIDE_PENDING[0] = True
-        try:
+    if join:
+        # one join per backward pass, keyed by the autograd graph-task id (robust against a backward pass that
+        # raised before its callback ran); outside a backward pass: join right away
+        task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
+        if task is None or task < 0:
+            try:
+                if task is None and not _SIDE_PENDING[0]:
+                    _SIDE_PENDING[0] = True
+                    torch.autograd.Variable._execution_engine.queue_callback(_side_join)
+                elif task is not None:
+                    _side_join()
+            except RuntimeError:
+                _side_join()
+        elif _SIDE_PENDING[0] != ("task", task):
+            _SIDE_PENDING[0] = ("task", task)
             torch.autograd.Variable._execution_engine.queue_callback(_side_join)
-        except RuntimeError:          # not inside a backward pass: join right away
-            _side_join()
     return out
 
 
