@@ -194,7 +194,8 @@ def run_ours(args):
     model = unet.UNet(1, 2, args.bilinear).to(dev).to(memory_format=torch.channels_last).train()
     if world > 1:
         ddp.broadcast_module_state(model)
-    reducer = ddp.GradAllReducer(model) if world > 1 else None
+    bucket_mb = int(os.environ.get("UNETB200_DDP_BUCKET_MB", "256"))   # one bucket: the step runs as graphs, nothing overlaps it
+    reducer = ddp.GradAllReducer(model, bucket_bytes=bucket_mb << 20) if world > 1 else None
     if args.torch_optim:
         opt = torch.optim.RMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999, foreach=True,
                                   capturable=(args.graph != "off"))
@@ -332,7 +333,7 @@ def run_ours(args):
             graphed_b = None
             if reducer is not None:
                 reducer.remove()
-                reducer = ddp.GradAllReducer(model)       # back to hook-driven eager mode
+                reducer = ddp.GradAllReducer(model, bucket_bytes=bucket_mb << 20)       # back to hook-driven eager mode
             torch.cuda.synchronize()
         if world > 1:                                     # every rank must take the same path
             flag = torch.tensor([1 if graphed is not None else 0], device=dev)
@@ -340,7 +341,7 @@ def run_ours(args):
             if flag.item() == 0 and graphed is not None:
                 graphed = graphed_b = None
                 reducer.remove()
-                reducer = ddp.GradAllReducer(model)
+                reducer = ddp.GradAllReducer(model, bucket_bytes=bucket_mb << 20)
     if graphed is not None:
         def step(x, t):                                   # noqa: F811  (x, t are already in the static buffers when equal)
             if x is not graphed.static_inputs[0]:
@@ -364,7 +365,7 @@ def run_ours(args):
     step = eager_step                                     # the instrumented pass below times individual launches
     if reducer is not None and reducer.manual:
         reducer.remove()
-        reducer = ddp.GradAllReducer(model)
+        reducer = ddp.GradAllReducer(model, bucket_bytes=bucket_mb << 20)
 
     total_imgs = B * world * args.steps
     value = total_imgs / (ms / 1e3)

@@ -200,6 +200,20 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False):
     return y, z, pooled, coefs
 
 
+def _grad_kept_as_is(param, dW):
+    """True when autograd will simply keep `dW` as `param.grad` without reading it on the current stream: no
+    existing .grad to accumulate into, same layout and dtype (AccumulateGrad's layout contract), no tensor hooks
+    that would look at the gradient during backward, and not a double-backward pass.  Only then may the weight
+    gradient be produced on the side stream."""
+    if getattr(param, "grad", None) is not None or torch.is_grad_enabled():
+        return False
+    if dW.stride() != param.stride() or param.dtype != torch.float32 or dW.dtype != torch.float32:
+        return False
+    if getattr(param, "_backward_hooks", None) or getattr(param, "_post_accumulate_grad_hooks", None):
+        return False
+    return True
+
+
 def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None):
     """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta).  `param`: the Parameter object behind `w`."""
     param = w if param is None else param
@@ -221,7 +235,7 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None):
     # after the dgrad, on the side stream: overlaps the (memory-bound) BatchNorm backward of the previous layer
     # (only when AccumulateGrad will simply keep dW: an existing .grad would be accumulated into on the main stream)
     run = lambda: ops.gconv_wgrad(_gconv3x3(x, Cout, gy, cd), x, gy, dW, skw, si, so)  # noqa: E731
-    if getattr(param, "grad", None) is None and dW.stride() == param.stride() and param.dtype == torch.float32:
+    if _grad_kept_as_is(param, dW):
         ops.on_side_stream(run, x, gy)      # AccumulateGrad keeps dW as it is (same layout, no other owner)
     else:
         run()                               # it would accumulate / re-layout dW on the main stream right away
@@ -384,7 +398,7 @@ class UpCatConvTFn(torch.autograd.Function):
             # after the dgrad, on the side stream (see conv_bn_relu_bwd)
             run = lambda: ops.gconv_wgrad(d, x1, gup, dW, 0, s_ci, s_co, sq=s_q)  # noqa: E731
             pT = getattr(ctx, "param_obj", wT)
-            if getattr(pT, "grad", None) is None and dW.stride() == pT.stride() and pT.dtype == torch.float32:
+            if _grad_kept_as_is(pT, dW):
                 ops.on_side_stream(run, x1, g)
             else:
                 run()
