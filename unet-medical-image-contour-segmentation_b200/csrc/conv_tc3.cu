@@ -843,12 +843,18 @@ int tc3_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   P.ptiles_per_split = (w.ptiles + splits - 1) / splits;
   P.N = d->N; P.K = g.K;
   P.partials = partials;
-  constexpr int ST = 7;
-  constexpr int smem = ST * (2 * 10240 + 8192) + 1024 + 256;
-  static_assert(smem <= 227 * 1024, "shared memory budget");
+  // pipeline depth: 7 stages fill the SM's shared memory; UNETB200_TC3W_STAGES=5 leaves ~85 KB for co-resident
+  // memory-bound kernels of the main stream (A/B switch)
+  static const int st_env = getenv("UNETB200_TC3W_STAGES") ? atoi(getenv("UNETB200_TC3W_STAGES")) : 7;
+  const bool deep = st_env >= 7;
+  const int smem = (deep ? 7 : 5) * (2 * 10240 + 8192) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc3_wgrad_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc3_wgrad_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         7 * (2 * 10240 + 8192) + 1024 + 256);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc3_wgrad_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               5 * (2 * 10240 + 8192) + 1024 + 256);
     if (e != cudaSuccess) return cuda_fail(e, "tc3_wgrad smem attribute");
     configured = true;
   }
@@ -864,7 +870,7 @@ int tc3_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_wgrad_kernel<ST>, P);
+  cudaError_t e = deep ? cudaLaunchKernelEx(&cfg, tc3_wgrad_kernel<7>, P) : cudaLaunchKernelEx(&cfg, tc3_wgrad_kernel<5>, P);
   if (e != cudaSuccess) return cuda_fail(e, "tc3_wgrad launch");
   return 0;
 }
