@@ -205,7 +205,65 @@ def width_gate(cls_name, nc, ncls, bilinear, B, H, W, mode):
     return res
 
 
+def full_size_gate():
+    """BASELINE.json's full sizes, through size-independent properties (the CPU oracle needs minutes there):
+    configs[1]/[2] -- B=16, 512x512 training step: the bf16 and the tf32 tensor-core paths are two independent
+    roundings of the same arithmetic, so their logits / loss / BatchNorm statistics must agree at the bf16 level and
+    every gradient must be finite; configs[4] -- UNet(3,4) eval forward at B=8, 1024x1024: bf16 vs tf32 argmax masks."""
+    import unet
+    from unetb200 import losses as UL
+    res = []
+    st = O.build_state(1, 2, False, seed=0)
+    img, msk = O.synthetic_batch(16, 1, 2, 512, 512)
+    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    t = msk.to(DEV)
+    outs = {}
+    for mode in ("bf16", "tf32"):
+        os.environ["UNET_B200_PRECISION"] = "tf32"
+        m = unet.UNet(1, 2, False)
+        m.load_state_dict(st)
+        m = m.to(DEV).to(memory_format=torch.channels_last).train()
+        with torch.autocast("cuda", enabled=(mode == "bf16")):
+            logits = m(x)
+            loss = UL.training_criterion(logits, t, boundary_coeff=0.2, edge_width=51, edge_weight=7)
+        loss.backward()
+        torch.cuda.synchronize()
+        finite = all(bool(torch.isfinite(p.grad).all()) for p in m.parameters())
+        gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters())).item()
+        outs[mode] = (logits.float(), float(loss), finite, gn,
+                      {k: v.float().clone() for k, v in m.state_dict().items() if "running" in k})
+        del m, logits, loss
+    lb, lt = outs["bf16"][0], outs["tf32"][0]
+    res.append(("full512_logits_bf16_vs_tf32_maxrel", ((lb - lt).abs().max() / lt.abs().max()).item(), 1e-1))
+    res.append(("full512_argmax_mismatch", (lb.argmax(1) != lt.argmax(1)).float().mean().item(), 3e-2))
+    res.append(("full512_loss_rel", abs(outs["bf16"][1] - outs["tf32"][1]) / abs(outs["tf32"][1]), 5e-3))
+    res.append(("full512_grads_finite", 0.0 if outs["bf16"][2] and outs["tf32"][2] else 1.0, 0.0))
+    res.append(("full512_grad_norm_rel", abs(outs["bf16"][3] - outs["tf32"][3]) / outs["tf32"][3], 0.5))
+    res.append(("full512_running_stats", max(rel(outs["bf16"][4][k].cpu(), outs["tf32"][4][k].cpu()) for k in outs["bf16"][4]), 3e-2))
+    del outs, lb, lt
+    torch.cuda.empty_cache()
+    # configs[4]: inference, 3 -> 4 classes, 1024 x 1024
+    st = O.build_state(3, 4, False, seed=0)
+    img, _ = O.synthetic_batch(8, 3, 4, 1024, 1024)
+    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    lg = {}
+    for mode in ("bf16", "tf32"):
+        m = unet.UNet(3, 4, False)
+        m.load_state_dict(st)
+        m = m.to(DEV).to(memory_format=torch.channels_last).eval()
+        with torch.inference_mode(), torch.autocast("cuda", enabled=(mode == "bf16")):
+            lg[mode] = m(x).float()
+        del m
+    res.append(("infer1024_logits_bf16_vs_tf32_maxrel", ((lg["bf16"] - lg["tf32"]).abs().max() / lg["tf32"].abs().max()).item(), 1e-1))
+    res.append(("infer1024_argmax_mismatch", (lg["bf16"].argmax(1) != lg["tf32"].argmax(1)).float().mean().item(), 3e-2))
+    res.append(("infer1024_finite", 0.0 if bool(torch.isfinite(lg["bf16"]).all()) else 1.0, 0.0))
+    del lg
+    torch.cuda.empty_cache()
+    return res
+
+
 GROUPS = {
+    "unet_full_size": lambda gd: full_size_gate(),
     "unet_widths": lambda gd: width_gate("UNet_S", 1, 3, False, 2, 64, 64, "fp32") + width_gate("UNet_S", 1, 3, False, 2, 128, 128, "bf16")
                    + width_gate("UNet_T", 3, 2, True, 1, 64, 96, "fp32"),
     "graph_side_stream": lambda gd: graph_gate(),
