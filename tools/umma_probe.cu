@@ -294,6 +294,60 @@ __global__ void __launch_bounds__(128, 1) shift_kernel(const __nv_bfloat16* X, c
   if (warp == 1) tmem_dealloc(tmem_base, 64);
 }
 
+// ---------------------------------------------------------------- check (c): MN-major operands (wgrad form)
+// D[h*64 + c][n] = sum over an 8x8 pixel tile of X[(i + a) * box_w + j + dx0 + h][c] * Y[i * 8 + j][n]
+// X = box of box_w-pixel rows (128 B per pixel, absolute-address swizzle), A is MN-major with its two 64-row halves
+// `lbo` bytes apart (lbo = 128: the same box shifted by one pixel) and 8-pixel groups `box_w * 128` bytes apart.
+__global__ void __launch_bounds__(128, 1) mn_kernel(const __nv_bfloat16* X, const __nv_bfloat16* Y, float* D, int xrows,
+                                                     int box_w, int a, int dx0, int lbo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sx = smem;                 // xrows x 128 B (<= 48 KB)
+  uint8_t* sy = smem + 49152;         // 64 pixels x 128 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 49152 + 8192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < xrows * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    const uint32_t addr = smem_u32(sx) + r * 128;
+    *reinterpret_cast<uint4*>(sx + r * 128 + ((c ^ ((addr >> 7) & 7)) << 4)) = *reinterpret_cast<const uint4*>(X + (size_t)r * 64 + c * 8);
+  }
+  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sy + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(Y + (size_t)r * 64 + c * 8);
+  }
+  if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(false, true, true, 128, 64);
+    if (elect_one()) {
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t astart = smem_u32(sx) + ((2 * k + a) * box_w + dx0) * 128;
+        const uint64_t da = make_desc(astart, lbo, box_w * 128, kLayoutSW128);
+        const uint64_t db = make_desc(smem_u32(sy) + k * 2048, 8192, 1024, kLayoutSW128);
+        umma<false>(tmem_base, da, db, idesc, k > 0);
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
+    for (int e = 0; e < 32; ++e) D[(size_t)(warp * 32 + lane) * 64 + ch * 32 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 static void run_check() {
@@ -365,9 +419,51 @@ static void run_check() {
   }
 }
 
+static void run_check_mn() {
+  const int xrows = 384;
+  std::vector<__nv_bfloat16> hX(xrows * 64), hY(64 * 64);
+  std::vector<float> fX(xrows * 64), fY(64 * 64);
+  srand(3);
+  for (size_t i = 0; i < hX.size(); ++i) { fX[i] = bf((rand() % 31 - 15) / 8.f); hX[i] = __float2bfloat16(fX[i]); }
+  for (size_t i = 0; i < hY.size(); ++i) { fY[i] = bf((rand() % 9 - 4) / 4.f); hY[i] = __float2bfloat16(fY[i]); }
+  __nv_bfloat16 *dX, *dY; float* dD;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dY, hY.size() * 2)); CK(cudaMalloc(&dD, 128 * 64 * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dY, hY.data(), hY.size() * 2, cudaMemcpyHostToDevice));
+  const int smem = 49152 + 8192 + 1024 + 256;
+  CK(cudaFuncSetAttribute(mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  struct Case { int box_w, a, dx0, lbo_pixels; };   // lbo in pixels (x128 B); 80 = a second box 10 rows x 8 px further
+  const Case cases[] = {{8, 0, 0, 80}, {8, 1, 0, 80}, {8, 2, 0, 80}, {9, 0, 0, 1}, {9, 1, 0, 1}, {9, 2, 0, 1}, {10, 1, 1, 1}, {10, 2, 0, 100}};
+  for (const Case& c : cases) {
+    CK(cudaMemset(dD, 0xff, 128 * 64 * 4));
+    mn_kernel<<<1, 128, smem>>>(dX, dY, dD, xrows, c.box_w, c.a, c.dx0, c.lbo_pixels * 128);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("check(c) box_w=%d: CUDA error %s\n", c.box_w, cudaGetErrorString(e)); exit(1); }
+    std::vector<float> hD(128 * 64);
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    for (int m = 0; m < 128; ++m) {
+      const int h = m / 64, ch = m % 64;
+      for (int n = 0; n < 64; ++n) {
+        double ref = 0;
+        for (int i = 0; i < 8; ++i)
+          for (int j = 0; j < 8; ++j) {
+            const int xp = (i + c.a) * c.box_w + j + c.dx0 + h * c.lbo_pixels;
+            ref += (double)fX[xp * 64 + ch] * fY[(i * 8 + j) * 64 + n];
+          }
+        const double er = fabs(ref - hD[m * 64 + n]);
+        if (!(er <= maxerr)) maxerr = er;
+      }
+    }
+    printf("check(c) MN-major box_w=%2d dy=%d dx0=%d lbo=%4d px: max abs err %.3g %s\n", c.box_w, c.a, c.dx0, c.lbo_pixels, maxerr,
+           maxerr < 1e-3 ? "OK" : "MISMATCH");
+  }
+}
+
 int main(int argc, char** argv) {
   const char* mode = argc > 1 ? argv[1] : "all";
   if (!strcmp(mode, "check") || !strcmp(mode, "all")) run_check();
+  if (!strcmp(mode, "checkmn") || !strcmp(mode, "all")) run_check_mn();
   if (!strcmp(mode, "rate") || !strcmp(mode, "all")) run_rate();
   return 0;
 }
