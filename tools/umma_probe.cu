@@ -70,7 +70,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* g, uint32_t byt
 constexpr int kRing = 4;
 template <int CG>
 __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int fill_bytes, const uint8_t* gsrc,
-                                                      long long* out) {
+                                                      long long* out, int mn) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;                    // 4 x 16 KB
@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int fill
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0 && rank == 0) {
-    const uint32_t idesc = make_idesc(false, false, false, 128 * CG, N);
-    const uint64_t a_t = make_desc(smem_u32(a_ring), 16, 1024), b_t = make_desc(smem_u32(b_ring), 16, 1024);
+    // mn = 1: both operands MN-major (the wgrad form: K = pixels), K step = 16 rows of 128 B
+    const uint32_t idesc = make_idesc(false, mn != 0, mn != 0, 128 * CG, N);
+    const uint64_t a_t = make_desc(smem_u32(a_ring), mn ? 8192 : 16, 1024), b_t = make_desc(smem_u32(b_ring), mn ? 8192 : 16, 1024);
+    const uint32_t kstep = mn ? 128u : 2u;
     const uint32_t dcol2 = N <= 256 ? (uint32_t)N : 0u;
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
@@ -109,11 +111,11 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int N, int iters, int fill
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           if (CG == 2) {
-            umma2(tmem_base, a0 + 2 * kk, b0 + 2 * kk, idesc, 1);
-            umma2(tmem_base + dcol2, a0 + 512 + 2 * kk, b0 + 2 * kk, idesc, 1);
+            umma2(tmem_base, a0 + kstep * (kk & (mn ? 1 : 3)), b0 + kstep * (kk & (mn ? 1 : 3)), idesc, 1);
+            umma2(tmem_base + dcol2, a0 + 512 + kstep * (kk & (mn ? 1 : 3)), b0 + kstep * (kk & (mn ? 1 : 3)), idesc, 1);
           } else {
-            umma<false>(tmem_base, a0 + 2 * kk, b0 + 2 * kk, idesc, 1);
-            umma<false>(tmem_base + dcol2, a0 + 512 + 2 * kk, b0 + 2 * kk, idesc, 1);
+            umma<false>(tmem_base, a0 + kstep * (kk & (mn ? 1 : 3)), b0 + kstep * (kk & (mn ? 1 : 3)), idesc, 1);
+            umma<false>(tmem_base + dcol2, a0 + 512 + kstep * (kk & (mn ? 1 : 3)), b0 + kstep * (kk & (mn ? 1 : 3)), idesc, 1);
           }
         }
         if (CG == 2) umma_commit2(&done[s], 3); else umma_commit(&done[s]);
@@ -159,9 +161,11 @@ static void run_rate() {
   long long* out;
   CK(cudaMalloc(&out, 148 * sizeof(long long)));
   const int iters = 4000;
+  for (int mn = 0; mn <= 1; ++mn)
   for (int cg = 1; cg <= 2; ++cg)
     for (int N : {64, 128, 256})
-      for (int fill : {0, 4096, 8192, 16384}) {
+      for (int fill : {0, 8192}) {
+        if (mn && N == 256) continue;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(148);
         cfg.blockDim = dim3(128);
@@ -171,8 +175,8 @@ static void run_rate() {
         at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         for (int rep = 0; rep < 2; ++rep) {
-          if (cg == 1) CK(cudaLaunchKernelEx(&cfg, rate_kernel<1>, N, iters, fill, (const uint8_t*)gsrc, out));
-          else CK(cudaLaunchKernelEx(&cfg, rate_kernel<2>, N, iters, fill, (const uint8_t*)gsrc, out));
+          if (cg == 1) CK(cudaLaunchKernelEx(&cfg, rate_kernel<1>, N, iters, fill, (const uint8_t*)gsrc, out, mn));
+          else CK(cudaLaunchKernelEx(&cfg, rate_kernel<2>, N, iters, fill, (const uint8_t*)gsrc, out, mn));
           CK(cudaDeviceSynchronize());
         }
         std::vector<long long> h(148);
@@ -181,7 +185,7 @@ static void run_rate() {
         for (auto v : h) if (v > 0) { sum += v; ++n; if (v > mx) mx = v; }
         const double per = sum / n / (iters * 8.0);
         const double floor = 128.0 * N / 256.0;            // cycles per 128 x N x 16 MMA per SM at 8192 FLOP/cycle/SM
-        printf("cta_group::%d N=%3d fill=%5d B/step: %.1f cycles/MMA (max CTA %.1f), floor %.0f -> %.0f%% of tensor peak\n", cg, N,
+        printf("%s cta_group::%d N=%3d fill=%5d B/step: %.1f cycles/MMA (max CTA %.1f), floor %.0f -> %.0f%% of tensor peak\n", mn ? "MN-major" : "K-major ", cg, N,
                fill, per, mx / (iters * 8.0), floor, 100.0 * floor / per);
       }
 }

@@ -743,13 +743,9 @@ int tc2_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy
 int tc2_wgrad_splits(const unetb200_gconv_t* d) {
   Tc2WPlan w;
   if (!tc2_wgrad_plan(d, &w)) return 1;
-  long long tiles = (long long)w.mtiles * w.ntiles;
-  long long want = ((long long)sm_count() * 2 + tiles - 1) / tiles;
-  long long max_by_k = (w.ptiles + 15) / 16;            // at least 16 pixel tiles (1024 pixels) per split
-  if (want > max_by_k) want = max_by_k;
-  if (want > 512) want = 512;
-  if (want < 1) want = 1;
-  return (int)want;
+  const long long tiles = (long long)w.mtiles * w.ntiles;
+  const long long max_by_k = (w.ptiles + 15) / 16;      // at least 16 pixel tiles (1024 pixels) per split
+  return pick_splits(tiles, sm_count(), max_by_k);      // one CTA per SM: whole waves (297 CTAs would cost 3 waves)
 }
 
 template <typename T, int BN, int ST>

@@ -811,12 +811,8 @@ int tc3_wgrad_splits(const unetb200_gconv_t* d) {
   Tc3WPlan w;
   if (!tc3_wgrad_plan(d, &w)) return 1;
   const long long pairs = (long long)w.mpairs * w.ntiles;
-  long long want = ((long long)(sm_count() / 2) * 2 + pairs - 1) / pairs;   // about two waves of CTA pairs
-  long long max_by_k = (w.ptiles + 15) / 16;            // at least 16 pixel tiles (1024 pixels) per split
-  if (want > max_by_k) want = max_by_k;
-  if (want > 512) want = 512;
-  if (want < 1) want = 1;
-  return (int)want;
+  const long long max_by_k = (w.ptiles + 15) / 16;      // at least 16 pixel tiles (1024 pixels) per split
+  return pick_splits(pairs, sm_count() / 2, max_by_k);  // one CTA pair per SM pair: whole waves
 }
 
 int tc3_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,

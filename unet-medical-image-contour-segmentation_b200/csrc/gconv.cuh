@@ -17,6 +17,29 @@ struct GconvDev {
 
 int gconv_validate(const unetb200_gconv_t* d, GconvDev* out);
 
+// Split count for a split-K grid of `tiles` work items per split on `slots` one-per-SM execution slots (SMs, or SM
+// pairs for cluster kernels): these kernels hold a whole SM each, so the grid runs in waves and a grid of 2.03
+// waves costs 3.  Returns the smallest split count (<= smax) whose last wave is (nearly) full, preferring about
+// two waves.
+inline int pick_splits(long long tiles, int slots, long long smax) {
+  if (tiles < 1) tiles = 1;
+  if (smax < 1) smax = 1;
+  long long lim = (4LL * slots + tiles - 1) / tiles;     // never more than ~4 waves of splits
+  if (lim > smax) lim = smax;
+  if (lim > 512) lim = 512;
+  if (lim < 1) lim = 1;
+  double best = -1.0;
+  long long pick = 1;
+  for (long long s = 1; s <= lim; ++s) {
+    const long long ctas = tiles * s;
+    const long long waves = (ctas + slots - 1) / slots;
+    const double eff = (double)ctas / (double)(waves * slots);
+    // prefer fuller waves; among equals, more splits (more of the machine busy) -- eff is maximal at exact multiples
+    if (eff > best + 1e-9 || (eff > best - 0.005 && ctas <= 2LL * slots)) { best = eff > best ? eff : best; pick = s; }
+  }
+  return (int)pick;
+}
+
 // tcgen05 engine (conv_tc.cu).  *_supported() return 1 when the shape/dtype/alignment fits.
 int tc_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
 long long tc_fprop_tiles(const unetb200_gconv_t* d);
