@@ -145,11 +145,15 @@ def graph_gate():
     m1, step1 = make()
     l1 = [float(step1(x, t).detach()) for _ in range(5)]
     ops._SIDE_ON = side_was
-    # graph (2 eager warm-up steps + 1 captured... the capture itself does not execute), then replays
+    # graph (2 eager warm-up steps + 1 captured... the capture itself does not execute), then replays -- with the
+    # weight gradients on the side stream, the most intricate schedule the library offers
+    wg_was = ops._WGRAD_SIDE
+    ops._WGRAD_SIDE = True
     m2, step2 = make()
     g = GraphedStep(step2, (x, t), warmup=2)
     l2 = [float(g.replay().detach()) for _ in range(3)]
     torch.cuda.synchronize()
+    ops._WGRAD_SIDE = wg_was
     # bf16 training from random init is chaotic (a ReLU-mask flip changes later steps), so the multi-step comparison
     # only has to catch gross errors (a race gives NaN or errors >> 1); the tight check is the single-step one below
     res = [("graph_loss_step3", abs(l2[0] - l1[2]) / abs(l1[2]), 2e-3),
@@ -165,6 +169,7 @@ def graph_gate():
     # one backward from identical weights: side-stream weight gradients == single-stream weight gradients
     def grads_of(side):
         ops._SIDE_ON = side
+        ops._WGRAD_SIDE = side
         m = unet.UNet(1, 2, False)
         m.load_state_dict(st)
         m = m.to(DEV).to(memory_format=torch.channels_last).train()
@@ -173,8 +178,9 @@ def graph_gate():
         loss.backward()
         torch.cuda.synchronize()
         return {k: host(p.grad) for k, p in m.named_parameters()}
+    wgrad_side_was = ops._WGRAD_SIDE
     ga, gb = grads_of(False), grads_of(True)
-    ops._SIDE_ON = side_was
+    ops._SIDE_ON, ops._WGRAD_SIDE = side_was, wgrad_side_was
     res.append(("side_stream_grads_vs_single_stream_rel_l2", max(O.rel_l2(gb[k], ga[k]) for k in ga), 1e-3))
     res.append(("graph_losses_finite", 0.0 if all(v == v and abs(v) < 1e3 for v in l1 + l2) else 1.0, 0.0))
     return res

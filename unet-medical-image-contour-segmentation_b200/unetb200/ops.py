@@ -80,13 +80,17 @@ def _run(name, fn, *args, kernels=1, flops=0.0, nbytes=0.0):
 # on a second stream -- ordered after the dgrad of the same layer -- lets the memory-bound kernels of the next
 # layer run on the SM resources the tensor kernel leaves idle.  The streams are joined by an autograd-engine
 # callback at the end of the backward pass (so callers such as the reference train.py need no change), and the
-# operands are kept alive until then.  UNETB200_WGRAD_STREAM=0 turns this off.
+# operands are kept alive until then.  UNETB200_WGRAD_STREAM=1 turns this on (see _WGRAD_SIDE below);
+# UNETB200_SIDE_STREAM=0 disables the side stream altogether (also the operand pre-packing).
 import os as _os
 
 _SIDE = {}            # device index -> torch.cuda.Stream
 _SIDE_KEEP = []       # tensors the side stream still reads
 _SIDE_PENDING = [False]
-_SIDE_ON = _os.environ.get("UNETB200_WGRAD_STREAM", "1") != "0"
+_SIDE_ON = _os.environ.get("UNETB200_SIDE_STREAM", "1") != "0"          # master switch (prepack + wgrad)
+# weight gradients on the side stream: OFF by default -- it paid (+4 %) while the wgrad grids had a nearly empty
+# third wave for the BatchNorm kernels to fill; with wave-exact split counts the serial order is 1-2 % faster
+_WGRAD_SIDE = _os.environ.get("UNETB200_WGRAD_STREAM", "0") != "0"
 
 
 def _wait_side(s):
@@ -119,8 +123,9 @@ def side_enabled():
 
 def on_side_stream(fn, *keep, join=True):
     """Run fn() on the side stream, ordered after everything enqueued so far on the current stream.  join=True
-    queues the end-of-backward join; join=False leaves ordering to events recorded by fn (see functional.prepack)."""
-    if not _SIDE_ON or _PROFILE is not None:
+    queues the end-of-backward join (weight gradients); join=False leaves ordering to events recorded by fn
+    (see functional.prepack)."""
+    if not _SIDE_ON or _PROFILE is not None or (join and not _WGRAD_SIDE):
         return fn()
     dev = torch.cuda.current_device()
     side = _SIDE.get(dev)
