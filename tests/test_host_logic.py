@@ -79,3 +79,41 @@ def test_precision_policy(monkeypatch):
     x = torch.zeros(1)
     assert UF.compute_dtype(x) == torch.float32
     assert UF.compute_dtype(x.bfloat16()) == torch.bfloat16      # (autocast -> bf16 is checked on the GPU)
+
+
+def test_wgrad_split_counts_fill_whole_waves():
+    """The tcgen05 wgrad kernels hold one CTA (or CTA pair) per SM, so a split-K grid runs in waves: the plan
+    must not launch e.g. 297 CTAs on 148 SMs (2.007 waves cost 3 -- this cost 1.2 ms/step before pick_splits).
+    Host-only: unetb200_gconv_wgrad_plan needs no GPU (148 SMs assumed without one)."""
+    import ctypes as C
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "unet-medical-image-contour-segmentation_b200"))
+    from unetb200 import _lib
+    lib = _lib.load()
+    B = 16
+    # (Cin, Cout, H) of the 3x3 convolutions of UNet(1,2) at 512x512 that run on tcgen05
+    layers = [(64, 64, 512), (128, 64, 512), (64, 128, 256), (128, 128, 256), (256, 128, 256), (128, 256, 128),
+              (256, 256, 128), (512, 256, 128), (256, 512, 64), (512, 512, 64), (1024, 512, 64), (512, 1024, 32),
+              (1024, 1024, 32)]
+    for cin, cout, hw in layers:
+        d = _lib.GConv()
+        d.dtype, d.algo = _lib.BF16, _lib.ALGO_TC
+        d.B, d.Hm, d.Wm, d.Cin, d.ntaps = B, hw, hw, cin, 9
+        for t in range(9):
+            d.tap_dy[t], d.tap_dx[t] = t // 3 - 1, t % 3 - 1
+        d.in_scale, d.in_off_y, d.in_off_x, d.Hin, d.Win, d.ld_in = 1, 0, 0, hw, hw, cin
+        d.N, d.nquad, d.out_scale, d.out_off_y, d.out_off_x, d.Hout, d.Wout, d.ld_out = cout, 1, 1, 0, 0, hw, hw, cout
+        splits, used = C.c_int(0), C.c_int(0)
+        assert lib.unetb200_gconv_wgrad_plan(C.byref(d), C.byref(splits), C.byref(used)) == 0
+        assert used.value == _lib.ALGO_TC
+        chunks = cin // 64
+        if cout % 128 == 0 and (3 * chunks) % 4 == 0:          # CTA-pair kernel: slots = SM pairs
+            tiles, slots = (3 * chunks // 4) * (cout // 128), 74
+        else:                                                   # single-CTA kernel: two units per M tile
+            bn = 128 if cout % 128 == 0 else 64
+            tiles, slots = ((3 * chunks + 1) // 2) * (cout // bn), 148
+        ctas = tiles * splits.value
+        waves = -(-ctas // slots)
+        assert ctas / (waves * slots) >= 0.95, (cin, cout, hw, splits.value, ctas, waves)
