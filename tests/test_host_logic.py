@@ -117,3 +117,32 @@ def test_wgrad_split_counts_fill_whole_waves():
         ctas = tiles * splits.value
         waves = -(-ctas // slots)
         assert ctas / (waves * slots) >= 0.95, (cin, cout, hw, splits.value, ctas, waves)
+
+
+def test_side_stream_eligibility_rules():
+    """A weight gradient may be produced on the side stream only when autograd will keep the tensor untouched
+    (functional._grad_kept_as_is): pure host logic, checked on CPU tensors."""
+    import os
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "unet-medical-image-contour-segmentation_b200"))
+    from unetb200 import functional as UF
+    w = torch.nn.Parameter(torch.randn(8, 4, 3, 3).contiguous(memory_format=torch.channels_last))
+    with torch.no_grad():
+        g_same = torch.empty_like(w)
+        g_other = torch.empty(8, 4, 3, 3)
+        assert UF._grad_kept_as_is(w, g_same)
+        assert not UF._grad_kept_as_is(w, g_other)                      # layout contract: autograd would re-layout it
+        w.grad = torch.zeros_like(w)
+        assert not UF._grad_kept_as_is(w, g_same)                       # accumulation into an existing .grad
+        w.grad = None
+        h = w.register_hook(lambda g: g)
+        assert not UF._grad_kept_as_is(w, g_same)                       # a tensor hook reads the gradient during backward
+        h.remove()
+        h2 = w.register_post_accumulate_grad_hook(lambda p: None)
+        assert not UF._grad_kept_as_is(w, g_same)
+        h2.remove()
+        assert UF._grad_kept_as_is(w, g_same)
+        assert not UF._grad_kept_as_is(w, g_same.double())
+    assert not UF._grad_kept_as_is(w, g_same)                           # grad mode on: double backward would clone
