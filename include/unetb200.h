@@ -250,6 +250,49 @@ int unetb200_rmsprop_step(float* const* w, float* const* g, float* const* sq, fl
                           float alpha, float eps, float weight_decay, float momentum, int write_clipped_grad,
                           void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Callers either side of the step: evaluate / predict tail and the
+ * uint8 input pipeline.  Byte / index work: results are exact.
+ * ------------------------------------------------------------------------------------------- */
+#define UNETB200_U8 3
+/* evaluate.py:111-117 (mode 0: pred = argmax over classes == cls, true = target == cls) and
+ * evaluate.py:56-66 (mode 1, C == 1: pred = sigmoid(logit) > 0.5 with the sigmoid rounded to `dtype`,
+ * true = floor(target / 2) which must be 0 or 1), followed by dice_coeff(pred, true,
+ * reduce_batch_first=False) (dice_score.py:5-25; per image, mean over the batch).
+ * logits element (b,c,h,w) lives at logits[b*sb + c*sc + h*sh + w*sw]; target is contiguous [B][H][W]
+ * (tgt_dtype UNETB200_F32 or UNETB200_I64) or NULL (prediction only).
+ *   pred_out : NULL, or contiguous [B][H][W] of pred_dtype (UNETB200_I64 / UNETB200_U8): the argmax
+ *              index (mode 0) or the 0/1 prediction (mode 1)
+ *   counts   : int64[B][4] = {sum pred*true, sum pred, sum true, #targets outside {0,1} (mode 1)};
+ *              zeroed by the callee
+ *   dice_out : NULL, or float[1] = mean dice (NaN when mode 1 saw an invalid target: the reference
+ *              raises AssertionError)                                                          */
+int unetb200_eval_counts(const void* logits, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                         const void* target, int tgt_dtype, int B, int C, int H, int W, int cls, int mode,
+                         void* pred_out, int pred_dtype, int64_t* counts, float epsilon, float* dice_out,
+                         void* stream);
+/* predict.py:26-27: F.interpolate(logits, (H, W), mode='bilinear') (align_corners=False, result rounded
+ * to `dtype` like ATen's output tensor) followed by argmax(dim=1) (first maximum).  logits [B][C][h][w]
+ * by strides as above; out contiguous [B][H][W] of out_dtype (UNETB200_I64 / UNETB200_U8).      */
+int unetb200_resize_argmax(const void* logits, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B,
+                           int C, int h, int w, int H, int W, void* out, int out_dtype, void* stream);
+/* data_loading.py:65-89 (BasicDataset.preprocess, scale == 1) + :91-98 (rotation augmentation) for a
+ * batch of equally sized uint8 images already in device memory.
+ *   src   : uint8 [B][H][W][C] (numpy.asarray of the PIL image; C <= 4)
+ *   rot   : NULL, or device int32[B]: quarter turns counter-clockwise (PIL Image.rotate(90*k,
+ *           expand=True) == numpy.rot90(a, k)); `transposed` != 0 says every k is odd on a non-square
+ *           image, i.e. the output is [W][H] (the caller checks the parity on the host)
+ *   dst   : float [B][Ho][Wo][C] = channels_last storage of the logical [B, C, Ho, Wo] batch:
+ *           float32(v) / 255 when the image holds any value > 1 (data_loading.py:86-87), else float32(v)
+ *   flags : device int32[B] workspace (per-image "any value > 1"), zeroed by the callee          */
+int unetb200_preprocess_image_u8(const uint8_t* src, int B, int H, int W, int C, const int32_t* rot, int transposed,
+                                 float* dst, int32_t* flags, void* stream);
+/* mask branch of preprocess (data_loading.py:73-79): gray level -> class index, 255 -> 2, 128 -> 1,
+ * anything else 0 (lut == NULL) or lut[v] (device int64[256]); same rotation; dst int64 [B][Ho][Wo]
+ * (what .long() makes of it at data_loading.py:132).                                            */
+int unetb200_preprocess_mask_u8(const uint8_t* src, int B, int H, int W, const int32_t* rot, int transposed,
+                                const int64_t* lut, int64_t* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

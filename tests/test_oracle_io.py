@@ -1,0 +1,82 @@
+"""CPU: oracle/io_oracle.py (input pipeline, evaluate / predict tails) against the fixtures generated from the
+reference itself by tests/golden/make_golden_io.py, plus the host-side argument logic of unetb200.data /
+unetb200.eval_tail.  No access to /root/reference, no compute calls into the CUDA library."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import io_oracle as IO
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gio():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_io_v1.pt"), weights_only=False)
+
+
+def test_pipeline_matches_reference_arrays(gio):
+    assert len(gio["pipeline"]) == 16
+    for c in gio["pipeline"]:
+        img, msk = IO.make_batch([c["img"].numpy()], [c["msk"].numpy()], [c["k"]])
+        assert img.dtype == torch.float32 and msk.dtype == torch.int64
+        assert torch.equal(img[0], c["out_img"]), (c["tag"], c["k"])
+        assert torch.equal(msk[0], c["out_msk"]), (c["tag"], c["k"])
+    # the /255 branch is data dependent (data_loading.py:86): an image without a value > 1 is NOT scaled
+    lo = [c for c in gio["pipeline"] if c["tag"] == "gray_binary_24x24"][0]
+    assert lo["out_img"].max().item() == 1.0 and set(lo["out_img"].unique().tolist()) <= {0.0, 1.0}
+
+
+def test_rotation_is_counter_clockwise_quarter_turns():
+    a = np.arange(6, dtype=np.uint8).reshape(2, 3)
+    assert IO.rotate(a, 1).tolist() == [[2, 5], [1, 4], [0, 3]]
+    assert IO.rotate(a, 2).tolist() == [[5, 4, 3], [2, 1, 0]]
+    assert IO.rotate(a, 3).tolist() == [[3, 0], [4, 1], [5, 2]]
+
+
+def test_evaluate_tails(gio):
+    for c in gio["eval_mc"]:
+        idx, dice, counts = IO.eval_multiclass(c["logits"], c["true"], c["c"])
+        assert torch.equal(idx, c["idx"]) and torch.equal(dice, c["dice"]), c["tag"]
+        assert counts.shape == (c["logits"].shape[0], 3)
+    empty = [c for c in gio["eval_mc"] if c["tag"] == "mc_empty"][0]
+    assert empty["dice"].item() == 1.0                     # sets_sum == 0 -> inter -> eps/eps
+    for c in gio["eval_bin"]:
+        binary, dice, _ = IO.eval_binary(c["logits"], c["true"])
+        assert torch.equal(binary, c["binary"]) and torch.equal(dice, c["dice"]), c["tag"]
+    with pytest.raises(AssertionError):
+        IO.eval_binary(torch.zeros(1, 1, 4, 4), torch.full((1, 4, 4), 5.0))
+
+
+def test_predict_tail(gio):
+    for c in gio["predict"]:
+        assert torch.equal(IO.predict_tail(c["logits"], c["size"]), c["idx"]), c["tag"]
+        ex = IO.resize_argmax_exact(c["logits"], c["size"])
+        agree = (ex == c["idx"]).float().mean().item()
+        assert agree >= (1.0 if c["tag"].startswith("same") else 0.999), (c["tag"], agree)
+
+
+def test_host_argument_logic():
+    from unetb200 import data, eval_tail
+    assert data.check_rotations(None, 2, 4, 6) == (None, False)
+    assert data.check_rotations([1, 3], 2, 4, 6) == ([1, 3], True)
+    assert data.check_rotations([0, 2], 2, 4, 6) == ([0, 2], False)
+    assert data.check_rotations([0, 1, 6, 7], 4, 8, 8) == ([0, 1, 2, 3], False)      # square: any mix stacks
+    with pytest.raises(ValueError):
+        data.check_rotations([0, 1], 2, 4, 6)
+    with pytest.raises(ValueError):
+        data.check_rotations([0], 2, 4, 4)
+    with pytest.raises(ValueError):
+        data._as_u8_batch([np.zeros((4, 4), np.uint8), np.zeros((4, 5), np.uint8)], "t")
+    with pytest.raises(ValueError):
+        data._as_u8_batch(np.zeros((1, 4, 4), np.float32), "t")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        data.preprocess_batch([np.zeros((4, 4), np.uint8)], device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        eval_tail.argmax_class_dice(torch.zeros(1, 3, 4, 4), torch.zeros(1, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        eval_tail.resize_argmax(torch.zeros(1, 3, 4, 4), (8, 8))
+    with pytest.raises(ValueError):
+        eval_tail.binary_dice(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4))

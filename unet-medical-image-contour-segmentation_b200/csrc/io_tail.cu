@@ -1,0 +1,363 @@
+// The two ends of the step that touch bytes instead of activations:
+//   * evaluate.py:111-117 / :56-66  -- argmax (or sigmoid threshold) + per-image class counts -> dice_coeff
+//   * predict.py:26-27              -- F.interpolate(bilinear, align_corners=False) + argmax
+//   * data_loading.py:65-89, 91-98  -- uint8 image -> fp32 (/255 when any value > 1), mask gray level -> class index,
+//                                      the 90/180/270 degree rotation augmentation
+// All of them are HBM-bound byte/integer passes: one coalesced read, one coalesced write, counts through
+// warp shuffles -> shared memory -> one 64-bit atomic per block.  Integer results are exact by construction.
+#include "common.cuh"
+
+namespace ub {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long block_count(unsigned v, unsigned* smem) {
+  // sum of a per-thread count over the block; valid in thread 0
+  v = __reduce_add_sync(0xffffffffu, v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  unsigned long long r = 0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += smem[i];
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ float load_target(const T* p);
+template <>
+__device__ __forceinline__ float load_target<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float load_target<long long>(const long long* p) { return (float)*p; }
+
+template <typename O>
+__device__ __forceinline__ void store_index(O* p, int v) { *p = (O)v; }
+
+// first maximum over the class axis; NaN counts as the maximum (torch.argmax)
+template <typename T>
+__device__ __forceinline__ int argmax_classes(const T* p, int64_t sc, int C) {
+  float best = Elem<T>::ld(p);
+  int idx = 0;
+  for (int c = 1; c < C; ++c) {
+    float v = Elem<T>::ld(p + c * sc);
+    if (v > best || (v != v && best == best)) { best = v; idx = c; }
+  }
+  return idx;
+}
+
+// ------------------------------------------------------------------------------------------
+// evaluate tail.  mode 0 (evaluate.py:111-117): pred = (argmax_c logits == cls), true = (target == cls)
+//                 mode 1 (evaluate.py:56-66, n_classes == 1): pred = (sigmoid(z) rounded to T) > 0.5,
+//                         true = floor(target / 2), which must be 0 or 1 (the reference asserts it)
+// counts[b] = {sum pred*true, sum pred, sum true, #invalid targets}
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TT, typename O>
+__global__ void eval_counts_kernel(const T* __restrict__ logits, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                                   const TT* __restrict__ target, int C, int H, int W, int cls, int mode,
+                                   O* __restrict__ pred_out, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned sm[32];
+  const int b = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const T* lb = logits + b * sb;
+  const TT* tb = target ? target + b * HW : nullptr;
+  O* ob = pred_out ? pred_out + b * HW : nullptr;
+  unsigned ni = 0, np = 0, nt = 0, nbad = 0;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(p / W), w = (int)(p - (int64_t)h * W);
+    const T* px = lb + h * sh + w * sw;
+    int label;
+    bool pb;
+    if (mode == 0) {
+      label = argmax_classes<T>(px, sc, C);
+      pb = label == cls;
+    } else {
+      const float z = Elem<T>::ld(px);
+      pb = Elem<T>::round(1.f / (1.f + expf(-z))) > 0.5f;
+      label = pb ? 1 : 0;
+    }
+    if (ob) store_index<O>(ob + p, label);
+    bool tbit = false;
+    if (tb) {
+      const float t = load_target<TT>(tb + p);
+      if (mode == 0) {
+        tbit = t == (float)cls;
+      } else {
+        const float th = floorf(t * 0.5f);
+        tbit = th == 1.f;
+        nbad += !(th == 0.f || th == 1.f);
+      }
+    }
+    ni += pb && tbit;
+    np += pb;
+    nt += tbit;
+  }
+  unsigned long long r0 = block_count(ni, sm), r1 = block_count(np, sm), r2 = block_count(nt, sm),
+                     r3 = block_count(nbad, sm);
+  if (threadIdx.x == 0) {
+    unsigned long long* c = counts + 4 * b;
+    if (r0) atomicAdd(c + 0, r0);
+    if (r1) atomicAdd(c + 1, r1);
+    if (r2) atomicAdd(c + 2, r2);
+    if (r3) atomicAdd(c + 3, r3);
+  }
+}
+
+// dice_coeff(pred, true, reduce_batch_first=False) on [B,H,W] 0/1 tensors (dice_score.py:5-25): per image
+// inter = 2*I, sets = P + T (fp32 sums of 0/1 values are exact below 2^24), sets == 0 -> inter, mean over B.
+__global__ void eval_dice_finalize_kernel(const unsigned long long* __restrict__ counts, int B, float eps,
+                                          float* __restrict__ out) {
+  if (threadIdx.x || blockIdx.x) return;
+  float acc = 0.f;
+  unsigned long long bad = 0;
+  for (int b = 0; b < B; ++b) {
+    const unsigned long long* c = counts + 4 * b;
+    const float inter = 2.f * (float)c[0];
+    float sets = (float)c[1] + (float)c[2];
+    if (sets == 0.f) sets = inter;
+    acc += (inter + eps) / (sets + eps);
+    bad += c[3];
+  }
+  out[0] = bad ? NAN : acc / (float)B;
+}
+
+// ------------------------------------------------------------------------------------------
+// predict tail: upsample_bilinear2d(align_corners=False) of every class plane, rounded to the storage
+// type like ATen's output tensor, then first-max argmax.  ATen's source index (UpSample.h,
+// area_pixel_compute_source_index): src = scale*(dst+0.5)-0.5 clamped at 0, scale = in/out in fp32.
+// ------------------------------------------------------------------------------------------
+struct Lerp { int i0, di; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_index(int dst, float scale, int in_size) {
+  // ATen's order, without FMA contraction so the host restatement reproduces it bit for bit
+  float src = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);
+  if (src < 0.f) src = 0.f;
+  Lerp r;
+  r.i0 = min((int)src, in_size - 1);
+  r.di = r.i0 < in_size - 1 ? 1 : 0;
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+template <typename T, typename O>
+__global__ void resize_argmax_kernel(const T* __restrict__ logits, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                                     int C, int h, int w, int H, int W, float scale_h, float scale_w,
+                                     O* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int64_t HW = (int64_t)H * W;
+  const T* lb = logits + b * sb;
+  O* ob = out + b * HW;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    const int oy = (int)(p / W), ox = (int)(p - (int64_t)oy * W);
+    const Lerp ly = lerp_index(oy, scale_h, h), lx = lerp_index(ox, scale_w, w);
+    const T* p00 = lb + ly.i0 * sh + lx.i0 * sw;
+    const int64_t dy = ly.di * sh, dx = lx.di * sw;
+    float best = 0.f;
+    int idx = 0;
+    for (int c = 0; c < C; ++c) {
+      const T* q = p00 + c * sc;
+      const float v00 = Elem<T>::ld(q), v01 = Elem<T>::ld(q + dx), v10 = Elem<T>::ld(q + dy),
+                  v11 = Elem<T>::ld(q + dy + dx);
+      const float top = __fadd_rn(__fmul_rn(lx.l0, v00), __fmul_rn(lx.l1, v01));
+      const float bot = __fadd_rn(__fmul_rn(lx.l0, v10), __fmul_rn(lx.l1, v11));
+      float v = __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
+      v = Elem<T>::round(v);
+      if (c == 0 || v > best || (v != v && best == best)) { best = v; idx = c; }
+    }
+    store_index<O>(ob + p, idx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// input pipeline: tiles of 32x32 output pixels; the matching input tile is read row-major (coalesced along the
+// input x axis), staged in shared memory, and written row-major along the output x axis, so a 90/270 degree
+// rotation costs no uncoalesced access.  rot = k means numpy.rot90(a, k) == PIL Image.rotate(90 k, expand=True)
+// (counter-clockwise); output pixel (i, j) reads input pixel
+//   k=0: (i, j)   k=1: (j, W-1-i)   k=2: (H-1-i, W-1-j)   k=3: (H-1-j, i)
+// ------------------------------------------------------------------------------------------
+constexpr int kTile = 32;
+constexpr int kMaxImgC = 4;
+
+__global__ void u8_any_gt1_kernel(const uint8_t* __restrict__ src, int64_t per_image, int* __restrict__ flags) {
+  const int b = blockIdx.y;
+  const uint8_t* s = src + b * per_image;
+  bool any = false;
+  const int64_t nvec = (reinterpret_cast<uintptr_t>(s) & 15) == 0 ? per_image / 16 : 0;
+  const uint4* v = reinterpret_cast<const uint4*>(s);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 q = v[i];
+    // a byte is > 1 iff any of its bits 1..7 is set
+    any |= ((q.x | q.y | q.z | q.w) & 0xfefefefeu) != 0;
+  }
+  for (int64_t i = nvec * 16 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_image;
+       i += (int64_t)gridDim.x * blockDim.x)
+    any |= s[i] > 1;
+  if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flags + b, 1);
+}
+
+struct ImageOp {        // data_loading.py:82-87: float32(v) / 255.0 when the image has a value > 1, else float32(v)
+  const int* flags;
+  typedef float out_t;
+  __device__ __forceinline__ float apply(uint8_t v, int b) const {
+    return flags[b] ? __fdiv_rn((float)v, 255.f) : (float)v;
+  }
+};
+struct MaskOp {         // data_loading.py:74-79: 255 -> 2, 128 -> 1, everything else 0; or a caller-supplied table
+  const long long* lut;
+  typedef long long out_t;
+  __device__ __forceinline__ long long apply(uint8_t v, int) const {
+    if (lut) return lut[v];
+    return v == 255 ? 2 : (v == 128 ? 1 : 0);
+  }
+};
+
+template <typename Op>
+__global__ void __launch_bounds__(256) rot_convert_kernel(const uint8_t* __restrict__ src, int H, int W, int C,
+                                                          const int* __restrict__ rot, int Ho, int Wo, Op op,
+                                                          typename Op::out_t* __restrict__ dst) {
+  __shared__ uint8_t tile[kTile][kTile * kMaxImgC + 4];
+  const int b = blockIdx.z;
+  const int k = rot ? (rot[b] & 3) : 0;
+  const int i0 = blockIdx.y * kTile, j0 = blockIdx.x * kTile;   // output tile origin (row, column)
+  // input tile origin
+  int y0, x0;
+  switch (k) {
+    case 0: y0 = i0; x0 = j0; break;
+    case 1: y0 = j0; x0 = W - kTile - i0; break;
+    case 2: y0 = H - kTile - i0; x0 = W - kTile - j0; break;
+    default: y0 = H - kTile - j0; x0 = i0; break;
+  }
+  const uint8_t* sb = src + (int64_t)b * H * W * C;
+  const int rowbytes = kTile * C;
+  for (int t = threadIdx.x; t < kTile * rowbytes; t += blockDim.x) {
+    const int ty = t / rowbytes, tb = t - ty * rowbytes;
+    const int y = y0 + ty, xb = x0 * C + tb;
+    uint8_t v = 0;
+    if (y >= 0 && y < H && xb >= 0 && xb < W * C) v = sb[(int64_t)y * W * C + xb];
+    tile[ty][tb] = v;
+  }
+  __syncthreads();
+  typename Op::out_t* db = dst + (int64_t)b * Ho * Wo * C;
+  for (int t = threadIdx.x; t < kTile * rowbytes; t += blockDim.x) {
+    const int ti = t / rowbytes, r = t - ti * rowbytes;
+    const int tj = r / C, c = r - tj * C;
+    const int i = i0 + ti, j = j0 + tj;
+    if (i >= Ho || j >= Wo) continue;
+    int y, x;
+    switch (k) {
+      case 0: y = i; x = j; break;
+      case 1: y = j; x = W - 1 - i; break;
+      case 2: y = H - 1 - i; x = W - 1 - j; break;
+      default: y = H - 1 - j; x = i; break;
+    }
+    typename Op::out_t v = 0;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = op.apply(tile[y - y0][(x - x0) * C + c], b);
+    db[((int64_t)i * Wo + j) * C + c] = v;
+  }
+}
+
+}  // namespace ub
+
+using namespace ub;
+typedef __nv_bfloat16 bf16;
+
+static inline int tail_grid(int64_t work_per_image, int B, int threads) {
+  int64_t b = (work_per_image + threads - 1) / threads;
+  int64_t cap = ((int64_t)sm_count() * 8 + B - 1) / B;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+extern "C" {
+
+int unetb200_eval_counts(const void* logits, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
+                         const void* target, int tgt_dtype, int B, int C, int H, int W, int cls, int mode,
+                         void* pred_out, int pred_dtype, int64_t* counts, float epsilon, float* dice_out,
+                         void* stream) {
+  UB_CHECK_ARG(dtype == UNETB200_F32 || dtype == UNETB200_BF16, "eval_counts: logits dtype");
+  UB_CHECK_ARG(target == nullptr || tgt_dtype == UNETB200_F32 || tgt_dtype == UNETB200_I64,
+               "eval_counts: target dtype");
+  UB_CHECK_ARG(pred_out == nullptr || pred_dtype == UNETB200_I64 || pred_dtype == UNETB200_U8,
+               "eval_counts: prediction dtype must be int64 or uint8");
+  UB_CHECK_ARG(B > 0 && B <= 65535 && C >= 1 && H > 0 && W > 0, "eval_counts: bad shape B=%d C=%d H=%d W=%d", B, C,
+               H, W);
+  UB_CHECK_ARG(mode == 0 || (mode == 1 && C == 1), "eval_counts: mode %d needs C == 1 (got %d)", mode, C);
+  UB_CHECK_ARG(counts != nullptr, "eval_counts: counts workspace");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)B * 4 * sizeof(int64_t), s);
+  if (e != cudaSuccess) return cuda_fail(e, "eval_counts memset");
+  dim3 grid(tail_grid((int64_t)H * W, B, 256), B);
+  unsigned long long* cnt = (unsigned long long*)counts;
+  const bool u8 = pred_out && pred_dtype == UNETB200_U8;
+#define GO3(T, TT, O)                                                                                      \
+  eval_counts_kernel<T, TT, O><<<grid, 256, 0, s>>>((const T*)logits, sb, sc, sh, sw, (const TT*)target, C, H, W, \
+                                                    cls, mode, (O*)pred_out, cnt)
+#define GO2(T, TT)            \
+  do {                        \
+    if (u8) GO3(T, TT, uint8_t); \
+    else GO3(T, TT, long long);  \
+  } while (0)
+  if (dtype == UNETB200_BF16) {
+    if (tgt_dtype == UNETB200_I64) GO2(bf16, long long); else GO2(bf16, float);
+  } else {
+    if (tgt_dtype == UNETB200_I64) GO2(float, long long); else GO2(float, float);
+  }
+#undef GO2
+#undef GO3
+  if (dice_out) eval_dice_finalize_kernel<<<1, 32, 0, s>>>(cnt, B, epsilon, dice_out);
+  UB_LAUNCH_CHECK("eval_counts");
+  return 0;
+}
+
+int unetb200_resize_argmax(const void* logits, int dtype, int64_t sb, int64_t sc, int64_t sh, int64_t sw, int B,
+                           int C, int h, int w, int H, int W, void* out, int out_dtype, void* stream) {
+  UB_CHECK_ARG(dtype == UNETB200_F32 || dtype == UNETB200_BF16, "resize_argmax: logits dtype");
+  UB_CHECK_ARG(out_dtype == UNETB200_I64 || out_dtype == UNETB200_U8, "resize_argmax: output dtype");
+  UB_CHECK_ARG(B > 0 && B <= 65535 && C >= 1 && h > 0 && w > 0 && H > 0 && W > 0, "resize_argmax: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(tail_grid((int64_t)H * W, B, 256), B);
+  const float sch = (float)h / (float)H, scw = (float)w / (float)W;
+#define GO(T, O) \
+  resize_argmax_kernel<T, O><<<grid, 256, 0, s>>>((const T*)logits, sb, sc, sh, sw, C, h, w, H, W, sch, scw, (O*)out)
+  if (dtype == UNETB200_BF16) {
+    if (out_dtype == UNETB200_U8) GO(bf16, uint8_t); else GO(bf16, long long);
+  } else {
+    if (out_dtype == UNETB200_U8) GO(float, uint8_t); else GO(float, long long);
+  }
+#undef GO
+  UB_LAUNCH_CHECK("resize_argmax");
+  return 0;
+}
+
+int unetb200_preprocess_image_u8(const uint8_t* src, int B, int H, int W, int C, const int32_t* rot, int transposed,
+                                 float* dst, int32_t* flags, void* stream) {
+  UB_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0 && C >= 1 && C <= kMaxImgC,
+               "preprocess_image_u8: bad shape B=%d H=%d W=%d C=%d (C <= %d)", B, H, W, C, kMaxImgC);
+  UB_CHECK_ARG(src && dst && flags, "preprocess_image_u8: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(flags, 0, (size_t)B * sizeof(int32_t), s);
+  if (e != cudaSuccess) return cuda_fail(e, "preprocess_image_u8 memset");
+  const int64_t per_image = (int64_t)H * W * C;
+  u8_any_gt1_kernel<<<dim3(tail_grid(per_image / 16 + 1, B, 256), B), 256, 0, s>>>(src, per_image, flags);
+  const int Ho = transposed ? W : H, Wo = transposed ? H : W;
+  dim3 grid((Wo + kTile - 1) / kTile, (Ho + kTile - 1) / kTile, B);
+  rot_convert_kernel<ImageOp><<<grid, 256, 0, s>>>(src, H, W, C, rot, Ho, Wo, ImageOp{flags}, dst);
+  UB_LAUNCH_CHECK("preprocess_image_u8");
+  return 0;
+}
+
+int unetb200_preprocess_mask_u8(const uint8_t* src, int B, int H, int W, const int32_t* rot, int transposed,
+                                const int64_t* lut, int64_t* dst, void* stream) {
+  UB_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && W > 0, "preprocess_mask_u8: bad shape B=%d H=%d W=%d", B, H, W);
+  UB_CHECK_ARG(src && dst, "preprocess_mask_u8: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int Ho = transposed ? W : H, Wo = transposed ? H : W;
+  dim3 grid((Wo + kTile - 1) / kTile, (Ho + kTile - 1) / kTile, B);
+  rot_convert_kernel<MaskOp><<<grid, 256, 0, s>>>(src, H, W, 1, rot, Ho, Wo, MaskOp{(const long long*)lut},
+                                                  (long long*)dst);
+  UB_LAUNCH_CHECK("preprocess_mask_u8");
+  return 0;
+}
+}

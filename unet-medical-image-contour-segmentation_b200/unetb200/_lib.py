@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libunetb200.so")
 
-F32, BF16, I64 = 0, 1, 2
+F32, BF16, I64, U8 = 0, 1, 2, 3
 ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_PREFER_TC = 0, 1, 2, 3
 E_INVALID, E_CUDA, E_NOMEM = -1, -2, -3
 
@@ -75,6 +75,11 @@ PROTOTYPES = {
     "unetb200_grad_sqnorm": (C.c_int, [c_p, c_p, C.c_int, c_p, c_p]),
     "unetb200_rmsprop_step": (C.c_int, [c_p, c_p, c_p, c_p, c_p, C.c_int, c_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                         C.c_float, C.c_float, C.c_int, c_p]),
+    "unetb200_eval_counts": (C.c_int, [c_p, C.c_int, c_i64, c_i64, c_i64, c_i64, c_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, c_p, C.c_int, c_p, C.c_float, c_p, c_p]),
+    "unetb200_resize_argmax": (C.c_int, [c_p, C.c_int, c_i64, c_i64, c_i64, c_i64] + [C.c_int] * 6 + [c_p, C.c_int, c_p]),
+    "unetb200_preprocess_image_u8": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p, C.c_int, c_p, c_p, c_p]),
+    "unetb200_preprocess_mask_u8": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, c_p, C.c_int, c_p, c_p, c_p]),
 }
 
 _lib = None
