@@ -79,7 +79,9 @@ def check_pipeline_full_size():
     imgs = torch.randint(0, 256, (16, 512, 512), dtype=torch.uint8, generator=g)
     msks = torch.tensor([0, 128, 255], dtype=torch.uint8)[torch.randint(0, 3, (16, 512, 512), generator=g)]
     base = UD.preprocess_batch(imgs, msks, None, device=DEV)
-    want = (imgs.to(DEV).float() / 255.0).unsqueeze(1)
+    # true division on the host like numpy's (data_loading.py:87); torch's CUDA `x / 255.0` multiplies by the
+    # rounded reciprocal and differs in the last bit for ~half of the byte values
+    want = torch.from_numpy(imgs.numpy().astype(np.float32) / 255.0).unsqueeze(1)
     out.append(("pipe_full_values", ndiff(base["image"], want), 0))
     want_m = (msks.to(DEV) == 255).long() * 2 + (msks.to(DEV) == 128).long()
     out.append(("pipe_full_mask", ndiff(base["mask"], want_m), 0))
@@ -133,27 +135,53 @@ def check_eval_tail(gio=None):
     return out
 
 
+def _predict_case(out, tag, logits, size, index_dtype=torch.int64):
+    """Three gates per case.  (1) bit-exact against the op-by-op restatement of ATen's CUDA arithmetic (fp32 lambdas,
+    value rounded to the storage type, first maximum).  (2) Against the reference expression itself: the CPU fixture /
+    CPU ``F.interpolate(...).argmax`` -- exact for fp32 and for the identity resize; for bf16 ATen's *CPU* kernel
+    rounds the interpolation weights to bf16 (UpSampleKernel.cpp stores them as scalar_t) while its *CUDA* kernel --
+    the one predict.py runs on a GPU -- keeps them in fp32 like ours, so the CPU comparison carries a 5e-3 budget and
+    the CUDA comparison (same device, torch's own kernel, FMA contraction the only difference) 2e-4.  (3) Every pixel
+    that differs from the argmax of the fp32 interpolation must be a near tie: top-2 margin within the bf16 rounding
+    of the two values."""
+    import torch.nn.functional as F
+    H, W = size
+    for layout in ("nhwc", "nchw"):
+        lg = _dev_logits(logits) if layout == "nhwc" else logits.to(DEV).contiguous()
+        idx = UE.resize_argmax(lg, size, index_dtype=index_dtype).long()
+        out.append((f"predict_exact_{tag}_{layout}", ndiff(idx, IO.resize_argmax_exact(logits, size)), 0))
+        same = logits.shape[-2:] == (H, W)
+        bf = logits.dtype == torch.bfloat16
+        dis = 1.0 - (idx.cpu() == IO.predict_tail(logits, size)).float().mean().item()
+        out.append((f"predict_ref_cpu_{tag}_{layout}", dis, 0.0 if same else (5e-3 if bf else 1e-4)))
+        tidx = F.interpolate(lg, size, mode="bilinear").argmax(dim=1)          # predict.py:26-27 on this device
+        dis = 1.0 - (idx == tidx).float().mean().item()
+        out.append((f"predict_ref_cuda_{tag}_{layout}", dis, 0.0 if same else 2e-4))
+        up32 = F.interpolate(logits.float(), size, mode="bilinear")
+        top2 = up32.topk(2, dim=1).values
+        wrong = idx.cpu() != up32.argmax(dim=1)
+        if wrong.any():
+            margin = (top2[:, 0] - top2[:, 1])[wrong]
+            budget = (top2[:, 0].abs().maximum(top2[:, 1].abs())[wrong]) * (2.0 ** -7 if bf else 2.0 ** -20) + 1e-7
+            out.append((f"predict_near_tie_{tag}_{layout}", (margin / budget).max().item(), 1.0))
+
+
 def check_predict_tail(gio=None):
     gio = gio or load_golden_io()
     out = []
     for c in gio["predict"]:
-        for layout in ("nhwc", "nchw"):
-            lg = _dev_logits(c["logits"]) if layout == "nhwc" else c["logits"].to(DEV).contiguous()
-            idx = UE.resize_argmax(lg, c["size"])
-            # bit-exact against the op-by-op restatement of ATen's arithmetic ...
-            out.append((f"predict_exact_{c['tag']}_{layout}", ndiff(idx, IO.resize_argmax_exact(c["logits"], c["size"])), 0))
-            # ... and against the reference fixture (F.interpolate + argmax); the identity resize must be exact
-            dis = 1.0 - (idx.cpu() == c["idx"]).float().mean().item()
-            out.append((f"predict_ref_{c['tag']}_{layout}", dis, 0.0 if c["tag"].startswith("same") else 1e-3))
+        _predict_case(out, c["tag"], c["logits"], c["size"])
+        # the committed reference fixture (generated by the reference expression in the build container)
+        idx = UE.resize_argmax(_dev_logits(c["logits"]), c["size"])
+        dis = 1.0 - (idx.cpu() == c["idx"]).float().mean().item()
+        bf = c["logits"].dtype == torch.bfloat16
+        out.append((f"predict_fixture_{c['tag']}", dis, 0.0 if c["tag"].startswith("same") else (5e-3 if bf else 1e-4)))
     g = torch.Generator().manual_seed(22)
     for tag, (B, C, h, w, H, W, dt) in {"up_big_bf16": (2, 4, 128, 160, 300, 333, torch.bfloat16),
                                         "same_bf16": (2, 3, 96, 128, 96, 128, torch.bfloat16),
                                         "down_f32": (1, 3, 257, 129, 100, 64, torch.float32)}.items():
         lg = torch.randn(B, C, h, w, generator=g).to(dt)
-        idx = UE.resize_argmax(_dev_logits(lg), (H, W), index_dtype=torch.uint8)
-        out.append((f"predict_exact_{tag}", ndiff(idx.long(), IO.resize_argmax_exact(lg, (H, W))), 0))
-        dis = 1.0 - (idx.long().cpu() == IO.predict_tail(lg, (H, W))).float().mean().item()
-        out.append((f"predict_ref_{tag}", dis, 0.0 if tag.startswith("same") else 1e-3))
+        _predict_case(out, tag, lg, (H, W), index_dtype=torch.uint8)
     return out
 
 
