@@ -29,14 +29,41 @@ L2_BYTES = 126e6
 
 
 def timed(fn, sets, iters):
-    """average ms per call of fn(*sets[i % len(sets)])"""
+    """average DEVICE ms per call of fn(*sets[i]): one pass over all input sets is captured in a CUDA graph (the
+    C-ABI calls only enqueue on the stream they are given) and replayed, so the ~40 us of Python / ctypes / allocator
+    time per call does not hide the kernel time; CUDA events on the replaying stream."""
     for i in range(min(3, len(sets))):
         fn(*sets[i])
     torch.cuda.synchronize()
+    if ONCE:
+        return 0.0
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            keep = [fn(*a) for a in sets]
+        reps = max(1, iters // len(sets))
+        graph.replay()
+        side.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(side)
+        for _ in range(reps):
+            graph.replay()
+        e.record(side)
+        side.synchronize()
+    del keep
+    return s.elapsed_time(e) / (reps * len(sets))
+
+
+def timed_eager(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for i in range(iters):
-        fn(*sets[i % len(sets)])
+    for _ in range(iters):
+        fn()
     e.record()
     torch.cuda.synchronize()
     return s.elapsed_time(e) / iters
@@ -47,15 +74,15 @@ def ncopies(nbytes):
 
 
 def report(name, nbytes, ours_ms, ref_ms, note):
-    return {"op": name, "algorithmic_bytes": nbytes, "ms": ours_ms, "gbs": nbytes / ours_ms / 1e6,
-            "frac_of_hbm_peak": nbytes / ours_ms / 1e6 / PEAK, "reference_chain_ms": ref_ms,
-            "speedup_vs_reference_chain": ref_ms / ours_ms, "workload": note}
+    return {"op": name, "algorithmic_bytes": nbytes, "ms": ours_ms, "gbs": nbytes / ours_ms / 1e6 if ours_ms else None,
+            "frac_of_hbm_peak": nbytes / ours_ms / 1e6 / PEAK if ours_ms else None, "reference_chain_ms": ref_ms,
+            "speedup_vs_reference_chain": (ref_ms / ours_ms) if ours_ms and ref_ms else None, "workload": note}
 
 
 def main():
     out = []
     g = torch.Generator().manual_seed(0)
-    iters = 1 if ONCE else 50
+    iters = 1 if ONCE else 60
 
     # ---- evaluate tail: B=16, 3 classes, 512x512, bf16 NHWC logits (autocast output), float32 mask (evaluate.py:49)
     B, C, H, W = 16, 3, 512, 512
@@ -154,8 +181,8 @@ def main():
         def e2e_ref():          # train.py:113-114 on an already pre-processed host batch (host preprocessing NOT counted)
             return (hf.to(device=dev, dtype=torch.float32, memory_format=torch.channels_last, non_blocking=True),
                     hl.to(device=dev, dtype=torch.long, non_blocking=True))
-        t_o = timed(lambda: e2e_ours(), [()], 30)
-        t_r = timed(lambda: e2e_ref(), [()], 30)
+        t_o = timed_eager(e2e_ours, 30)
+        t_r = timed_eager(e2e_ref, 30)
         out.append({"op": "input batch host -> HBM, ready for the step", "ms": t_o, "reference_chain_ms": t_r,
                     "speedup_vs_reference_chain": t_r / t_o, "h2d_bytes": B * H * W * 2 + 4 * B,
                     "reference_h2d_bytes": B * H * W * 12,

@@ -35,63 +35,83 @@ __device__ __forceinline__ float load_target<long long>(const long long* p) { re
 template <typename O>
 __device__ __forceinline__ void store_index(O* p, int v) { *p = (O)v; }
 
-// first maximum over the class axis; NaN counts as the maximum (torch.argmax)
-template <typename T>
-__device__ __forceinline__ int argmax_classes(const T* p, int64_t sc, int C) {
-  float best = Elem<T>::ld(p);
-  int idx = 0;
-  for (int c = 1; c < C; ++c) {
-    float v = Elem<T>::ld(p + c * sc);
-    if (v > best || (v != v && best == best)) { best = v; idx = c; }
-  }
-  return idx;
-}
-
 // ------------------------------------------------------------------------------------------
 // evaluate tail.  mode 0 (evaluate.py:111-117): pred = (argmax_c logits == cls), true = (target == cls)
 //                 mode 1 (evaluate.py:56-66, n_classes == 1): pred = (sigmoid(z) rounded to T) > 0.5,
 //                         true = floor(target / 2), which must be 0 or 1 (the reference asserts it)
 // counts[b] = {sum pred*true, sum pred, sum true, #invalid targets}
 // ------------------------------------------------------------------------------------------
+constexpr int kEvalUnroll = 4;   // pixels per thread and iteration: four independent load chains in flight
+
 template <typename T, typename TT, typename O>
-__global__ void eval_counts_kernel(const T* __restrict__ logits, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
-                                   const TT* __restrict__ target, int C, int H, int W, int cls, int mode,
-                                   O* __restrict__ pred_out, unsigned long long* __restrict__ counts) {
+__global__ void __launch_bounds__(256) eval_counts_kernel(const T* __restrict__ logits, int64_t sb, int64_t sc,
+                                                          int64_t sh, int64_t sw, const TT* __restrict__ target, int C,
+                                                          int H, int W, int cls, int mode, O* __restrict__ pred_out,
+                                                          unsigned long long* __restrict__ counts) {
   __shared__ unsigned sm[32];
+  constexpr int U = kEvalUnroll;
   const int b = blockIdx.y;
   const int64_t HW = (int64_t)H * W;
   const T* lb = logits + b * sb;
   const TT* tb = target ? target + b * HW : nullptr;
   O* ob = pred_out ? pred_out + b * HW : nullptr;
   unsigned ni = 0, np = 0, nt = 0, nbad = 0;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
-    const int h = (int)(p / W), w = (int)(p - (int64_t)h * W);
-    const T* px = lb + h * sh + w * sw;
-    int label;
-    bool pb;
-    if (mode == 0) {
-      label = argmax_classes<T>(px, sc, C);
-      pb = label == cls;
-    } else {
-      const float z = Elem<T>::ld(px);
-      pb = Elem<T>::round(1.f / (1.f + expf(-z))) > 0.5f;
-      label = pb ? 1 : 0;
-    }
-    if (ob) store_index<O>(ob + p, label);
-    bool tbit = false;
-    if (tb) {
-      const float t = load_target<TT>(tb + p);
-      if (mode == 0) {
-        tbit = t == (float)cls;
+  const bool flat = sh == (int64_t)W * sw;
+  // a block covers U consecutive runs of blockDim.x pixels; every run is one coalesced access per warp
+  for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; p0 < HW;
+       p0 += (int64_t)gridDim.x * blockDim.x * U) {
+    int64_t p[U];
+    const T* px[U];
+    float t[U], best[U];
+    int label[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      p[u] = p0 + (int64_t)u * blockDim.x;
+      const int64_t q = p[u] < HW ? p[u] : HW - 1;      // out-of-range lanes re-read the last pixel, count nothing
+      if (flat) {                                       // rows are back to back: no division
+        px[u] = lb + q * sw;
       } else {
-        const float th = floorf(t * 0.5f);
-        tbit = th == 1.f;
-        nbad += !(th == 0.f || th == 1.f);
+        const unsigned h = (unsigned)q / (unsigned)W, w = (unsigned)q - h * (unsigned)W;
+        px[u] = lb + h * sh + w * sw;
+      }
+      t[u] = tb ? load_target<TT>(tb + q) : 0.f;
+      best[u] = Elem<T>::ld(px[u]);
+      label[u] = 0;
+    }
+    if (mode == 0) {
+      for (int c = 1; c < C; ++c) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float v = Elem<T>::ld(px[u] + c * sc);
+          // first maximum; NaN counts as the maximum (torch.argmax)
+          if (v > best[u] || (v != v && best[u] == best[u])) { best[u] = v; label[u] = c; }
+        }
       }
     }
-    ni += pb && tbit;
-    np += pb;
-    nt += tbit;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p[u] >= HW) continue;
+      bool pb, tbit = false;
+      if (mode == 0) {
+        pb = label[u] == cls;
+      } else {
+        pb = Elem<T>::round(1.f / (1.f + expf(-best[u]))) > 0.5f;
+        label[u] = pb ? 1 : 0;
+      }
+      if (ob) store_index<O>(ob + p[u], label[u]);
+      if (tb) {
+        if (mode == 0) {
+          tbit = t[u] == (float)cls;
+        } else {
+          const float th = floorf(t[u] * 0.5f);
+          tbit = th == 1.f;
+          nbad += !(th == 0.f || th == 1.f);
+        }
+      }
+      ni += pb && tbit;
+      np += pb;
+      nt += tbit;
+    }
   }
   unsigned long long r0 = block_count(ni, sm), r1 = block_count(np, sm), r2 = block_count(nt, sm),
                      r3 = block_count(nbad, sm);
@@ -149,7 +169,7 @@ __global__ void resize_argmax_kernel(const T* __restrict__ logits, int64_t sb, i
   const T* lb = logits + b * sb;
   O* ob = out + b * HW;
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
-    const int oy = (int)(p / W), ox = (int)(p - (int64_t)oy * W);
+    const int oy = (int)((unsigned)p / (unsigned)W), ox = (int)((unsigned)p - (unsigned)oy * (unsigned)W);
     const Lerp ly = lerp_index(oy, scale_h, h), lx = lerp_index(ox, scale_w, w);
     const T* p00 = lb + ly.i0 * sh + lx.i0 * sw;
     const int64_t dy = ly.di * sh, dx = lx.di * sw;
@@ -283,12 +303,13 @@ int unetb200_eval_counts(const void* logits, int dtype, int64_t sb, int64_t sc, 
                "eval_counts: prediction dtype must be int64 or uint8");
   UB_CHECK_ARG(B > 0 && B <= 65535 && C >= 1 && H > 0 && W > 0, "eval_counts: bad shape B=%d C=%d H=%d W=%d", B, C,
                H, W);
+  UB_CHECK_ARG((int64_t)H * W < (1ll << 31), "eval_counts: H*W must be below 2^31");
   UB_CHECK_ARG(mode == 0 || (mode == 1 && C == 1), "eval_counts: mode %d needs C == 1 (got %d)", mode, C);
   UB_CHECK_ARG(counts != nullptr, "eval_counts: counts workspace");
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)B * 4 * sizeof(int64_t), s);
   if (e != cudaSuccess) return cuda_fail(e, "eval_counts memset");
-  dim3 grid(tail_grid((int64_t)H * W, B, 256), B);
+  dim3 grid(tail_grid(((int64_t)H * W + kEvalUnroll - 1) / kEvalUnroll, B, 256), B);
   unsigned long long* cnt = (unsigned long long*)counts;
   const bool u8 = pred_out && pred_dtype == UNETB200_U8;
 #define GO3(T, TT, O)                                                                                      \
@@ -316,6 +337,7 @@ int unetb200_resize_argmax(const void* logits, int dtype, int64_t sb, int64_t sc
   UB_CHECK_ARG(dtype == UNETB200_F32 || dtype == UNETB200_BF16, "resize_argmax: logits dtype");
   UB_CHECK_ARG(out_dtype == UNETB200_I64 || out_dtype == UNETB200_U8, "resize_argmax: output dtype");
   UB_CHECK_ARG(B > 0 && B <= 65535 && C >= 1 && h > 0 && w > 0 && H > 0 && W > 0, "resize_argmax: bad shape");
+  UB_CHECK_ARG((int64_t)H * W < (1ll << 31), "resize_argmax: H*W must be below 2^31");
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(tail_grid((int64_t)H * W, B, 256), B);
   const float sch = (float)h / (float)H, scw = (float)w / (float)W;
