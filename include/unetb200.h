@@ -95,6 +95,18 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
                          const float* bias, void* y, double* stats, float* stats_ws, int* algo_used,
                          void* stream);
 
+/* Inference form of conv3x3 -> BatchNorm2d (running statistics) -> ReLU (unet_parts.py:15-20 under
+ * .eval(), evaluate.py:30, predict.py:17): z = relu(gconv(x, Wp) * scale[n] + shift[n]) computed in the
+ * epilogue of the tcgen05 kernel, so the activation is written once and the separate BatchNorm pass
+ * (4 B per element) disappears.  scale_shift = float[2*N] (scale then shift, 16-byte aligned; rows 2-3
+ * of unetb200_bn_eval_coeffs' output).  _supported returns 1 when the fused kernel covers the shape
+ * (3x3, stride 1, C_in and N multiples of 64, tcgen05 eligible); otherwise run unetb200_gconv_fprop +
+ * unetb200_bn_relu_apply. */
+int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                               const void* z);
+int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                     const float* scale_shift, void* z, void* stream);
+
 /* Weight gradient of the same generalised conv:
  *   dWp[(t,c)][n] = sum_m A[m][(t,c)] * G[m][n],  G[m][n] = gy at the destination of (m,n).
  * The reduction over m is split `splits` ways; partial s is written (not accumulated) to

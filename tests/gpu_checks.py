@@ -728,6 +728,65 @@ def check_optim():
     return out
 
 
+def check_conv_bnfold():
+    """Inference form of conv3x3 -> BatchNorm(running statistics) -> ReLU folded into the tcgen05 epilogue
+    (unetb200_gconv_fprop_affine_relu) against PyTorch-CPU fp32 on the same (dtype-rounded) inputs, and against the
+    unfused two-kernel path.  Covers both N blocks (64 / 128), the 8x32 tile variant (W <= 8), ragged tile edges,
+    a destination that is a channel slice of a wider concat buffer, the fused max-pool follow-up, bf16 and tf32."""
+    out = []
+    g = gen(41)
+    os.environ["UNET_B200_PRECISION"] = "tf32"
+    try:
+        for (B, Ci, Co, H, W, dt_, sliced, pool) in ((2, 64, 64, 40, 36, BF, False, False), (1, 128, 128, 32, 48, BF, True, True),
+                                                    (2, 64, 128, 16, 8, BF, False, True), (1, 256, 64, 24, 24, BF, True, False),
+                                                    (1, 64, 128, 20, 28, FP, False, True), (3, 128, 256, 8, 8, BF, False, False)):
+            x = rq(torch.randn(B, Ci, H, W, generator=g), dt_ if dt_ == BF else FP)
+            w = torch.randn(Co, Ci, 3, 3, generator=g) * (2.0 / (9 * Ci)) ** 0.5
+            bn = torch.nn.BatchNorm2d(Co)
+            with torch.no_grad():
+                bn.weight.copy_(0.5 + torch.rand(Co, generator=g))
+                bn.bias.copy_(0.3 * torch.randn(Co, generator=g))
+                bn.running_mean.copy_(0.2 * torch.randn(Co, generator=g))
+                bn.running_var.copy_(0.5 + torch.rand(Co, generator=g))
+            bn.eval()
+            wq = rq(w, dt_) if dt_ == BF else w
+            with torch.no_grad():
+                ref = F.relu(bn(F.conv2d(x, wq, padding=1)))
+                ref_pool = F.max_pool2d(ref, 2)
+            bnd = torch.nn.BatchNorm2d(Co).to(DEV)
+            bnd.load_state_dict(bn.state_dict())
+            bnd.eval()
+            xd = dev_nhwc(x, dt_)
+            wd = w.to(DEV)
+            res = {}
+            for fold in (True, False):
+                dst = None
+                if sliced:
+                    buf = ops.empty_nhwc(B, 2 * Co, H, W, dt_, DEV)
+                    buf.fill_(7.0)
+                    dst = ops.channel_slice(buf, 0, Co)
+                with torch.no_grad():
+                    y, z, pooled, _ = UF.conv_bn_relu_fwd(xd, wd, bnd, False, out=dst, want_pool=pool, fold=fold)
+                if fold:
+                    out.append((f"bnfold_taken_{Ci}_{Co}_{H}x{W}_{dt_}", 0.0 if y is None else 1.0, 0))
+                    if sliced:
+                        out.append((f"bnfold_slice_untouched_{Ci}_{Co}", float((host(buf[:, Co:]) != 7.0).sum().item()), 0))
+                res[fold] = (host(z), host(pooled) if pool else None)
+            tol = TOL[BF] if dt_ == BF else 2e-3          # fp32 storage runs on tf32 tensor cores here
+            tag = f"{Ci}_{Co}_{H}x{W}_{dt_}{'_slice' if sliced else ''}"
+            out.append((f"bnfold_vs_fp32_{tag}", rel(res[True][0], ref), tol))
+            out.append((f"bnfold_vs_unfused_{tag}", rel(res[True][0], res[False][0]), tol))
+            if pool:
+                out.append((f"bnfold_pool_vs_fp32_{tag}", rel(res[True][1], ref_pool), tol))
+                # the pooled tensor is exactly the max-pool of the z that was stored
+                zs = res[True][0]
+                out.append((f"bnfold_pool_exact_{tag}", float((F.max_pool2d(zs, 2) != res[True][1]).sum().item()), 0))
+            out.append((f"bnfold_relu_{tag}", float((res[True][0] < 0).sum().item()), 0))
+    finally:
+        os.environ.pop("UNET_B200_PRECISION", None)
+    return out
+
+
 GROUPS = {
     "layout": lambda gd: check_layout_ops(),
     "bn_fwd": lambda gd: check_bn_forward(),
@@ -744,6 +803,7 @@ GROUPS = {
     "conv_tc_tf32": lambda gd: check_conv_tc_tf32(),
     "conv_layouts": lambda gd: check_conv_layouts(),
     "optim": lambda gd: check_optim(),
+    "conv_bnfold": lambda gd: check_conv_bnfold(),
     "parts_fp32": lambda gd: check_parts(gd, "fp32"),
     "parts_bf16": lambda gd: check_parts(gd, "bf16"),
     "calib_small": lambda gd: sum((calibrate(1, 2, False, 2, 128, 128, m) for m in ("fp32", "tf32", "bf16")), []),

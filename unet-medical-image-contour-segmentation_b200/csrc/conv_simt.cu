@@ -556,6 +556,29 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   return 0;
 }
 
+// conv3x3 -> BatchNorm(eval) -> ReLU with the normalisation folded into the tcgen05 epilogue (inference only)
+int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* z) {
+  GconvDev g;
+  if (gconv_validate(d, &g)) return 0;
+  if (getenv("UNETB200_NO_BN_FOLD") || getenv("UNETB200_TC_V1") || d->algo == UNETB200_ALGO_SIMT) return 0;
+  if (d->N % 128 != 0 && d->N % 64 != 0) return 0;
+  if (d->dtype == UNETB200_BF16 && d->N % 256 == 0 && getenv("UNETB200_TC3_MAXBN") && atoi(getenv("UNETB200_TC3_MAXBN")) >= 256)
+    return 0;
+  return tc_fprop_supported(d, x, wp, z) && tc3_fprop_supported(d, x, wp, nullptr, z);
+}
+
+int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, const void* wp, const float* scale_shift,
+                                     void* z, void* stream) {
+  GconvDev g;
+  int rc = gconv_validate(d, &g);
+  if (rc) return rc;
+  UB_CHECK_ARG(x && wp && z && scale_shift, "gconv_fprop_affine_relu: null pointer");
+  UB_CHECK_ARG(unetb200_gconv_fprop_affine_relu_supported(d, x, wp, z),
+               "gconv_fprop_affine_relu: shape not covered by the fused kernel (query _supported first and run "
+               "gconv_fprop + bn_relu_apply instead)");
+  return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift);
+}
+
 int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_used) {
   GconvDev g;
   int rc = gconv_validate(d, &g);

@@ -162,6 +162,8 @@ struct alignas(64) Tc3Params {
   int m_tiles, m_groups, total_groups;   // m_groups = ceil(m_tiles / CG); one "group" = CG tiles of one n-block
   int Hm, Wm, B;
   float* stats_ws;           // [n_block][cta][8 epilogue warps][2][BLOCK_N]
+  const float* affine;       // AFFINE kernels only: scale[N] then shift[N] (eval-mode BatchNorm folded into the epilogue)
+  int N;
 };
 
 constexpr uint32_t kA3Stage = 44032;    // 43 KB >= the largest halo box: 34 rows x 10 px x 128 B
@@ -169,7 +171,10 @@ constexpr int kEpi3Stage = 4096;        // 32 rows x 128 B per epilogue warp
 constexpr int kEpi3Warps = 8;           // two per TMEM lane quadrant: one per 128-row sub-tile
 constexpr int kTc3Threads = 64 + 32 * kEpi3Warps;
 
-template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG, int TPS>
+// AFFINE: inference form of conv -> BatchNorm(running statistics) -> ReLU (unet_parts.py:15-20 under .eval()): the
+// epilogue stores relu(acc * scale[n] + shift[n]) instead of the raw convolution, so the activation is written once
+// and the separate 4 B/element BatchNorm pass disappears.  A separate instantiation: the training kernels are unchanged.
+template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG, int TPS, bool AFFINE = false>
 __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_constant__ Tc3Params p) {
   constexpr bool TF32 = sizeof(T) == 4;
   constexpr int EPR = 128 / sizeof(T);
@@ -351,6 +356,19 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
           if (lane == 0) tma_store_wait_read_all();                   // the previous store has finished reading `buf`
           tmem_ld_fence();
           __syncwarp();
+          if constexpr (AFFINE) {
+            // channel of v[k] is n0 + cb * EPR + k for every lane: warp-uniform 16-byte coefficient loads
+            const float4* sc4 = reinterpret_cast<const float4*>(p.affine + n0 + cb * EPR);
+            const float4* sh4 = reinterpret_cast<const float4*>(p.affine + p.N + n0 + cb * EPR);
+#pragma unroll
+            for (int k4 = 0; k4 < EPR / 4; ++k4) {
+              const float4 a = __ldg(sc4 + k4), c = __ldg(sh4 + k4);
+              v[4 * k4 + 0] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * k4 + 0]), a.x, c.x), 0.f));
+              v[4 * k4 + 1] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * k4 + 1]), a.y, c.y), 0.f));
+              v[4 * k4 + 2] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * k4 + 2]), a.z, c.z), 0.f));
+              v[4 * k4 + 3] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * k4 + 3]), a.w, c.w), 0.f));
+            }
+          }
           const uint32_t dst = buf_s + lane * 128;
 #pragma unroll
           for (int h = 0; h < EPR / 32; ++h) {
@@ -497,13 +515,13 @@ long long tc3_stats_workspace(const unetb200_gconv_t* d) {
   return (long long)pl.n_blocks * pl.grid * kEpi3Warps * 2 * pl.BN;
 }
 
-template <typename T, int BN, int SA, int SB, int ACC, int CG, int TPS>
+template <typename T, int BN, int SA, int SB, int ACC, int CG, int TPS, bool AFFINE = false>
 static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
   constexpr int smem = SA * kA3Stage + SB * TPS * (BN / CG) * 128 + kEpi3Warps * kEpi3Stage + 1024 + 256;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS>,
+    cudaError_t e = cudaFuncSetAttribute(tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS, AFFINE>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cuda_fail(e, "tc3_conv smem attribute");
     configured = true;
@@ -520,7 +538,7 @@ static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS>, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS, AFFINE>, P);
   if (e != cudaSuccess) return cuda_fail(e, "tc3_conv launch");
   return 0;
 }
@@ -555,8 +573,12 @@ __global__ void __launch_bounds__(1024) tc3_stats_reduce_kernel(const float* __r
 }
 
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
-              float* stats_ws, cudaStream_t stream) {
+              float* stats_ws, cudaStream_t stream, const float* affine) {
   Tc3Plan pl;
+  if (affine && (stats || (reinterpret_cast<uintptr_t>(affine) & 15))) {
+    set_error("tc3_fprop: the affine epilogue takes no statistics and needs 16-byte aligned coefficients");
+    return UNETB200_E_INVALID;
+  }
   if (!tc3_plan(d, &pl)) { set_error("tc3_fprop: unsupported shape"); return UNETB200_E_INVALID; }
   const int esz = d->dtype == UNETB200_BF16 ? 2 : 4;
   Tc3Params P;
@@ -585,6 +607,22 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   P.total_groups = pl.m_groups * pl.n_blocks;
   P.Hm = d->Hm; P.Wm = d->Wm; P.B = d->B;
   P.stats_ws = stats ? stats_ws : nullptr;
+  P.affine = affine;
+  P.N = d->N;
+  if (affine) {
+    // BatchNorm-folded inference epilogue: the pair kernel with N block 128 / 64 (the shapes of the path)
+    if (pl.BN == 256) { set_error("tc3_fprop: affine epilogue supports N blocks of 64 / 128"); return UNETB200_E_INVALID; }
+    if (d->dtype == UNETB200_BF16) {
+      if (pl.CG == 2) return pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 3, 2, 2, 3, true>(P, pl.grid, stream)
+                                          : tc3_launch<__nv_bfloat16, 64, 3, 3, 2, 2, 3, true>(P, pl.grid, stream);
+      return pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 6, 2, 1, 1, true>(P, pl.grid, stream)
+                          : tc3_launch<__nv_bfloat16, 64, 3, 6, 2, 1, 1, true>(P, pl.grid, stream);
+    }
+    if (pl.CG == 2) return pl.BN == 128 ? tc3_launch<float, 128, 2, 3, 2, 2, 3, true>(P, pl.grid, stream)
+                                        : tc3_launch<float, 64, 3, 3, 2, 2, 3, true>(P, pl.grid, stream);
+    return pl.BN == 128 ? tc3_launch<float, 128, 2, 6, 2, 1, 1, true>(P, pl.grid, stream)
+                        : tc3_launch<float, 64, 3, 6, 2, 1, 1, true>(P, pl.grid, stream);
+  }
   if (stats) {
     cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * (size_t)tc3_stats_workspace(d), stream);
     if (e != cudaSuccess) return cuda_fail(e, "tc3 stats workspace memset");

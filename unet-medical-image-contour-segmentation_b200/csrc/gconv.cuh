@@ -66,7 +66,7 @@ int tc2_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
 int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, const void* y);
 long long tc3_stats_workspace(const unetb200_gconv_t* d);
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
-              float* stats_ws, cudaStream_t stream);
+              float* stats_ws, cudaStream_t stream, const float* affine = nullptr);
 
 int tc3_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int tc3_wgrad_splits(const unetb200_gconv_t* d);

@@ -172,12 +172,28 @@ def _gconv3x3(x, Cout, y, dtype):
                           Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(y))
 
 
-def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False):
-    """x NHWC -> (y raw conv output, z = relu(bn(y)), pooled or None, coefs[4,C])."""
+def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False):
+    """x NHWC -> (y raw conv output, z = relu(bn(y)), pooled or None, coefs[4,C]).
+
+    fold=True (no backward will follow) with running statistics: BatchNorm + ReLU are folded into the conv epilogue
+    (one write of z, no y) when the fused tcgen05 kernel covers the shape."""
     B, Cin, H, W = x.shape
     Cout = w.shape[0]
     cd, dev = x.dtype, x.device
     wp = pack3x3_fprop(w, cd)
+    if fold and not (training or bn.running_mean is None) and Cout % 2 == 0:
+        z = out if out is not None else ops.empty_nhwc(B, Cout, H, W, cd, dev)
+        d = _gconv3x3(x, Cout, z, cd)
+        if ops.gconv_fprop_affine_relu_supported(d, x, wp, z):
+            gamma = _f32c(bn.weight) if bn.weight is not None else None
+            beta = _f32c(bn.bias) if bn.bias is not None else None
+            coefs = ops.bn_eval_coeffs(gamma, beta, bn.running_mean, bn.running_var, bn.eps, Cout)
+            ops.gconv_fprop_affine_relu(d, x, wp, coefs, z)
+            pooled = None
+            if want_pool:
+                pooled = ops.empty_nhwc(B, Cout, H // 2, W // 2, cd, dev)
+                ops.maxpool2_fwd(z, pooled)
+            return None, z, pooled, coefs
     y = ops.empty_nhwc(B, Cout, H, W, cd, dev)
     use_batch = training or bn.running_mean is None
     stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if use_batch else None
@@ -266,8 +282,10 @@ class _Cfg:
 class DoubleConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, cfg):
-        y1, z1, _, c1 = conv_bn_relu_fwd(x, w1, cfg.bn1, cfg.training)
-        y2, z2, pooled, c2 = conv_bn_relu_fwd(z1, w2, cfg.bn2, cfg.training, out=cfg.out, want_pool=cfg.want_pool)
+        fold = not cfg.save
+        y1, z1, _, c1 = conv_bn_relu_fwd(x, w1, cfg.bn1, cfg.training, fold=fold)
+        y2, z2, pooled, c2 = conv_bn_relu_fwd(z1, w2, cfg.bn2, cfg.training, out=cfg.out, want_pool=cfg.want_pool,
+                                              fold=fold)
         ctx.batch_stats = (cfg.training or cfg.bn1.running_mean is None, cfg.training or cfg.bn2.running_mean is None)
         ctx.has_pool = pooled is not None
         if cfg.save:

@@ -318,6 +318,18 @@ def gconv_fprop(d, x, wp, bias, y, stats, kind="fprop"):
     return used.value
 
 
+def gconv_fprop_affine_relu_supported(d, x, wp, z):
+    return bool(lib().unetb200_gconv_fprop_affine_relu_supported(C.byref(d), _p(x), _p(wp), _p(z)))
+
+
+def gconv_fprop_affine_relu(d, x, wp, coefs, z):
+    """z = relu(conv(x, wp) * scale + shift) in the tcgen05 epilogue (inference; coefs rows 2, 3 = scale, shift)."""
+    _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu, C.byref(d), _p(x), _p(wp), _p(coefs[2]), _p(z),
+         _stream(), flops=gconv_flops(d))
+    if _PROFILE is not None:
+        _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + _shape_tag(d)
+
+
 def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0):
     """dst (parameter layout, fp32) = weight gradient; dst[t*st + c*sc + q*sq + co*sn], n = q*Cq + co."""
     splits, used = C.c_int(0), C.c_int(0)
