@@ -105,6 +105,106 @@ first_conv_fprop_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
   }
 }
 
+// C_in = 2..4 (RGB input, BASELINE configs[4]): the kernel above re-reads its 9*C_in weight vectors from shared
+// memory for every pixel (54 LDS.128 per 216 FMAs at C_in = 3: shared-memory bandwidth bound, 2.75 ms for the
+// 8 x 1024 x 1024 first layer).  Here a thread owns FOUR horizontally adjacent pixels x 8 output channels: one weight
+// vector feeds 32 FMAs and the 3 x 6 input window is loaded once for the four pixels.
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256)
+first_conv_fprop_px4_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ wp, T* __restrict__ y,
+                            float* __restrict__ stats_ws) {
+  constexpr int K = 9 * CIN;
+  __shared__ float sstat[2][256];
+  __shared__ float sw[K * 256];                          // [(window position, c)][n]
+  __shared__ int tmap[9];
+  const int G = d.N >> 3, lanes = 256 / G;
+  const int g = threadIdx.x % G, lane = threadIdx.x / G;
+  const bool active = lane < lanes;
+  for (int i = threadIdx.x; i < 2 * 256; i += 256) (&sstat[0][0])[i] = 0.f;
+  if (threadIdx.x < 9) tmap[(d.tap_dy[threadIdx.x] + 1) * 3 + d.tap_dx[threadIdx.x] + 1] = threadIdx.x;
+  __syncthreads();
+  for (int e = threadIdx.x; e < K * d.N; e += 256) {
+    const int n = e / K, k = e - n * K;                  // k = (window position, c) -> packed index (tap, c)
+    const int pos = k / CIN, c = k - pos * CIN;
+    sw[k * d.N + n] = Elem<T>::ld(wp + (long long)n * K + tmap[pos] * CIN + c);
+  }
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (active) {
+    const int Wq = d.Wm >> 2;                            // W % 4 == 0 (checked on the host)
+    const int Mq = d.B * d.Hm * Wq, qstride = gridDim.x * lanes;
+    for (int mq = blockIdx.x * lanes + lane; mq < Mq; mq += qstride) {
+      const int jq = mq % Wq, r = mq / Wq;
+      const int pi = r % d.Hm, b = r / d.Hm;
+      const int j0 = jq << 2;
+      float acc[4][8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[p][i] = 0.f;
+      // one window row at a time (not unrolled: 6 * C_in live inputs + 32 accumulators stay in registers)
+#pragma unroll 1
+      for (int a = 0; a < 3; ++a) {
+        const int gi = pi - 1 + a;
+        const bool rok = (unsigned)gi < (unsigned)d.Hin;
+        float xr[6][CIN];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc) {
+          const int gj = j0 - 1 + cc;
+          const bool ok = rok && (unsigned)gj < (unsigned)d.Win;
+          const T* src = x + ((long long)(b * d.Hin + (ok ? gi : pi)) * d.Win + (ok ? gj : j0)) * d.ld_in;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            const float v = Elem<T>::ld(src + c);
+            xr[cc][c] = ok ? v : 0.f;
+          }
+        }
+        const float* wa = &sw[a * 3 * CIN * d.N + g * 8];
+#pragma unroll
+        for (int cw = 0; cw < 3; ++cw)
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            const float* wrow = wa + (cw * CIN + c) * d.N;
+            const float4 w0 = *reinterpret_cast<const float4*>(wrow);
+            const float4 w1 = *reinterpret_cast<const float4*>(wrow + 4);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const float xe = xr[p + cw][c];
+              acc[p][0] = fmaf(xe, w0.x, acc[p][0]); acc[p][1] = fmaf(xe, w0.y, acc[p][1]);
+              acc[p][2] = fmaf(xe, w0.z, acc[p][2]); acc[p][3] = fmaf(xe, w0.w, acc[p][3]);
+              acc[p][4] = fmaf(xe, w1.x, acc[p][4]); acc[p][5] = fmaf(xe, w1.y, acc[p][5]);
+              acc[p][6] = fmaf(xe, w1.z, acc[p][6]); acc[p][7] = fmaf(xe, w1.w, acc[p][7]);
+            }
+          }
+      }
+      T* dst = y + ((long long)(b * d.Hm + pi) * d.Wm + j0) * d.ld_out + g * 8;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[p][i] = Elem<T>::round(acc[p][i]);
+          s[i] += acc[p][i];
+          q[i] += acc[p][i] * acc[p][i];
+        }
+        store8(dst + (long long)p * d.ld_out, acc[p]);
+      }
+    }
+  }
+  if (stats_ws) {
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { atomicAdd(&sstat[0][g * 8 + i], s[i]); atomicAdd(&sstat[1][g * 8 + i], q[i]); }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * d.N; e += 256) {
+      const int which = e / d.N, c = e - which * d.N;
+      stats_ws[((long long)blockIdx.x * 2 + which) * d.N + c] = sstat[which][c];
+    }
+  }
+}
+
 // dWp[(t)][n] partial per block (C_in == 1): partials[block][9][N]
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -422,6 +522,19 @@ static bool first_tiled_ok(const unetb200_gconv_t* d) {
   return (long long)d->B * d->Hin * d->Win < (1LL << 31);
 }
 
+// four pixels per thread (C_in = 2..4): needs the plain 3x3 window and W % 4 == 0
+static bool first_px4_ok(const unetb200_gconv_t* d) {
+  if (getenv("UNETB200_FIRST_V1")) return false;
+  if (d->Cin < 2 || d->Cin > 4 || (d->Wm & 3)) return false;
+  bool seen[9] = {false};
+  for (int t = 0; t < 9; ++t) {
+    const int dy = d->tap_dy[t], dx = d->tap_dx[t];
+    if (dy < -1 || dy > 1 || dx < -1 || dx > 1 || seen[(dy + 1) * 3 + dx + 1]) return false;
+    seen[(dy + 1) * 3 + dx + 1] = true;
+  }
+  return true;
+}
+
 static bool first_common(const unetb200_gconv_t* d) {
   if (d->ntaps != 9 || d->in_scale != 1 || d->out_scale != 1 || d->nquad != 1) return false;
   if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) return false;
@@ -466,6 +579,20 @@ int first_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, con
                                                                   stats ? stats_ws : nullptr, tiles_w, tiles_h, ntiles);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "first_conv_fprop_tiled");
+    if (stats) return launch_stats_reduce(stats_ws, blocks, 2 * d->N, stats, s);
+    return 0;
+  }
+  if (first_px4_ok(d)) {
+#define GO4(T, CIN) \
+  first_conv_fprop_px4_kernel<T, CIN><<<blocks, 256, 0, s>>>(g, (const T*)x, (const T*)wp, (T*)y, stats ? stats_ws : nullptr)
+    if (d->dtype == UNETB200_BF16) {
+      if (d->Cin == 2) GO4(__nv_bfloat16, 2); else if (d->Cin == 3) GO4(__nv_bfloat16, 3); else GO4(__nv_bfloat16, 4);
+    } else {
+      if (d->Cin == 2) GO4(float, 2); else if (d->Cin == 3) GO4(float, 3); else GO4(float, 4);
+    }
+#undef GO4
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "first_conv_fprop_px4");
     if (stats) return launch_stats_reduce(stats_ws, blocks, 2 * d->N, stats, s);
     return 0;
   }
