@@ -80,3 +80,73 @@ def test_host_argument_logic():
         eval_tail.resize_argmax(torch.zeros(1, 3, 4, 4), (8, 8))
     with pytest.raises(ValueError):
         eval_tail.binary_dice(torch.zeros(1, 2, 4, 4), torch.zeros(1, 4, 4))
+
+
+def test_evaluate_host_logic(monkeypatch):
+    """unetb200.eval_tail.evaluate's control flow (per-batch scores, post-processing leg, min rule, return triple,
+    eval()/train() switching) with the device tails replaced by the oracle: it must reproduce evaluate.py:12-173."""
+    from unetb200 import eval_tail, losses
+
+    def fake_mc(mask_pred, mask_true, c=2, index_dtype=torch.int64, epsilon=1e-6):
+        idx, dice, counts = IO.eval_multiclass(mask_pred.float(), mask_true.float(), c)
+        return idx.to(index_dtype), dice, counts
+
+    def fake_bin(mask_pred, mask_true, index_dtype=torch.uint8, epsilon=1e-6):
+        binary, dice, counts = IO.eval_binary(mask_pred.float(), mask_true.float())
+        return binary.to(index_dtype), dice, counts
+    monkeypatch.setattr(eval_tail, "argmax_class_dice", fake_mc)
+    monkeypatch.setattr(eval_tail, "binary_dice", fake_bin)
+    monkeypatch.setattr(losses, "dice_coeff", IO.dice_coeff)
+
+    class Net(torch.nn.Module):
+        def __init__(self, n_classes):
+            super().__init__()
+            self.n_classes = n_classes
+            self.conv = torch.nn.Conv2d(1, n_classes, 3, padding=1)
+
+        def forward(self, x):
+            return self.conv(x)
+
+    def erode(m):                                   # a stand-in for utils.post_process.postprocess_mask
+        out = m.copy()
+        out[::2] = 0
+        return out
+
+    dev = torch.device("cpu")
+    for ncls in (3, 1):
+        torch.manual_seed(ncls)
+        net = Net(ncls).train()
+        g = torch.Generator().manual_seed(5)
+        batches = [{"image": torch.rand(2, 1, 16, 16, generator=g),
+                    "mask": torch.randint(0, 3 if ncls > 1 else 4, (2, 16, 16), generator=g)} for _ in range(3)]
+        # literal restatement of the reference loop
+        orig, post = [], []
+        with torch.inference_mode():
+            net.eval()
+            for b in batches:
+                lg = net(b["image"])
+                if ncls == 1:
+                    binary, d, _ = IO.eval_binary(lg, b["mask"].float())
+                    orig.append(d.item())
+                    pp = torch.stack([torch.from_numpy((erode(m.numpy().astype(np.uint8) * 255) // 255).astype(np.float32))
+                                      for m in binary])
+                    true = b["mask"].float() // 2
+                    post.append(IO.dice_coeff(pp, true, reduce_batch_first=False).item())
+                else:
+                    idx, d, _ = IO.eval_multiclass(lg, b["mask"].float(), 2)
+                    orig.append(d.item())
+                    pp = torch.stack([torch.from_numpy(erode(m.numpy().astype(np.uint8))) for m in idx])
+                    post.append(IO.dice_coeff((pp == 2).float(), (b["mask"] == 2).float(), reduce_batch_first=False).item())
+            net.train()
+        got = eval_tail.evaluate(net, batches, dev, amp=False, postprocess=True, postprocess_fn=erode)
+        assert net.training
+        assert abs(got[0] - sum(orig) / 3) < 1e-6 and abs(got[1] - sum(post) / 3) < 1e-6
+        want_min = min(min(o, p) for o, p in zip(orig, post)) if ncls == 1 else min(orig)     # evaluate.py:85 vs :121
+        assert abs(got[2] - want_min) < 1e-6
+        got = eval_tail.evaluate(net, batches, dev, amp=False, postprocess=False)
+        assert got[1] == got[0] and abs(got[2] - min(orig)) < 1e-6                            # evaluate.py:169-170
+    assert eval_tail.evaluate(Net(3), [], dev, amp=False) == (0, 0, 10)
+    with pytest.raises(ValueError):
+        eval_tail.evaluate(Net(3), [], dev, amp=False, postprocess=True)
+    with pytest.raises(NotImplementedError):
+        eval_tail.evaluate(Net(3), [], dev, amp=False, epoch_pred_dir="/tmp/x")
