@@ -150,3 +150,28 @@ def test_evaluate_host_logic(monkeypatch):
         eval_tail.evaluate(Net(3), [], dev, amp=False, postprocess=True)
     with pytest.raises(NotImplementedError):
         eval_tail.evaluate(Net(3), [], dev, amp=False, epoch_pred_dir="/tmp/x")
+
+
+def test_oracle_properties():
+    """Size-independent properties the GPU full-size gates rely on, checked on the oracle itself."""
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, size=(5, 7, 3), dtype=np.uint8)
+    for k in range(4):
+        assert np.array_equal(IO.rotate(IO.rotate(a, k), 4 - k), a)
+        assert np.array_equal(IO.rotate(a, k + 4), IO.rotate(a, k))
+    imgs = rng.integers(0, 256, size=(4, 6, 6), dtype=np.uint8)
+    msks = np.array([0, 128, 255], dtype=np.uint8)[rng.integers(0, 3, size=(4, 6, 6))]
+    base_i, base_m = IO.make_batch(list(imgs), list(msks), [0] * 4)
+    rot_i, rot_m = IO.make_batch(list(imgs), list(msks), [0, 1, 2, 3])
+    for b in range(4):
+        assert torch.equal(rot_i[b], torch.rot90(base_i[b], b, dims=(1, 2)))
+        assert torch.equal(rot_m[b], torch.rot90(base_m[b], b, dims=(0, 1)))
+    assert base_i.max() <= 1.0 and set(base_m.unique().tolist()) <= {0, 1, 2}
+    g = torch.Generator().manual_seed(2)
+    lg = torch.randn(3, 4, 9, 11, generator=g)
+    true = lg.argmax(1).float()
+    idx, dice, counts = IO.eval_multiclass(lg, true, 2)
+    assert abs(dice.item() - 1.0) < 1e-6                        # prediction == truth
+    assert (counts[:, 0] <= counts[:, 1]).all() and (counts[:, 0] <= counts[:, 2]).all()
+    assert torch.equal(IO.resize_argmax_exact(lg, (9, 11)), idx)  # identity resize is the plain argmax
+    assert torch.equal(IO.predict_tail(lg, (9, 11)), idx)
