@@ -104,55 +104,100 @@ def param_names(state):
 
 
 # --------------------------------------------------------------------------------------
+# storage-rounding model (optional; the default is the reference's plain fp32 arithmetic)
+# --------------------------------------------------------------------------------------
+class _RoundSTE(torch.autograd.Function):
+    """Round a tensor through a narrower storage type; the gradient arriving at the same point is stored in that
+    type too (``both=True``: activations), or passes through unrounded (``both=False``: weights, whose gradient
+    stays fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype, both):
+        ctx.dtype, ctx.both = dtype, both
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.to(ctx.dtype).to(g.dtype) if ctx.both else g), None, None
+
+
+class Rounding:
+    """Where a reduced-precision run of the SAME arithmetic stores its tensors.
+
+    The reference under ``torch.autocast`` (train.py:116) keeps activations and conv weights in a 16-bit type
+    between kernels while every kernel accumulates in fp32.  ``Rounding(torch.bfloat16)`` restates exactly that
+    on top of the fp32 restatement below: every tensor written between two ops (conv output, BatchNorm+ReLU
+    output, pooled / upsampled / transposed-conv output, logits) and every gradient flowing back through the same
+    point is rounded to ``dtype`` (round-to-nearest-even); 3x3 / transposed conv weights are rounded on use, their
+    gradients are not; BatchNorm parameters, statistics and the 1x1 OutConv weights stay fp32.  What is left
+    between such a run and a real bf16 implementation is accumulation order only, which is what makes this the
+    *tight* checker for a bf16 backward pass (a ReLU-mask flip needs an fp32-level difference to straddle zero).
+    ``None`` = no rounding = the reference's fp32 CPU path."""
+
+    def __init__(self, dtype=None):
+        self.dtype = dtype
+
+    def act(self, t):
+        return t if self.dtype is None else _RoundSTE.apply(t, self.dtype, True)
+
+    def weight(self, t):
+        return t if self.dtype is None else _RoundSTE.apply(t, self.dtype, False)
+
+
+EXACT = Rounding(None)
+
+
+# --------------------------------------------------------------------------------------
 # forward pieces
 # --------------------------------------------------------------------------------------
-def double_conv(st, prefix, x, training=True):
+def double_conv(st, prefix, x, training=True, q=EXACT):
     """(conv3x3 pad1 no-bias -> BatchNorm2d -> ReLU) x 2   (unet_parts.py:14-24)."""
     for idx in (0, 3):
-        x = F.conv2d(x, st[f"{prefix}.{idx}.weight"], None, padding=1)
+        x = q.act(F.conv2d(x, q.weight(st[f"{prefix}.{idx}.weight"]), None, padding=1))
         bn = f"{prefix}.{idx + 1}"
         x = F.batch_norm(x, st[bn + ".running_mean"], st[bn + ".running_var"],
                          st[bn + ".weight"], st[bn + ".bias"], training, BN_MOMENTUM, BN_EPS)
         if training:
             st[bn + ".num_batches_tracked"] += 1
-        x = F.relu(x)
+        x = q.act(F.relu(x))
     return x
 
 
-def down(st, name, x, training=True):
+def down(st, name, x, training=True, q=EXACT):
     """MaxPool2d(2) then DoubleConv  (unet_parts.py:31-37)."""
-    return double_conv(st, f"{name}.maxpool_conv.1.double_conv", F.max_pool2d(x, 2), training)
+    return double_conv(st, f"{name}.maxpool_conv.1.double_conv", F.max_pool2d(x, 2), training, q)
 
 
-def up(st, name, x1, x2, bilinear, training=True):
+def up(st, name, x1, x2, bilinear, training=True, q=EXACT):
     """Upsample x1, pad to x2, cat([x2, x1]) (skip first), DoubleConv  (unet_parts.py:80-98)."""
     if bilinear:
-        x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+        x1 = q.act(F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True))
     else:
-        x1 = F.conv_transpose2d(x1, st[f"{name}.up.weight"], st[f"{name}.up.bias"], stride=2)
+        x1 = q.act(F.conv_transpose2d(x1, q.weight(st[f"{name}.up.weight"]), st[f"{name}.up.bias"], stride=2))
     dy = x2.size(2) - x1.size(2)
     dx = x2.size(3) - x1.size(3)
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
-    return double_conv(st, f"{name}.conv.double_conv", torch.cat([x2, x1], dim=1), training)
+    return double_conv(st, f"{name}.conv.double_conv", torch.cat([x2, x1], dim=1), training, q)
 
 
-def out_conv(st, x):
+def out_conv(st, x, q=EXACT):
     """1x1 conv with bias  (unet_parts.py:103-106)."""
-    return F.conv2d(x, st["outc.conv.weight"], st["outc.conv.bias"])
+    return q.act(F.conv2d(x, st["outc.conv.weight"], st["outc.conv.bias"]))
 
 
-def unet_forward(st, x, bilinear=False, training=True):
+def unet_forward(st, x, bilinear=False, training=True, q=EXACT):
     """UNet.forward wiring  (unet_model.py:27-38)."""
-    x1 = double_conv(st, "inc.double_conv", x, training)
-    x2 = down(st, "down1", x1, training)
-    x3 = down(st, "down2", x2, training)
-    x4 = down(st, "down3", x3, training)
-    x5 = down(st, "down4", x4, training)
-    y = up(st, "up1", x5, x4, bilinear, training)
-    y = up(st, "up2", y, x3, bilinear, training)
-    y = up(st, "up3", y, x2, bilinear, training)
-    y = up(st, "up4", y, x1, bilinear, training)
-    return out_conv(st, y)
+    x = q.act(x)
+    x1 = double_conv(st, "inc.double_conv", x, training, q)
+    x2 = down(st, "down1", x1, training, q)
+    x3 = down(st, "down2", x2, training, q)
+    x4 = down(st, "down3", x3, training, q)
+    x5 = down(st, "down4", x4, training, q)
+    y = up(st, "up1", x5, x4, bilinear, training, q)
+    y = up(st, "up2", y, x3, bilinear, training, q)
+    y = up(st, "up3", y, x2, bilinear, training, q)
+    y = up(st, "up4", y, x1, bilinear, training, q)
+    return out_conv(st, y, q)
 
 
 # --------------------------------------------------------------------------------------
@@ -333,12 +378,58 @@ def synthetic_batch(batch, n_channels, n_classes, h, w, rank=0):
     return img, msk
 
 
-def training_step(st, images, masks, n_classes, bilinear=False, boundary_coeff=0.0):
-    """Forward + loss + backward on CPU fp32.  Returns (logits, loss, {name: grad})."""
+def structured_batch(batch, n_channels, n_classes, h, w, seed=5):
+    """Contour-style synthetic data: class-index masks made of filled disks (classes 1..n_classes-1 on background
+    0, like the 0 / 128 / 255 contour masks the reference maps to class ids, data_loading.py:70-77) and images
+    whose grey level follows the mask plus noise, box-filtered and clipped to [0, 1] (cf. /255,
+    data_loading.py:86-87).  Unlike :func:`synthetic_batch` (pure noise, random labels) a network can learn
+    this, which is what :func:`conditioned_state` needs."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    msk = torch.zeros(batch, h, w, dtype=torch.long)
+    for b in range(batch):
+        for c in range(1, max(n_classes, 2)):
+            for _ in range(2):
+                cy, cx, rr = torch.rand(3, generator=g).tolist()
+                r = (0.10 + 0.15 * rr) * min(h, w)
+                msk[b][((yy - cy * h) ** 2 + (xx - cx * w) ** 2) < r * r] = c
+    level = msk.float() / max(n_classes - 1, 1)
+    img = (0.2 + 0.6 * level).unsqueeze(1).expand(batch, n_channels, h, w)
+    img = img + 0.05 * torch.randn(batch, n_channels, h, w, generator=g)
+    return F.avg_pool2d(img, 3, 1, 1).clamp(0, 1).contiguous(), msk
+
+
+def conditioned_state(n_channels, n_classes, bilinear=False, steps=10, lr=1e-3, size=128, batch=2, seed=0):
+    """A *well-conditioned* parameter state: ``steps`` fp32 CPU training steps of the reference arithmetic
+    (forward + CE + dice, train.py:137-142; plain RMSprop alpha 0.99 eps 1e-8, the optimizer family of
+    train.py:80) on one :func:`structured_batch`, starting from the reference's seeded default init.
+
+    Why it exists: at random init BatchNorm beta = 0 puts every ReLU threshold at the batch mean and random labels
+    make the weight gradients incoherent sums, so *any* reduced-precision run -- cuDNN's included -- sits tens of
+    per cent from the fp32 gradients (tests/gpu_e2e.py).  A few steps on learnable data give non-trivial BatchNorm
+    gamma / beta / running statistics, confident logits and coherent gradients; there north_star's own bf16
+    tolerances are attainable and are gated.  The state is too large to commit (31 M values); it is re-derived
+    deterministically where it is used, and tests/golden/make_golden_cond.py pins the recipe against the
+    *reference modules + torch.optim.RMSprop* run the same way."""
+    st = build_state(n_channels, n_classes, bilinear, seed=seed)
+    img, msk = structured_batch(batch, n_channels, n_classes, size, size)
+    names = param_names(st)
+    sq = {k: torch.zeros_like(st[k]) for k in names}
+    for _ in range(steps):
+        _, _, g = training_step(st, img, msk, n_classes, bilinear)
+        for k in names:                       # torch.optim.RMSprop(lr, alpha=0.99, eps=1e-8): its single-tensor
+            sq[k].mul_(0.99).addcmul_(g[k], g[k], value=1 - 0.99)        # update, op for op (the trajectory is
+            st[k] = st[k].addcdiv(g[k], sq[k].sqrt().add_(1e-8), value=-lr)   # chaotic: one ulp grows to 1e-1)
+    return st
+
+
+def training_step(st, images, masks, n_classes, bilinear=False, boundary_coeff=0.0, q=EXACT):
+    """Forward + loss + backward on CPU fp32 (``q``: optional storage-rounding model, see :class:`Rounding`).
+    Returns (logits, loss, {name: grad})."""
     names = param_names(st)
     leaves = {k: st[k].detach().clone().requires_grad_(True) for k in names}
     work = OrderedDict((k, leaves[k] if k in leaves else v.clone()) for k, v in st.items())
-    logits = unet_forward(work, images, bilinear, training=True)
+    logits = unet_forward(work, images, bilinear, training=True, q=q)
     loss = train_loss(logits, masks, n_classes, boundary_coeff)
     grads = torch.autograd.grad(loss, [leaves[k] for k in names])
     for k in st:                       # running stats were updated in the working copy
