@@ -42,7 +42,7 @@ def main():
             loss.backward()
             opt.step()
         st = O.conditioned_state(nc, ncls, bil, STEPS, LR, SIZE, BATCH)
-        rsd = ref.state_dict()
+        rsd = {k: v.detach().clone() for k, v in ref.state_dict().items()}   # (the live dict moves with the next forward)
         worst = 0.0
         for k in rsd:
             if rsd[k].dtype.is_floating_point:
