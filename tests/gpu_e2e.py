@@ -211,65 +211,132 @@ def width_gate(cls_name, nc, ncls, bilinear, B, H, W, mode):
     return res
 
 
-def full_size_gate():
-    """BASELINE.json's full sizes, through size-independent properties (the CPU oracle needs minutes there):
-    configs[1]/[2] -- B=16, 512x512 training step: the bf16 and the tf32 tensor-core paths are two independent
-    roundings of the same arithmetic, so their logits / loss / BatchNorm statistics must agree at the bf16 level and
-    every gradient must be finite; configs[4] -- UNet(3,4) eval forward at B=8, 1024x1024: bf16 vs tf32 argmax masks."""
+_COND = {}
+
+
+def _cond_state(nc, ncls, bilinear):
+    """oracle.conditioned_state (10 fp32 CPU steps of the reference arithmetic on structured data), cached."""
+    key = (nc, ncls, bilinear)
+    if key not in _COND:
+        _COND[key] = O.conditioned_state(nc, ncls, bilinear)
+    return {k: v.clone() for k, v in _COND[key].items()}
+
+
+def _dice_of(logits, msk, ncls):
+    return float(O.multiclass_dice_coeff(torch.softmax(logits.float(), 1),
+                                         torch.nn.functional.one_hot(msk, ncls).permute(0, 3, 1, 2).float(),
+                                         reduce_batch_first=True))
+
+
+def north_star_gate(nc, ncls, bilinear, B, H, W, mode="bf16", boundary_coeff=0.2, state="conditioned",
+                    vs_torch_gpu=True, storage_tol=2e-2):
+    """north_star's OWN tolerances, on a well-conditioned configuration (non-trivial BatchNorm gamma / beta / running
+    statistics after ten reference training steps, contour-style masks): bf16 -- logits and gradients within 2e-2
+    relative, dice within 1e-3, argmax equal on >= 99.9 % of the pixels; fp32/TF32 -- 1e-3.
+
+    Two oracles: (1) the fp32 CPU restatement of the reference (the bar above); (2) the same restatement with bf16
+    *storage* (oracle.Rounding): it differs from a real bf16 implementation by accumulation order only, so every one
+    of the 64 gradient tensors has to match it within ``storage_tol`` -- a mis-scaled dgrad / wgrad in a single layer
+    cannot hide behind ReLU-mask flips there, not even at random initialisation (state='random')."""
     import unet
-    from unetb200 import losses as UL
+    tag = f"ns{nc}_{ncls}_{'bil' if bilinear else 'convT'}_{B}x{H}x{W}_{mode}_{state}"
+    if state == "conditioned":
+        st = _cond_state(nc, ncls, bilinear)
+        img, msk = O.structured_batch(B, nc, ncls, H, W, seed=9)
+    else:
+        st = O.build_state(nc, ncls, bilinear, seed=0)
+        img, msk = O.synthetic_batch(B, nc, ncls, H, W)
+    names = O.param_names(st)
+    ref_st = {k: v.clone() for k, v in st.items()}
+    r_logits, r_loss, r_grads = O.training_step(ref_st, img, msk, ncls, bilinear, boundary_coeff=boundary_coeff)
+    model = unet.UNet(nc, ncls, bilinear)
+    model.load_state_dict(st)
+    model = model.to(DEV).to(memory_format=torch.channels_last).train()
+    os.environ["UNET_B200_PRECISION"] = {"tf32": "tf32", "tf32x3": "tf32x3"}.get(mode, "fp32")
+    logits, loss, grads = G.unet_step_gpu(model, img, msk, amp=(mode == "bf16"), boundary_coeff=boundary_coeff)
+    tol = 2e-2 if mode == "bf16" else 1e-3
+    cat = lambda g: torch.cat([g[k].reshape(-1).double() for k in names])  # noqa: E731
     res = []
-    st = O.build_state(1, 2, False, seed=0)
-    img, msk = O.synthetic_batch(16, 1, 2, 512, 512)
-    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
-    t = msk.to(DEV)
-    outs = {}
-    for mode in ("bf16", "tf32"):
-        os.environ["UNET_B200_PRECISION"] = "tf32"
-        m = unet.UNet(1, 2, False)
-        m.load_state_dict(st)
-        m = m.to(DEV).to(memory_format=torch.channels_last).train()
-        with torch.autocast("cuda", enabled=(mode == "bf16")):
-            logits = m(x)
-            loss = UL.training_criterion(logits, t, boundary_coeff=0.2, edge_width=51, edge_weight=7)
-        loss.backward()
-        torch.cuda.synchronize()
-        finite = all(bool(torch.isfinite(p.grad).all()) for p in m.parameters())
-        gn = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters())).item()
-        outs[mode] = (logits.float(), float(loss), finite, gn,
-                      {k: v.float().clone() for k, v in m.state_dict().items() if "running" in k})
-        del m, logits, loss
-    lb, lt = outs["bf16"][0], outs["tf32"][0]
-    res.append(("full512_logits_bf16_vs_tf32_maxrel", ((lb - lt).abs().max() / lt.abs().max()).item(), 1e-1))
-    res.append(("full512_argmax_mismatch", (lb.argmax(1) != lt.argmax(1)).float().mean().item(), 3e-2))
-    res.append(("full512_loss_rel", abs(outs["bf16"][1] - outs["tf32"][1]) / abs(outs["tf32"][1]), 5e-3))
-    res.append(("full512_grads_finite", 0.0 if outs["bf16"][2] and outs["tf32"][2] else 1.0, 0.0))
-    res.append(("full512_grad_norm_rel", abs(outs["bf16"][3] - outs["tf32"][3]) / outs["tf32"][3], 0.5))
-    res.append(("full512_running_stats", max(rel(outs["bf16"][4][k].cpu(), outs["tf32"][4][k].cpu()) for k in outs["bf16"][4]), 3e-2))
-    del outs, lb, lt
-    torch.cuda.empty_cache()
-    # configs[4]: inference, 3 -> 4 classes, 1024 x 1024
-    st = O.build_state(3, 4, False, seed=0)
-    img, _ = O.synthetic_batch(8, 3, 4, 1024, 1024)
-    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
-    lg = {}
-    for mode in ("bf16", "tf32"):
-        m = unet.UNet(3, 4, False)
-        m.load_state_dict(st)
-        m = m.to(DEV).to(memory_format=torch.channels_last).eval()
-        with torch.inference_mode(), torch.autocast("cuda", enabled=(mode == "bf16")):
-            lg[mode] = m(x).float()
-        del m
-    res.append(("infer1024_logits_bf16_vs_tf32_maxrel", ((lg["bf16"] - lg["tf32"]).abs().max() / lg["tf32"].abs().max()).item(), 1e-1))
-    res.append(("infer1024_argmax_mismatch", (lg["bf16"].argmax(1) != lg["tf32"].argmax(1)).float().mean().item(), 3e-2))
-    res.append(("infer1024_finite", 0.0 if bool(torch.isfinite(lg["bf16"]).all()) else 1.0, 0.0))
-    del lg
-    torch.cuda.empty_cache()
+    if state == "conditioned":
+        l2 = [O.rel_l2(grads[k], r_grads[k]) for k in names]
+        mx = [rel(grads[k], r_grads[k]) for k in names]
+        res += [(f"{tag}_logits_maxrel", rel(logits, r_logits), tol),
+                (f"{tag}_argmax_mismatch", (logits.argmax(1) != r_logits.argmax(1)).float().mean().item(), 1e-3),
+                (f"{tag}_dice_abs", abs(_dice_of(logits, msk, ncls) - _dice_of(r_logits, msk, ncls)), 1e-3),
+                (f"{tag}_loss_rel", abs(loss - float(r_loss)) / abs(float(r_loss)), 1e-3),
+                (f"{tag}_grad_all_rel_l2", O.rel_l2(cat(grads), cat(r_grads)), tol),
+                (f"{tag}_grad_l2_median", statistics.median(l2), tol),
+                (f"{tag}_grad_maxrel_median", statistics.median(mx), tol),
+                # the deepest layers (8x8 .. 32x32 maps, gradients ~1e-5) keep a few ReLU flips even here: bf16
+                # STORAGE of the reference arithmetic itself sits at 3.6e-2 (tests/test_oracle_cond.py)
+                (f"{tag}_grad_l2_worst", max(l2), 4 * tol if mode == "bf16" else 5 * tol)]
+        sd = model.state_dict()
+        res.append((f"{tag}_running_stats", max(rel(host(sd[k]), ref_st[k]) for k in sd if "running" in k), tol))
+    if mode == "bf16":
+        e_st = {k: v.clone() for k, v in st.items()}
+        e_logits, e_loss, e_grads = O.training_step(e_st, img, msk, ncls, bilinear, boundary_coeff=boundary_coeff,
+                                                    q=O.Rounding(torch.bfloat16))
+        el2 = {k: O.rel_l2(grads[k], e_grads[k]) for k in names}
+        wk = max(el2, key=el2.get)
+        res += [(f"{tag}_vs_bf16_storage_oracle_logits", rel(logits, e_logits), storage_tol),
+                (f"{tag}_vs_bf16_storage_oracle_loss", abs(loss - float(e_loss)) / abs(float(e_loss)), 1e-3),
+                (f"{tag}_vs_bf16_storage_oracle_argmax", (logits.argmax(1) != e_logits.argmax(1)).float().mean().item(), 1e-3),
+                (f"{tag}_vs_bf16_storage_oracle_grad_l2_median", statistics.median(el2.values()), storage_tol),
+                (f"{tag}_vs_bf16_storage_oracle_grad_l2_worst[{wk}]", el2[wk], storage_tol),
+                (f"{tag}_vs_bf16_storage_oracle_grad_all", O.rel_l2(cat(grads), cat(e_grads)), storage_tol)]
+        if os.environ.get("UNETB200_TEST_VERBOSE"):
+            for k in names:
+                print(f"      grad {k:<50s} vs fp32 {O.rel_l2(grads[k], r_grads[k]):.3e}  vs bf16-storage {el2[k]:.3e}  "
+                      f"storage-vs-fp32 {O.rel_l2(e_grads[k], r_grads[k]):.3e}")
+    if vs_torch_gpu and mode in ("bf16", "tf32"):
+        # ours against the reference's own GPU path (torch ATen / cuDNN, test-only) under the same precision
+        t_logits, t_loss, t_grads = G.torch_gpu_step(st, img, msk, ncls, bilinear, mode)
+        tl2 = [O.rel_l2(grads[k], t_grads[k]) for k in names]
+        res += [(f"{tag}_vs_torch_gpu_logits", rel(logits, t_logits), tol if state == "conditioned" else 1e-1),
+                (f"{tag}_vs_torch_gpu_grad_l2_median", statistics.median(tl2), tol if state == "conditioned" else 6e-1)]
     return res
 
 
+def full_size_gate(which):
+    """BASELINE.json's configurations at their FULL sizes against the CPU oracle (about a minute of host time each).
+
+    'c2': configs[1]/[3]  UNet(1,2,False) bf16 training step, B=16, 512x512, CE + dice + 0.2*boundary -- against the fp32
+          oracle with north_star's bf16 tolerances and against the bf16-storage oracle (every gradient tensor).
+    'c3': configs[2]      UNet(1,2,True) bilinear, fp32/TF32 exactness mode, B=16, 512x512 -- 1e-3.
+    'c5': configs[4]      UNet(3,4,False).eval() forward, B=8, 1024x1024, bf16 -- logits 2e-2, argmax 99.9 %."""
+    import unet
+    if which == "c2":
+        return north_star_gate(1, 2, False, 16, 512, 512, "bf16", boundary_coeff=0.2, vs_torch_gpu=False)
+    if which == "c3":
+        mode = os.environ.get("UNETB200_C3_MODE", "tf32x3")
+        return north_star_gate(1, 2, True, 16, 512, 512, mode, boundary_coeff=0.2, vs_torch_gpu=False)
+    assert which == "c5"
+    st = _cond_state(3, 4, False)
+    img, _ = O.structured_batch(8, 3, 4, 1024, 1024, seed=9)
+    r_logits = O.unet_forward({k: v.clone() for k, v in st.items()}, img, False, training=False)
+    e_logits = O.unet_forward({k: v.clone() for k, v in st.items()}, img, False, training=False,
+                              q=O.Rounding(torch.bfloat16))
+    model = unet.UNet(3, 4, False)
+    model.load_state_dict(st)
+    model = model.to(DEV).to(memory_format=torch.channels_last).eval()
+    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    with torch.inference_mode(), torch.autocast("cuda", enabled=True):
+        logits = host(model(x).float())
+    tag = "c5_infer3_4_8x1024x1024_bf16"
+    return [(f"{tag}_logits_maxrel", rel(logits, r_logits), 2e-2),
+            (f"{tag}_argmax_mismatch", (logits.argmax(1) != r_logits.argmax(1)).float().mean().item(), 1e-3),
+            (f"{tag}_vs_bf16_storage_oracle_logits", rel(logits, e_logits), 2e-2),
+            (f"{tag}_vs_bf16_storage_oracle_argmax", (logits.argmax(1) != e_logits.argmax(1)).float().mean().item(), 1e-3),
+            (f"{tag}_finite", 0.0 if bool(torch.isfinite(logits).all()) else 1.0, 0.0)]
+
+
 GROUPS = {
-    "unet_full_size": lambda gd: full_size_gate(),
+    "full_c2": lambda gd: full_size_gate("c2"),
+    "full_c3": lambda gd: full_size_gate("c3"),
+    "full_c5": lambda gd: full_size_gate("c5"),
+    "north_star_bf16": lambda gd: north_star_gate(1, 2, False, 2, 128, 128) + north_star_gate(1, 2, False, 4, 256, 256, vs_torch_gpu=False),
+    "north_star_bf16_b": lambda gd: north_star_gate(1, 2, True, 2, 128, 128) + north_star_gate(3, 4, False, 2, 128, 160),
+    "storage_oracle_random_init": lambda gd: north_star_gate(1, 2, False, 2, 128, 128, state="random") + north_star_gate(1, 2, True, 2, 64, 64, state="random", boundary_coeff=0.0),
     "unet_widths": lambda gd: width_gate("UNet_S", 1, 3, False, 2, 64, 64, "fp32") + width_gate("UNet_S", 1, 3, False, 2, 128, 128, "bf16")
                    + width_gate("UNet_T", 3, 2, True, 1, 64, 96, "fp32"),
     "graph_side_stream": lambda gd: graph_gate(),
