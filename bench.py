@@ -602,7 +602,9 @@ def bench_train(ctx):
                 # gradients are complete are all-reduced eagerly on NCCL's stream while the next segment runs
                 # (ddp.SegmentedStep) -- only the last, small bucket (inc.*) is exposed before the optimizer graph
                 reducer.remove()
-                seg = ddp.SegmentedStep(model, reducer, fwd_loss, clip_and_step, opt, (img_d, msk_d))
+                for p in model.parameters():
+                    p.grad = None
+                seg = ddp.SegmentedStep(model, fwd_loss, clip_and_step, (img_d, msk_d))
                 graphed = seg
                 graph_note = seg.describe()
         except Exception as exc:  # noqa: BLE001

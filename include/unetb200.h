@@ -126,6 +126,16 @@ int unetb200_wgrad_reduce(const float* partials, int splits, int ntaps, int Cin,
  * parameter (OIHW / IOHW) into the K-major [N][(t,c)] operand layout of gconv, any tap order. */
 int unetb200_pack_weights(const float* src, void* dst, int dst_dtype, int64_t n0, int64_t n1,
                           int64_t n2, int64_t s0, int64_t s1, int64_t s2, int64_t off, void* stream);
+/* The same for a whole list of parameters in ONE launch (the weights of a network change together, at the
+ * optimizer step: train.py:159): job j packs src -> dst exactly like unetb200_pack_weights.  All jobs share
+ * dst_dtype. */
+typedef struct unetb200_pack_job {
+  const float* src;
+  void* dst;
+  int64_t n0, n1, n2;
+  int64_t s0, s1, s2, off;
+} unetb200_pack_job_t;
+int unetb200_pack_weights_multi(const unetb200_pack_job_t* jobs, int njobs, int dst_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm2d + ReLU (+ MaxPool2d) -- unet_parts.py:16-17,19-20,32.  Memory-bound, vectorised.

@@ -30,30 +30,46 @@ def _emulate_pack(w, n0, n1, n2, s0, s1, s2, off):
     return flat[w.storage_offset() + off + i0 * s0 + i1 * s1 + i2 * s2]
 
 
-def _capture_pack(fn, w, monkeypatch):
-    got = {}
-
-    def fake(wt, dtype, n0, n1, n2, s0, s1, s2, off=0):
-        got["v"] = _emulate_pack(wt, n0, n1, n2, s0, s1, s2, off)
-        return got["v"].reshape(n0, n1 * n2)
-    monkeypatch.setattr(UF, "_pack", fake)
-    fn(w, torch.float32)
-    return got["v"]
+def _capture_pack(kind, w):
+    """the job functional._JOBS[kind] describes for `w`, executed by the emulation above"""
+    src, (n0, n1, n2), (s0, s1, s2), off, shape = UF._JOBS[kind](w)
+    assert shape[0] * shape[1] == n0 * n1 * n2
+    return _emulate_pack(src, n0, n1, n2, s0, s1, s2, off)
 
 
-def test_pack_index_maps(monkeypatch):
+def test_pack_index_maps():
     g = torch.Generator().manual_seed(0)
     for fmt in (torch.contiguous_format, torch.channels_last):
         w = torch.randn(6, 4, 3, 3, generator=g).contiguous(memory_format=fmt)       # OIHW
-        p = _capture_pack(UF.pack3x3_fprop, w, monkeypatch)                           # [co][t][ci]
+        p = _capture_pack("f3", w)                                                    # [co][t][ci]
         assert torch.equal(p, w.permute(0, 2, 3, 1).reshape(6, 9, 4))
-        p = _capture_pack(UF.pack3x3_dgrad, w, monkeypatch)                           # [ci][t'][co], flipped taps
+        p = _capture_pack("d3", w)                                                    # [ci][t'][co], flipped taps
         assert torch.equal(p, w.flip(2, 3).permute(1, 2, 3, 0).reshape(4, 9, 6))
         wt = torch.randn(8, 5, 2, 2, generator=g).contiguous(memory_format=fmt)      # IOHW
-        p = _capture_pack(UF.packT_fprop, wt, monkeypatch)                            # [q][co][ci]
+        p = _capture_pack("fT", wt)                                                   # [q][co][ci]
         assert torch.equal(p, wt.permute(2, 3, 1, 0).reshape(4, 5, 8))
-        p = _capture_pack(UF.packT_dgrad, wt, monkeypatch)                            # [ci][q][co]
+        p = _capture_pack("dT", wt)                                                   # [ci][q][co]
         assert torch.equal(p, wt.permute(0, 2, 3, 1).reshape(8, 4, 5))
+
+
+def test_grad_sinks_are_offered_only_when_nothing_accumulates():
+    w = torch.nn.Parameter(torch.randn(4, 3, 3, 3).contiguous(memory_format=torch.channels_last))
+    buf = torch.zeros(w.numel())
+    view = buf.as_strided(w.shape, w.stride())
+    UF.set_grad_sinks([w], [view])
+    d = UF.grad_dst(w)
+    assert d is not None and d is not view and d.data_ptr() == view.data_ptr() and d.stride() == w.stride()
+    w.grad = torch.zeros_like(w)
+    assert UF.grad_dst(w) is None                      # an existing .grad would be accumulated into: no sink
+    UF.set_grad_sinks([w], [view], always=True)
+    assert UF.grad_dst(w) is not None                  # the owner of p.grad drives backward through autograd.grad
+    UF.clear_grad_sinks([w])
+    assert UF.grad_dst(w) is None
+    try:
+        UF.set_grad_sinks([w], [torch.zeros(4, 3, 3, 3)])   # contiguous view for a channels_last parameter
+        raise AssertionError("layout mismatch accepted")
+    except ValueError:
+        pass
 
 
 def test_dgrad_packing_is_the_conv_transpose():

@@ -481,6 +481,64 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(const float* __rest
   }
 }
 
+// ---- multi-tensor weight packing ------------------------------------------------------------------------------
+// Every 3x3 / transposed-conv weight of the network is packed into its GEMM operand(s) by ONE launch per step (the
+// job table travels by value in the kernel parameters): job j is dst[i0][i1][i2] = cast(src[off + i0*s0 + i1*s1 +
+// i2*s2]), cut into 32 (i0) x 32 (i2) tiles per i1.  A tile is read along whichever of i0 / i2 is contiguous in the
+// source and always written along i2 (contiguous in the destination), through shared memory when the two differ.
+constexpr int kMaxPackJobs = 40;
+struct PackJob {
+  const float* src;
+  void* dst;
+  long long s0, s1, s2, off;
+  int n0, n1, n2;
+  int tiles2;      // ceil(n2 / 32)
+  int block0;      // first block of this job
+  int pad_;
+};
+struct alignas(16) PackTable {
+  PackJob job[kMaxPackJobs];
+  int njobs;
+};
+
+template <typename D>
+__global__ void __launch_bounds__(256) pack_multi_kernel(const __grid_constant__ PackTable T) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = T.njobs - 1;
+  while (lo < hi) {                   // last job with block0 <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (T.job[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob& J = T.job[lo];
+  int b = blockIdx.x - J.block0;
+  const int i1 = b % J.n1;
+  b /= J.n1;
+  const int c0 = (b % J.tiles2) * 32, a0 = (b / J.tiles2) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* src = J.src + J.off + (long long)i1 * J.s1;
+  D* dst = reinterpret_cast<D*>(J.dst);
+  if (J.s0 == 1 && J.s2 != 1) {       // source contiguous along i0: transpose the tile
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i2 = c0 + ty + 8 * r, i0 = a0 + tx;
+      tile[ty + 8 * r][tx] = (i0 < J.n0 && i2 < J.n2) ? src[i0 + (long long)i2 * J.s2] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i0 = a0 + ty + 8 * r, i2 = c0 + tx;
+      if (i0 < J.n0 && i2 < J.n2) Elem<D>::st(dst + ((long long)i0 * J.n1 + i1) * J.n2 + i2, tile[tx][ty + 8 * r]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i0 = a0 + ty + 8 * r, i2 = c0 + tx;
+      if (i0 < J.n0 && i2 < J.n2)
+        Elem<D>::st(dst + ((long long)i0 * J.n1 + i1) * J.n2 + i2, src[(long long)i0 * J.s0 + (long long)i2 * J.s2]);
+    }
+  }
+}
+
 static bool simt_vec_ok(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y) {
   const size_t esz = d->dtype == UNETB200_BF16 ? 2 : 4;
   const int Cq = d->N / d->nquad;
@@ -692,6 +750,36 @@ int unetb200_pack_weights(const float* src, void* dst, int dst_dtype, int64_t n0
   else
     pack_weights_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(src, (float*)dst, n0, n1, n2, s0, s1, s2, off);
   UB_LAUNCH_CHECK("pack_weights");
+  return 0;
+}
+
+int unetb200_pack_weights_multi(const unetb200_pack_job_t* jobs, int njobs, int dst_dtype, void* stream) {
+  UB_CHECK_ARG(dst_dtype == UNETB200_F32 || dst_dtype == UNETB200_BF16, "pack_weights_multi: dtype");
+  UB_CHECK_ARG(jobs && njobs >= 1, "pack_weights_multi: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int first = 0; first < njobs; first += kMaxPackJobs) {
+    const int count = njobs - first < kMaxPackJobs ? njobs - first : kMaxPackJobs;
+    PackTable T;
+    long long blocks = 0;
+    for (int i = 0; i < count; ++i) {
+      const unetb200_pack_job_t& j = jobs[first + i];
+      UB_CHECK_ARG(j.src && j.dst && j.n0 > 0 && j.n1 > 0 && j.n2 > 0 && j.n0 < (1LL << 31) && j.n1 < (1LL << 31) &&
+                       j.n2 < (1LL << 31),
+                   "pack_weights_multi: job %d", first + i);
+      PackJob& J = T.job[i];
+      J.src = j.src; J.dst = j.dst; J.s0 = j.s0; J.s1 = j.s1; J.s2 = j.s2; J.off = j.off;
+      J.n0 = (int)j.n0; J.n1 = (int)j.n1; J.n2 = (int)j.n2;
+      J.tiles2 = (J.n2 + 31) / 32;
+      J.block0 = (int)blocks;
+      J.pad_ = 0;
+      blocks += (long long)((J.n0 + 31) / 32) * J.tiles2 * J.n1;
+      UB_CHECK_ARG(blocks < (1LL << 31), "pack_weights_multi: too many tiles");
+    }
+    T.njobs = count;
+    if (dst_dtype == UNETB200_BF16) pack_multi_kernel<bf16><<<(unsigned)blocks, 256, 0, s>>>(T);
+    else pack_multi_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(T);
+  }
+  UB_LAUNCH_CHECK("pack_weights_multi");
   return 0;
 }
 }

@@ -76,7 +76,10 @@ __global__ void __launch_bounds__(256) rmsprop_step_kernel(const __grid_constant
   float coef = 1.f;
   if (sumsq) {
     const float total = (float)sqrt(*sumsq);
-    coef = fminf(max_norm / (total + 1e-6f), 1.f);          // torch.nn.utils.clip_grad_norm_
+    // torch.nn.utils.clip_grad_norm_: clamp(max_norm / (total + 1e-6), max=1); a non-finite norm propagates to
+    // every gradient as it does in torch (fminf alone would drop a NaN)
+    const float c = max_norm / (total + 1e-6f);
+    coef = (c == c) ? fminf(c, 1.f) : c;
   }
   float* w = t.w[ti];
   float* g = t.g[ti];

@@ -20,6 +20,7 @@ from .unet_parts import DoubleConv, Down, OutConv, Up, _prep
 
 class _UNetBase(nn.Module):
     _BASE = 64
+    _taps = None          # dict to fill with the named intermediate tensors of the next forward, or None
 
     def __init__(self, n_channels, n_classes, bilinear=False):
         super().__init__()
@@ -49,22 +50,22 @@ class _UNetBase(nn.Module):
         b = self._BASE
         dev, cd = x.device, x.dtype
         from unetb200 import functional as UF
-        forked = UF.prepack(self, cd, need_dgrad=torch.is_grad_enabled())
+        UF.prepack(self, cd, need_dgrad=torch.is_grad_enabled())
         # concat buffers of the four Up stages: [skip | upsampled], at the skip's resolution
         cats = [ops.empty_nhwc(B, 2 * b * (1 << k), H >> k, W >> k, cd, dev) for k in range(4)]
         skips = [ops.channel_slice(cats[k], 0, b * (1 << k)) for k in range(4)]
         x1, p = self.inc.run(x, out=skips[0], want_pool=True)
         x2, p = self.down1.run(p, out=skips[1], want_pool=True)
-        x3, p = self.down2.run(p, out=skips[2], want_pool=True)
-        x4, p = self.down3.run(p, out=skips[3], want_pool=True)
-        y = self.down4.run(p)
-        y = self.up1.run(y, x4, cat=cats[3])
-        y = self.up2.run(y, x3, cat=cats[2])
-        y = self.up3.run(y, x2, cat=cats[1])
+        x3, p3 = self.down2.run(p, out=skips[2], want_pool=True)
+        x4, p = self.down3.run(p3, out=skips[3], want_pool=True)
+        x5 = self.down4.run(p)
+        y = self.up1.run(x5, x4, cat=cats[3])
+        u2 = self.up2.run(y, x3, cat=cats[2])
+        y = self.up3.run(u2, x2, cat=cats[1])
         y = self.up4.run(y, x1, cat=cats[0])
         out = self.outc.run(y)
-        if forked and not torch.is_grad_enabled():
-            ops.side_stream_sync()        # no backward will join the side stream: do it here (it finished long ago)
+        if self._taps is not None:        # cut points of a segmented backward pass (unetb200.ddp.SegmentedStep)
+            self._taps.update(x1=x1, x2=x2, x3=x3, x4=x4, x5=x5, p3=p3, u2=u2)
         return out
 
     def use_checkpointing(self):

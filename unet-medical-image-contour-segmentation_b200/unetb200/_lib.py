@@ -35,6 +35,12 @@ class GConv(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    """Mirror of unetb200_pack_job_t."""
+    _fields_ = [("src", c_p), ("dst", c_p), ("n0", c_i64), ("n1", c_i64), ("n2", c_i64),
+                ("s0", c_i64), ("s1", c_i64), ("s2", c_i64), ("off", c_i64)]
+
+
 # name -> (restype, argtypes); every symbol include/unetb200.h declares
 PROTOTYPES = {
     "unetb200_version": (C.c_int, []),
@@ -49,6 +55,7 @@ PROTOTYPES = {
     "unetb200_wgrad_reduce": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_i64, c_i64, c_i64, c_i64,
                                         C.c_int, c_p]),
     "unetb200_pack_weights": (C.c_int, [c_p, c_p, C.c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_p]),
+    "unetb200_pack_weights_multi": (C.c_int, [C.POINTER(PackJob), C.c_int, C.c_int, c_p]),
     "unetb200_bn_finalize": (C.c_int, [c_p, c_i64, c_p, c_p, C.c_float, C.c_float, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, c_p]),
     "unetb200_bn_eval_coeffs": (C.c_int, [c_p, c_p, c_p, c_p, C.c_float, c_p, c_p, c_p, c_p, C.c_int, c_p]),
     "unetb200_bn_relu_apply": (C.c_int, [c_p, c_i64, c_p, c_p, c_p, c_i64, c_p, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),

@@ -61,57 +61,83 @@ def _w_src(w):
     return w, so, si, skw
 
 
-def _pack(w, dtype, n0, n1, n2, s0, s1, s2, off=0):
-    dst = torch.empty((n0, n1 * n2), dtype=dtype, device=w.device)
-    ops._run("pack_weights", ops.lib().unetb200_pack_weights, ops._p(w), ops._p(dst), ops._DT[dtype], n0, n1, n2, s0,
-             s1, s2, off, ops._stream(), nbytes=dst.numel() * (4 + dst.element_size()))
-    return dst
-
-
-def _pack3x3_fprop(w, dtype):
+def _job3x3_fprop(w):
+    """OIHW -> Wp[co][(kh,kw)][ci]"""
     Co, Ci = w.shape[:2]
     w, so, si, st = _w_src(w)
-    return _pack(w, dtype, Co, 9, Ci, so, st, si)
+    return w, (Co, 9, Ci), (so, st, si), 0, (Co, 9 * Ci)
 
 
-def _pack3x3_dgrad(w, dtype):
+def _job3x3_dgrad(w):
+    """OIHW -> Wp[ci][(kh',kw')][co] = W[co][ci][2-kh'][2-kw']"""
     Co, Ci = w.shape[:2]
     w, so, si, st = _w_src(w)
-    return _pack(w, dtype, Ci, 9, Co, si, -st, so, off=8 * st)
+    return w, (Ci, 9, Co), (si, -st, so), 8 * st, (Ci, 9 * Co)
 
 
-def _packT_fprop(w, dtype):
+def _jobT_fprop(w):
+    """IOHW [Ci,Co,2,2] -> Wp[(q,co)][ci]"""
     Ci, Co = w.shape[:2]
     w, s_ci, s_co, st = _w_src(w)
-    return _pack(w, dtype, 4, Co, Ci, st, s_co, s_ci).view(4 * Co, Ci)
+    return w, (4, Co, Ci), (st, s_co, s_ci), 0, (4 * Co, Ci)
 
 
-def _packT_dgrad(w, dtype):
+def _jobT_dgrad(w):
+    """IOHW -> Wp[ci][(q,co)]"""
     Ci, Co = w.shape[:2]
     w, s_ci, s_co, st = _w_src(w)
-    return _pack(w, dtype, Ci, 4, Co, s_ci, st, s_co)
+    return w, (Ci, 4, Co), (s_ci, st, s_co), 0, (Ci, 4 * Co)
 
 
-# GEMM operands packed ahead of their use, on the side stream, at the start of a whole-network forward
-# (`prepack`): the ~40 small pack kernels of a step then run in the shadow of the first convolutions instead of
-# in front of each one.  Entries are valid for one forward/backward pass of the same parameter version.
-_PRE = {}          # (id(w), kind) -> (packed, ready event, dtype, parameter version)
-_PACKERS = {"f3": _pack3x3_fprop, "d3": _pack3x3_dgrad, "fT": _packT_fprop, "dT": _packT_dgrad}
+_JOBS = {"f3": _job3x3_fprop, "d3": _job3x3_dgrad, "fT": _jobT_fprop, "dT": _jobT_dgrad}
+
+
+def _pack_many(items, dtype):
+    """items: [(parameter, kind)] -> list of packed GEMM operands, written by ONE multi-tensor launch into one
+    buffer (the weights of a network change together, at the optimizer step)."""
+    specs = [_JOBS[kind](w) for w, kind in items]
+    sizes = [sh[0] * sh[1] for _, _, _, _, sh in specs]
+    starts, total = [], 0
+    for n in sizes:
+        starts.append(total)
+        total += (n + 127) // 128 * 128            # keep every operand 256-byte aligned (TMA needs 16)
+    flat = torch.empty(total, dtype=dtype, device=items[0][0].device)
+    jobs = (_lib.PackJob * len(specs))()
+    outs = []
+    es = flat.element_size()
+    for j, ((src, n, st, off, shape), o) in enumerate(zip(specs, starts)):
+        jobs[j].src, jobs[j].dst = src.data_ptr(), flat.data_ptr() + o * es
+        jobs[j].n0, jobs[j].n1, jobs[j].n2 = n
+        jobs[j].s0, jobs[j].s1, jobs[j].s2 = st
+        jobs[j].off = off
+        outs.append(flat[o:o + shape[0] * shape[1]].view(shape))
+    ops._run("pack_weights", ops.lib().unetb200_pack_weights_multi, jobs, len(specs), ops._DT[dtype], ops._stream(),
+             nbytes=float(sum(sizes)) * (4 + es))
+    return outs
+
+
+# GEMM operands packed ahead of their use by one launch at the start of a whole-network forward (`prepack`).  An
+# entry is valid while the parameter object, its storage, its version counter, dtype and device are unchanged:
+# FusedRMSprop bumps the version of every tensor it updates through raw pointers, so a cached operand can never
+# outlive its weights (and inference re-uses the operands across calls: no pack launch at all).
+_PRE = {}          # (id(w), kind) -> (packed, dtype, parameter version, weakref(w), data_ptr)
+
+
+def _pre_valid(ent, w, dtype):
+    return (ent is not None and ent[1] == dtype and ent[2] == w._version and ent[3]() is w
+            and ent[4] == w.data_ptr() and ent[0].device == w.device)
 
 
 def _packed(w, dtype, kind):
     ent = _PRE.get((id(w), kind))
-    if ent is not None and ent[2] == dtype and ent[3] == w._version and ent[0].device == w.device:
-        torch.cuda.current_stream().wait_event(ent[1])
+    if _pre_valid(ent, w, dtype):
         return ent[0]
-    return _PACKERS[kind](w, dtype)
+    return _pack_many([(w, kind)], dtype)[0]
 
 
 def prepack(model, dtype, need_dgrad):
-    """Pack every 3x3 / transposed conv weight of `model` on the side stream (see ops.on_side_stream)."""
-    _PRE.clear()
-    if not ops.side_enabled():
-        return False
+    """Pack every 3x3 / transposed conv weight of `model` into its fprop (and dgrad) GEMM operand: one launch."""
+    import weakref
     jobs = []
     for m in model.modules():
         if isinstance(m, torch.nn.ConvTranspose2d) and m.kernel_size == (2, 2):
@@ -124,15 +150,16 @@ def prepack(model, dtype, need_dgrad):
                 jobs.append((m.weight, "d3"))
     if not jobs or not all(w.is_cuda for w, _ in jobs):
         return False
-
-    def run():
-        for w, kind in jobs:
-            packed = _PACKERS[kind](w, dtype)
-            ev = torch.cuda.Event()
-            ev.record()
-            _PRE[(id(w), kind)] = (packed, ev, dtype, w._version)
-
-    ops.on_side_stream(run, join=False)
+    # a training step being captured into a CUDA graph must contain its own pack launch: on replay the weights have
+    # moved although no Python-visible version counter has
+    force = need_dgrad and torch.cuda.is_current_stream_capturing()
+    todo = [(w, kind) for w, kind in jobs if force or not _pre_valid(_PRE.get((id(w), kind)), w, dtype)]
+    if len(_PRE) > 4 * len(jobs) + 64:                  # entries of parameters that no longer exist
+        for key in [k for k, e in _PRE.items() if e[3]() is None]:
+            del _PRE[key]
+    if todo:
+        for (w, kind), packed in zip(todo, _pack_many(todo, dtype)):
+            _PRE[(id(w), kind)] = (packed, dtype, w._version, weakref.ref(w), w.data_ptr())
     return True
 
 
@@ -154,6 +181,45 @@ def packT_fprop(w, dtype):
 def packT_dgrad(w, dtype):
     """IOHW -> Wp[ci][(q,co)]"""
     return _packed(w, dtype, "dT")
+
+
+# ------------------------------------------------------------------------------------------------
+# gradient sinks: where a parameter's gradient is to be written
+# ------------------------------------------------------------------------------------------------
+# A data-parallel reducer (ddp.GradAllReducer) registers, per parameter, an fp32 view of its all-reduce bucket
+# with the parameter's shape and strides.  The backward kernels then write the gradient straight into the bucket
+# (no per-step copy of 124 MB into the buckets); autograd receives a fresh alias of that view, so AccumulateGrad
+# adopts it as p.grad without a copy.  Used only when nothing has to be accumulated: p.grad is None, or the
+# reducer runs backward through torch.autograd.grad and owns p.grad (`always`).
+_GRAD_SINK = {}    # id(param) -> (weakref(param), view, always)
+
+
+def set_grad_sinks(params, views, always=False):
+    import weakref
+    for p, v in zip(params, views):
+        if v.dtype != torch.float32 or v.shape != p.shape or v.stride() != p.stride():
+            raise ValueError("unetb200: a gradient sink must be an fp32 tensor with the parameter's shape and strides")
+        _GRAD_SINK[id(p)] = (weakref.ref(p), v, bool(always))
+
+
+def clear_grad_sinks(params=None):
+    if params is None:
+        _GRAD_SINK.clear()
+    else:
+        for p in params:
+            _GRAD_SINK.pop(id(p), None)
+
+
+def grad_dst(param, like=None):
+    """Fresh alias of `param`'s gradient sink if one is registered and usable now, else None."""
+    ent = _GRAD_SINK.get(id(param))
+    if ent is None or ent[0]() is not param:
+        return None
+    if not ent[2] and getattr(param, "grad", None) is not None:
+        return None
+    if like is not None and (tuple(like.shape) != tuple(ent[1].shape) or like.stride() != ent[1].stride()):
+        return None
+    return ent[1].detach()
 
 
 def _f32c(t):
@@ -230,16 +296,29 @@ def _grad_kept_as_is(param, dW):
     return True
 
 
-def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None):
-    """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta).  `param`: the Parameter object behind `w`."""
+def _vec_dst(param, Cc):
+    """gradient sink of a [C] parameter (BatchNorm gamma / beta, a bias), if any"""
+    if param is None:
+        return None
+    d = grad_dst(param)
+    return d if d is not None and d.dim() == 1 and d.numel() == Cc and d.is_contiguous() else None
+
+
+def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_params=(None, None)):
+    """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta).  `param`: the Parameter object behind `w`;
+    `bn_params`: the BatchNorm weight / bias Parameter objects (only to look up their gradient sinks)."""
     param = w if param is None else param
     B, Cin, H, W = x.shape
     Cout = w.shape[0]
     cd = x.dtype
-    gy, dgamma, dbeta = ops.bn_relu_bwd(gz, y, coefs, batch_stats)
+    gy, dgamma, dbeta = ops.bn_relu_bwd(gz, y, coefs, batch_stats, _vec_dst(bn_params[0], Cout),
+                                        _vec_dst(bn_params[1], Cout))
     # the gradient takes the parameter's own memory layout (OIHW or channels_last): AccumulateGrad then keeps it
-    # without a copy, and for channels_last the split reduction writes it coalesced
-    dW = torch.empty_like(w, dtype=torch.float32)
+    # without a copy, and for channels_last the split reduction writes it coalesced; with a registered sink
+    # (data-parallel bucket view) it is written there
+    dW = grad_dst(param)
+    if dW is None:
+        dW = torch.empty_like(w, dtype=torch.float32)
     so, si, skh, skw = dW.stride()
     if skh != 3 * skw or dW.shape != (Cout, Cin, 3, 3):
         dW = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
@@ -290,7 +369,7 @@ class DoubleConvFn(torch.autograd.Function):
         ctx.has_pool = pooled is not None
         if cfg.save:
             ctx.save_for_backward(x, y1, z1, y2, z2, c1, c2, w1, w2)
-            ctx.param_objs = (w1, w2)            # the Parameter objects themselves (their .grad decides the wgrad stream)
+            ctx.param_objs = (w1, g1, b1, w2, g2, b2)   # the Parameter objects themselves (.grad / gradient sinks)
         if pooled is None:
             return z2
         return z2, pooled
@@ -316,9 +395,11 @@ class DoubleConvFn(torch.autograd.Function):
         if gz is None:
             raise RuntimeError("DoubleConvFn.backward called without any output gradient")
         need = ctx.needs_input_grad
-        p1, p2 = getattr(ctx, "param_objs", (w1, w2))
-        gz1, dW2, dg2, db2 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True, param=p2)
-        gx, dW1, dg1, db1 = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0], param=p1)
+        p1, pg1, pb1, p2, pg2, pb2 = getattr(ctx, "param_objs", (w1, None, None, w2, None, None))
+        gz1, dW2, dg2, db2 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True, param=p2,
+                                              bn_params=(pg2, pb2))
+        gx, dW1, dg1, db1 = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0], param=p1,
+                                             bn_params=(pg1, pb1))
         return (gx, dW1 if need[1] else None, dg1 if need[2] else None, db1 if need[3] else None,
                 dW2 if need[4] else None, dg2 if need[5] else None, db2 if need[6] else None, None)
 
@@ -384,6 +465,7 @@ class UpCatConvTFn(torch.autograd.Function):
         if cfg.save:
             ctx.save_for_backward(x1, wT)
             ctx.param_obj = wT
+            ctx.bias_obj = bT
         return cat
 
     @staticmethod
@@ -403,7 +485,10 @@ class UpCatConvTFn(torch.autograd.Function):
             d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, h, w, C1, ops.TAPS1, 1, (0, 0), h, w, ops.nhwc_ld(x1),
                                4 * Cup, 4, 2, off, H, W, ld)
             # gradient in the parameter's own layout (see conv_bn_relu_bwd); quadrant q = kh*2 + kw must stay linear
-            dW = torch.empty_like(wT, dtype=torch.float32)
+            pT = getattr(ctx, "param_obj", wT)
+            dW = grad_dst(pT)
+            if dW is None:
+                dW = torch.empty_like(wT, dtype=torch.float32)
             if dW.shape != (C1, Cup, 2, 2) or dW.stride(2) != 2 * dW.stride(3):
                 dW = torch.empty((C1, Cup, 2, 2), dtype=torch.float32, device=g.device)
             s_ci, s_co, _, s_q = dW.stride()
@@ -423,7 +508,7 @@ class UpCatConvTFn(torch.autograd.Function):
         if need[3]:
             region = gup if not padded else ops.to_nhwc(
                 gup[:, :, off[0]:off[0] + 2 * h, off[1]:off[1] + 2 * w].contiguous(memory_format=torch.channels_last), cd)
-            dB = ops.channel_sum(region)
+            dB = ops.channel_sum(region, _vec_dst(getattr(ctx, "bias_obj", None), Cup))
         return gx1, g2, dW, dB, None
 
 
@@ -467,6 +552,7 @@ class OutConvFn(torch.autograd.Function):
         ops.outconv_fwd(x, w2, _f32c(b) if b is not None else None, logits)
         if cfg.save:
             ctx.save_for_backward(x, w2)
+            ctx.param_objs = (w, b)
         ctx.has_bias = b is not None
         return logits.permute(0, 3, 1, 2)
 
@@ -478,7 +564,12 @@ class OutConvFn(torch.autograd.Function):
         g = ops.to_nhwc(glogits, x.dtype, packed=True)
         need = ctx.needs_input_grad
         gx = ops.empty_nhwc(B, Cc, H, W, x.dtype, x.device) if need[0] else None
-        dw = torch.empty((K, Cc, 1, 1), dtype=torch.float32, device=x.device)
-        db = torch.empty(K, dtype=torch.float32, device=x.device)
+        pw, pb = getattr(ctx, "param_objs", (None, None))
+        dw = grad_dst(pw) if pw is not None else None
+        if dw is None or not dw.is_contiguous() and not dw.is_contiguous(memory_format=torch.channels_last):
+            dw = torch.empty((K, Cc, 1, 1), dtype=torch.float32, device=x.device)
+        db = _vec_dst(pb, K)
+        if db is None:
+            db = torch.empty(K, dtype=torch.float32, device=x.device)
         ops.outconv_bwd(x, w2, g, gx, dw, db)
         return gx, dw if need[1] else None, db if (need[2] and ctx.has_bias) else None, None

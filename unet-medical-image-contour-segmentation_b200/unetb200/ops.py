@@ -251,10 +251,11 @@ def add_channels_(a, b):
     return a
 
 
-def channel_sum(g):
+def channel_sum(g, out=None):
     B, Cc, H, W = g.shape
     acc = torch.empty(Cc, dtype=torch.float64, device=g.device)
-    out = torch.empty(Cc, dtype=torch.float32, device=g.device)
+    if out is None:
+        out = torch.empty(Cc, dtype=torch.float32, device=g.device)
     _run("channel_sum", lib().unetb200_channel_sum, _p(g), dt(g), nhwc_ld(g), B * H * W, Cc, _p(acc), _p(out),
          _stream(), kernels=2, nbytes=g.numel() * g.element_size())
     return out
@@ -385,8 +386,8 @@ def maxpool2_bwd(x, gp, gx, accumulate):
          nbytes=x.numel() * x.element_size() * (3.25 if accumulate else 2.25))
 
 
-def bn_relu_bwd(gz, y, coefs, training):
-    """Returns (gy, dgamma, dbeta) for z = relu(bn(y))."""
+def bn_relu_bwd(gz, y, coefs, training, dgamma=None, dbeta=None):
+    """Returns (gy, dgamma, dbeta) for z = relu(bn(y)); `dgamma` / `dbeta`: optional fp32 [C] destinations."""
     B, Cc, H, W = y.shape
     dev = y.device
     es = y.element_size()
@@ -395,8 +396,10 @@ def bn_relu_bwd(gz, y, coefs, training):
     _run("bn_relu_bwd_reduce", L.unetb200_bn_relu_bwd_reduce, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]),
          _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(sums), dt(y), B, H, W, Cc, _stream(),
          nbytes=2.0 * y.numel() * es)
-    dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
-    dbeta = torch.empty(Cc, dtype=torch.float32, device=dev)
+    if dgamma is None:
+        dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
+    if dbeta is None:
+        dbeta = torch.empty(Cc, dtype=torch.float32, device=dev)
     coef = torch.empty((2, Cc), dtype=torch.float32, device=dev)
     _run("bn_bwd_finalize", L.unetb200_bn_bwd_finalize, _p(sums), B * H * W, 1 if training else 0, _p(dgamma),
          _p(dbeta), _p(coef), Cc, _stream())

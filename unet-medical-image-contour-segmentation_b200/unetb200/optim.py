@@ -50,15 +50,18 @@ class FusedRMSprop(torch.optim.Optimizer):
         return arrs, numel, n
 
     @torch.no_grad()
-    def step(self, closure=None, clip_max_norm=None):
+    def step(self, closure=None, clip_max_norm=None, write_clipped_grad=True):
         """One update.  clip_max_norm: fold clip_grad_norm_(all params of this optimizer, clip_max_norm) in;
-        returns the total gradient norm (a 0-dim device tensor) in that case, else the closure's loss."""
+        returns the total gradient norm (a 0-dim device tensor) in that case, else the closure's loss.  Like
+        clip_grad_norm_ (train.py:157) the clipped gradients are written back to ``p.grad`` (same pass, one more
+        store per element); ``write_clipped_grad=False`` leaves ``p.grad`` unclipped."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         groups = []
         all_grads = []
+        steps = []
         for group in self.param_groups:
             ps, gs, sqs, moms = [], [], [], []
             for p in group["params"]:
@@ -79,7 +82,7 @@ class FusedRMSprop(torch.optim.Optimizer):
                     g = torch.empty_like(p, memory_format=torch.preserve_format).copy_(g)
                 if st["square_avg"].stride() != p.stride() or not _dense(p):
                     raise ValueError("FusedRMSprop: parameters must be dense and state must share their layout")
-                st["step"] += 1
+                steps.append(st["step"])
                 ps.append(p)
                 gs.append(g)
                 sqs.append(st["square_avg"])
@@ -90,6 +93,7 @@ class FusedRMSprop(torch.optim.Optimizer):
                 all_grads += gs
         if not groups:
             return loss
+        torch._foreach_add_(steps, 1)                  # one launch for all step counters
         ops.side_stream_sync()
         norm = None
         sumsq = None
@@ -105,5 +109,9 @@ class FusedRMSprop(torch.optim.Optimizer):
                      ops._p(sumsq) if sumsq is not None else C.c_void_p(0),
                      float(clip_max_norm) if clip_max_norm is not None else 0.0, float(group["lr"]),
                      float(group["alpha"]), float(group["eps"]), float(group["weight_decay"]), float(group["momentum"]),
-                     0, ops._stream(), nbytes=4.0 * sum(p.numel() for p in ps) * (7 if moms else 5))
+                     1 if (clip_max_norm is not None and write_clipped_grad) else 0, ops._stream(),
+                     nbytes=4.0 * sum(p.numel() for p in ps) * (7 if moms else 5))
+            # the kernel writes through raw pointers: tell autograd (saved-tensor checks) and the packed-operand
+            # cache of unetb200.functional that these tensors changed
+            torch._C._increment_version(ps)
         return norm if clip_max_norm is not None else loss
