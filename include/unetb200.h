@@ -137,6 +137,14 @@ typedef struct unetb200_pack_job {
 } unetb200_pack_job_t;
 int unetb200_pack_weights_multi(const unetb200_pack_job_t* jobs, int njobs, int dst_dtype, void* stream);
 
+/* fp32 exactness mode on the tensor cores ("3xTF32", BASELINE.json configs[2]): x = hi + lo with hi = x rounded
+ * to TF32.  out[p][0:C | C:2C | 2C:3C] = [hi | lo | hi] (pattern 0: left operand -- activations, output
+ * gradients) or [hi | hi | lo] (pattern 1: right operand -- packed weights, p = (n, tap)), so that the ordinary
+ * gconv kernels compute hi*hi + lo*hi + hi*lo as one convolution over 3*C input channels (fp32 accumulation;
+ * the result is within ~2^-22 of the fp32 product sum the reference's nn.Conv2d computes on the CPU). */
+int unetb200_split_tf32(const float* x, int64_t ld_x, float* out, int64_t npix, int C, int pattern,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm2d + ReLU (+ MaxPool2d) -- unet_parts.py:16-17,19-20,32.  Memory-bound, vectorised.
  * ------------------------------------------------------------------------------------------- */

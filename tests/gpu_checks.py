@@ -327,6 +327,8 @@ def _conv3x3_case(B, Ci, Co, H, W, dt_, algo, seed, slice_io=False):
     gy = rq(torch.randn(ref.shape, generator=g), dt_)
     ref.backward(gy)
     tol = 2e-5 if dt_ == FP and algo == _lib.ALGO_SIMT else (2e-3 if dt_ == FP else 1.2e-2)
+    if dt_ == FP and ops.x3_mode() and algo != _lib.ALGO_SIMT:
+        tol = 3e-5                     # 3xTF32: fp32-level results from the tensor cores
     tag = f"{Ci}to{Co}_{H}x{W}_{str(dt_)[6:]}_{'simt' if algo == _lib.ALGO_SIMT else 'tc'}{'_slice' if slice_io else ''}"
     xd = in_slice(x.detach(), dt_, 64) if slice_io else dev_nhwc(x.detach(), dt_)
     wdev = w.to(DEV)
@@ -376,6 +378,8 @@ def _convT_case(B, Ci, Co, h, w_, pad, dt_, algo, seed):
     ref.backward(gy)
     off = (pad[0] // 2, pad[1] // 2)
     tol = 2e-5 if dt_ == FP and algo == _lib.ALGO_SIMT else (2e-3 if dt_ == FP else 1.2e-2)
+    if dt_ == FP and ops.x3_mode() and algo != _lib.ALGO_SIMT:
+        tol = 3e-5                     # 3xTF32: fp32-level results from the tensor cores
     tag = f"{Ci}to{Co}_{h}x{w_}_pad{pad[0]}{pad[1]}_{str(dt_)[6:]}_{'simt' if algo == _lib.ALGO_SIMT else 'tc'}"
     xd = dev_nhwc(x.detach(), dt_)
     # destination = second half of a concat buffer [skip(Co) | up(Co)]
@@ -787,6 +791,28 @@ def check_conv_bnfold():
     return out
 
 
+def check_conv_tc_x3():
+    """UNET_B200_PRECISION=tf32x3: the same tcgen05 kind::tf32 kernels on hi/lo-split operands must give fp32-level
+    results (3e-5 instead of plain TF32's 2e-3) for fprop, dgrad, wgrad of the 3x3 convs and of ConvTranspose."""
+    old = os.environ.get("UNET_B200_PRECISION")
+    os.environ["UNET_B200_PRECISION"] = "tf32x3"
+    try:
+        out = []
+        T = _lib.ALGO_TC
+        out += _conv3x3_case(2, 64, 64, 10, 12, FP, T, 31)
+        out += _conv3x3_case(1, 64, 128, 16, 16, FP, T, 32)
+        out += _conv3x3_case(1, 128, 64, 7, 9, FP, T, 33, slice_io=True)
+        out += _conv3x3_case(1, 256, 256, 16, 24, FP, T, 36)
+        out += _convT_case(2, 64, 64, 6, 5, (0, 0), FP, T, 34)
+        out += _convT_case(1, 128, 64, 4, 4, (1, 0), FP, T, 35)
+        return [(n + "_x3", e, t) for n, e, t in out]
+    finally:
+        if old is None:
+            os.environ.pop("UNET_B200_PRECISION", None)
+        else:
+            os.environ["UNET_B200_PRECISION"] = old
+
+
 GROUPS = {
     "layout": lambda gd: check_layout_ops(),
     "bn_fwd": lambda gd: check_bn_forward(),
@@ -801,6 +827,7 @@ GROUPS = {
     "conv_tc_first": lambda gd: check_conv_tc_fprop_small(),
     "conv_tc": lambda gd: check_conv_tc(),
     "conv_tc_tf32": lambda gd: check_conv_tc_tf32(),
+    "conv_tc_x3": lambda gd: check_conv_tc_x3(),
     "conv_layouts": lambda gd: check_conv_layouts(),
     "optim": lambda gd: check_optim(),
     "conv_bnfold": lambda gd: check_conv_bnfold(),

@@ -489,6 +489,8 @@ GROUPS = {
     "full_c2": lambda gd: full_size_gate("c2"),
     "full_c3": lambda gd: full_size_gate("c3"),
     "full_c5": lambda gd: full_size_gate("c5"),
+    "north_star_tf32x3": lambda gd: north_star_gate(1, 2, True, 2, 128, 128, "tf32x3", vs_torch_gpu=False)
+                         + north_star_gate(1, 2, False, 2, 64, 96, "tf32x3", vs_torch_gpu=False),
     "segments": lambda gd: segments_gate(),
     "prepack": lambda gd: prepack_gate(),
     "north_star_bf16": lambda gd: north_star_gate(1, 2, False, 2, 128, 128) + north_star_gate(1, 2, False, 4, 256, 256, vs_torch_gpu=False),

@@ -50,7 +50,7 @@ def test_conv_simt(G, golden):
     _assert_all(G.all_groups()["conv_simt"](golden))
 
 
-@pytest.mark.parametrize("group", ["conv_tc_first", "conv_tc", "conv_tc_tf32", "conv_layouts", "conv_bnfold"])
+@pytest.mark.parametrize("group", ["conv_tc_first", "conv_tc", "conv_tc_tf32", "conv_tc_x3", "conv_layouts", "conv_bnfold"])
 def test_conv_tcgen05(G, golden, group):
     _assert_all(G.all_groups()[group](golden))
 
@@ -61,6 +61,6 @@ def test_parts_against_reference_fixtures(G, golden, group):
 
 
 @pytest.mark.parametrize("group", ["unet_fp32", "unet_fp32_b", "unet_tf32", "unet_bf16", "unet_bf16_bil", "unet_infer", "graph_side_stream", "unet_widths",
-                                   "segments", "prepack", "north_star_bf16", "north_star_bf16_b", "full_c2", "full_c3", "full_c5"])
+                                   "north_star_tf32x3", "segments", "prepack", "north_star_bf16", "north_star_bf16_b", "full_c2", "full_c3", "full_c5"])
 def test_unet_training_step(G, golden, group):
     _assert_all(G.all_groups()[group](golden))

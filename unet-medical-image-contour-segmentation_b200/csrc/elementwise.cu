@@ -679,6 +679,50 @@ typedef __nv_bfloat16 bf16;
 
 #define UB_DTYPE_OK(dt) UB_CHECK_ARG((dt) == UNETB200_F32 || (dt) == UNETB200_BF16, "unsupported dtype %d", (int)(dt))
 
+// ---- 3xTF32 operand split (fp32 exactness mode on the tensor cores) ------------------------------------------
+// x = hi + lo exactly, hi = x rounded to TF32's 10-bit mantissa (round half away from zero on the magnitude bits),
+// lo = x - hi (representable: at most 13 significant bits).  A product x*w is then recovered to ~2^-22 relative from
+// three kind::tf32 MMAs hi*hi + lo*hi + hi*lo (lo*lo ~ 2^-24 is dropped) accumulated in fp32 -- independent of how
+// the tensor core converts its fp32 inputs, because every value fed to it already is a TF32 number or gets rounded
+// at 2^-11 of an already 2^-11-small term.  Written as ONE tensor with three channel groups, so that the ordinary
+// implicit-GEMM kernels run it as a convolution over 3*C input channels:
+//   pattern 0 (left operand: activations / output gradients)  [hi | lo | hi]
+//   pattern 1 (right operand: packed weights, per tap)         [hi | hi | lo]
+__device__ __forceinline__ float tf32_hi(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float((u + 0x1000u) & 0xffffe000u);
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, int64_t ld_x, float* __restrict__ out,
+                                                         int64_t npix, int CV, int pattern) {
+  const int64_t total = npix * CV;
+  const int C = CV * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / CV;
+    const int c = (int)(i - p * CV) * V;
+    float v[V], hi[V], lo[V];
+    if (V == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(x + p * ld_x + c);
+      v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+    } else {
+      v[0] = x[p * ld_x + c];
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) { hi[k] = tf32_hi(v[k]); lo[k] = v[k] - hi[k]; }
+    float* o = out + p * 3 * C + c;
+    const float* g1 = pattern == 0 ? lo : hi;
+    const float* g2 = pattern == 0 ? hi : lo;
+    if (V == 4) {
+      *reinterpret_cast<float4*>(o) = make_float4(hi[0], hi[1 % V], hi[2 % V], hi[3 % V]);
+      *reinterpret_cast<float4*>(o + C) = make_float4(g1[0], g1[1 % V], g1[2 % V], g1[3 % V]);
+      *reinterpret_cast<float4*>(o + 2 * C) = make_float4(g2[0], g2[1 % V], g2[2 % V], g2[3 % V]);
+    } else {
+      o[0] = hi[0]; o[C] = g1[0]; o[2 * C] = g2[0];
+    }
+  }
+}
+
 extern "C" {
 
 int unetb200_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float eps,
@@ -1008,6 +1052,17 @@ int unetb200_channel_sum(const void* g, int dtype, int64_t ld, int64_t npix, int
     channel_sum_kernel<float><<<dim3((unsigned)gx_, gy_), 256, 0, s>>>((const float*)g, ld, npix, C, CB, acc);
   double_to_float_kernel<<<(C + 127) / 128, 128, 0, s>>>(acc, out, C);
   UB_LAUNCH_CHECK("channel_sum");
+  return 0;
+}
+
+int unetb200_split_tf32(const float* x, int64_t ld_x, float* out, int64_t npix, int C, int pattern, void* stream) {
+  UB_CHECK_ARG(x && out && npix > 0 && C > 0 && ld_x >= C && (pattern == 0 || pattern == 1), "split_tf32: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (C % 4 == 0 && ld_x % 4 == 0 && aligned16(x) && aligned16(out))
+    split_tf32_kernel<4><<<grid_for(npix * (C / 4), 256, 16), 256, 0, s>>>(x, ld_x, out, npix, C / 4, pattern);
+  else
+    split_tf32_kernel<1><<<grid_for(npix * C, 256, 16), 256, 0, s>>>(x, ld_x, out, npix, C, pattern);
+  UB_LAUNCH_CHECK("split_tf32");
   return 0;
 }
 }

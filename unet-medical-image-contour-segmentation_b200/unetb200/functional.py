@@ -33,18 +33,19 @@ def compute_dtype(x):
 
 def conv_algo(dtype):
     """bf16 -> tcgen05 when the layer shape fits.  fp32 -> UNET_B200_PRECISION: 'tf32' runs the
-    tcgen05 kind::tf32 engine (what cuDNN does for the reference with allow_tf32=True), 'fp32'
-    runs exact fp32 FMAs on the CUDA cores."""
+    tcgen05 kind::tf32 engine (what cuDNN does for the reference with allow_tf32=True), 'tf32x3' the
+    same engine on hi/lo-split operands (three MMAs per product: fp32-level results, north_star's
+    1e-3 mode on the tensor cores), 'fp32' exact fp32 FMAs on the CUDA cores."""
     if dtype == torch.bfloat16:
         return ALGO_AUTO
     mode = os.environ.get("UNET_B200_PRECISION", "").lower()
     if mode == "":
         mode = "tf32" if torch.backends.cudnn.allow_tf32 else "fp32"
-    if mode == "tf32":
+    if mode in ("tf32", "tf32x3"):       # tf32x3: the 3-term split of ops.x3_active (fp32-level results)
         return ALGO_PREFER_TC
     if mode == "fp32":
         return ALGO_SIMT
-    raise ValueError(f"UNET_B200_PRECISION must be 'tf32' or 'fp32', got {mode!r}")
+    raise ValueError(f"UNET_B200_PRECISION must be 'tf32', 'tf32x3' or 'fp32', got {mode!r}")
 
 
 def _w_src(w):
@@ -324,12 +325,14 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_pa
         dW = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=x.device)
         so, si, skh, skw = dW.stride()
     gx = None
+    dw_desc = _gconv3x3(x, Cout, gy, cd)
+    gs = ops.x3_split(gy) if (ops.x3_active(dw_desc) and Cout >= 16) else None   # 3xTF32: one split serves both GEMMs
     if need_gx:
         gx = ops.empty_nhwc(B, Cin, H, W, cd, x.device)
-        ops.gconv_fprop(_gconv3x3(gy, Cin, gx, cd), gy, pack3x3_dgrad(w, cd), None, gx, None, kind="dgrad")
+        ops.gconv_fprop(_gconv3x3(gy, Cin, gx, cd), gy, pack3x3_dgrad(w, cd), None, gx, None, kind="dgrad", x_split=gs)
     # after the dgrad, on the side stream: overlaps the (memory-bound) BatchNorm backward of the previous layer
     # (only when AccumulateGrad will simply keep dW: an existing .grad would be accumulated into on the main stream)
-    run = lambda: ops.gconv_wgrad(_gconv3x3(x, Cout, gy, cd), x, gy, dW, skw, si, so)  # noqa: E731
+    run = lambda: ops.gconv_wgrad(dw_desc, x, gy, dW, skw, si, so, gy_split=gs)  # noqa: E731
     if _grad_kept_as_is(param, dW):
         ops.on_side_stream(run, x, gy)      # AccumulateGrad keeps dW as it is (same layout, no other owner)
     else:

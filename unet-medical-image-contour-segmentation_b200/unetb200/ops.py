@@ -304,46 +304,129 @@ def gconv_flops(d):
     return 2.0 * d.B * d.Hm * d.Wm * d.N * d.ntaps * d.Cin
 
 
-def gconv_fprop(d, x, wp, bias, y, stats, kind="fprop"):
+def gconv_bytes(d, es):
+    """Algorithmic bytes of one launch: every input element, weight and output element once (the taps of a 3x3
+    window are served from L2 / shared memory, not HBM)."""
+    m_in = d.B * d.Hin * d.Win if d.in_scale == 1 else d.B * d.Hm * d.Wm * d.ntaps
+    return float(es) * (m_in * d.Cin + d.B * d.Hm * d.Wm * d.N + d.N * d.ntaps * d.Cin)
+
+
+# ---- fp32 exactness mode on the tensor cores: 3xTF32 ---------------------------------------------------------
+def x3_mode():
+    return os.environ.get("UNET_B200_PRECISION", "").lower() == "tf32x3"
+
+
+def x3_active(d):
+    """UNET_B200_PRECISION=tf32x3: fp32 convolutions with C_in >= 16 run as ONE tcgen05 kind::tf32 implicit GEMM over
+    3*C_in channels [hi | lo | hi] x [hi | hi | lo] (unetb200_split_tf32), i.e. hi*hi + lo*hi + hi*lo with fp32
+    accumulation -- fp32-level results (~1e-6) at a third of the TF32 rate.  The first layer (C_in <= 4) and OutConv
+    are exact fp32 CUDA-core kernels in every mode."""
+    return d.dtype == F32 and d.algo in (ALGO_TC, _lib.ALGO_PREFER_TC) and d.Cin >= 16 and x3_mode()
+
+
+def x3_split(x):
+    """NHWC fp32 [B,C,H,W] (any pixel stride) -> packed NHWC [B,3C,H,W] = [hi | lo | hi]."""
+    B, Cc, H, W = x.shape
+    out = empty_nhwc(B, 3 * Cc, H, W, torch.float32, x.device)
+    _run("split_tf32", lib().unetb200_split_tf32, _p(x), nhwc_ld(x), _p(out), B * H * W, Cc, 0, _stream(),
+         nbytes=16.0 * x.numel())
+    return out
+
+
+def x3_split_rows(wp, rows, Cc):
+    """packed weights [rows][C] (rows = (n, tap)) -> [rows][3C] = [hi | hi | lo]."""
+    out = torch.empty((rows * 3 * Cc,), dtype=torch.float32, device=wp.device)
+    _run("split_tf32_w", lib().unetb200_split_tf32, _p(wp), Cc, _p(out), rows, Cc, 1, _stream(), nbytes=16.0 * rows * Cc)
+    return out
+
+
+def _x3_desc(d, ld_in=None, ld_out=None, triple=True):
+    d3 = GConv.from_buffer_copy(d)
+    if triple:
+        d3.Cin = 3 * d.Cin
+    if ld_in is not None:
+        d3.ld_in = ld_in
+    if ld_out is not None:
+        d3.ld_out = ld_out
+    return d3
+
+
+def gconv_fprop(d, x, wp, bias, y, stats, kind="fprop", x_split=None):
     used = C.c_int(0)
     ws = None
+    flops, nbytes = gconv_flops(d), gconv_bytes(d, 2 if d.dtype == BF16 else 4)
+    tag = _shape_tag(d)
+    if x3_active(d):
+        xs = x_split if x_split is not None else x3_split(x)
+        wp = x3_split_rows(wp, d.N * d.ntaps, d.Cin)
+        d = _x3_desc(d, ld_in=3 * d.Cin)
+        x = xs
+        kind = kind + "_x3"
     if stats is not None:
         n = lib().unetb200_gconv_stats_workspace(C.byref(d))
         if n < 0:
             _lib.check(-1, "gconv_stats_workspace")
         ws = torch.empty(n, dtype=torch.float32, device=x.device)
     _run(f"conv_{kind}", lib().unetb200_gconv_fprop, C.byref(d), _p(x), _p(wp), _p(bias), _p(y), _p(stats), _p(ws),
-         C.byref(used), _stream(), kernels=2 if stats is not None else 1, flops=gconv_flops(d))
+         C.byref(used), _stream(), kernels=2 if stats is not None else 1, flops=flops, nbytes=nbytes)
     if _PROFILE is not None:
-        _PROFILE[-1][0] = f"conv_{kind}_{_ALGO_NAME.get(used.value, '?')}" + _shape_tag(d)
+        _PROFILE[-1][0] = f"conv_{kind}_{_ALGO_NAME.get(used.value, '?')}" + tag
     return used.value
 
 
 def gconv_fprop_affine_relu_supported(d, x, wp, z):
+    if x3_active(d):
+        d = _x3_desc(d, ld_in=3 * d.Cin)
     return bool(lib().unetb200_gconv_fprop_affine_relu_supported(C.byref(d), _p(x), _p(wp), _p(z)))
 
 
 def gconv_fprop_affine_relu(d, x, wp, coefs, z):
     """z = relu(conv(x, wp) * scale + shift) in the tcgen05 epilogue (inference; coefs rows 2, 3 = scale, shift)."""
+    flops, nbytes = gconv_flops(d), gconv_bytes(d, 2 if d.dtype == BF16 else 4)
+    tag = _shape_tag(d)
+    if x3_active(d):
+        x = x3_split(x)
+        wp = x3_split_rows(wp, d.N * d.ntaps, d.Cin)
+        d = _x3_desc(d, ld_in=3 * d.Cin)
     _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu, C.byref(d), _p(x), _p(wp), _p(coefs[2]), _p(z),
-         _stream(), flops=gconv_flops(d))
+         _stream(), flops=flops, nbytes=nbytes)
     if _PROFILE is not None:
-        _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + _shape_tag(d)
+        _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + tag
 
 
-def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0):
-    """dst (parameter layout, fp32) = weight gradient; dst[t*st + c*sc + q*sq + co*sn], n = q*Cq + co."""
+def _wgrad_once(d, x, gy, dst, st, sc, sn, sq, accumulate, flops, tag):
     splits, used = C.c_int(0), C.c_int(0)
     _lib.check(lib().unetb200_gconv_wgrad_plan(C.byref(d), C.byref(splits), C.byref(used)), "gconv_wgrad_plan")
     K = d.ntaps * d.Cin
     partials = torch.empty(splits.value * K * d.N, dtype=torch.float32, device=x.device)
     d2 = GConv.from_buffer_copy(d)
     d2.algo = used.value
-    _run(f"conv_wgrad_{_ALGO_NAME.get(used.value, '?')}" + _shape_tag(d), lib().unetb200_gconv_wgrad, C.byref(d2), _p(x), _p(gy),
-         _p(partials), splits.value, _stream(), flops=gconv_flops(d))
+    es = 2 if d.dtype == BF16 else 4
+    _run(f"conv_wgrad_{_ALGO_NAME.get(used.value, '?')}" + tag, lib().unetb200_gconv_wgrad, C.byref(d2), _p(x), _p(gy),
+         _p(partials), splits.value, _stream(), flops=flops,
+         nbytes=float(es) * d.B * (d.Hin * d.Win * d.Cin + d.Hout * d.Wout * (d.N // d.nquad)) + 4.0 * K * d.N)
     _run("wgrad_reduce", lib().unetb200_wgrad_reduce, _p(partials), splits.value, d.ntaps, d.Cin, d.N,
-         d.N // d.nquad, _p(dst), st, sc, sq, sn, 0, _stream(), nbytes=4.0 * K * d.N * (splits.value + 1))
+         d.N // d.nquad, _p(dst), st, sc, sq, sn, 1 if accumulate else 0, _stream(),
+         nbytes=4.0 * K * d.N * (splits.value + 1))
     return used.value
+
+
+def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0, x_split=None, gy_split=None):
+    """dst (parameter layout, fp32) = weight gradient; dst[t*st + c*sc + q*sq + co*sn], n = q*Cq + co."""
+    if not x3_active(d):
+        return _wgrad_once(d, x, gy, dst, st, sc, sn, sq, False, gconv_flops(d), _shape_tag(d))
+    # 3xTF32: dW = hi(x)^T hi(g) + lo(x)^T hi(g) + hi(x)^T lo(g), the last two accumulated by the split reduction
+    xs = x_split if x_split is not None else x3_split(x)
+    gs = gy_split if gy_split is not None else x3_split(gy)
+    Cg = gy.shape[1]
+    d2 = _x3_desc(d, ld_in=3 * d.Cin, ld_out=3 * Cg, triple=False)
+    x_hi, x_lo = channel_slice(xs, 0, d.Cin), channel_slice(xs, d.Cin, d.Cin)
+    g_hi, g_lo = channel_slice(gs, 0, Cg), channel_slice(gs, Cg, Cg)
+    tag = "_x3" + _shape_tag(d)
+    used = _wgrad_once(d2, x_hi, g_hi, dst, st, sc, sn, sq, False, gconv_flops(d), tag)
+    _wgrad_once(d2, x_lo, g_hi, dst, st, sc, sn, sq, True, 0.0, tag)
+    _wgrad_once(d2, x_hi, g_lo, dst, st, sc, sn, sq, True, 0.0, tag)
+    return used
 
 
 # ------------------------------------------------------------------------------------------------
