@@ -54,18 +54,25 @@ class _UNetBase(nn.Module):
         # concat buffers of the four Up stages: [skip | upsampled], at the skip's resolution
         cats = [ops.empty_nhwc(B, 2 * b * (1 << k), H >> k, W >> k, cd, dev) for k in range(4)]
         skips = [ops.channel_slice(cats[k], 0, b * (1 << k)) for k in range(4)]
+        taps = self._taps
+        cut = UF.CutFn.apply if taps is not None else (lambda t: t)
         x1, p = self.inc.run(x, out=skips[0], want_pool=True)
         x2, p = self.down1.run(p, out=skips[1], want_pool=True)
         x3, p3 = self.down2.run(p, out=skips[2], want_pool=True)
-        x4, p = self.down3.run(p3, out=skips[3], want_pool=True)
+        p3c = cut(p3)
+        x4, p = self.down3.run(p3c, out=skips[3], want_pool=True)
         x5 = self.down4.run(p)
-        y = self.up1.run(x5, x4, cat=cats[3])
-        u2 = self.up2.run(y, x3, cat=cats[2])
-        y = self.up3.run(u2, x2, cat=cats[1])
-        y = self.up4.run(y, x1, cat=cats[0])
+        x5c, x4c, x3c = cut(x5), cut(x4), cut(x3)
+        y = self.up1.run(x5c, x4c, cat=cats[3])
+        u2 = self.up2.run(y, x3c, cat=cats[2])
+        u2c, x2c, x1c = cut(u2), cut(x2), cut(x1)
+        y = self.up3.run(u2c, x2c, cat=cats[1])
+        y = self.up4.run(y, x1c, cat=cats[0])
         out = self.outc.run(y)
-        if self._taps is not None:        # cut points of a segmented backward pass (unetb200.ddp.SegmentedStep)
-            self._taps.update(x1=x1, x2=x2, x3=x3, x4=x4, x5=x5, p3=p3, u2=u2)
+        if taps is not None:
+            # cut points of a segmented backward pass (unetb200.ddp.SegmentedStep): name -> (tensor, its cut alias)
+            taps.update(x1=(x1, x1c), x2=(x2, x2c), x3=(x3, x3c), x4=(x4, x4c), x5=(x5, x5c), p3=(p3, p3c),
+                        u2=(u2, u2c))
         return out
 
     def use_checkpointing(self):

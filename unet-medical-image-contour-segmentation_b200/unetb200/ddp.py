@@ -262,7 +262,7 @@ def segment_params(model):
 def segmented_backward(model, loss, taps, params_by_segment, after_segment=None):
     """The backward pass of `loss` through a unetb200 UNet, run as len(SEGMENTS) torch.autograd.grad calls cut at
     the activations ``model._taps`` recorded during the forward pass (u2 = output of up2; x1..x5 = encoder outputs /
-    skips; p3 = pooled output of down2).  Returns the list of per-segment gradient lists (parameter order of
+    skips; p3 = pooled output of down2; each as (tensor, cut alias), see functional.CutFn).  Returns the list of per-segment gradient lists (parameter order of
     `params_by_segment`).  after_segment(k): called when segment k's gradients have been enqueued."""
     t = taps
     out = []
@@ -275,10 +275,12 @@ def segmented_backward(model, loss, taps, params_by_segment, after_segment=None)
             after_segment(k)
         return res[len(ps):]
 
-    g_u2, g_x2, g_x1 = run(0, [loss], None, [t["u2"], t["x2"], t["x1"]])
-    g_x5, g_x4, g_x3 = run(1, [t["u2"]], [g_u2], [t["x5"], t["x4"], t["x3"]])
-    (g_p3,) = run(2, [t["x5"], t["x4"]], [g_x5, g_x4], [t["p3"]])
-    run(3, [t["x3"], t["p3"], t["x2"], t["x1"]], [g_x3, g_p3, g_x2, g_x1], [])
+    src = lambda *names: [t[n][0] for n in names]      # noqa: E731  the tensors themselves (segment outputs)
+    cut = lambda *names: [t[n][1] for n in names]      # noqa: E731  their cut aliases (where a segment stops)
+    g_u2, g_x2, g_x1 = run(0, [loss], None, cut("u2", "x2", "x1"))
+    g_x5, g_x4, g_x3 = run(1, src("u2"), [g_u2], cut("x5", "x4", "x3"))
+    (g_p3,) = run(2, src("x5", "x4"), [g_x5, g_x4], cut("p3"))
+    run(3, src("x3", "p3", "x2", "x1"), [g_x3, g_p3, g_x2, g_x1], [])
     return out
 
 
@@ -334,11 +336,13 @@ class SegmentedStep:
             return res[len(ps):]
 
         t = taps
-        g_u2, g_x2, g_x1 = seg_capture(0, [self.static_loss], None, [t["u2"], t["x2"], t["x1"]])
-        g_x5, g_x4, g_x3 = seg_capture(1, [t["u2"]], [g_u2], [t["x5"], t["x4"], t["x3"]])
-        (g_p3,) = seg_capture(2, [t["x5"], t["x4"]], [g_x5, g_x4], [t["p3"]])
-        seg_capture(3, [t["x3"], t["p3"], t["x2"], t["x1"]], [g_x3, g_p3, g_x2, g_x1], [])
-        del t, taps, g_u2, g_x2, g_x1, g_x5, g_x4, g_x3, g_p3
+        src = lambda *names: [t[n][0] for n in names]      # noqa: E731
+        cut = lambda *names: [t[n][1] for n in names]      # noqa: E731
+        g_u2, g_x2, g_x1 = seg_capture(0, [self.static_loss], None, cut("u2", "x2", "x1"))
+        g_x5, g_x4, g_x3 = seg_capture(1, src("u2"), [g_u2], cut("x5", "x4", "x3"))
+        (g_p3,) = seg_capture(2, src("x5", "x4"), [g_x5, g_x4], cut("p3"))
+        seg_capture(3, src("x3", "p3", "x2", "x1"), [g_x3, g_p3, g_x2, g_x1], [])
+        del t, taps, src, cut, g_u2, g_x2, g_x1, g_x5, g_x4, g_x3, g_p3
         self._keep = state
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=pool, **kw):

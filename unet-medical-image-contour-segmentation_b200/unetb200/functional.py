@@ -354,6 +354,22 @@ class ToNHWCFn(torch.autograd.Function):
         return ops.to_nhwc(g, dt), None
 
 
+class CutFn(torch.autograd.Function):
+    """Identity that gives a tensor its own autograd node: a cut point of a segmented backward pass
+    (unetb200.ddp.segmented_backward).  torch.autograd.grad(..., inputs=[t]) executes every node from which t's
+    PRODUCER can be reached -- for a skip tensor that is the whole rest of the network (its producer also emits the
+    pooled tensor the deeper stages consume).  Requesting the gradient at the cut alias instead stops the engine
+    there; the next segment then starts from the producer's own output with that gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
 class _Cfg:
     """Non-tensor arguments of a Function call."""
 
