@@ -328,7 +328,7 @@ def _conv3x3_case(B, Ci, Co, H, W, dt_, algo, seed, slice_io=False):
     ref.backward(gy)
     tol = 2e-5 if dt_ == FP and algo == _lib.ALGO_SIMT else (2e-3 if dt_ == FP else 1.2e-2)
     if dt_ == FP and ops.x3_mode() and algo != _lib.ALGO_SIMT:
-        tol = 3e-5                     # 3xTF32: fp32-level results from the tensor cores
+        tol = 5e-5                     # 3xTF32: fp32-level results from the tensor cores
     tag = f"{Ci}to{Co}_{H}x{W}_{str(dt_)[6:]}_{'simt' if algo == _lib.ALGO_SIMT else 'tc'}{'_slice' if slice_io else ''}"
     xd = in_slice(x.detach(), dt_, 64) if slice_io else dev_nhwc(x.detach(), dt_)
     wdev = w.to(DEV)
@@ -379,7 +379,7 @@ def _convT_case(B, Ci, Co, h, w_, pad, dt_, algo, seed):
     off = (pad[0] // 2, pad[1] // 2)
     tol = 2e-5 if dt_ == FP and algo == _lib.ALGO_SIMT else (2e-3 if dt_ == FP else 1.2e-2)
     if dt_ == FP and ops.x3_mode() and algo != _lib.ALGO_SIMT:
-        tol = 3e-5                     # 3xTF32: fp32-level results from the tensor cores
+        tol = 5e-5                     # 3xTF32: fp32-level results from the tensor cores
     tag = f"{Ci}to{Co}_{h}x{w_}_pad{pad[0]}{pad[1]}_{str(dt_)[6:]}_{'simt' if algo == _lib.ALGO_SIMT else 'tc'}"
     xd = dev_nhwc(x.detach(), dt_)
     # destination = second half of a concat buffer [skip(Co) | up(Co)]
@@ -793,7 +793,7 @@ def check_conv_bnfold():
 
 def check_conv_tc_x3():
     """UNET_B200_PRECISION=tf32x3: the same tcgen05 kind::tf32 kernels on hi/lo-split operands must give fp32-level
-    results (3e-5 instead of plain TF32's 2e-3) for fprop, dgrad, wgrad of the 3x3 convs and of ConvTranspose."""
+    results (5e-5 instead of plain TF32's 2e-3) for fprop, dgrad, wgrad of the 3x3 convs and of ConvTranspose."""
     old = os.environ.get("UNET_B200_PRECISION")
     os.environ["UNET_B200_PRECISION"] = "tf32x3"
     try:
