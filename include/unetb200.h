@@ -107,6 +107,19 @@ int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const 
 int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, const void* wp,
                                      const float* scale_shift, void* z, void* stream);
 
+/* Data gradient of conv3x3 (autograd of unet_parts.py:18) fused with the reduction pass of the BatchNorm2d + ReLU
+ * backward of the layer below it (unet_parts.py:16-17; inside a DoubleConv the second conv's input IS that layer's
+ * activation z = relu(bn(yprev))): gx = gconv(g, Wp_dgrad) is written as by unetb200_gconv_fprop, and the epilogue
+ * -- which holds the rounded gx tile anyway -- also reads the matching yprev tile and accumulates
+ *   sums[0][c] += sum gx*mask,  sums[1][c] += sum gx*mask*xhat,   mask = (yprev*scale + shift > 0),
+ *   xhat = (yprev - mean)*invstd        (exactly unetb200_bn_relu_bwd_reduce on the stored gx; `sums` zeroed by the caller)
+ * so that pass (one more read of gx and yprev, 4 B per element) is not run.  coefs = float[4][N]: mean, invstd, scale,
+ * shift (unetb200_bn_finalize's outputs, contiguous).  ws = float[unetb200_gconv_stats_workspace(d)].  _supported
+ * returns 1 when the fused tcgen05 kernel covers the shape; otherwise run gconv_fprop + bn_relu_bwd_reduce. */
+int unetb200_gconv_dgrad_bnbwd_supported(const unetb200_gconv_t* d, const void* g, const void* wp, const void* gx);
+int unetb200_gconv_dgrad_bnbwd(const unetb200_gconv_t* d, const void* g, const void* wp, void* gx, const void* yprev,
+                               int64_t ld_yprev, const float* coefs, double* sums, float* ws, void* stream);
+
 /* Weight gradient of the same generalised conv:
  *   dWp[(t,c)][n] = sum_m A[m][(t,c)] * G[m][n],  G[m][n] = gy at the destination of (m,n).
  * The reduction over m is split `splits` ways; partial s is written (not accumulated) to

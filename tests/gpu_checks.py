@@ -813,7 +813,68 @@ def check_conv_tc_x3():
             os.environ["UNET_B200_PRECISION"] = old
 
 
+def _dgrad_bnbwd_case(B, Ci, Co, H, W, dt_, seed, slice_y=False):
+    """dgrad of conv3x3 (Co -> Ci channels) with the BatchNorm-backward reduction of the layer below fused into its
+    epilogue: gx must equal the plain dgrad bit for bit, the sums must equal unetb200_bn_relu_bwd_reduce on that gx
+    (fp32 partials, different order: 1e-5) and a CPU fp64 evaluation of the same formula on the stored gx."""
+    res = []
+    if dt_ == FP and ops.x3_mode():
+        return res                      # the 3xTF32 split runs the plain kernels
+    g = gen(seed)
+    gy = rq(torch.randn(B, Co, H, W, generator=g), dt_)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Co ** 0.5)
+    yprev = rq(torch.randn(B, Ci, H, W, generator=g), dt_)
+    gamma, beta = torch.rand(Ci, generator=g) + 0.5, torch.randn(Ci, generator=g) * 0.3
+    tag = f"{Co}to{Ci}_{B}x{H}x{W}_{str(dt_)[6:]}{'_slice' if slice_y else ''}"
+    gyd = dev_nhwc(gy, dt_)
+    yd = in_slice(yprev, dt_, 64) if slice_y else dev_nhwc(yprev, dt_)
+    stats = torch.stack([yprev.double().sum((0, 2, 3)), (yprev.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    coefs = ops.bn_finalize(stats, B * H * W, gamma.to(DEV), beta.to(DEV), 1e-5, 0.0, None, None, Ci)
+    wd = UF.pack3x3_dgrad(w.to(DEV), dt_)
+    algo = _lib.ALGO_TC if dt_ == BF else _lib.ALGO_PREFER_TC
+    gx0 = ops.empty_nhwc(B, Ci, H, W, dt_, DEV)
+    gx1 = ops.empty_nhwc(B, Ci, H, W, dt_, DEV)
+    d = ops.make_gconv(ops._DT[dt_], algo, B, H, W, Co, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(gyd),
+                       Ci, 1, 1, (0, 0), H, W, ops.nhwc_ld(gx0))
+    ops.gconv_fprop(d, gyd, wd, None, gx0, None, kind="dgrad")
+    ok = ops.gconv_dgrad_bnbwd_supported(d, gyd, wd, gx1)
+    res.append((f"bnbwd_supported_{tag}", 0.0 if ok else 1.0, 0.0))
+    if not ok:
+        return res
+    sums = ops.gconv_dgrad_bnbwd(d, gyd, wd, gx1, yd, coefs)
+    res.append((f"bnbwd_gx_bitequal_{tag}", (host(gx1) - host(gx0)).abs().max().item(), 0.0))
+    ref = torch.zeros((2, Ci), dtype=torch.float64, device=DEV)
+    L = ops.lib()
+    _lib.check(L.unetb200_bn_relu_bwd_reduce(ops._p(gx0), ops.nhwc_ld(gx0), ops._p(yd), ops.nhwc_ld(yd), ops._p(coefs[2]),
+                                             ops._p(coefs[3]), ops._p(coefs[0]), ops._p(coefs[1]), ops._p(ref), ops.dt(yd),
+                                             B, H, W, Ci, ops._stream()), "bn_relu_bwd_reduce")
+    c = host(coefs).double()
+    gxh, yh = host(gx0).double(), yprev.double()
+    sh = lambda v: v.reshape(1, -1, 1, 1)  # noqa: E731
+    mask = (torch.addcmul(sh(c[3]).float(), yprev, sh(c[2]).float()) > 0).double()   # fp32 fma like the kernels (ties aside)
+    gm = gxh * mask
+    cpu = torch.stack([gm.sum((0, 2, 3)), (gm * (yh - sh(c[0])) * sh(c[1])).sum((0, 2, 3))])
+    scale = cpu.abs().max().item() + 1e-30
+    res.append((f"bnbwd_sums_vs_kernel_{tag}", (sums.cpu() - ref.cpu()).abs().max().item() / scale, 1e-5))
+    res.append((f"bnbwd_sums_vs_cpu_{tag}", (sums.cpu() - cpu).abs().max().item() / scale, 2e-4))
+    return res
+
+
+def check_dgrad_bnbwd():
+    out = []
+    out += _dgrad_bnbwd_case(2, 64, 64, 16, 24, BF, 71)
+    out += _dgrad_bnbwd_case(1, 128, 128, 20, 12, BF, 72)
+    out += _dgrad_bnbwd_case(2, 128, 256, 9, 7, BF, 73)            # ragged tiles: rows outside the M grid must not count
+    out += _dgrad_bnbwd_case(3, 64, 128, 20, 8, BF, 74)            # stacked sub-tile geometry (W <= 8)
+    out += _dgrad_bnbwd_case(2, 64, 64, 40, 36, BF, 75, slice_y=True)
+    out += _dgrad_bnbwd_case(1, 256, 128, 33, 17, BF, 76)
+    out += _dgrad_bnbwd_case(2, 64, 64, 16, 24, FP, 77)            # tf32 engine, fp32 storage
+    out += _dgrad_bnbwd_case(1, 128, 64, 19, 21, FP, 78)
+    return out
+
+
 GROUPS = {
+    "dgrad_bnbwd": lambda gd: check_dgrad_bnbwd(),
     "layout": lambda gd: check_layout_ops(),
     "bn_fwd": lambda gd: check_bn_forward(),
     "maxpool": lambda gd: check_maxpool(),

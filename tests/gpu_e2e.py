@@ -401,6 +401,7 @@ def segments_gate():
         ticks = torch.zeros((), device=DEV)
         step = ddp.SegmentedStep(m, fwd_loss(m), lambda: ticks.add_(1), (x, t), warmup=1)
         before = float(ticks)
+        nbt0 = int(m.state_dict()["inc.double_conv.1.num_batches_tracked"])   # warm-up steps ran, the captures did not
         for _ in range(2):
             ld = step(x, t)
         torch.cuda.synchronize()
@@ -408,7 +409,7 @@ def segments_gate():
         res.append((f"{tag}_graph_loss_equal", abs(float(ld) - float(la)), 1e-6))
         res.append((f"{tag}_graph_grads_equal", max(rel(host(p.grad), ga[k]) for k, p in m.named_parameters()), 1e-6))
         sd = m.state_dict()
-        res.append((f"{tag}_graph_bn_steps", float(abs(int(sd["inc.double_conv.1.num_batches_tracked"]) - 4)), 0.0))
+        res.append((f"{tag}_graph_bn_steps", float(abs(int(sd["inc.double_conv.1.num_batches_tracked"]) - nbt0 - 2)), 0.0))
         step.release()
         res.append((f"{tag}_sinks_released", float(len(UF._GRAD_SINK)), 0.0))
     return res

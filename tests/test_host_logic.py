@@ -127,9 +127,8 @@ def test_wgrad_split_counts_fill_whole_waves():
         chunks = cin // 64
         if cout % 128 == 0 and (3 * chunks) % 4 == 0:          # CTA-pair kernel: slots = SM pairs
             tiles, slots = (3 * chunks // 4) * (cout // 128), 74
-        else:                                                   # single-CTA kernel: two units per M tile
-            bn = 128 if cout % 128 == 0 else 64
-            tiles, slots = ((3 * chunks + 1) // 2) * (cout // bn), 148
+        else:                                                   # N-stacked kernel: one CTA per (x chunk, dY group)
+            tiles, slots = chunks * (cout // 64), 148
         ctas = tiles * splits.value
         waves = -(-ctas // slots)
         assert ctas / (waves * slots) >= 0.95, (cin, cout, hw, splits.value, ctas, waves)

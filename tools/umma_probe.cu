@@ -190,6 +190,111 @@ static void run_rate() {
       }
 }
 
+
+// ---------------------------------------------------------------- rate2: MN-major shapes of the N-stacked wgrad
+// cta_group::1 (or ::2), both operands MN-major (K = pixels).  B = `N / 64` sub-tiles of 64 channels `lbo_b` bytes apart
+// (128 B = the same halo box shifted by one pixel, i.e. overlapping reads; 8192 = separate tiles), 8-pixel groups
+// `sbo_b` bytes apart.  M = 64 / 128 per CTA.  Reports cycles per MMA against the tensor floor M*N*16*2 / 8192.
+template <int CG>
+__global__ void __launch_bounds__(128, 1) rate2_kernel(int M, int N, int lbo_b, int sbo_b, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;                    // 4 x 16 KB
+  uint8_t* b_ring = smem + 4 * 16384;        // 4 x 32 KB
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 4 * 16384 + 4 * 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + kRing);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kRing; ++i) mbar_init(&done[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { if (CG == 2) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc(false, true, true, M * CG, N);
+    const uint64_t a_t = make_desc(smem_u32(a_ring), 8192, 1024), b_t = make_desc(smem_u32(b_ring), lbo_b, sbo_b);
+    const uint32_t dcol2 = 2 * N <= 512 ? (uint32_t)N : 0u;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % kRing;
+      if (it >= kRing) mbar_wait(&done[s], ((it / kRing) - 1) & 1);
+      tc_fence_after();
+      const uint64_t a0 = a_t + s * (16384 >> 4), b0 = b_t + s * (32768 >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ka = (uint32_t)(kk * 2 * 1024) >> 4, kb = (uint32_t)(kk * 2 * sbo_b) >> 4;
+          if (CG == 2) {
+            umma2(tmem_base, a0 + ka, b0 + kb, idesc, 1);
+            umma2(tmem_base + dcol2, a0 + 64 + ka, b0 + kb, idesc, 1);
+          } else {
+            umma<false>(tmem_base, a0 + ka, b0 + kb, idesc, 1);
+            umma<false>(tmem_base + dcol2, a0 + 64 + ka, b0 + kb, idesc, 1);
+          }
+        }
+        if (CG == 2) umma_commit2(&done[s], 3); else umma_commit(&done[s]);
+      }
+      __syncwarp();
+    }
+    for (int it = iters > kRing ? iters - kRing : 0; it < iters; ++it) mbar_wait(&done[it % kRing], (it / kRing) & 1);
+    long long t1 = clock64();
+    if (lane == 0) out[blockIdx.x] = t1 - t0;
+  } else if (warp == 0) {
+    for (int it = 0; it < iters; ++it) mbar_wait(&done[it % kRing], (it / kRing) & 1);
+    if (lane == 0) out[blockIdx.x] = 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == 1) { if (CG == 2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+}
+
+static void run_rate2() {
+  const int smem = 4 * 16384 + 4 * 32768 + 1024 + 256;
+  CK(cudaFuncSetAttribute(rate2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  CK(cudaFuncSetAttribute(rate2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  long long* out;
+  CK(cudaMalloc(&out, 148 * sizeof(long long)));
+  const int iters = 4000;
+  struct Case { int cg, M, N, lbo, sbo; };
+  const Case cases[] = {{1, 128, 64, 8192, 1024},  {1, 128, 128, 8192, 1024}, {1, 128, 192, 8192, 1024}, {1, 128, 256, 8192, 1024},
+                        {1, 128, 128, 128, 1280},  {1, 128, 192, 128, 1280},  {1, 128, 256, 128, 1280},
+                        {1, 64, 64, 8192, 1024},   {1, 64, 128, 128, 1280},   {1, 64, 192, 128, 1280},   {1, 64, 256, 128, 1280},
+                        {2, 128, 128, 8192, 1024}, {2, 128, 192, 8192, 1024}, {2, 128, 256, 8192, 1024}, {2, 128, 256, 128, 1280},
+                        {2, 64, 128, 8192, 1024},  {2, 64, 256, 8192, 1024}};
+  for (const Case& c : cases) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c.cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    for (int rep = 0; rep < 2; ++rep) {
+      if (c.cg == 1) CK(cudaLaunchKernelEx(&cfg, rate2_kernel<1>, c.M, c.N, c.lbo, c.sbo, iters, out));
+      else CK(cudaLaunchKernelEx(&cfg, rate2_kernel<2>, c.M, c.N, c.lbo, c.sbo, iters, out));
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("rate2 cg=%d M=%d N=%d: CUDA error %s\n", c.cg, c.M, c.N, cudaGetErrorString(e)); exit(1); }
+    }
+    std::vector<long long> h(148);
+    CK(cudaMemcpy(h.data(), out, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+    double sum = 0; int n = 0;
+    for (auto v : h) if (v > 0) { sum += v; ++n; }
+    const double per = sum / n / (iters * 8.0);
+    const double floor = (double)c.M * c.N / 256.0;      // per SM: M x N x 16 x 2 FLOP at 8192 FLOP/cycle
+    printf("rate2 MN-major cta_group::%d M/CTA=%3d N=%3d lboB=%4d sboB=%4d: %.1f cycles/MMA, floor %.0f -> %.0f%% of tensor peak\n",
+           c.cg, c.M, c.N, c.lbo, c.sbo, per, floor, 100.0 * floor / per);
+  }
+}
+
 // ---------------------------------------------------------------- check (a): cta_group::2 GEMM
 // D[256][N] = A[256][64] * B[N][64]^T, bf16 in, fp32 out.  CTA r of the pair holds A rows [128r, 128r+128) and
 // B rows [N/2 r, N/2 r + N/2), both K-major SWIZZLE_128B at the same shared-memory offsets.
@@ -469,5 +574,6 @@ int main(int argc, char** argv) {
   if (!strcmp(mode, "check") || !strcmp(mode, "all")) run_check();
   if (!strcmp(mode, "checkmn") || !strcmp(mode, "all")) run_check_mn();
   if (!strcmp(mode, "rate") || !strcmp(mode, "all")) run_rate();
+  if (!strcmp(mode, "rate2") || !strcmp(mode, "all")) run_rate2();
   return 0;
 }

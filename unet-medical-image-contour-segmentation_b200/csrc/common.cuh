@@ -29,6 +29,10 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 int sm_count();
+// cudaFuncAttributeMaxDynamicSharedMemorySize for `func`, applied once per (device, function) under a mutex: forward
+// runs on the Python main thread, backward on the autograd engine's device thread, and one process may drive
+// several GPUs (the attribute is per device).
+int set_max_dynamic_smem(const void* func, int bytes, const char* what);
 
 template <typename T>
 struct Elem;

@@ -515,7 +515,8 @@ first_conv_wgrad_tiled_kernel(GconvDev d, const T* __restrict__ x, const T* __re
 }
 
 static bool first_tiled_ok(const unetb200_gconv_t* d) {
-  if (getenv("UNETB200_FIRST_V1")) return false;
+  static const bool v1 = getenv("UNETB200_FIRST_V1") != nullptr;
+  if (v1) return false;
   if (d->Cin != 1 || d->N != 64 || d->ld_out % 8) return false;
   for (int t = 0; t < 9; ++t)
     if (d->tap_dy[t] < -1 || d->tap_dy[t] > 1 || d->tap_dx[t] < -1 || d->tap_dx[t] > 1) return false;
@@ -524,7 +525,8 @@ static bool first_tiled_ok(const unetb200_gconv_t* d) {
 
 // four pixels per thread (C_in = 2..4): needs the plain 3x3 window and W % 4 == 0
 static bool first_px4_ok(const unetb200_gconv_t* d) {
-  if (getenv("UNETB200_FIRST_V1")) return false;
+  static const bool v1 = getenv("UNETB200_FIRST_V1") != nullptr;
+  if (v1) return false;
   if (d->Cin < 2 || d->Cin > 4 || (d->Wm & 3)) return false;
   bool seen[9] = {false};
   for (int t = 0; t < 9; ++t) {

@@ -568,8 +568,7 @@ int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
   GconvDev g;
   if (gconv_validate(d, &g)) return -1;
   long long simt_tiles = (g.M + FBM - 1) / FBM;
-  long long tc_tiles = tc_fprop_tiles(d);
-  long long tiles = simt_tiles > tc_tiles ? simt_tiles : tc_tiles;
+  long long tiles = simt_tiles;
   long long ft = first_fprop_tiles(d);
   if (ft > tiles) tiles = ft;
   long long n = tiles * 2 * g.N;
@@ -593,10 +592,8 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (algo_used) *algo_used = algo;
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_fprop_supported(d, x, wp, y), "gconv_fprop: tcgen05 path requested but shape/alignment unsupported");
-    static const bool use_v1 = getenv("UNETB200_TC_V1") != nullptr;      // first-generation kernel, for A/B runs
-    if (!use_v1 && tc3_fprop_supported(d, x, wp, bias, y)) return tc3_fprop(d, g, x, wp, y, stats, stats_ws, s);
-    if (!use_v1 && tc2_fprop_supported(d, x, wp, y)) return tc2_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
-    return tc_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
+    if (tc3_fprop_supported(d, x, wp, bias, y)) return tc3_fprop(d, g, x, wp, y, stats, stats_ws, s);
+    return tc2_fprop(d, g, x, wp, bias, y, stats, stats_ws, s);
   }
   UB_CHECK_ARG(algo == UNETB200_ALGO_SIMT, "gconv_fprop: unknown algo %d", algo);
   if (!bias && first_fprop_supported(d, y)) return first_fprop(d, g, x, wp, y, stats, stats_ws, s);
@@ -618,10 +615,11 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
 int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* z) {
   GconvDev g;
   if (gconv_validate(d, &g)) return 0;
-  if (getenv("UNETB200_NO_BN_FOLD") || getenv("UNETB200_TC_V1") || d->algo == UNETB200_ALGO_SIMT) return 0;
+  static const bool off = getenv("UNETB200_NO_BN_FOLD") != nullptr;
+  static const bool wide = getenv("UNETB200_TC3_MAXBN") && atoi(getenv("UNETB200_TC3_MAXBN")) >= 256;
+  if (off || d->algo == UNETB200_ALGO_SIMT) return 0;
   if (d->N % 128 != 0 && d->N % 64 != 0) return 0;
-  if (d->dtype == UNETB200_BF16 && d->N % 256 == 0 && getenv("UNETB200_TC3_MAXBN") && atoi(getenv("UNETB200_TC3_MAXBN")) >= 256)
-    return 0;
+  if (d->dtype == UNETB200_BF16 && d->N % 256 == 0 && wide) return 0;
   return tc_fprop_supported(d, x, wp, z) && tc3_fprop_supported(d, x, wp, nullptr, z);
 }
 
@@ -637,6 +635,28 @@ int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, c
   return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift);
 }
 
+// dgrad of a 3x3 convolution + the reduction pass of the BatchNorm/ReLU backward of the layer that produced its input
+int unetb200_gconv_dgrad_bnbwd_supported(const unetb200_gconv_t* d, const void* g, const void* wp, const void* gx) {
+  GconvDev gd;
+  if (gconv_validate(d, &gd)) return 0;
+  static const bool off = getenv("UNETB200_NO_BNBWD_FUSE") != nullptr;
+  if (off || d->algo == UNETB200_ALGO_SIMT) return 0;
+  return tc_fprop_supported(d, g, wp, gx) && tc3_fprop_supported(d, g, wp, nullptr, gx) && tc3_bnbwd_supported(d);
+}
+
+int unetb200_gconv_dgrad_bnbwd(const unetb200_gconv_t* d, const void* g, const void* wp, void* gx, const void* yprev,
+                               int64_t ld_yprev, const float* coefs, double* sums, float* ws, void* stream) {
+  GconvDev gd;
+  int rc = gconv_validate(d, &gd);
+  if (rc) return rc;
+  UB_CHECK_ARG(g && wp && gx && yprev && coefs && sums && ws, "gconv_dgrad_bnbwd: null pointer");
+  UB_CHECK_ARG(ld_yprev >= d->N, "gconv_dgrad_bnbwd: ld_yprev < N");
+  UB_CHECK_ARG(unetb200_gconv_dgrad_bnbwd_supported(d, g, wp, gx),
+               "gconv_dgrad_bnbwd: shape not covered by the fused kernel (query _supported first and run gconv_fprop + "
+               "bn_relu_bwd_reduce instead)");
+  return tc3_fprop(d, gd, g, wp, gx, sums, ws, (cudaStream_t)stream, nullptr, yprev, (long long)ld_yprev, coefs);
+}
+
 int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_used) {
   GconvDev g;
   int rc = gconv_validate(d, &g);
@@ -648,9 +668,8 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
   if (algo_used) *algo_used = algo;
   if (splits) {
     if (algo == UNETB200_ALGO_TC)
-      *splits = (!getenv("UNETB200_TC_V1") && tc3_wgrad_supported(d, nullptr, nullptr)) ? tc3_wgrad_splits(d)
-                : (!getenv("UNETB200_TC_V1") && tc2_wgrad_supported(d, nullptr, nullptr)) ? tc2_wgrad_splits(d)
-                                                                                          : tc_wgrad_splits(d, g);
+      *splits = tc4_wgrad_preferred(d) ? tc4_wgrad_splits(d)
+                : tc3_wgrad_supported(d, nullptr, nullptr) ? tc3_wgrad_splits(d) : tc2_wgrad_splits(d);
     else if (first_wgrad_supported(d, nullptr)) *splits = first_wgrad_splits(d);
     else *splits = simt_wgrad_splits(g);
   }
@@ -668,15 +687,16 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_wgrad_supported(d, nullptr, nullptr) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path requested but shape/alignment unsupported");
-    if (!getenv("UNETB200_TC_V1") && tc3_wgrad_supported(d, nullptr, nullptr)) {
+    if (tc4_wgrad_preferred(d)) {
+      UB_CHECK_ARG(tc4_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path needs 16-byte aligned operands");
+      return tc4_wgrad(d, g, x, gy, partials, splits, s);
+    }
+    if (tc3_wgrad_supported(d, nullptr, nullptr)) {
       UB_CHECK_ARG(tc3_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path needs 16-byte aligned operands");
       return tc3_wgrad(d, g, x, gy, partials, splits, s);
     }
-    if (!getenv("UNETB200_TC_V1") && tc2_wgrad_supported(d, nullptr, nullptr)) {
-      UB_CHECK_ARG(tc2_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path needs 16-byte aligned operands");
-      return tc2_wgrad(d, g, x, gy, partials, splits, s);
-    }
-    return tc_wgrad(d, g, x, gy, partials, splits, s);
+    UB_CHECK_ARG(tc2_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path needs 16-byte aligned operands");
+    return tc2_wgrad(d, g, x, gy, partials, splits, s);
   }
   if (first_wgrad_supported(d, nullptr)) {
     UB_CHECK_ARG(first_wgrad_supported(d, gy) && splits == first_wgrad_splits(d),

@@ -448,13 +448,9 @@ template <typename T, int BN, int SA, int SB, int ACC>
 static int tc2_launch(const Tc2Params& P, int grid, cudaStream_t s) {
   constexpr int smem = SA * kAStage + SB * BN * 128 + kEpiWarps * kEpiStage + 1024 + 256;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc2_fprop_kernel<T, BN, SA, SB, ACC>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "tc2_fprop smem attribute");
-    configured = true;
-  }
+  if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(&tc2_fprop_kernel<T, BN, SA, SB, ACC>), smem,
+                                    "tc2_fprop smem attribute"))
+    return rc;
   tc2_fprop_kernel<T, BN, SA, SB, ACC><<<grid, kTc2Threads, smem, s>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "tc2_fprop launch");
@@ -753,12 +749,9 @@ static int tc2_launch_wgrad(const Tc2WParams& P, dim3 grid, cudaStream_t s) {
   constexpr int EPR = 128 / sizeof(T);
   constexpr int smem = ST * ((128 / EPR) * 10240 + (BN / EPR) * 8192) + 1024 + 256;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc2_wgrad_kernel<T, BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "tc2_wgrad smem attribute");
-    configured = true;
-  }
+  if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(&tc2_wgrad_kernel<T, BN, ST>), smem,
+                                    "tc2_wgrad smem attribute"))
+    return rc;
   tc2_wgrad_kernel<T, BN, ST><<<grid, 192, smem, s>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "tc2_wgrad launch");

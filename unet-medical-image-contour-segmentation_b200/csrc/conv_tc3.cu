@@ -164,6 +164,11 @@ struct alignas(64) Tc3Params {
   float* stats_ws;           // [n_block][cta][8 epilogue warps][2][BLOCK_N]
   const float* affine;       // AFFINE kernels only: scale[N] then shift[N] (eval-mode BatchNorm folded into the epilogue)
   int N;
+  // BNBWD kernels only (dgrad whose output is the gradient of z = relu(bn(yprev))): the raw conv output of the
+  // previous layer and its BatchNorm coefficients [4][N] = mean, invstd, scale, shift
+  const void* yprev;
+  long long ld_yprev;
+  const float* bnc;
 };
 
 constexpr uint32_t kA3Stage = 44032;    // 43 KB >= the largest halo box: 34 rows x 10 px x 128 B
@@ -174,8 +179,17 @@ constexpr int kTc3Threads = 64 + 32 * kEpi3Warps;
 // AFFINE: inference form of conv -> BatchNorm(running statistics) -> ReLU (unet_parts.py:15-20 under .eval()): the
 // epilogue stores relu(acc * scale[n] + shift[n]) instead of the raw convolution, so the activation is written once
 // and the separate 4 B/element BatchNorm pass disappears.  A separate instantiation: the training kernels are unchanged.
-template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG, int TPS, bool AFFINE = false>
+//
+// EPI_BNBWD: the convolution is a dgrad whose output g is the gradient of z = relu(bn(yprev)) of the previous layer
+// (DoubleConv: conv2's dgrad feeds conv1's BatchNorm + ReLU backward).  The epilogue, which holds the rounded g tile
+// anyway, also reads the matching yprev tile and accumulates sum(g * mask) and sum(g * mask * xhat) per channel --
+// the reduction pass of the BatchNorm backward (unetb200_bn_relu_bwd_reduce: one read of g and of yprev, 4 B per
+// element) disappears.  Partial sums take the same route as the forward statistics (per-warp registers -> workspace
+// -> fp64 reduce, fixed order).
+constexpr int EPI_PLAIN = 0, EPI_AFFINE = 1, EPI_BNBWD = 2;
+template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG, int TPS, int EPI = EPI_PLAIN>
 __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_constant__ Tc3Params p) {
+  constexpr bool AFFINE = EPI == EPI_AFFINE, BNBWD = EPI == EPI_BNBWD;
   constexpr bool TF32 = sizeof(T) == 4;
   constexpr int EPR = 128 / sizeof(T);
   constexpr uint32_t kBTap = (BLOCK_N / CG) * 128;     // one tap's weight tile (this CTA's half of it)
@@ -329,6 +343,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
       }
     };
     const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&t_empty[0]), 0);
+    constexpr int CPL = TF32 ? 1 : 2;                                   // channels per lane and 128-byte block
+    float bmu[BNBWD ? NCB : 1][CPL], bis[BNBWD ? NCB : 1][CPL], bsc[BNBWD ? NCB : 1][CPL], bsh[BNBWD ? NCB : 1][CPL];
     for (int gt = group0; gt < p.total_groups; gt += ngroups) {
       const int nb = gt / p.m_groups;
       int mt = (gt - nb * p.m_groups) * CG + (int)rank;
@@ -338,7 +354,22 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
       const int ti = mt % p.tiles_h;
       const int b = mt / p.tiles_h;
       const int n0 = nb * BLOCK_N;
-      if (nb != cur_nb) { flush(cur_nb); cur_nb = nb; }
+      if (nb != cur_nb) {
+        flush(cur_nb);
+        cur_nb = nb;
+        if constexpr (BNBWD) {
+#pragma unroll
+          for (int cb = 0; cb < NCB; ++cb)
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              const int ch = n0 + cb * EPR + CPL * lane + k;
+              bmu[cb][k] = __ldg(p.bnc + ch);
+              bis[cb][k] = __ldg(p.bnc + p.N + ch);
+              bsc[cb][k] = __ldg(p.bnc + 2 * p.N + ch);
+              bsh[cb][k] = __ldg(p.bnc + 3 * p.N + ch);
+            }
+        }
+      }
       const int pi0 = ti * p.tile_h + s * p.sub1_di + 4 * quad;       // first image row of this warp's 4 x 8 patch
       const int pj0 = tj * p.tile_w + s * p.sub1_dj;
       // rows of this warp: r = lane -> pixel (pi0 + r / 8, pj0 + r % 8); bit r of valid_rows: inside the M grid
@@ -394,7 +425,43 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
             tma_store_4d(&p.o_map, buf, n0 + cb * EPR, pj0, pi0, b);
             tma_store_commit();
           }
-          if (p.stats_ws) {
+          if constexpr (BNBWD) {
+            // lane = 32-bit word of the 128-byte row (one fp32 / two bf16 channels), over the 32 rows (pixels) of the
+            // patch: g from the staged (rounded) tile, yprev straight from global memory (a warp reads one full
+            // 128-byte row per request); rows outside the M grid contribute nothing
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+            uint32_t u[32], yv[32];
+            const char* ybase = reinterpret_cast<const char*>(p.yprev) +
+                                ((((long long)b * p.Hm + pi0) * p.Wm + pj0) * p.ld_yprev + n0 + cb * EPR) * (long long)sizeof(T) +
+                                lane * 4;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              yv[r] = 0u;
+              if ((valid_rows >> r) & 1u)
+                yv[r] = __ldg(reinterpret_cast<const uint32_t*>(
+                    ybase + ((long long)(r >> 3) * p.Wm + (r & 7)) * p.ld_yprev * (long long)sizeof(T)));
+            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              u[r] = lds_u32(buf_s + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const bool live = (valid_rows >> r) & 1u;
+              if constexpr (TF32) {
+                const float yy = __uint_as_float(yv[r]);
+                const float gg = (live && fmaf(yy, bsc[cb][0], bsh[cb][0]) > 0.f) ? __uint_as_float(u[r]) : 0.f;
+                s0 += gg; q0 += gg * ((yy - bmu[cb][0]) * bis[cb][0]);
+              } else {
+                const float ya = __uint_as_float(yv[r] << 16), yb = __uint_as_float(yv[r] & 0xffff0000u);
+                const float ga = (live && fmaf(ya, bsc[cb][0], bsh[cb][0]) > 0.f) ? __uint_as_float(u[r] << 16) : 0.f;
+                const float gb = (live && fmaf(yb, bsc[cb][1], bsh[cb][1]) > 0.f) ? __uint_as_float(u[r] & 0xffff0000u) : 0.f;
+                s0 += ga; q0 += ga * ((ya - bmu[cb][0]) * bis[cb][0]);
+                s1 += gb; q1 += gb * ((yb - bmu[cb][1]) * bis[cb][1]);
+              }
+            }
+            st[cb][0] += s0; st[cb][1] += q0;
+            if constexpr (!TF32) { st[cb][2] += s1; st[cb][3] += q1; }
+          } else if (p.stats_ws) {
             // lane = 32-bit word of the 128-byte row: sum the rounded values over the 32 rows (branch-free,
             // all loads issued up front; rows outside the M grid are multiplied by 0)
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
@@ -501,7 +568,8 @@ static bool tc3_plan(const unetb200_gconv_t* d, Tc3Plan* pl) {
 }
 
 int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, const void* y) {
-  if (getenv("UNETB200_NO_TC3") || bias) return 0;      // the 3x3 convolutions of the path are bias-free (unet_parts.py:15,18)
+  static const bool off = getenv("UNETB200_NO_TC3") != nullptr;
+  if (off || bias) return 0;      // the 3x3 convolutions of the path are bias-free (unet_parts.py:15,18)
   if (d->dtype == UNETB200_F32 && d->algo != UNETB200_ALGO_TC && d->algo != UNETB200_ALGO_PREFER_TC) return 0;
   Tc3Plan pl;
   if (!tc3_plan(d, &pl)) return 0;
@@ -515,17 +583,13 @@ long long tc3_stats_workspace(const unetb200_gconv_t* d) {
   return (long long)pl.n_blocks * pl.grid * kEpi3Warps * 2 * pl.BN;
 }
 
-template <typename T, int BN, int SA, int SB, int ACC, int CG, int TPS, bool AFFINE = false>
+template <typename T, int BN, int SA, int SB, int ACC, int CG, int TPS, int EPI = EPI_PLAIN>
 static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
   constexpr int smem = SA * kA3Stage + SB * TPS * (BN / CG) * 128 + kEpi3Warps * kEpi3Stage + 1024 + 256;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS, AFFINE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return cuda_fail(e, "tc3_conv smem attribute");
-    configured = true;
-  }
+  if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(&tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS, EPI>), smem,
+                                    "tc3_conv smem attribute"))
+    return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kTc3Threads);
@@ -538,7 +602,7 @@ static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS, AFFINE>, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS, EPI>, P);
   if (e != cudaSuccess) return cuda_fail(e, "tc3_conv launch");
   return 0;
 }
@@ -572,9 +636,21 @@ __global__ void __launch_bounds__(1024) tc3_stats_reduce_kernel(const float* __r
   }
 }
 
-int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
-              float* stats_ws, cudaStream_t stream, const float* affine) {
+int tc3_bnbwd_supported(const unetb200_gconv_t* d) {
   Tc3Plan pl;
+  if (!tc3_plan(d, &pl)) return 0;
+  return pl.CG == 2 && pl.BN != 256;
+}
+
+int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
+              float* stats_ws, cudaStream_t stream, const float* affine, const void* yprev, long long ld_yprev,
+              const float* bnc) {
+  Tc3Plan pl;
+  if (yprev && (affine || !stats || !stats_ws || !bnc || (reinterpret_cast<uintptr_t>(yprev) & 3) ||
+                (ld_yprev * (d->dtype == UNETB200_BF16 ? 2 : 4)) % 4)) {
+    set_error("tc3_fprop: the BatchNorm-backward epilogue needs sums, a workspace, coefficients and 4-byte aligned yprev rows");
+    return UNETB200_E_INVALID;
+  }
   if (affine && (stats || (reinterpret_cast<uintptr_t>(affine) & 15))) {
     set_error("tc3_fprop: the affine epilogue takes no statistics and needs 16-byte aligned coefficients");
     return UNETB200_E_INVALID;
@@ -609,25 +685,36 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   P.stats_ws = stats ? stats_ws : nullptr;
   P.affine = affine;
   P.N = d->N;
+  P.yprev = yprev;
+  P.ld_yprev = ld_yprev;
+  P.bnc = bnc;
   if (affine) {
     // BatchNorm-folded inference epilogue: the pair kernel with N block 128 / 64 (the shapes of the path)
     if (pl.BN == 256) { set_error("tc3_fprop: affine epilogue supports N blocks of 64 / 128"); return UNETB200_E_INVALID; }
     if (d->dtype == UNETB200_BF16) {
-      if (pl.CG == 2) return pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 3, 2, 2, 3, true>(P, pl.grid, stream)
-                                          : tc3_launch<__nv_bfloat16, 64, 3, 3, 2, 2, 3, true>(P, pl.grid, stream);
-      return pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 6, 2, 1, 1, true>(P, pl.grid, stream)
-                          : tc3_launch<__nv_bfloat16, 64, 3, 6, 2, 1, 1, true>(P, pl.grid, stream);
+      if (pl.CG == 2) return pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 3, 2, 2, 3, EPI_AFFINE>(P, pl.grid, stream)
+                                          : tc3_launch<__nv_bfloat16, 64, 3, 3, 2, 2, 3, EPI_AFFINE>(P, pl.grid, stream);
+      return pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 6, 2, 1, 1, EPI_AFFINE>(P, pl.grid, stream)
+                          : tc3_launch<__nv_bfloat16, 64, 3, 6, 2, 1, 1, EPI_AFFINE>(P, pl.grid, stream);
     }
-    if (pl.CG == 2) return pl.BN == 128 ? tc3_launch<float, 128, 2, 3, 2, 2, 3, true>(P, pl.grid, stream)
-                                        : tc3_launch<float, 64, 3, 3, 2, 2, 3, true>(P, pl.grid, stream);
-    return pl.BN == 128 ? tc3_launch<float, 128, 2, 6, 2, 1, 1, true>(P, pl.grid, stream)
-                        : tc3_launch<float, 64, 3, 6, 2, 1, 1, true>(P, pl.grid, stream);
+    if (pl.CG == 2) return pl.BN == 128 ? tc3_launch<float, 128, 2, 3, 2, 2, 3, EPI_AFFINE>(P, pl.grid, stream)
+                                        : tc3_launch<float, 64, 3, 3, 2, 2, 3, EPI_AFFINE>(P, pl.grid, stream);
+    return pl.BN == 128 ? tc3_launch<float, 128, 2, 6, 2, 1, 1, EPI_AFFINE>(P, pl.grid, stream)
+                        : tc3_launch<float, 64, 3, 6, 2, 1, 1, EPI_AFFINE>(P, pl.grid, stream);
   }
   if (stats) {
     cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * (size_t)tc3_stats_workspace(d), stream);
     if (e != cudaSuccess) return cuda_fail(e, "tc3 stats workspace memset");
   }
-  if (d->dtype == UNETB200_BF16) {
+  if (yprev) {
+    if (pl.CG != 2 || pl.BN == 256) { set_error("tc3_fprop: BatchNorm-backward epilogue: CTA pairs, N blocks of 64 / 128"); return UNETB200_E_INVALID; }
+    if (d->dtype == UNETB200_BF16)
+      rc = pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream)
+                        : tc3_launch<__nv_bfloat16, 64, 3, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream);
+    else
+      rc = pl.BN == 128 ? tc3_launch<float, 128, 2, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream)
+                        : tc3_launch<float, 64, 3, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream);
+  } else if (d->dtype == UNETB200_BF16) {
     if (pl.CG == 2) {
       if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 2, 1, 2, 3>(P, pl.grid, stream);
       else if (pl.BN == 128) rc = tc3_launch<__nv_bfloat16, 128, 2, 3, 2, 2, 3>(P, pl.grid, stream);
@@ -809,7 +896,8 @@ struct Tc3WPlan {
 };
 
 static bool tc3_wgrad_plan(const unetb200_gconv_t* d, Tc3WPlan* w) {
-  if (getenv("UNETB200_NO_TC3") || getenv("UNETB200_NO_TC3W")) return false;
+  static const bool off = getenv("UNETB200_NO_TC3") != nullptr || getenv("UNETB200_NO_TC3W") != nullptr;
+  if (off) return false;
   if (d->dtype != UNETB200_BF16) return false;
   if (d->nquad != 1 || d->in_scale != 1 || d->out_scale != 1 || d->ntaps != 9) return false;
   if (d->in_off_y || d->in_off_x) return false;
@@ -882,16 +970,9 @@ int tc3_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   static const int st_env = getenv("UNETB200_TC3W_STAGES") ? atoi(getenv("UNETB200_TC3W_STAGES")) : 7;
   const bool deep = st_env >= 7;
   const int smem = (deep ? 7 : 5) * (2 * 10240 + 8192) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc3_wgrad_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         7 * (2 * 10240 + 8192) + 1024 + 256);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc3_wgrad_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               5 * (2 * 10240 + 8192) + 1024 + 256);
-    if (e != cudaSuccess) return cuda_fail(e, "tc3_wgrad smem attribute");
-    configured = true;
-  }
+  if (int rc = deep ? set_max_dynamic_smem(reinterpret_cast<const void*>(&tc3_wgrad_kernel<7>), smem, "tc3_wgrad smem attribute")
+                    : set_max_dynamic_smem(reinterpret_cast<const void*>(&tc3_wgrad_kernel<5>), smem, "tc3_wgrad smem attribute"))
+    return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)w.mpairs * 2, (unsigned)w.ntiles, (unsigned)splits);
   cfg.blockDim = dim3(192);

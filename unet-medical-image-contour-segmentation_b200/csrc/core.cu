@@ -2,6 +2,8 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -31,6 +33,20 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+int set_max_dynamic_smem(const void* func, int bytes, const char* what) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  std::lock_guard<std::mutex> lock(mu);
+  if (done.count({dev, func})) return 0;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  done.insert({dev, func});
+  return 0;
 }
 
 }  // namespace ub

@@ -40,16 +40,10 @@ inline int pick_splits(long long tiles, int slots, long long smax) {
   return (int)pick;
 }
 
-// tcgen05 engine (conv_tc.cu).  *_supported() return 1 when the shape/dtype/alignment fits.
+// tcgen05 engines, common gate (tc_host.cu): 1 when the shape/dtype/alignment fits one of the kernel generations.
 int tc_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
-long long tc_fprop_tiles(const unetb200_gconv_t* d);
-int tc_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, const float* bias, void* y,
-             double* stats, float* stats_ws, cudaStream_t stream);
-int launch_stats_reduce(const float* ws, long long ntiles, int C2, double* stats, cudaStream_t s);
 int tc_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
-int tc_wgrad_splits(const unetb200_gconv_t* d, const GconvDev& g);
-int tc_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
-             cudaStream_t stream);
+int launch_stats_reduce(const float* ws, long long ntiles, int C2, double* stats, cudaStream_t s);
 
 // persistent tcgen05 engine, second generation (conv_tc2.cu)
 int tc2_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
@@ -66,11 +60,20 @@ int tc2_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
 int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, const void* y);
 long long tc3_stats_workspace(const unetb200_gconv_t* d);
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
-              float* stats_ws, cudaStream_t stream, const float* affine = nullptr);
+              float* stats_ws, cudaStream_t stream, const float* affine = nullptr, const void* yprev = nullptr,
+              long long ld_yprev = 0, const float* bnc = nullptr);
+int tc3_bnbwd_supported(const unetb200_gconv_t* d);
 
 int tc3_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int tc3_wgrad_splits(const unetb200_gconv_t* d);
 int tc3_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
+              cudaStream_t stream);
+
+// N-stacked wgrad for the narrow 3x3 layers, fourth generation (conv_tc4.cu)
+int tc4_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int tc4_wgrad_preferred(const unetb200_gconv_t* d);
+int tc4_wgrad_splits(const unetb200_gconv_t* d);
+int tc4_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
               cudaStream_t stream);
 
 // first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)

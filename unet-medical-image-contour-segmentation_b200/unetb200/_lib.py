@@ -50,6 +50,8 @@ PROTOTYPES = {
     "unetb200_gconv_fprop": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p, c_p, C.POINTER(C.c_int), c_p]),
     "unetb200_gconv_fprop_affine_relu_supported": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p]),
     "unetb200_gconv_fprop_affine_relu": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p]),
+    "unetb200_gconv_dgrad_bnbwd_supported": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p]),
+    "unetb200_gconv_dgrad_bnbwd": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, C.c_int64, c_p, c_p, c_p, c_p]),
     "unetb200_gconv_wgrad_plan": (C.c_int, [C.POINTER(GConv), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "unetb200_gconv_wgrad": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, C.c_int, c_p]),
     "unetb200_wgrad_reduce": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_i64, c_i64, c_i64, c_i64,

@@ -305,15 +305,19 @@ def _vec_dst(param, Cc):
     return d if d is not None and d.dim() == 1 and d.numel() == Cc and d.is_contiguous() else None
 
 
-def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_params=(None, None)):
-    """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta).  `param`: the Parameter object behind `w`;
-    `bn_params`: the BatchNorm weight / bias Parameter objects (only to look up their gradient sinks)."""
+def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_params=(None, None), sums=None,
+                     below=None):
+    """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta, sums_below).  `param`: the Parameter object behind `w`;
+    `bn_params`: the BatchNorm weight / bias Parameter objects (only to look up their gradient sinks); `sums`: the
+    BatchNorm-backward reduction of THIS stage if the kernel that produced gz already made it; `below` = (y, coefs)
+    of the conv-BN-ReLU stage whose activation is `x`: its reduction is then made by this stage's dgrad epilogue
+    when the fused kernel covers the shape and returned as sums_below (else None)."""
     param = w if param is None else param
     B, Cin, H, W = x.shape
     Cout = w.shape[0]
     cd = x.dtype
     gy, dgamma, dbeta = ops.bn_relu_bwd(gz, y, coefs, batch_stats, _vec_dst(bn_params[0], Cout),
-                                        _vec_dst(bn_params[1], Cout))
+                                        _vec_dst(bn_params[1], Cout), sums=sums)
     # the gradient takes the parameter's own memory layout (OIHW or channels_last): AccumulateGrad then keeps it
     # without a copy, and for channels_last the split reduction writes it coalesced; with a registered sink
     # (data-parallel bucket view) it is written there
@@ -327,9 +331,15 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_pa
     gx = None
     dw_desc = _gconv3x3(x, Cout, gy, cd)
     gs = ops.x3_split(gy) if (ops.x3_active(dw_desc) and Cout >= 16) else None   # 3xTF32: one split serves both GEMMs
+    sums_below = None
     if need_gx:
         gx = ops.empty_nhwc(B, Cin, H, W, cd, x.device)
-        ops.gconv_fprop(_gconv3x3(gy, Cin, gx, cd), gy, pack3x3_dgrad(w, cd), None, gx, None, kind="dgrad", x_split=gs)
+        dd = _gconv3x3(gy, Cin, gx, cd)
+        wd = pack3x3_dgrad(w, cd)
+        if below is not None and gs is None and ops.gconv_dgrad_bnbwd_supported(dd, gy, wd, gx):
+            sums_below = ops.gconv_dgrad_bnbwd(dd, gy, wd, gx, below[0], below[1])
+        else:
+            ops.gconv_fprop(dd, gy, wd, None, gx, None, kind="dgrad", x_split=gs)
     # after the dgrad, on the side stream: overlaps the (memory-bound) BatchNorm backward of the previous layer
     # (only when AccumulateGrad will simply keep dW: an existing .grad would be accumulated into on the main stream)
     run = lambda: ops.gconv_wgrad(dw_desc, x, gy, dW, skw, si, so, gy_split=gs)  # noqa: E731
@@ -337,7 +347,7 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_pa
         ops.on_side_stream(run, x, gy)      # AccumulateGrad keeps dW as it is (same layout, no other owner)
     else:
         run()                               # it would accumulate / re-layout dW on the main stream right away
-    return gx, dW, dgamma, dbeta
+    return gx, dW, dgamma, dbeta, sums_below
 
 
 class ToNHWCFn(torch.autograd.Function):
@@ -415,10 +425,11 @@ class DoubleConvFn(torch.autograd.Function):
             raise RuntimeError("DoubleConvFn.backward called without any output gradient")
         need = ctx.needs_input_grad
         p1, pg1, pb1, p2, pg2, pb2 = getattr(ctx, "param_objs", (w1, None, None, w2, None, None))
-        gz1, dW2, dg2, db2 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True, param=p2,
-                                              bn_params=(pg2, pb2))
-        gx, dW1, dg1, db1 = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0], param=p1,
-                                             bn_params=(pg1, pb1))
+        # conv2's dgrad output is the gradient of z1 = relu(bn1(y1)): its epilogue makes bn1's backward reduction
+        gz1, dW2, dg2, db2, sums1 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True, param=p2,
+                                                     bn_params=(pg2, pb2), below=(y1, c1))
+        gx, dW1, dg1, db1, _ = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0], param=p1,
+                                                bn_params=(pg1, pb1), sums=sums1)
         return (gx, dW1 if need[1] else None, dg1 if need[2] else None, db1 if need[3] else None,
                 dW2 if need[4] else None, dg2 if need[5] else None, db2 if need[6] else None, None)
 

@@ -394,6 +394,28 @@ def gconv_fprop_affine_relu(d, x, wp, coefs, z):
         _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + tag
 
 
+def gconv_dgrad_bnbwd_supported(d, g, wp, gx):
+    return (not x3_active(d)) and bool(lib().unetb200_gconv_dgrad_bnbwd_supported(C.byref(d), _p(g), _p(wp), _p(gx)))
+
+
+def gconv_dgrad_bnbwd(d, g, wp, gx, yprev, coefs_prev):
+    """gx = dgrad conv; returns fp64 sums[2, C] of the BatchNorm + ReLU backward of the layer whose raw output is
+    `yprev` (gx is the gradient of relu(bn(yprev))): the reduce pass rides in the tcgen05 epilogue."""
+    flops, nbytes = gconv_flops(d), gconv_bytes(d, 2 if d.dtype == BF16 else 4)
+    tag = _shape_tag(d)
+    sums = torch.zeros((2, d.N), dtype=torch.float64, device=g.device)
+    n = lib().unetb200_gconv_stats_workspace(C.byref(d))
+    if n < 0:
+        _lib.check(-1, "gconv_stats_workspace")
+    ws = torch.empty(n, dtype=torch.float32, device=g.device)
+    if not coefs_prev.is_contiguous():
+        raise ValueError("unetb200: BatchNorm coefficients must be a contiguous [4, C] tensor")
+    _run("conv_dgrad_tc" + tag, lib().unetb200_gconv_dgrad_bnbwd, C.byref(d), _p(g), _p(wp), _p(gx), _p(yprev),
+         nhwc_ld(yprev), _p(coefs_prev), _p(sums), _p(ws), _stream(), kernels=2, flops=flops,
+         nbytes=nbytes + float(yprev.numel()) * yprev.element_size())
+    return sums
+
+
 def _wgrad_once(d, x, gy, dst, st, sc, sn, sq, accumulate, flops, tag):
     splits, used = C.c_int(0), C.c_int(0)
     _lib.check(lib().unetb200_gconv_wgrad_plan(C.byref(d), C.byref(splits), C.byref(used)), "gconv_wgrad_plan")
@@ -469,16 +491,18 @@ def maxpool2_bwd(x, gp, gx, accumulate):
          nbytes=x.numel() * x.element_size() * (3.25 if accumulate else 2.25))
 
 
-def bn_relu_bwd(gz, y, coefs, training, dgamma=None, dbeta=None):
-    """Returns (gy, dgamma, dbeta) for z = relu(bn(y)); `dgamma` / `dbeta`: optional fp32 [C] destinations."""
+def bn_relu_bwd(gz, y, coefs, training, dgamma=None, dbeta=None, sums=None):
+    """Returns (gy, dgamma, dbeta) for z = relu(bn(y)); `dgamma` / `dbeta`: optional fp32 [C] destinations; `sums`:
+    the fp64 [2, C] reduction when the kernel that produced gz already made it (gconv_dgrad_bnbwd)."""
     B, Cc, H, W = y.shape
     dev = y.device
     es = y.element_size()
-    sums = torch.zeros((2, Cc), dtype=torch.float64, device=dev)
     L = lib()
-    _run("bn_relu_bwd_reduce", L.unetb200_bn_relu_bwd_reduce, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]),
-         _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(sums), dt(y), B, H, W, Cc, _stream(),
-         nbytes=2.0 * y.numel() * es)
+    if sums is None:
+        sums = torch.zeros((2, Cc), dtype=torch.float64, device=dev)
+        _run("bn_relu_bwd_reduce", L.unetb200_bn_relu_bwd_reduce, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]),
+             _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(sums), dt(y), B, H, W, Cc, _stream(),
+             nbytes=2.0 * y.numel() * es)
     if dgamma is None:
         dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
     if dbeta is None:
