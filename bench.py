@@ -229,9 +229,11 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # one timed step = a bounded sample of the workload: the full per-GPU batch when a step fits the budget
-    # (B=16 at 512x512 is 15-60 s on 16-32 cores), measured after one untimed step
-    batch = a.batch if a.workload == "train" else min(a.batch, 2)
+    # one timed step = a bounded sample of the workload: 2 images.  Measured on the GPU box's 16 host cores
+    # (profiles/r2_bench_reference_b16.json): 2 images take 1.44 s/step (1.39 img/s), but the full batch of 16 took
+    # 596 s for ONE step (0.027 img/s: the fp32 activations + autograd state of B=16 at 512x512 no longer fit the
+    # box's memory comfortably), so the full batch would neither finish the driver's --steps 20 nor flatter the CPU.
+    batch = min(a.batch, 2)
     rate, n, nw, med, kind = cpu_reference_rate(a, a.steps, min(a.warmup, 1), budget_s=170.0, batch=batch)
     cores = os.cpu_count() or 1
     src = ("unmodified reference modules (baseline/_ref: unet, utils.dice_score, utils.boundary_loss)" if kind == "reference"

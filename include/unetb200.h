@@ -240,6 +240,17 @@ int64_t unetb200_outconv_bwd_workspace(int64_t npix, int C, int ncls);
 int unetb200_outconv_bwd(const void* x, int64_t ld_x, const float* w, const void* glogits,
                          void* gx, int64_t ld_gx, float* dw, float* dbias, float* workspace,
                          int dtype, int64_t npix, int C, int ncls, void* stream);
+/* The same, fused with the reduction pass of the BatchNorm2d + ReLU backward of the stage below (the OutConv input
+ * is x = relu(bn(yprev)) of the last DoubleConv, unet_model.py:25,37): additionally
+ *   sums[0][c] += sum gx*mask, sums[1][c] += sum gx*mask*xhat   (gx as stored; see unetb200_gconv_dgrad_bnbwd)
+ * with coefs = float[4][C] (mean, invstd, scale, shift) and `sums` = double[2*C] zeroed by the caller.  _supported
+ * returns 1 when the vectorised kernel covers the shape (C % 8 == 0, C/8 a power of two <= 32, 16-byte aligned rows). */
+int unetb200_outconv_bwd_bnbwd_supported(const void* x, int64_t ld_x, const void* gx, int64_t ld_gx,
+                                         const void* yprev, int64_t ld_yprev, int dtype, int C, int ncls);
+int unetb200_outconv_bwd_bnbwd(const void* x, int64_t ld_x, const float* w, const void* glogits, void* gx,
+                               int64_t ld_gx, float* dw, float* dbias, float* workspace, const void* yprev,
+                               int64_t ld_yprev, const float* coefs, double* sums, int dtype, int64_t npix, int C,
+                               int ncls, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * losses

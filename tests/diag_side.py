@@ -14,6 +14,7 @@ img, msk = O.synthetic_batch(2, 1, 2, 64, 64)
 x = img.to(DEV).contiguous(memory_format=torch.channels_last); t = msk.to(DEV)
 def grads_of(side):
     ops._SIDE_ON = side
+    ops._WGRAD_SIDE = side
     m = unet.UNet(1, 2, False); m.load_state_dict(st)
     m = m.to(DEV).to(memory_format=torch.channels_last).train()
     with torch.autocast("cuda", enabled=amp):
@@ -24,5 +25,8 @@ runs = [("single", False), ("single", False), ("side", True), ("side", True), ("
 res = [grads_of(s) for _, s in runs]
 base = res[0][0]
 for (name, _), (g, l) in zip(runs, res):
-    worst = max(((O.rel_l2(g[k], base[k]), k) for k in base))
-    print(f"{name:7s} loss {l:.6f}  worst rel-L2 vs run0: {worst[0]:.3e} ({worst[1]})")
+    errs = sorted(((O.rel_l2(g[k], base[k]), k) for k in base), reverse=True)
+    print(f"{name:7s} loss {l:.6f}  worst rel-L2 vs run0: " + ", ".join(f"{e:.2e} {k}" for e, k in errs[:4]))
+    if errs[0][0] > 1e-4 and os.environ.get("DIAG_ALL"):
+        for k in reversed(list(base)):           # backward order
+            print(f"      {O.rel_l2(g[k], base[k]):.2e} {k}")

@@ -860,8 +860,52 @@ def _dgrad_bnbwd_case(B, Ci, Co, H, W, dt_, seed, slice_y=False):
     return res
 
 
+def _outconv_bnbwd_case(B, C, K, H, W, dt_, seed):
+    """OutConv backward with the BatchNorm-backward reduction of the stage below fused in: gx / dW / db as without
+    the fusion, sums equal to unetb200_bn_relu_bwd_reduce on the stored gx."""
+    res = []
+    g = gen(seed)
+    yprev = rq(torch.randn(B, C, H, W, generator=g), dt_)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    w = (torch.randn(K, C, generator=g) * 0.3).to(DEV)
+    gl = dev_nhwc(rq(torch.randn(B, K, H, W, generator=g), dt_), dt_)
+    yd = dev_nhwc(yprev, dt_)
+    stats = torch.stack([yprev.double().sum((0, 2, 3)), (yprev.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    coefs = ops.bn_finalize(stats, B * H * W, gamma.to(DEV), beta.to(DEV), 1e-5, 0.0, None, None, C)
+    x = ops.empty_nhwc(B, C, H, W, dt_, DEV)
+    ops.bn_relu_apply(yd, coefs, x, None)
+    tag = f"{C}to{K}_{B}x{H}x{W}_{str(dt_)[6:]}"
+    outs = []
+    was, ops.OUTCONV_FUSE = ops.OUTCONV_FUSE, True            # opt-in in the product (slower at the path's shape)
+    for below in (None, (yd, coefs)):
+        gx = ops.empty_nhwc(B, C, H, W, dt_, DEV)
+        dw = torch.empty((K, C, 1, 1), device=DEV)
+        db = torch.empty(K, device=DEV)
+        glp = gl.permute(0, 2, 3, 1).contiguous()          # packed NHWC logits gradient [B, H, W, K]
+        sums = ops.outconv_bwd(x, w, glp, gx, dw, db, below=below)
+        outs.append((gx, dw, db, sums))
+    ops.OUTCONV_FUSE = was
+    (gx0, dw0, db0, s0), (gx1, dw1, db1, s1) = outs
+    res.append((f"outconv_bnbwd_fused_{tag}", 0.0 if (s0 is None and s1 is not None) else 1.0, 0.0))
+    if s1 is None:
+        return res
+    res.append((f"outconv_bnbwd_gx_bitequal_{tag}", (host(gx1) - host(gx0)).abs().max().item(), 0.0))
+    res.append((f"outconv_bnbwd_dw_{tag}", rel(host(dw1), host(dw0)), 1e-5))
+    res.append((f"outconv_bnbwd_db_{tag}", rel(host(db1), host(db0)), 1e-5))
+    ref = torch.zeros((2, C), dtype=torch.float64, device=DEV)
+    _lib.check(ops.lib().unetb200_bn_relu_bwd_reduce(ops._p(gx0), ops.nhwc_ld(gx0), ops._p(yd), ops.nhwc_ld(yd),
+                                                     ops._p(coefs[2]), ops._p(coefs[3]), ops._p(coefs[0]), ops._p(coefs[1]),
+                                                     ops._p(ref), ops.dt(yd), B, H, W, C, ops._stream()), "bn_relu_bwd_reduce")
+    scale = ref.abs().max().item() + 1e-30
+    res.append((f"outconv_bnbwd_sums_{tag}", (s1 - ref).abs().max().item() / scale, 1e-5))
+    return res
+
+
 def check_dgrad_bnbwd():
     out = []
+    out += _outconv_bnbwd_case(2, 64, 2, 24, 20, BF, 81)
+    out += _outconv_bnbwd_case(1, 64, 4, 33, 17, BF, 82)
+    out += _outconv_bnbwd_case(2, 16, 3, 9, 11, FP, 83)
     out += _dgrad_bnbwd_case(2, 64, 64, 16, 24, BF, 71)
     out += _dgrad_bnbwd_case(1, 128, 128, 20, 12, BF, 72)
     out += _dgrad_bnbwd_case(2, 128, 256, 9, 7, BF, 73)            # ragged tiles: rows outside the M grid must not count

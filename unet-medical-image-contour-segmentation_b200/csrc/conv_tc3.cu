@@ -166,8 +166,7 @@ struct alignas(64) Tc3Params {
   int N;
   // BNBWD kernels only (dgrad whose output is the gradient of z = relu(bn(yprev))): the raw conv output of the
   // previous layer and its BatchNorm coefficients [4][N] = mean, invstd, scale, shift
-  const void* yprev;
-  long long ld_yprev;
+  CUtensorMap y_map;         // yprev view, box {128 B, 8, 4, 1} (the geometry of o_map)
   const float* bnc;
 };
 
@@ -202,14 +201,16 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + SA * kA3Stage;
   uint8_t* epi = b_ring + SB * kBStage;                // 8 warps x 4 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + kEpi3Warps * kEpi3Stage);
+  uint8_t* yst = epi + kEpi3Warps * kEpi3Stage;        // BNBWD: 8 warps x 4 KB, the yprev patch of the warp's current block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(yst + (BNBWD ? kEpi3Warps * kEpi3Stage : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + SA;
   uint64_t* b_full = a_empty + SA;
   uint64_t* b_empty = b_full + SB;
   uint64_t* t_full = b_empty + SB;
   uint64_t* t_empty = t_full + ACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + ACC);
+  uint64_t* y_full = t_empty + ACC;                    // BNBWD: one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_full + kEpi3Warps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -221,6 +222,10 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < ACC; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], kEpi3Warps * CG); }
+    if constexpr (BNBWD) {
+      tma_prefetch_desc(&p.y_map);
+      for (int s = 0; s < kEpi3Warps; ++s) mbar_init(&y_full[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_cg<CG>(tmem_slot, 512);
@@ -345,6 +350,28 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
     const uint32_t t_empty_leader0 = mapa_u32(smem_u32(&t_empty[0]), 0);
     constexpr int CPL = TF32 ? 1 : 2;                                   // channels per lane and 128-byte block
     float bmu[BNBWD ? NCB : 1][CPL], bis[BNBWD ? NCB : 1][CPL], bsc[BNBWD ? NCB : 1][CPL], bsh[BNBWD ? NCB : 1][CPL];
+    // BNBWD: the warp's 32 x 128 B patch of yprev for (group gt2, channel block cb2) is fetched by TMA into the warp's
+    // own buffer as soon as that buffer is free -- i.e. one block ahead, while the warp still waits for the MMAs of
+    // the block -- so the loads cost no registers and no exposed latency; tiles / rows outside the tensor are
+    // zero-filled by TMA.  Every (group, block) of this CTA is fetched and awaited, valid or not.
+    uint8_t* ybuf = yst + ew * kEpi3Stage;
+    const uint32_t ybuf_s = smem_u32(ybuf);
+    uint32_t yph = 0;
+    auto y_fetch = [&](int gt2, int cb2) {                               // lane 0 only
+      const int nb2 = gt2 / p.m_groups;
+      int mt2 = (gt2 - nb2 * p.m_groups) * CG + (int)rank;
+      const bool valid2 = mt2 < p.m_tiles;
+      const int tj2 = mt2 % p.tiles_w;
+      mt2 /= p.tiles_w;
+      const int ti2 = mt2 % p.tiles_h;
+      const int b2 = valid2 ? mt2 / p.tiles_h : p.B;
+      mbar_expect_tx(&y_full[ew], kEpi3Stage);
+      tma_load_4d(ybuf, &p.y_map, &y_full[ew], nb2 * BLOCK_N + cb2 * EPR, tj2 * p.tile_w + s * p.sub1_dj,
+                  ti2 * p.tile_h + s * p.sub1_di + 4 * quad, b2);
+    };
+    if constexpr (BNBWD) {
+      if (lane == 0 && group0 < p.total_groups) y_fetch(group0, 0);
+    }
     for (int gt = group0; gt < p.total_groups; gt += ngroups) {
       const int nb = gt / p.m_groups;
       int mt = (gt - nb * p.m_groups) * CG + (int)rank;
@@ -427,23 +454,23 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
           }
           if constexpr (BNBWD) {
             // lane = 32-bit word of the 128-byte row (one fp32 / two bf16 channels), over the 32 rows (pixels) of the
-            // patch: g from the staged (rounded) tile, yprev straight from global memory (a warp reads one full
-            // 128-byte row per request); rows outside the M grid contribute nothing
+            // patch: g from the staged (rounded) tile, yprev from the TMA-fetched patch (same swizzle); rows outside
+            // the M grid contribute nothing
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
             uint32_t u[32], yv[32];
-            const char* ybase = reinterpret_cast<const char*>(p.yprev) +
-                                ((((long long)b * p.Hm + pi0) * p.Wm + pj0) * p.ld_yprev + n0 + cb * EPR) * (long long)sizeof(T) +
-                                lane * 4;
+            mbar_wait(&y_full[ew], yph);
+            yph ^= 1;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
-              yv[r] = 0u;
-              if ((valid_rows >> r) & 1u)
-                yv[r] = __ldg(reinterpret_cast<const uint32_t*>(
-                    ybase + ((long long)(r >> 3) * p.Wm + (r & 7)) * p.ld_yprev * (long long)sizeof(T)));
+              const uint32_t off = r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2));
+              u[r] = lds_u32(buf_s + off);
+              yv[r] = lds_u32(ybuf_s + off);
             }
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              u[r] = lds_u32(buf_s + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            __syncwarp();                                                 // every lane has read the yprev patch
+            if (lane == 0) {
+              if (cb + 1 < NCB) y_fetch(gt, cb + 1);
+              else if (gt + ngroups < p.total_groups) y_fetch(gt + ngroups, 0);
+            }
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
               const bool live = (valid_rows >> r) & 1u;
@@ -495,6 +522,20 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
             }
             st[cb][0] += s0; st[cb][1] += q0;
             if constexpr (!TF32) { st[cb][2] += s1; st[cb][3] += q1; }
+          }
+        }
+      }
+      if constexpr (BNBWD) {
+        if (valid_rows == 0u) {                                         // keep the yprev pipeline in step
+#pragma unroll 1
+          for (int cb = 0; cb < NCB; ++cb) {
+            mbar_wait(&y_full[ew], yph);
+            yph ^= 1;
+            __syncwarp();
+            if (lane == 0) {
+              if (cb + 1 < NCB) y_fetch(gt, cb + 1);
+              else if (gt + ngroups < p.total_groups) y_fetch(gt + ngroups, 0);
+            }
           }
         }
       }
@@ -585,7 +626,7 @@ long long tc3_stats_workspace(const unetb200_gconv_t* d) {
 
 template <typename T, int BN, int SA, int SB, int ACC, int CG, int TPS, int EPI = EPI_PLAIN>
 static int tc3_launch(const Tc3Params& P, int grid, cudaStream_t s) {
-  constexpr int smem = SA * kA3Stage + SB * TPS * (BN / CG) * 128 + kEpi3Warps * kEpi3Stage + 1024 + 256;
+  constexpr int smem = SA * kA3Stage + SB * TPS * (BN / CG) * 128 + (EPI == EPI_BNBWD ? 2 : 1) * kEpi3Warps * kEpi3Stage + 1024 + 256;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(&tc3_conv_kernel<T, BN, SA, SB, ACC, CG, TPS, EPI>), smem,
                                     "tc3_conv smem attribute"))
@@ -646,9 +687,9 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
               float* stats_ws, cudaStream_t stream, const float* affine, const void* yprev, long long ld_yprev,
               const float* bnc) {
   Tc3Plan pl;
-  if (yprev && (affine || !stats || !stats_ws || !bnc || (reinterpret_cast<uintptr_t>(yprev) & 3) ||
-                (ld_yprev * (d->dtype == UNETB200_BF16 ? 2 : 4)) % 4)) {
-    set_error("tc3_fprop: the BatchNorm-backward epilogue needs sums, a workspace, coefficients and 4-byte aligned yprev rows");
+  if (yprev && (affine || !stats || !stats_ws || !bnc || !aligned16(yprev) ||
+                (ld_yprev * (d->dtype == UNETB200_BF16 ? 2 : 4)) % 16)) {
+    set_error("tc3_fprop: the BatchNorm-backward epilogue needs sums, a workspace, coefficients and 16-byte aligned yprev rows");
     return UNETB200_E_INVALID;
   }
   if (affine && (stats || (reinterpret_cast<uintptr_t>(affine) & 15))) {
@@ -685,9 +726,12 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   P.stats_ws = stats ? stats_ws : nullptr;
   P.affine = affine;
   P.N = d->N;
-  P.yprev = yprev;
-  P.ld_yprev = ld_yprev;
   P.bnc = bnc;
+  if (yprev) {
+    rc = encode_act_box(&P.y_map, d->dtype, yprev, d->N, d->Wm, d->Hm, d->B, ld_yprev, (long long)d->Wm * ld_yprev,
+                        (long long)d->Hm * d->Wm * ld_yprev, 8, 4, false);
+    if (rc) return rc;
+  }
   if (affine) {
     // BatchNorm-folded inference epilogue: the pair kernel with N block 128 / 64 (the shapes of the path)
     if (pl.BN == 256) { set_error("tc3_fprop: affine epilogue supports N blocks of 64 / 128"); return UNETB200_E_INVALID; }
@@ -708,12 +752,17 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   }
   if (yprev) {
     if (pl.CG != 2 || pl.BN == 256) { set_error("tc3_fprop: BatchNorm-backward epilogue: CTA pairs, N blocks of 64 / 128"); return UNETB200_E_INVALID; }
+    // N block 64 (the full-resolution layers, one A stage = one whole tile): 3 A stages + 2 weight stages measured
+    // 0.439 ms against 0.535 ms for 2 + 3 (64 -> 64 channels, B = 16, 512x512; the plain dgrad takes 0.311 ms and the
+    // separate reduction pass 0.180 ms) -- UNETB200_BNBWD64_CFG=0 restores 2 + 3 for A/B runs
+    static const int cfg64 = getenv("UNETB200_BNBWD64_CFG") ? atoi(getenv("UNETB200_BNBWD64_CFG")) : 1;
     if (d->dtype == UNETB200_BF16)
       rc = pl.BN == 128 ? tc3_launch<__nv_bfloat16, 128, 2, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream)
-                        : tc3_launch<__nv_bfloat16, 64, 3, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream);
+           : cfg64 == 1 ? tc3_launch<__nv_bfloat16, 64, 3, 2, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream)
+                        : tc3_launch<__nv_bfloat16, 64, 2, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream);
     else
       rc = pl.BN == 128 ? tc3_launch<float, 128, 2, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream)
-                        : tc3_launch<float, 64, 3, 3, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream);
+                        : tc3_launch<float, 64, 3, 2, 2, 2, 3, EPI_BNBWD>(P, pl.grid, stream);
   } else if (d->dtype == UNETB200_BF16) {
     if (pl.CG == 2) {
       if (pl.BN == 256) rc = tc3_launch<__nv_bfloat16, 256, 2, 2, 1, 2, 3>(P, pl.grid, stream);

@@ -77,6 +77,9 @@ PROTOTYPES = {
     "unetb200_outconv_fwd": (C.c_int, [c_p, c_i64, c_p, c_p, c_p, C.c_int, c_i64, C.c_int, C.c_int, c_p]),
     "unetb200_outconv_bwd_workspace": (c_i64, [c_i64, C.c_int, C.c_int]),
     "unetb200_outconv_bwd": (C.c_int, [c_p, c_i64, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, C.c_int, c_i64, C.c_int, C.c_int, c_p]),
+    "unetb200_outconv_bwd_bnbwd_supported": (C.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, C.c_int, C.c_int, C.c_int]),
+    "unetb200_outconv_bwd_bnbwd": (C.c_int, [c_p, c_i64, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, C.c_int,
+                                             c_i64, C.c_int, C.c_int, c_p]),
     "unetb200_ce_dice_fwd": (C.c_int, [c_p, C.c_int, c_p, c_i64, C.c_int, C.c_float, c_p, c_p, c_p, c_p]),
     "unetb200_ce_dice_bwd": (C.c_int, [c_p, C.c_int, c_p, c_i64, C.c_int, c_p, c_p, c_p, c_p]),
     "unetb200_dice_fwd": (C.c_int, [c_p, c_p, c_i64, c_i64, C.c_float, c_p, c_p, c_p, c_p]),

@@ -223,6 +223,50 @@ def grad_dst(param, like=None):
     return ent[1].detach()
 
 
+# ------------------------------------------------------------------------------------------------
+# BatchNorm-backward reductions made by the kernel that PRODUCES a gradient (cross-Function hand-off)
+# ------------------------------------------------------------------------------------------------
+# forward: a conv-BN-ReLU stage registers, for its activation z = relu(bn(y)), the pair (y, coefs) that its backward
+# reduction needs; the consumer of z (OutConv, ...) looks it up and saves it.  backward: the consumer's kernel writes
+# the gradient g of z and, in the same pass, sum(g*mask) / sum(g*mask*xhat); it leaves them here keyed by g's
+# storage, and the stage's own backward takes them instead of running unetb200_bn_relu_bwd_reduce.
+_BNBWD_MIN_N = int(os.environ.get("UNETB200_BNBWD_MIN_N", "0"))        # A/B switches: fuse only for these widths
+_BNBWD_MAX_N = int(os.environ.get("UNETB200_BNBWD_MAX_N", "1000000"))
+_BN_OF_ACT = {}    # data_ptr(z) -> (weakref(y), weakref(coefs), shape)
+_GRAD_SUMS = {}    # data_ptr(g) -> (sums, shape)
+
+
+def register_bn_of(z, y, coefs):
+    import weakref
+    if len(_BN_OF_ACT) > 256:
+        for k in [k for k, e in _BN_OF_ACT.items() if e[0]() is None]:
+            del _BN_OF_ACT[k]
+    _BN_OF_ACT[z.data_ptr()] = (weakref.ref(y), weakref.ref(coefs), tuple(z.shape))
+
+
+def bn_of(z):
+    ent = _BN_OF_ACT.get(z.data_ptr())
+    if ent is None or ent[2] != tuple(z.shape):
+        return None
+    y, coefs = ent[0](), ent[1]()
+    if y is None or coefs is None or y.shape != z.shape or y.dtype != z.dtype:
+        return None
+    return y, coefs
+
+
+def leave_grad_sums(g, sums):
+    if len(_GRAD_SUMS) > 64:
+        _GRAD_SUMS.clear()
+    _GRAD_SUMS[g.data_ptr()] = (sums, tuple(g.shape))
+
+
+def take_grad_sums(g):
+    ent = _GRAD_SUMS.pop(g.data_ptr(), None)
+    if ent is None or ent[1] != tuple(g.shape):
+        return None
+    return ent[0]
+
+
 def _f32c(t):
     t = t.detach()
     if t.dtype != torch.float32 or not t.is_contiguous():
@@ -336,7 +380,8 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_pa
         gx = ops.empty_nhwc(B, Cin, H, W, cd, x.device)
         dd = _gconv3x3(gy, Cin, gx, cd)
         wd = pack3x3_dgrad(w, cd)
-        if below is not None and gs is None and ops.gconv_dgrad_bnbwd_supported(dd, gy, wd, gx):
+        if (below is not None and gs is None and _BNBWD_MIN_N <= Cin <= _BNBWD_MAX_N
+                and ops.gconv_dgrad_bnbwd_supported(dd, gy, wd, gx)):
             sums_below = ops.gconv_dgrad_bnbwd(dd, gy, wd, gx, below[0], below[1])
         else:
             ops.gconv_fprop(dd, gy, wd, None, gx, None, kind="dgrad", x_split=gs)
@@ -399,6 +444,8 @@ class DoubleConvFn(torch.autograd.Function):
         if cfg.save:
             ctx.save_for_backward(x, y1, z1, y2, z2, c1, c2, w1, w2)
             ctx.param_objs = (w1, g1, b1, w2, g2, b2)   # the Parameter objects themselves (.grad / gradient sinks)
+            if y2 is not None:
+                register_bn_of(z2, y2, c2)
         if pooled is None:
             return z2
         return z2, pooled
@@ -408,7 +455,11 @@ class DoubleConvFn(torch.autograd.Function):
         x, y1, z1, y2, z2, c1, c2, w1, w2 = ctx.saved_tensors
         cd = x.dtype
         gz = ops.to_nhwc(gz2, cd) if gz2 is not None else None
+        # reduction of bn2's backward already made by the kernel that wrote gz (OutConv backward)?  Only valid while
+        # gz is exactly that tensor: not after the pool gradient has been accumulated into it below.
+        sums2 = take_grad_sums(gz) if gz is not None else None
         if ctx.has_pool and gpooled is not None:
+            sums2 = None
             gp = ops.to_nhwc(gpooled, cd)
             if gz is None:
                 gz = ops.empty_nhwc(*z2.shape, cd, x.device)
@@ -427,7 +478,7 @@ class DoubleConvFn(torch.autograd.Function):
         p1, pg1, pb1, p2, pg2, pb2 = getattr(ctx, "param_objs", (w1, None, None, w2, None, None))
         # conv2's dgrad output is the gradient of z1 = relu(bn1(y1)): its epilogue makes bn1's backward reduction
         gz1, dW2, dg2, db2, sums1 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True, param=p2,
-                                                     bn_params=(pg2, pb2), below=(y1, c1))
+                                                     bn_params=(pg2, pb2), below=(y1, c1), sums=sums2)
         gx, dW1, dg1, db1, _ = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0], param=p1,
                                                 bn_params=(pg1, pb1), sums=sums1)
         return (gx, dW1 if need[1] else None, dg1 if need[2] else None, db1 if need[3] else None,
@@ -580,15 +631,26 @@ class OutConvFn(torch.autograd.Function):
         logits = torch.empty((B, H, W, K), dtype=x.dtype, device=x.device)
         w2 = _f32c(w).view(K, Cc)
         ops.outconv_fwd(x, w2, _f32c(b) if b is not None else None, logits)
+        ctx.below = False
         if cfg.save:
-            ctx.save_for_backward(x, w2)
+            below = bn_of(x)
+            if below is not None:
+                ctx.save_for_backward(x, w2, below[0], below[1])
+                ctx.below = True
+            else:
+                ctx.save_for_backward(x, w2)
             ctx.param_objs = (w, b)
         ctx.has_bias = b is not None
         return logits.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, glogits):
-        x, w2 = ctx.saved_tensors
+        below = None
+        if ctx.below:
+            x, w2, yb, cb = ctx.saved_tensors
+            below = (yb, cb)
+        else:
+            x, w2 = ctx.saved_tensors
         B, Cc, H, W = x.shape
         K = w2.shape[0]
         g = ops.to_nhwc(glogits, x.dtype, packed=True)
@@ -601,5 +663,7 @@ class OutConvFn(torch.autograd.Function):
         db = _vec_dst(pb, K)
         if db is None:
             db = torch.empty(K, dtype=torch.float32, device=x.device)
-        ops.outconv_bwd(x, w2, g, gx, dw, db)
+        sums = ops.outconv_bwd(x, w2, g, gx, dw, db, below=below)
+        if sums is not None:
+            leave_grad_sums(gx, sums)      # x = relu(bn(yb)): the stage below takes them in its backward
         return gx, dw if need[1] else None, db if (need[2] and ctx.has_bias) else None, None
