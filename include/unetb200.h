@@ -135,6 +135,17 @@ int unetb200_wgrad_reduce(const float* partials, int splits, int ntaps, int Cin,
                           float* dst, int64_t st, int64_t sc, int64_t sq, int64_t sn, int accumulate,
                           void* stream);
 
+/* The same for a whole list of layers in ONE launch (a backward pass produces ~22 weight gradients; their split
+ * reductions are small and launch bound one by one).  Jobs must not alias: two jobs writing the same dst (an
+ * accumulate chain) belong in separate calls. */
+typedef struct unetb200_reduce_job {
+  const float* partials;
+  float* dst;
+  int64_t st, sc, sq, sn;
+  int32_t splits, ntaps, Cin, N, Cq, accumulate;
+} unetb200_reduce_job_t;
+int unetb200_wgrad_reduce_multi(const unetb200_reduce_job_t* jobs, int njobs, void* stream);
+
 /* dst[i0][i1][i2] = cast(src[off + i0*s0 + i1*s1 + i2*s2]) (strides may be negative): packs an fp32
  * parameter (OIHW / IOHW) into the K-major [N][(t,c)] operand layout of gconv, any tap order. */
 int unetb200_pack_weights(const float* src, void* dst, int dst_dtype, int64_t n0, int64_t n1,
@@ -225,6 +236,10 @@ int unetb200_zero_channels(void* dst, int dtype, int64_t ld_dst, int64_t npix, i
 /* out[c] = sum_p g[p*ld + c]   (bias gradient of ConvTranspose2d); acc = double[C] workspace */
 int unetb200_channel_sum(const void* g, int dtype, int64_t ld, int64_t npix, int C, double* acc,
                          float* out, void* stream);
+/* dst[i] = (float)src[i]: hands per-channel fp64 sums made by a conv epilogue (the `stats` of unetb200_gconv_fprop run
+ * as a dgrad: column sums of the gradient it writes) to an fp32 parameter gradient -- the ConvTranspose2d bias
+ * gradient then needs no pass of its own over the concat gradient. */
+int unetb200_f64_to_f32(const double* src, float* dst, int n, void* stream);
 /* a += b on NHWC channel slices (skip-gradient accumulation) */
 int unetb200_add_channels(void* a, int64_t ld_a, const void* b, int64_t ld_b, int dtype,
                           int64_t npix, int C, void* stream);

@@ -3,7 +3,12 @@
 import json
 import sys
 
-runs = [json.load(open(p)) for p in sys.argv[1:]]
+def load(path):
+    lines = [ln for ln in open(path) if ln.lstrip().startswith("{")]
+    return json.loads(lines[-1])
+
+
+runs = [load(p) for p in sys.argv[1:]]
 print("value     ", "  ".join(f"{r['value']:9.1f}" for r in runs), " img/s")
 print("ms/step   ", "  ".join(f"{r['ms_per_step']:9.3f}" for r in runs))
 print("sm_mhz    ", "  ".join(f"{r.get('clocks', {}).get('sm_mhz', 0):9.0f}" for r in runs))

@@ -486,6 +486,104 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(const float* __rest
 // job table travels by value in the kernel parameters): job j is dst[i0][i1][i2] = cast(src[off + i0*s0 + i1*s1 +
 // i2*s2]), cut into 32 (i0) x 32 (i2) tiles per i1.  A tile is read along whichever of i0 / i2 is contiguous in the
 // source and always written along i2 (contiguous in the destination), through shared memory when the two differ.
+
+// Split reduction of MANY layers in one launch (the 22 per-layer launches of a backward pass were launch / ramp bound:
+// 0.64 ms for ~0.5 GB): job j reduces partials[s][(t,c)][n] over its splits in a fixed order (deterministic) and
+// scatters into the parameter layout exactly like unetb200_wgrad_reduce.  A block owns an 8 (k) x 32 (n) tile of
+// one job; its 8 split lanes each sum every 8th split (8 row loads in flight per thread), then the lanes are
+// combined in a fixed order through shared memory; the tile is written k-fastest (channels_last conv weight:
+// k-linear) or n-fastest (sn == 1), whichever is contiguous in the parameter.
+constexpr int kMaxReduceJobs = 32;
+struct ReduceJob {
+  const float* partials;
+  float* dst;
+  long long st, sc, sq, sn, K;
+  int splits, Cin, N, Cq;
+  int tiles_n, block0, accumulate, pad_;      // pad_ = tile mode: 0 = 32 x 32 (few splits), 1 = 8 x 32 x 8 split lanes
+};
+struct alignas(16) ReduceTable {
+  ReduceJob job[kMaxReduceJobs];
+  int njobs;
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_multi_kernel(const __grid_constant__ ReduceTable T) {
+  __shared__ float red[8][8][33];
+  int lo = 0, hi = T.njobs - 1;
+  while (lo < hi) {                   // last job with block0 <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (T.job[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const ReduceJob& J = T.job[lo];
+  const int local = (int)blockIdx.x - J.block0;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long total = J.K * J.N;
+  const int n0 = (local % J.tiles_n) * 32;
+  const int n = n0 + tx;
+  const bool n_fast = J.sn == 1;
+  auto store = [&](long long k, int nn, float v) {
+    if (k < J.K && nn < J.N) {
+      const long long t = k / J.Cin, c = k - t * J.Cin;
+      const int q = nn / J.Cq, co = nn - q * J.Cq;
+      float* o = J.dst + t * J.st + c * J.sc + q * J.sq + (long long)co * J.sn;
+      *o = J.accumulate ? *o + v : v;
+    }
+  };
+  if (J.pad_ == 0) {
+    // few splits (the deep layers: large K x N): a 32 (k) x 32 (n) tile per block, every thread sums 4 rows over the
+    // splits in order -- all 256 threads load, 12-30 KB per block
+    float (*tile)[33] = reinterpret_cast<float (*)[33]>(&red[0][0][0]);
+    const long long k0 = (long long)(local / J.tiles_n) * 32;
+    float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n < J.N) {
+      for (int sp = 0; sp < J.splits; ++sp) {
+        float v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const long long k = k0 + ty + 8 * r;
+          v[r] = k < J.K ? J.partials[(long long)sp * total + k * J.N + n] : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sacc[r] += v[r];
+      }
+    }
+    if (n_fast) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) store(k0 + ty + 8 * r, n, sacc[r]);
+      return;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = sacc[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) store(k0 + tx, n0 + ty + 8 * r, tile[tx][ty + 8 * r]);
+    return;
+  }
+  // many splits (the shallow layers: small K x N, split over > 100 CTAs): an 8 (k) x 32 (n) tile, 8 split lanes
+  const long long k0 = (long long)(local / J.tiles_n) * 8;
+  float acc[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+  if (n < J.N) {
+    for (int sp = ty; sp < J.splits; sp += 8) {
+      const float* p = J.partials + (long long)sp * total + k0 * J.N + n;
+      float v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = (k0 + r < J.K) ? p[(long long)r * J.N] : 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] += v[r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) red[ty][r][tx] = acc[r];
+  __syncthreads();
+  const int kl = n_fast ? (threadIdx.x >> 5) : (threadIdx.x & 7);
+  const int nl = n_fast ? (threadIdx.x & 31) : (threadIdx.x >> 3);
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v += red[j][kl][nl];
+  store(k0 + kl, n0 + nl, v);
+}
+
 constexpr int kMaxPackJobs = 40;
 struct PackJob {
   const float* src;
@@ -743,6 +841,36 @@ int unetb200_wgrad_reduce(const float* partials, int splits, int ntaps, int Cin,
   wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(partials, splits, Cin, K, N, Cq, dst, st, sc,
                                                                           sq, sn, accumulate);
   UB_LAUNCH_CHECK("wgrad_reduce");
+  return 0;
+}
+
+int unetb200_wgrad_reduce_multi(const unetb200_reduce_job_t* jobs, int njobs, void* stream) {
+  UB_CHECK_ARG(jobs && njobs >= 1, "wgrad_reduce_multi: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int first = 0; first < njobs; first += kMaxReduceJobs) {
+    const int count = njobs - first < kMaxReduceJobs ? njobs - first : kMaxReduceJobs;
+    ReduceTable T;
+    long long blocks = 0;
+    for (int i = 0; i < count; ++i) {
+      const unetb200_reduce_job_t& j = jobs[first + i];
+      UB_CHECK_ARG(j.partials && j.dst && j.splits >= 1 && j.ntaps >= 1 && j.Cin >= 1 && j.N >= 1 && j.Cq >= 1 &&
+                       j.N % j.Cq == 0,
+                   "wgrad_reduce_multi: job %d", first + i);
+      ReduceJob& J = T.job[i];
+      J.partials = j.partials; J.dst = j.dst; J.st = j.st; J.sc = j.sc; J.sq = j.sq; J.sn = j.sn;
+      J.K = (long long)j.ntaps * j.Cin;
+      J.splits = j.splits; J.Cin = j.Cin; J.N = j.N; J.Cq = j.Cq;
+      J.tiles_n = (j.N + 31) / 32;
+      J.block0 = (int)blocks;
+      J.accumulate = j.accumulate;
+      J.pad_ = j.splits >= 8 ? 1 : 0;
+      blocks += (J.pad_ ? (J.K + 7) / 8 : (J.K + 31) / 32) * J.tiles_n;
+      UB_CHECK_ARG(blocks < (1LL << 31), "wgrad_reduce_multi: too many tiles");
+    }
+    T.njobs = count;
+    wgrad_reduce_multi_kernel<<<(unsigned)blocks, 256, 0, s>>>(T);
+  }
+  UB_LAUNCH_CHECK("wgrad_reduce_multi");
   return 0;
 }
 

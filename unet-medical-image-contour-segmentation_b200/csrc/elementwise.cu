@@ -1055,6 +1055,13 @@ int unetb200_channel_sum(const void* g, int dtype, int64_t ld, int64_t npix, int
   return 0;
 }
 
+int unetb200_f64_to_f32(const double* src, float* dst, int n, void* stream) {
+  UB_CHECK_ARG(src && dst && n > 0, "f64_to_f32: bad args");
+  double_to_float_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(src, dst, n);
+  UB_LAUNCH_CHECK("f64_to_f32");
+  return 0;
+}
+
 int unetb200_split_tf32(const float* x, int64_t ld_x, float* out, int64_t npix, int C, int pattern, void* stream) {
   UB_CHECK_ARG(x && out && npix > 0 && C > 0 && ld_x >= C && (pattern == 0 || pattern == 1), "split_tf32: bad args");
   cudaStream_t s = (cudaStream_t)stream;

@@ -41,6 +41,13 @@ class PackJob(C.Structure):
                 ("s0", c_i64), ("s1", c_i64), ("s2", c_i64), ("off", c_i64)]
 
 
+class ReduceJob(C.Structure):
+    """Mirror of unetb200_reduce_job_t."""
+    _fields_ = [("partials", c_p), ("dst", c_p), ("st", c_i64), ("sc", c_i64), ("sq", c_i64), ("sn", c_i64),
+                ("splits", C.c_int32), ("ntaps", C.c_int32), ("Cin", C.c_int32), ("N", C.c_int32), ("Cq", C.c_int32),
+                ("accumulate", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/unetb200.h declares
 PROTOTYPES = {
     "unetb200_version": (C.c_int, []),
@@ -50,6 +57,7 @@ PROTOTYPES = {
     "unetb200_gconv_fprop": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p, c_p, C.POINTER(C.c_int), c_p]),
     "unetb200_gconv_fprop_affine_relu_supported": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p]),
     "unetb200_gconv_fprop_affine_relu": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p]),
+    "unetb200_wgrad_reduce_multi": (C.c_int, [C.POINTER(ReduceJob), C.c_int, c_p]),
     "unetb200_gconv_dgrad_bnbwd_supported": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p]),
     "unetb200_gconv_dgrad_bnbwd": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, C.c_int64, c_p, c_p, c_p, c_p]),
     "unetb200_gconv_wgrad_plan": (C.c_int, [C.POINTER(GConv), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -72,6 +80,7 @@ PROTOTYPES = {
     "unetb200_gather_nhwc": (C.c_int, [c_p, C.c_int, c_i64, c_i64, c_i64, c_i64, c_p, C.c_int, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),
     "unetb200_copy_channels": (C.c_int, [c_p, C.c_int, c_i64, c_p, C.c_int, c_i64, c_i64, C.c_int, c_p]),
     "unetb200_zero_channels": (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p]),
+    "unetb200_f64_to_f32": (C.c_int, [c_p, c_p, C.c_int, c_p]),
     "unetb200_channel_sum": (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_p, c_p]),
     "unetb200_add_channels": (C.c_int, [c_p, c_i64, c_p, c_i64, C.c_int, c_i64, C.c_int, c_p]),
     "unetb200_outconv_fwd": (C.c_int, [c_p, c_i64, c_p, c_p, c_p, C.c_int, c_i64, C.c_int, C.c_int, c_p]),

@@ -236,6 +236,14 @@ _BN_OF_ACT = {}    # data_ptr(z) -> (weakref(y), weakref(coefs), shape)
 _GRAD_SUMS = {}    # data_ptr(g) -> (sums, shape)
 
 
+# Column sums of a gradient made by the dgrad that writes it: the ConvTranspose2d bias gradient (unet_parts.py:73) is
+# the per-channel sum of the `up` half of the concat gradient, which the decoder's first conv's dgrad produces -- its
+# epilogue already knows how to sum the tile it stores (the forward BatchNorm statistics path).
+_WANT_COLSUM = {}    # data_ptr(concat buffer) -> shape: registered by UpCatConvTFn.forward, read by DoubleConvFn.forward
+_GRAD_COLSUM = {}    # data_ptr(concat gradient) -> (fp64 stats[2*C], shape)
+COLSUM_FUSE = os.environ.get("UNETB200_COLSUM_FUSE", "1") != "0"
+
+
 def register_bn_of(z, y, coefs):
     import weakref
     if len(_BN_OF_ACT) > 256:
@@ -341,6 +349,14 @@ def _grad_kept_as_is(param, dW):
     return True
 
 
+def _sink_owns(param, dW):
+    """True when dW IS the registered gradient sink of `param` in `always` mode: the data-parallel reducer drives the
+    backward pass through torch.autograd.grad and owns p.grad, so nothing reads dW before the pass (segment) ends."""
+    ent = _GRAD_SINK.get(id(param))
+    return (ent is not None and ent[0]() is param and ent[2] and dW.data_ptr() == ent[1].data_ptr()
+            and not torch.is_grad_enabled())
+
+
 def _vec_dst(param, Cc):
     """gradient sink of a [C] parameter (BatchNorm gamma / beta, a bias), if any"""
     if param is None:
@@ -350,7 +366,7 @@ def _vec_dst(param, Cc):
 
 
 def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_params=(None, None), sums=None,
-                     below=None):
+                     below=None, colsum=False):
     """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta, sums_below).  `param`: the Parameter object behind `w`;
     `bn_params`: the BatchNorm weight / bias Parameter objects (only to look up their gradient sinks); `sums`: the
     BatchNorm-backward reduction of THIS stage if the kernel that produced gz already made it; `below` = (y, coefs)
@@ -383,15 +399,27 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_pa
         if (below is not None and gs is None and _BNBWD_MIN_N <= Cin <= _BNBWD_MAX_N
                 and ops.gconv_dgrad_bnbwd_supported(dd, gy, wd, gx)):
             sums_below = ops.gconv_dgrad_bnbwd(dd, gy, wd, gx, below[0], below[1])
+        elif colsum and gs is None:
+            # x is an Up stage's concat buffer: leave the per-channel sums of its gradient for the ConvTranspose bias
+            cs = torch.zeros(2 * Cin, dtype=torch.float64, device=x.device)
+            ops.gconv_fprop(dd, gy, wd, None, gx, cs, kind="dgrad")
+            if len(_GRAD_COLSUM) > 16:
+                _GRAD_COLSUM.clear()
+            _GRAD_COLSUM[gx.data_ptr()] = (cs, tuple(gx.shape))
         else:
             ops.gconv_fprop(dd, gy, wd, None, gx, None, kind="dgrad", x_split=gs)
     # after the dgrad, on the side stream: overlaps the (memory-bound) BatchNorm backward of the previous layer
     # (only when AccumulateGrad will simply keep dW: an existing .grad would be accumulated into on the main stream)
-    run = lambda: ops.gconv_wgrad(dw_desc, x, gy, dW, skw, si, so, gy_split=gs)  # noqa: E731
-    if _grad_kept_as_is(param, dW):
+    kept = _grad_kept_as_is(param, dW)
+    side = kept and ops.wgrad_on_side_stream()
+    # nothing reads dW before the pass ends (AccumulateGrad keeps it as it is, or a data-parallel sink owns it):
+    # its split reduction joins the one multi-tensor launch at the end of the backward pass
+    defer = (kept or _sink_owns(param, dW)) and not side
+    run = lambda: ops.gconv_wgrad(dw_desc, x, gy, dW, skw, si, so, gy_split=gs, defer=defer)  # noqa: E731
+    if side:
         ops.on_side_stream(run, x, gy)      # AccumulateGrad keeps dW as it is (same layout, no other owner)
     else:
-        run()                               # it would accumulate / re-layout dW on the main stream right away
+        run()                               # (else it would accumulate / re-layout dW on the main stream right away)
     return gx, dW, dgamma, dbeta, sums_below
 
 
@@ -441,6 +469,7 @@ class DoubleConvFn(torch.autograd.Function):
                                               fold=fold)
         ctx.batch_stats = (cfg.training or cfg.bn1.running_mean is None, cfg.training or cfg.bn2.running_mean is None)
         ctx.has_pool = pooled is not None
+        ctx.colsum = bool(cfg.save) and _WANT_COLSUM.pop(x.data_ptr(), None) == tuple(x.shape)
         if cfg.save:
             ctx.save_for_backward(x, y1, z1, y2, z2, c1, c2, w1, w2)
             ctx.param_objs = (w1, g1, b1, w2, g2, b2)   # the Parameter objects themselves (.grad / gradient sinks)
@@ -480,7 +509,7 @@ class DoubleConvFn(torch.autograd.Function):
         gz1, dW2, dg2, db2, sums1 = conv_bn_relu_bwd(gz, z1, y2, w2, c2, ctx.batch_stats[1], True, param=p2,
                                                      bn_params=(pg2, pb2), below=(y1, c1), sums=sums2)
         gx, dW1, dg1, db1, _ = conv_bn_relu_bwd(gz1, x, y1, w1, c1, ctx.batch_stats[0], need[0], param=p1,
-                                                bn_params=(pg1, pb1), sums=sums1)
+                                                bn_params=(pg1, pb1), sums=sums1, colsum=ctx.colsum)
         return (gx, dW1 if need[1] else None, dg1 if need[2] else None, db1 if need[3] else None,
                 dW2 if need[4] else None, dg2 if need[5] else None, db2 if need[6] else None, None)
 
@@ -547,6 +576,10 @@ class UpCatConvTFn(torch.autograd.Function):
             ctx.save_for_backward(x1, wT)
             ctx.param_obj = wT
             ctx.bias_obj = bT
+            if bT is not None and not (dy or dx) and COLSUM_FUSE:
+                if len(_WANT_COLSUM) > 16:
+                    _WANT_COLSUM.clear()
+                _WANT_COLSUM[cat.data_ptr()] = tuple(cat.shape)
         return cat
 
     @staticmethod
@@ -580,16 +613,24 @@ class UpCatConvTFn(torch.autograd.Function):
             ops.gconv_fprop(dd, gup, packT_dgrad(wT, cd), None, gx1, None, kind="convT_dgrad")
         if need[2]:
             # after the dgrad, on the side stream (see conv_bn_relu_bwd)
-            run = lambda: ops.gconv_wgrad(d, x1, gup, dW, 0, s_ci, s_co, sq=s_q)  # noqa: E731
             pT = getattr(ctx, "param_obj", wT)
-            if _grad_kept_as_is(pT, dW):
+            kept = _grad_kept_as_is(pT, dW)
+            side = kept and ops.wgrad_on_side_stream()
+            defer = (kept or _sink_owns(pT, dW)) and not side
+            run = lambda: ops.gconv_wgrad(d, x1, gup, dW, 0, s_ci, s_co, sq=s_q, defer=defer)  # noqa: E731
+            if side:
                 ops.on_side_stream(run, x1, g)
             else:
                 run()
+        cs = _GRAD_COLSUM.pop(g.data_ptr(), None)
         if need[3]:
-            region = gup if not padded else ops.to_nhwc(
-                gup[:, :, off[0]:off[0] + 2 * h, off[1]:off[1] + 2 * w].contiguous(memory_format=torch.channels_last), cd)
-            dB = ops.channel_sum(region, _vec_dst(getattr(ctx, "bias_obj", None), Cup))
+            dst = _vec_dst(getattr(ctx, "bias_obj", None), Cup)
+            if cs is not None and cs[1] == tuple(g.shape) and not padded and g is gcat:
+                dB = ops.f64_to_f32(cs[0][C2:C2 + Cup], dst)      # summed by the dgrad epilogue that wrote g
+            else:
+                region = gup if not padded else ops.to_nhwc(
+                    gup[:, :, off[0]:off[0] + 2 * h, off[1]:off[1] + 2 * w].contiguous(memory_format=torch.channels_last), cd)
+                dB = ops.channel_sum(region, dst)
         return gx1, g2, dW, dB, None
 
 

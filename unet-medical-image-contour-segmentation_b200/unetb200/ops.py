@@ -121,6 +121,11 @@ def side_enabled():
     return _SIDE_ON and _PROFILE is None
 
 
+def wgrad_on_side_stream():
+    """True when on_side_stream(..., join=True) would really move the work to the side stream."""
+    return _SIDE_ON and _PROFILE is None and _WGRAD_SIDE
+
+
 def on_side_stream(fn, *keep, join=True):
     """Run fn() on the side stream, ordered after everything enqueued so far on the current stream.  join=True
     queues the end-of-backward join (weight gradients); join=False leaves ordering to events recorded by fn
@@ -258,6 +263,14 @@ def channel_sum(g, out=None):
         out = torch.empty(Cc, dtype=torch.float32, device=g.device)
     _run("channel_sum", lib().unetb200_channel_sum, _p(g), dt(g), nhwc_ld(g), B * H * W, Cc, _p(acc), _p(out),
          _stream(), kernels=2, nbytes=g.numel() * g.element_size())
+    return out
+
+
+def f64_to_f32(src, out=None):
+    """fp64 vector (a slice of conv-epilogue column sums) -> fp32 parameter gradient"""
+    if out is None:
+        out = torch.empty(src.numel(), dtype=torch.float32, device=src.device)
+    _run("bias_from_colsum", lib().unetb200_f64_to_f32, _p(src), _p(out), src.numel(), _stream())
     return out
 
 
@@ -416,7 +429,54 @@ def gconv_dgrad_bnbwd(d, g, wp, gx, yprev, coefs_prev):
     return sums
 
 
-def _wgrad_once(d, x, gy, dst, st, sc, sn, sq, accumulate, flops, tag):
+# ------------------------------------------------------------------------------------------------
+# deferred split reductions of the weight gradients: one multi-tensor launch per backward pass
+# ------------------------------------------------------------------------------------------------
+# A wgrad kernel writes `splits` partial results; reducing them layer by layer costs 22 small launches per step.
+# When nothing reads the gradient before the backward pass ends (functional._grad_kept_as_is, or a data-parallel
+# sink that owns p.grad), the reduction is queued and all queued layers are reduced by ONE launch from an autograd
+# engine callback at the end of the pass -- for a segmented backward (ddp.segmented_backward) that is the end of
+# each torch.autograd.grad call, i.e. before the segment's bucket is all-reduced.
+# NOTE the queue keeps the partials alive but only the ADDRESS of the gradient: AccumulateGrad adopts a gradient
+# tensor without copying only while nobody else references it (use_count check) -- a reference held here would make
+# it clone the not-yet-reduced buffer.  The gradient itself is kept alive by p.grad (or is a bucket view).
+_REDUCE_JOBS = []          # (partials, dst address, st, sc, sq, sn, splits, ntaps, Cin, N, Cq)
+_REDUCE_PENDING = [None]
+DEFER_REDUCE = _os.environ.get("UNETB200_DEFER_REDUCE", "1") != "0"
+
+
+def flush_wgrad_reduce():
+    """Reduce every queued weight gradient on the current stream (no-op when nothing is queued)."""
+    _REDUCE_PENDING[0] = None
+    if not _REDUCE_JOBS:
+        return
+    jobs = (_lib.ReduceJob * len(_REDUCE_JOBS))()
+    nbytes = 0.0
+    for j, (partials, dst, st, sc, sq, sn, splits, ntaps, Cin, N, Cq) in enumerate(_REDUCE_JOBS):
+        jobs[j].partials, jobs[j].dst = partials.data_ptr(), dst
+        jobs[j].st, jobs[j].sc, jobs[j].sq, jobs[j].sn = st, sc, sq, sn
+        jobs[j].splits, jobs[j].ntaps, jobs[j].Cin, jobs[j].N, jobs[j].Cq, jobs[j].accumulate = splits, ntaps, Cin, N, Cq, 0
+        nbytes += 4.0 * ntaps * Cin * N * (splits + 1)
+    n = len(_REDUCE_JOBS)
+    try:
+        _run("wgrad_reduce", lib().unetb200_wgrad_reduce_multi, jobs, n, _stream(), nbytes=nbytes,
+             kernels=(n + 31) // 32)
+    finally:
+        _REDUCE_JOBS.clear()
+
+
+def _queue_reduce(job):
+    _REDUCE_JOBS.append(job)
+    task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
+    if task is None or task < 0:
+        flush_wgrad_reduce()                         # not inside a backward pass: nothing to wait for
+        return
+    if _REDUCE_PENDING[0] != task:
+        _REDUCE_PENDING[0] = task
+        torch.autograd.Variable._execution_engine.queue_callback(flush_wgrad_reduce)
+
+
+def _wgrad_once(d, x, gy, dst, st, sc, sn, sq, accumulate, flops, tag, defer=False):
     splits, used = C.c_int(0), C.c_int(0)
     _lib.check(lib().unetb200_gconv_wgrad_plan(C.byref(d), C.byref(splits), C.byref(used)), "gconv_wgrad_plan")
     K = d.ntaps * d.Cin
@@ -427,16 +487,21 @@ def _wgrad_once(d, x, gy, dst, st, sc, sn, sq, accumulate, flops, tag):
     _run(f"conv_wgrad_{_ALGO_NAME.get(used.value, '?')}" + tag, lib().unetb200_gconv_wgrad, C.byref(d2), _p(x), _p(gy),
          _p(partials), splits.value, _stream(), flops=flops,
          nbytes=float(es) * d.B * (d.Hin * d.Win * d.Cin + d.Hout * d.Wout * (d.N // d.nquad)) + 4.0 * K * d.N)
+    if defer and not accumulate and DEFER_REDUCE:
+        _queue_reduce((partials, dst.data_ptr(), st, sc, sq, sn, splits.value, d.ntaps, d.Cin, d.N, d.N // d.nquad))
+        return used.value
     _run("wgrad_reduce", lib().unetb200_wgrad_reduce, _p(partials), splits.value, d.ntaps, d.Cin, d.N,
          d.N // d.nquad, _p(dst), st, sc, sq, sn, 1 if accumulate else 0, _stream(),
          nbytes=4.0 * K * d.N * (splits.value + 1))
     return used.value
 
 
-def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0, x_split=None, gy_split=None):
-    """dst (parameter layout, fp32) = weight gradient; dst[t*st + c*sc + q*sq + co*sn], n = q*Cq + co."""
+def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0, x_split=None, gy_split=None, defer=False):
+    """dst (parameter layout, fp32) = weight gradient; dst[t*st + c*sc + q*sq + co*sn], n = q*Cq + co.
+    defer=True: nothing reads dst before the end of the backward pass -- its split reduction may join the
+    one multi-tensor launch at the end of the pass (flush_wgrad_reduce)."""
     if not x3_active(d):
-        return _wgrad_once(d, x, gy, dst, st, sc, sn, sq, False, gconv_flops(d), _shape_tag(d))
+        return _wgrad_once(d, x, gy, dst, st, sc, sn, sq, False, gconv_flops(d), _shape_tag(d), defer=defer)
     # 3xTF32: dW = hi(x)^T hi(g) + lo(x)^T hi(g) + hi(x)^T lo(g), the last two accumulated by the split reduction
     xs = x_split if x_split is not None else x3_split(x)
     gs = gy_split if gy_split is not None else x3_split(gy)
