@@ -268,6 +268,22 @@ int unetb200_outconv_bwd_bnbwd(const void* x, int64_t ld_x, const float* w, cons
                                int ncls, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * SpatialAttention gate of UNet_SA -- unet_parts.py:39-60 (module) and :91-92 (x2 = x2 * attention(x2)):
+ *   stats[p] = (mean_c x[p][c], max_c x[p][c]);  gate[p] = sigmoid(conv7x7(stats)[p]) (2 -> 1 channels, padding 3,
+ *   no bias; w = float[2][7][7]);  out[p][c] = x[p][c] * gate[p].
+ * stats = float[npix][2] and gate = float[npix] are outputs of the forward call and inputs of the backward call,
+ * which returns dx (gradient of x through all three uses: the product, the mean and the max -- first maximum on
+ * ties, like torch.max) and dw = float[98].  Rounding points under `dtype` = bf16 follow the reference under
+ * autocast (statistics, conv output, gate and product each stored in bf16).  Memory-bound.
+ * ------------------------------------------------------------------------------------------- */
+int unetb200_sa_forward(const void* x, int64_t ld_x, const float* w, float* stats, float* gate, void* out,
+                        int64_t ld_out, int dtype, int B, int H, int W, int C, void* stream);
+int64_t unetb200_sa_backward_workspace(int B, int H, int W);   /* number of floats */
+int unetb200_sa_backward(const void* g, int64_t ld_g, const void* x, int64_t ld_x, const float* w,
+                         const float* stats, const float* gate, void* dx, int64_t ld_dx, float* dw,
+                         float* workspace, int dtype, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * losses
  * ------------------------------------------------------------------------------------------- */
 /* Fused criterion of train.py:137-142: CrossEntropyLoss(logits, target) +

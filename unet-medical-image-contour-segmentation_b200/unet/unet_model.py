@@ -20,6 +20,7 @@ from .unet_parts import DoubleConv, Down, OutConv, Up, _prep
 
 class _UNetBase(nn.Module):
     _BASE = 64
+    _ATTENTION = False    # UNet_SA: SpatialAttention gate on every skip tensor (unet_model.py:156-160)
     _taps = None          # dict to fill with the named intermediate tensors of the next forward, or None
 
     def __init__(self, n_channels, n_classes, bilinear=False):
@@ -34,10 +35,11 @@ class _UNetBase(nn.Module):
         self.down2 = Down(2 * b, 4 * b)
         self.down3 = Down(4 * b, 8 * b)
         self.down4 = Down(8 * b, 16 * b // factor)
-        self.up1 = Up(16 * b, 8 * b // factor, bilinear)
-        self.up2 = Up(8 * b, 4 * b // factor, bilinear)
-        self.up3 = Up(4 * b, 2 * b // factor, bilinear)
-        self.up4 = Up(2 * b, b, bilinear)
+        att = self._ATTENTION
+        self.up1 = Up(16 * b, 8 * b // factor, bilinear, use_attention=att)
+        self.up2 = Up(8 * b, 4 * b // factor, bilinear, use_attention=att)
+        self.up3 = Up(4 * b, 2 * b // factor, bilinear, use_attention=att)
+        self.up4 = Up(2 * b, b, bilinear, use_attention=att)
         self.outc = OutConv(b, n_classes)
 
     def forward(self, x):
@@ -53,7 +55,9 @@ class _UNetBase(nn.Module):
         UF.prepack(self, cd, need_dgrad=torch.is_grad_enabled())
         # concat buffers of the four Up stages: [skip | upsampled], at the skip's resolution
         cats = [ops.empty_nhwc(B, 2 * b * (1 << k), H >> k, W >> k, cd, dev) for k in range(4)]
-        skips = [ops.channel_slice(cats[k], 0, b * (1 << k)) for k in range(4)]
+        # (with attention the encoder keeps its own un-gated output -- the gate's backward needs it -- and the gate
+        # writes x * attention(x) into the skip half of the concat buffer)
+        skips = [None if self._ATTENTION else ops.channel_slice(cats[k], 0, b * (1 << k)) for k in range(4)]
         taps = self._taps
         cut = UF.CutFn.apply if taps is not None else (lambda t: t)
         x1, p = self.inc.run(x, out=skips[0], want_pool=True)
@@ -98,9 +102,7 @@ class UNet_T(_UNetBase):
     _BASE = 8
 
 
-class UNet_SA(nn.Module):
-    """Spatial-attention variant (reference unet_model.py:140-189): outside the B200 hot path."""
-
-    def __init__(self, *args, **kwargs):
-        super().__init__()
-        raise NotImplementedError("UNet_SA (spatial attention) is outside the B200 hot path; see SURVEY.md section 2, row 2b")
+class UNet_SA(_UNetBase):
+    """UNet with a SpatialAttention gate on every skip connection, base width 16 (reference unet_model.py:140-189)."""
+    _BASE = 16
+    _ATTENTION = True

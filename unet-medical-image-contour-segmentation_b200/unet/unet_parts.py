@@ -82,11 +82,26 @@ class Down(nn.Module):
 
 
 class SpatialAttention(nn.Module):
-    """Kept for import compatibility only (reference unet_parts.py:39-60); UNet never uses it."""
+    """sigmoid(conv7x7([mean_c x, max_c x]))  [reference unet_parts.py:39-60].  ``forward`` returns the attention map
+    like the reference; ``gate`` applies it (x * map, unet_parts.py:91-92) in the same kernels."""
 
     def __init__(self, kernel_size=7):
         super().__init__()
-        raise NotImplementedError("SpatialAttention / UNet_SA is outside the B200 hot path (SURVEY.md section 2, row 1b)")
+        assert kernel_size in (3, 7), "kernel size must be 3 or 7"
+        if kernel_size != 7:
+            raise NotImplementedError("unetb200: SpatialAttention(kernel_size=3) is never built by the reference models "
+                                      "(unet_parts.py:77 uses the default 7) and has no kernel here")
+        self.conv1 = nn.Conv2d(2, 1, kernel_size, padding=3, bias=False)
+        self.sigmoid = nn.Sigmoid()
+
+    def gate(self, x, out=None):
+        """x: NHWC compute-dtype tensor -> x * attention(x), optionally written into ``out``."""
+        cfg = _Cfg(out=out, save=_needs_graph(self, x))
+        return UF.SpatialGateFn.apply(x, self.conv1.weight, cfg)
+
+    def forward(self, x):
+        raise NotImplementedError("unetb200: the bare attention map is not exposed -- the reference only ever uses it as "
+                                  "x2 * attention(x2) (Up.forward, unet_parts.py:91-92), which is SpatialAttention.gate(x)")
 
 
 class Up(nn.Module):
@@ -95,8 +110,6 @@ class Up(nn.Module):
 
     def __init__(self, in_channels, out_channels, bilinear=True, use_attention=False):
         super().__init__()
-        if use_attention:
-            raise NotImplementedError("Up(use_attention=True) is outside the B200 hot path (SURVEY.md section 2, row 1b)")
         if bilinear:
             self.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
             self.conv = DoubleConv(in_channels, out_channels, in_channels // 2)
@@ -104,10 +117,15 @@ class Up(nn.Module):
             self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
             self.conv = DoubleConv(in_channels, out_channels)
         self.bilinear = bilinear
-        self.use_attention = False
-        self.attention = nn.Identity()
+        self.use_attention = use_attention
+        self.attention = SpatialAttention() if use_attention else nn.Identity()      # unet_parts.py:76-77
 
     def run(self, x1, x2, cat=None, out=None, want_pool=False):
+        """x2: the skip tensor.  With attention it is the UN-gated encoder output (kept for the gate's backward); the
+        gated copy is written into the skip half of ``cat`` when the caller pre-allocated the concat buffer."""
+        if self.use_attention:                         # unet_parts.py:91-92
+            dst = ops.channel_slice(cat, 0, x2.shape[1]) if cat is not None else None
+            x2 = self.attention.gate(x2, out=dst)
         cfg = _Cfg(cat=cat, save=_needs_graph(self, x1, x2))
         if self.bilinear:
             merged = UF.UpCatBilinearFn.apply(x1, x2, cfg)

@@ -80,6 +80,10 @@ PROTOTYPES = {
     "unetb200_gather_nhwc": (C.c_int, [c_p, C.c_int, c_i64, c_i64, c_i64, c_i64, c_p, C.c_int, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),
     "unetb200_copy_channels": (C.c_int, [c_p, C.c_int, c_i64, c_p, C.c_int, c_i64, c_i64, C.c_int, c_p]),
     "unetb200_zero_channels": (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p]),
+    "unetb200_sa_forward": (C.c_int, [c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),
+    "unetb200_sa_backward_workspace": (c_i64, [C.c_int, C.c_int, C.c_int]),
+    "unetb200_sa_backward": (C.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, c_p]),
     "unetb200_f64_to_f32": (C.c_int, [c_p, c_p, C.c_int, c_p]),
     "unetb200_channel_sum": (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_p, c_p]),
     "unetb200_add_channels": (C.c_int, [c_p, c_i64, c_p, c_i64, C.c_int, c_i64, C.c_int, c_p]),

@@ -662,6 +662,35 @@ class UpCatBilinearFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------
+# SpatialAttention gate (UNet_SA: unet_parts.py:39-60, applied to the skip tensor at :91-92)
+# ------------------------------------------------------------------------------------------------
+class SpatialGateFn(torch.autograd.Function):
+    """x2 * sigmoid(conv7x7([mean_c x2, max_c x2])), written into ``cfg.out`` (the skip half of the concat buffer)."""
+
+    @staticmethod
+    def forward(ctx, x, w, cfg):
+        B, Cc, H, W = x.shape
+        if tuple(w.shape) != (1, 2, 7, 7):
+            raise ValueError(f"unetb200: SpatialAttention supports the 7x7 kernel the reference builds, got {tuple(w.shape)}")
+        out = cfg.out if cfg.out is not None else ops.empty_nhwc(B, Cc, H, W, x.dtype, x.device)
+        wc = _f32c(w).reshape(-1)
+        stats, gate = ops.sa_forward(x, wc, out)
+        if cfg.save:
+            ctx.save_for_backward(x, wc, stats, gate)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, wc, stats, gate = ctx.saved_tensors
+        g = ops.to_nhwc(gout, x.dtype)
+        dx = ops.empty_nhwc(*x.shape, x.dtype, x.device)
+        dw = torch.empty(98, dtype=torch.float32, device=x.device)
+        ops.sa_backward(g, x, wc, stats, gate, dx, dw)
+        need = ctx.needs_input_grad
+        return (dx if need[0] else None), (dw.view(1, 2, 7, 7) if need[1] else None), None
+
+
+# ------------------------------------------------------------------------------------------------
 # OutConv
 # ------------------------------------------------------------------------------------------------
 class OutConvFn(torch.autograd.Function):

@@ -595,6 +595,27 @@ def upsample2x_bwd(gy, gx, off):
 
 
 # ------------------------------------------------------------------------------------------------
+# SpatialAttention gate (UNet_SA)
+# ------------------------------------------------------------------------------------------------
+def sa_forward(x, w, out):
+    """out = x * sigmoid(conv7x7([mean_c x, max_c x])); returns the fp32 maps (stats [B,H,W,2], gate [B,H,W])."""
+    B, Cc, H, W = x.shape
+    stats = torch.empty((B, H, W, 2), dtype=torch.float32, device=x.device)
+    gate = torch.empty((B, H, W), dtype=torch.float32, device=x.device)
+    _run("sa_forward", lib().unetb200_sa_forward, _p(x), nhwc_ld(x), _p(w), _p(stats), _p(gate), _p(out), nhwc_ld(out),
+         dt(x), B, H, W, Cc, _stream(), kernels=3, nbytes=3.0 * x.numel() * x.element_size())
+    return stats, gate
+
+
+def sa_backward(g, x, w, stats, gate, dx, dw):
+    B, Cc, H, W = x.shape
+    ws = torch.empty(lib().unetb200_sa_backward_workspace(B, H, W), dtype=torch.float32, device=x.device)
+    _run("sa_backward", lib().unetb200_sa_backward, _p(g), nhwc_ld(g), _p(x), nhwc_ld(x), _p(w), _p(stats), _p(gate),
+         _p(dx), nhwc_ld(dx), _p(dw), _p(ws), dt(x), B, H, W, Cc, _stream(), kernels=4,
+         nbytes=5.0 * x.numel() * x.element_size())
+
+
+# ------------------------------------------------------------------------------------------------
 # OutConv
 # ------------------------------------------------------------------------------------------------
 def outconv_fwd(x, w, bias, logits):
