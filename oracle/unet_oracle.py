@@ -168,8 +168,17 @@ def down(st, name, x, training=True, q=EXACT):
     return double_conv(st, f"{name}.maxpool_conv.1.double_conv", F.max_pool2d(x, 2), training, q)
 
 
+def spatial_attention(st, name, x, q=EXACT):
+    """SpatialAttention.forward (unet_parts.py:52-60): sigmoid(conv7x7(cat([mean_c x, max_c x]))), padding 3, no bias."""
+    avg = q.act(torch.mean(x, dim=1, keepdim=True))
+    mx, _ = torch.max(x, dim=1, keepdim=True)
+    a = q.act(F.conv2d(torch.cat([avg, mx], dim=1), q.weight(st[f"{name}.attention.conv1.weight"]), None, padding=3))
+    return q.act(torch.sigmoid(a))
+
+
 def up(st, name, x1, x2, bilinear, training=True, q=EXACT):
-    """Upsample x1, pad to x2, cat([x2, x1]) (skip first), DoubleConv  (unet_parts.py:80-98)."""
+    """Upsample x1, pad to x2, [x2 = x2 * attention(x2) for UNet_SA], cat([x2, x1]) (skip first), DoubleConv
+    (unet_parts.py:80-98).  The attention gate is present exactly when the state holds its 7x7 weight."""
     if bilinear:
         x1 = q.act(F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True))
     else:
@@ -177,6 +186,8 @@ def up(st, name, x1, x2, bilinear, training=True, q=EXACT):
     dy = x2.size(2) - x1.size(2)
     dx = x2.size(3) - x1.size(3)
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    if f"{name}.attention.conv1.weight" in st:              # unet_parts.py:91-92
+        x2 = q.act(x2 * spatial_attention(st, name, x2, q))
     return double_conv(st, f"{name}.conv.double_conv", torch.cat([x2, x1], dim=1), training, q)
 
 

@@ -211,6 +211,30 @@ def width_gate(cls_name, nc, ncls, bilinear, B, H, W, mode):
     return res
 
 
+def sa_gate_op():
+    """SpatialAttention gate (x * sigmoid(conv7x7([mean_c x, max_c x]))), forward and backward, against the fixture the
+    UNMODIFIED reference module produced (tests/golden/make_golden_sa.py): fp32 storage to 1e-5, bf16 storage to the
+    bf16 tolerance of the other memory-bound ops; also into a channel slice of a wider buffer (the concat buffer)."""
+    from unetb200 import functional as UF
+    from unetb200 import ops
+    g = torch.load(os.path.join(G.ROOT, "tests", "golden", "golden_sa_v1.pt"), weights_only=False)["gate"]
+    res = []
+    for dt_, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        x = G.dev_nhwc(g["x"], dt_).requires_grad_(True)
+        w = g["w"].to(DEV).requires_grad_(True)
+        B, C, H, W = x.shape
+        buf = ops.empty_nhwc(B, 2 * C, H, W, dt_, DEV)
+        buf.fill_(3.0)
+        out = UF.SpatialGateFn.apply(x, w, UF._Cfg(out=ops.channel_slice(buf, 0, C), save=True))
+        out.backward(g["gy"].to(DEV).to(dt_))
+        tag = str(dt_)[6:]
+        res.append((f"sa_gate_fwd_{tag}", rel(host(out), g["y"]), tol))
+        res.append((f"sa_gate_slice_untouched_{tag}", (host(ops.channel_slice(buf, C, C)) - 3.0).abs().max().item(), 0.0))
+        res.append((f"sa_gate_gx_{tag}", rel(host(x.grad), g["gx"]), tol if dt_ == torch.float32 else 3e-2))
+        res.append((f"sa_gate_gw_{tag}", rel(host(w.grad), g["gw"]), 1e-4 if dt_ == torch.float32 else 3e-2))
+    return res
+
+
 _COND = {}
 
 
@@ -498,6 +522,8 @@ GROUPS = {
     "north_star_bf16_b": lambda gd: north_star_gate(1, 2, True, 2, 128, 128) + north_star_gate(3, 4, False, 2, 128, 160),
     "unet_widths": lambda gd: width_gate("UNet_S", 1, 3, False, 2, 64, 64, "fp32") + width_gate("UNet_S", 1, 3, False, 2, 128, 128, "bf16")
                    + width_gate("UNet_T", 3, 2, True, 1, 64, 96, "fp32"),
+    "unet_sa": lambda gd: sa_gate_op() + width_gate("UNet_SA", 1, 2, False, 2, 64, 64, "fp32")
+               + width_gate("UNet_SA", 3, 3, True, 1, 48, 80, "fp32") + width_gate("UNet_SA", 1, 2, False, 2, 128, 128, "bf16"),
     "graph_side_stream": lambda gd: graph_gate(),
     "unet_infer": lambda gd: infer_gate(3, 4, False, 2, 128, 160, "fp32") + infer_gate(3, 4, False, 2, 128, 160, "bf16")
                   + infer_gate(1, 2, True, 1, 96, 96, "tf32"),
