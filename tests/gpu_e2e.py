@@ -211,6 +211,41 @@ def width_gate(cls_name, nc, ncls, bilinear, B, H, W, mode):
     return res
 
 
+def checkpoint_gate():
+    """UNet.use_checkpointing() (reference unet_model.py:40-50, reached from train.py:294-299 after an OOM): the same
+    step with every stage under activation re-computation gives the same loss, gradients, BatchNorm running statistics
+    and num_batches_tracked, with a lower peak of live memory."""
+    import unet
+    from unetb200 import losses as UL
+    st = O.build_state(1, 2, False, seed=0)
+    img, msk = O.synthetic_batch(4, 1, 2, 192, 192)
+    x = img.to(DEV).contiguous(memory_format=torch.channels_last)
+    t = msk.to(DEV)
+    res, out = [], {}
+    for mode in ("plain", "recompute"):
+        m = unet.UNet(1, 2, False)
+        m.load_state_dict(st)
+        m = m.to(DEV).to(memory_format=torch.channels_last).train()
+        if mode == "recompute":
+            m.use_checkpointing()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        with torch.autocast("cuda", enabled=True):
+            loss = UL.training_criterion(m(x), t, boundary_coeff=0.2)
+        after_fwd = torch.cuda.memory_allocated() - base
+        loss.backward()
+        torch.cuda.synchronize()
+        out[mode] = (float(loss.detach()), {k: host(p.grad) for k, p in m.named_parameters()},
+                     {k: host(v) for k, v in m.state_dict().items() if "running" in k or "tracked" in k}, after_fwd)
+    (l0, g0, s0, m0), (l1, g1, s1, m1) = out["plain"], out["recompute"]
+    res.append(("ckpt_loss_equal", abs(l1 - l0), 0.0))
+    res.append(("ckpt_grads_equal_rel_l2", max(O.rel_l2(g1[k], g0[k]) for k in g0), 1e-6))
+    res.append(("ckpt_bn_buffers_equal", max(float((s1[k].double() - s0[k].double()).abs().max()) for k in s0), 0.0))
+    res.append(("ckpt_live_after_forward_ratio", m1 / max(m0, 1), 0.6))
+    return res
+
+
 def sa_gate_op():
     """SpatialAttention gate (x * sigmoid(conv7x7([mean_c x, max_c x]))), forward and backward, against the fixture the
     UNMODIFIED reference module produced (tests/golden/make_golden_sa.py): fp32 storage to 1e-5, bf16 storage to the
@@ -524,6 +559,7 @@ GROUPS = {
                    + width_gate("UNet_T", 3, 2, True, 1, 64, 96, "fp32"),
     "unet_sa": lambda gd: sa_gate_op() + width_gate("UNet_SA", 1, 2, False, 2, 64, 64, "fp32")
                + width_gate("UNet_SA", 3, 3, True, 1, 48, 80, "fp32") + width_gate("UNet_SA", 1, 2, False, 2, 128, 128, "bf16"),
+    "checkpointing": lambda gd: checkpoint_gate(),
     "graph_side_stream": lambda gd: graph_gate(),
     "unet_infer": lambda gd: infer_gate(3, 4, False, 2, 128, 160, "fp32") + infer_gate(3, 4, False, 2, 128, 160, "bf16")
                   + infer_gate(1, 2, True, 1, 96, 96, "tf32"),

@@ -60,18 +60,19 @@ class _UNetBase(nn.Module):
         skips = [None if self._ATTENTION else ops.channel_slice(cats[k], 0, b * (1 << k)) for k in range(4)]
         taps = self._taps
         cut = UF.CutFn.apply if taps is not None else (lambda t: t)
-        x1, p = self.inc.run(x, out=skips[0], want_pool=True)
-        x2, p = self.down1.run(p, out=skips[1], want_pool=True)
-        x3, p3 = self.down2.run(p, out=skips[2], want_pool=True)
+        ck = self._stage if (self._checkpointing and taps is None and torch.is_grad_enabled()) else (lambda fn, *t: fn(*t))
+        x1, p = ck(lambda t: self.inc.run(t, out=skips[0], want_pool=True), x)
+        x2, p = ck(lambda t: self.down1.run(t, out=skips[1], want_pool=True), p)
+        x3, p3 = ck(lambda t: self.down2.run(t, out=skips[2], want_pool=True), p)
         p3c = cut(p3)
-        x4, p = self.down3.run(p3c, out=skips[3], want_pool=True)
-        x5 = self.down4.run(p)
+        x4, p = ck(lambda t: self.down3.run(t, out=skips[3], want_pool=True), p3c)
+        x5 = ck(lambda t: self.down4.run(t), p)
         x5c, x4c, x3c = cut(x5), cut(x4), cut(x3)
-        y = self.up1.run(x5c, x4c, cat=cats[3])
-        u2 = self.up2.run(y, x3c, cat=cats[2])
+        y = ck(lambda a, b_: self.up1.run(a, b_, cat=cats[3]), x5c, x4c)
+        u2 = ck(lambda a, b_: self.up2.run(a, b_, cat=cats[2]), y, x3c)
         u2c, x2c, x1c = cut(u2), cut(x2), cut(x1)
-        y = self.up3.run(u2c, x2c, cat=cats[1])
-        y = self.up4.run(y, x1c, cat=cats[0])
+        y = ck(lambda a, b_: self.up3.run(a, b_, cat=cats[1]), u2c, x2c)
+        y = ck(lambda a, b_: self.up4.run(a, b_, cat=cats[0]), y, x1c)
         out = self.outc.run(y)
         if taps is not None:
             # cut points of a segmented backward pass (unetb200.ddp.SegmentedStep): name -> (tensor, its cut alias)
@@ -79,11 +80,26 @@ class _UNetBase(nn.Module):
                         u2=(u2, u2c))
         return out
 
+    _checkpointing = False
+
+    @staticmethod
+    def _stage(fn, *tensors):
+        """One encoder / decoder stage under activation re-computation: only the stage's inputs stay resident, its raw
+        conv outputs and inner activations are re-computed (by the same deterministic kernels: bit-identical) when the
+        backward pass reaches it.  BatchNorm running statistics move once (functional.recompute_mode)."""
+        from contextlib import nullcontext
+
+        from torch.utils.checkpoint import checkpoint
+        from unetb200 import functional as UF
+        return checkpoint(fn, *tensors, use_reentrant=False, preserve_rng_state=False,
+                          context_fn=lambda: (nullcontext(), UF.recompute_mode()))
+
     def use_checkpointing(self):
-        """Called by train.py:299 after a CUDA OOM.  The reference's own implementation raises
-        TypeError (it calls checkpoint() without inputs, unet_model.py:40-50); here it is a logged
-        no-op: activations are already bf16 NHWC and the concat copies are fused away."""
-        logging.warning("unetb200: use_checkpointing() requested; activation re-computation is not implemented")
+        """Called by train.py:299 after a CUDA OOM: from the next forward on every DoubleConv / Down / Up stage is run
+        under activation re-computation (what the reference's unet_model.py:40-50 intends; its own implementation
+        raises TypeError because it calls checkpoint() without inputs).  Trades one extra forward pass of the stage
+        inside backward for ~2/3 of the saved activations; results are unchanged."""
+        logging.info("unetb200: activation re-computation enabled for the encoder / decoder stages")
         self._checkpointing = True
 
 

@@ -291,6 +291,23 @@ def _gconv3x3(x, Cout, y, dtype):
                           Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(y))
 
 
+# Activation re-computation (UNet.use_checkpointing, reference unet_model.py:40-50 / train.py:294-299): while a
+# checkpointed stage is re-run inside the backward pass its BatchNorm layers must normalise with the same batch
+# statistics but leave the running statistics and num_batches_tracked alone (the first run already moved them).
+_RECOMPUTE = [False]
+
+
+class recompute_mode:
+    """Context manager torch.utils.checkpoint enters around the re-run of a stage (context_fn)."""
+
+    def __enter__(self):
+        self.prev, _RECOMPUTE[0] = _RECOMPUTE[0], True
+
+    def __exit__(self, *exc):
+        _RECOMPUTE[0] = self.prev
+        return False
+
+
 def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False):
     """x NHWC -> (y raw conv output, z = relu(bn(y)), pooled or None, coefs[4,C]).
 
@@ -322,7 +339,7 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False):
     if use_batch:
         if bn.momentum is None and bn.running_mean is not None and training:
             raise ValueError("unetb200: BatchNorm2d(momentum=None) (cumulative average) is not supported")
-        update = training and bn.running_mean is not None
+        update = training and bn.running_mean is not None and not _RECOMPUTE[0]
         coefs = ops.bn_finalize(stats, B * H * W, gamma, beta, bn.eps, bn.momentum if update else 0.0,
                                 bn.running_mean if update else None, bn.running_var if update else None, Cout)
         if update and bn.num_batches_tracked is not None:
