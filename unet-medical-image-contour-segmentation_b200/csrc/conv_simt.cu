@@ -716,6 +716,7 @@ int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const 
   static const bool off = getenv("UNETB200_NO_BN_FOLD") != nullptr;
   static const bool wide = getenv("UNETB200_TC3_MAXBN") && atoi(getenv("UNETB200_TC3_MAXBN")) >= 256;
   if (off || d->algo == UNETB200_ALGO_SIMT) return 0;
+  if (first_tc_supported(d, z) && aligned16(wp)) return 1;            // first layer: thread-built im2col kernel
   if (d->N % 128 != 0 && d->N % 64 != 0) return 0;
   if (d->dtype == UNETB200_BF16 && d->N % 256 == 0 && wide) return 0;
   return tc_fprop_supported(d, x, wp, z) && tc3_fprop_supported(d, x, wp, nullptr, z);
@@ -730,6 +731,8 @@ int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, c
   UB_CHECK_ARG(unetb200_gconv_fprop_affine_relu_supported(d, x, wp, z),
                "gconv_fprop_affine_relu: shape not covered by the fused kernel (query _supported first and run "
                "gconv_fprop + bn_relu_apply instead)");
+  if (first_tc_supported(d, z) && aligned16(wp))
+    return first_tc_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
   return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift);
 }
 

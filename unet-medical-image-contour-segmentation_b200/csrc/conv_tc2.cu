@@ -412,7 +412,11 @@ static bool tc2_plan(const unetb200_gconv_t* d, Tc2Plan* pl) {
     for (int t = 0; t < d->ntaps; ++t)
       if (!used[t]) return false;
   }
-  static const int max_bn = getenv("UNETB200_TC2_MAXBN") ? atoi(getenv("UNETB200_TC2_MAXBN")) : 256;   // A/B runs
+  // N block: 256 (one accumulator set: the epilogue does not overlap the next tile) or 128 (two sets).  Measured at
+  // C2 (profiles/r2_bench_c2_c*.json): the ConvTranspose fprop (1 tap, 4 quadrants: epilogue heavy) runs 15 % faster
+  // with 128, its dgrad (4 taps, K = 4 C_out) 14 % slower; UNETB200_TC2_MAXBN overrides both for A/B runs
+  static const int env_bn = getenv("UNETB200_TC2_MAXBN") ? atoi(getenv("UNETB200_TC2_MAXBN")) : 0;
+  const int max_bn = env_bn ? env_bn : (d->nquad == 4 ? 128 : 256);
   // the N block may span quadrants (the epilogue resolves the quadrant per 128-byte channel block), so the block
   // width follows N = nquad * Cq: a 64-channel ConvTranspose reads its input once (N = 256) instead of 4 times
   const int epr_n = 128 / esz;

@@ -76,6 +76,12 @@ int tc4_wgrad_splits(const unetb200_gconv_t* d);
 int tc4_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* gy, float* partials, int splits,
               cudaStream_t stream);
 
+// first layer (C_in <= 4, N = 64, bf16) on the tensor cores: thread-built im2col rows (conv_first_tc.cu)
+int first_tc_supported(const unetb200_gconv_t* d, const void* y);
+long long first_tc_stats_rows(const unetb200_gconv_t* d);
+int first_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
+                   const float* affine, cudaStream_t s);
+
 // first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)
 int first_fprop_supported(const unetb200_gconv_t* d, const void* y);
 long long first_fprop_tiles(const unetb200_gconv_t* d);
