@@ -107,6 +107,17 @@ int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const 
 int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, const void* wp,
                                      const float* scale_shift, void* z, void* stream);
 
+/* The last conv of the network in inference, fused with OutConv (unet_model.py:25,37; unet_parts.py:100-106):
+ * logits[p][k] = sum_c relu(gconv(x, Wp)[p][c] * scale[c] + shift[c]) * oc_w[k][c] + oc_b[k], the activation rounded
+ * to `dtype` before the 1x1 conv like the stand-alone kernels; the 64-channel activation is never written.  The
+ * descriptor's destination fields are ignored (logits are packed [B][Hm][Wm][ncls]).  _supported: bf16, N = 64,
+ * n_classes <= 8, the CTA-pair kernel covers the shape. */
+int unetb200_gconv_fprop_affine_relu_outconv_supported(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                                       int ncls);
+int unetb200_gconv_fprop_affine_relu_outconv(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                             const float* scale_shift, const float* oc_w, const float* oc_b,
+                                             void* logits, int ncls, void* stream);
+
 /* Data gradient of conv3x3 (autograd of unet_parts.py:18) fused with the reduction pass of the BatchNorm2d + ReLU
  * backward of the layer below it (unet_parts.py:16-17; inside a DoubleConv the second conv's input IS that layer's
  * activation z = relu(bn(yprev))): gx = gconv(g, Wp_dgrad) is written as by unetb200_gconv_fprop, and the epilogue

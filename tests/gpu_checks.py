@@ -770,7 +770,7 @@ def check_conv_bnfold():
                     buf.fill_(7.0)
                     dst = ops.channel_slice(buf, 0, Co)
                 with torch.no_grad():
-                    y, z, pooled, _ = UF.conv_bn_relu_fwd(xd, wd, bnd, False, out=dst, want_pool=pool, fold=fold)
+                    y, z, pooled, _, _ = UF.conv_bn_relu_fwd(xd, wd, bnd, False, out=dst, want_pool=pool, fold=fold)
                 if fold:
                     out.append((f"bnfold_taken_{Ci}_{Co}_{H}x{W}_{dt_}", 0.0 if y is None else 1.0, 0))
                     if sliced:

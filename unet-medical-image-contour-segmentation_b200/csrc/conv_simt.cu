@@ -758,6 +758,29 @@ int unetb200_gconv_dgrad_bnbwd(const unetb200_gconv_t* d, const void* g, const v
   return tc3_fprop(d, gd, g, wp, gx, sums, ws, (cudaStream_t)stream, nullptr, yprev, (long long)ld_yprev, coefs);
 }
 
+// last conv of the network in inference: conv3x3 -> BatchNorm(eval) -> ReLU -> OutConv 1x1 + bias in one kernel
+int unetb200_gconv_fprop_affine_relu_outconv_supported(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                                       int ncls) {
+  GconvDev g;
+  if (gconv_validate(d, &g)) return 0;
+  static const bool off = getenv("UNETB200_NO_BN_FOLD") != nullptr || getenv("UNETB200_NO_OUTCONV_FOLD") != nullptr;
+  if (off || d->algo == UNETB200_ALGO_SIMT || !aligned16(x) || !aligned16(wp)) return 0;
+  return tc3_affine_outconv_supported(d, ncls);
+}
+
+int unetb200_gconv_fprop_affine_relu_outconv(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                             const float* scale_shift, const float* oc_w, const float* oc_b,
+                                             void* logits, int ncls, void* stream) {
+  GconvDev g;
+  int rc = gconv_validate(d, &g);
+  if (rc) return rc;
+  UB_CHECK_ARG(x && wp && scale_shift && oc_w && logits, "gconv_fprop_affine_relu_outconv: null pointer");
+  UB_CHECK_ARG(unetb200_gconv_fprop_affine_relu_outconv_supported(d, x, wp, ncls),
+               "gconv_fprop_affine_relu_outconv: shape not covered (query _supported first)");
+  Tc3OutConv oc = {oc_w, oc_b, logits, ncls};
+  return tc3_fprop(d, g, x, wp, logits, nullptr, nullptr, (cudaStream_t)stream, scale_shift, nullptr, 0, nullptr, &oc);
+}
+
 int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_used) {
   GconvDev g;
   int rc = gconv_validate(d, &g);

@@ -168,6 +168,12 @@ struct alignas(64) Tc3Params {
   // previous layer and its BatchNorm coefficients [4][N] = mean, invstd, scale, shift
   CUtensorMap y_map;         // yprev view, box {128 B, 8, 4, 1} (the geometry of o_map)
   const float* bnc;
+  // AFFINE_OUT kernels only: OutConv weights [ncls][64] / bias [ncls] (fp32, rounded to bf16 like the stand-alone
+  // kernel), destination logits [B][Hm][Wm][ncls] (bf16)
+  const float* oc_w;
+  const float* oc_b;
+  void* logits;
+  int ncls;
 };
 
 constexpr uint32_t kA3Stage = 44032;    // 43 KB >= the largest halo box: 34 rows x 10 px x 128 B
@@ -185,10 +191,17 @@ constexpr int kTc3Threads = 64 + 32 * kEpi3Warps;
 // the reduction pass of the BatchNorm backward (unetb200_bn_relu_bwd_reduce: one read of g and of yprev, 4 B per
 // element) disappears.  Partial sums take the same route as the forward statistics (per-warp registers -> workspace
 // -> fp64 reduce, fixed order).
-constexpr int EPI_PLAIN = 0, EPI_AFFINE = 1, EPI_BNBWD = 2;
+//
+// EPI_AFFINE_OUT: the last DoubleConv of the network in inference (N = 64 = all channels of the layer in one lane's
+// row) followed by OutConv (nn.Conv2d(64, n_classes, 1) + bias, unet_parts.py:100-106): each lane holds a pixel's 64
+// activated channels, so it also takes the n_classes dot products (weights as [channel][8 classes] in shared memory:
+// one warp-uniform 16/32-byte load per channel) and stores the logits; the last activation is never written (one
+// 2 B x 64 write and one read of it per pixel, and the OutConv pass, disappear).
+constexpr int EPI_PLAIN = 0, EPI_AFFINE = 1, EPI_BNBWD = 2, EPI_AFFINE_OUT = 3;
 template <typename T, int BLOCK_N, int SA, int SB, int ACC, int CG, int TPS, int EPI = EPI_PLAIN>
 __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_constant__ Tc3Params p) {
-  constexpr bool AFFINE = EPI == EPI_AFFINE, BNBWD = EPI == EPI_BNBWD;
+  constexpr bool OUTC = EPI == EPI_AFFINE_OUT, AFFINE = EPI == EPI_AFFINE || OUTC, BNBWD = EPI == EPI_BNBWD;
+  static_assert(!OUTC || (BLOCK_N == 64 && sizeof(T) == 2), "the OutConv epilogue is the bf16 N = 64 kernel");
   constexpr bool TF32 = sizeof(T) == 4;
   constexpr int EPR = 128 / sizeof(T);
   constexpr uint32_t kBTap = (BLOCK_N / CG) * 128;     // one tap's weight tile (this CTA's half of it)
@@ -229,6 +242,16 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_cg<CG>(tmem_slot, 512);
+  if constexpr (OUTC) {
+    // OutConv weights as [channel][8 classes] + bias[8] at the start of the (otherwise unused) staging area
+    float* ocs = reinterpret_cast<float*>(epi);
+    for (int i = threadIdx.x; i < 64 * 8 + 8; i += blockDim.x) {
+      const int c = i >> 3, k = i & 7;
+      float v = 0.f;
+      if (k < p.ncls) v = c < 64 ? __ldg(p.oc_w + k * 64 + c) : (p.oc_b ? __ldg(p.oc_b + k) : 0.f);
+      ocs[i] = __bfloat162float(__float2bfloat16_rn(v));
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (CG == 2) cluster_sync_all();           // barrier inits + TMEM allocation of both CTAs are in place
@@ -426,6 +449,32 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
               v[4 * k4 + 2] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * k4 + 2]), a.z, c.z), 0.f));
               v[4 * k4 + 3] = __float_as_uint(fmaxf(fmaf(__uint_as_float(v[4 * k4 + 3]), a.w, c.w), 0.f));
             }
+          }
+          if constexpr (OUTC) {
+            const float* ocs = reinterpret_cast<const float*>(epi);
+            float lg[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) lg[k] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+              const float z = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[c])));     // the activation as stored
+              const float4 w0 = *reinterpret_cast<const float4*>(ocs + c * 8);
+              lg[0] = fmaf(z, w0.x, lg[0]); lg[1] = fmaf(z, w0.y, lg[1]);
+              lg[2] = fmaf(z, w0.z, lg[2]); lg[3] = fmaf(z, w0.w, lg[3]);
+              if (p.ncls > 4) {
+                const float4 w1 = *reinterpret_cast<const float4*>(ocs + c * 8 + 4);
+                lg[4] = fmaf(z, w1.x, lg[4]); lg[5] = fmaf(z, w1.y, lg[5]);
+                lg[6] = fmaf(z, w1.z, lg[6]); lg[7] = fmaf(z, w1.w, lg[7]);
+              }
+            }
+            if ((valid_rows >> lane) & 1u) {
+              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.logits) +
+                                   (((long long)b * p.Hm + pi0 + (lane >> 3)) * p.Wm + pj0 + (lane & 7)) * p.ncls;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (k < p.ncls) out[k] = __float2bfloat16_rn(lg[k] + ocs[64 * 8 + k]);
+            }
+            continue;
           }
           const uint32_t dst = buf_s + lane * 128;
 #pragma unroll
@@ -683,9 +732,15 @@ int tc3_bnbwd_supported(const unetb200_gconv_t* d) {
   return pl.CG == 2 && pl.BN != 256;
 }
 
+int tc3_affine_outconv_supported(const unetb200_gconv_t* d, int ncls) {
+  Tc3Plan pl;
+  if (!tc3_plan(d, &pl)) return 0;
+  return d->dtype == UNETB200_BF16 && pl.CG == 2 && pl.BN == 64 && d->N == 64 && ncls >= 1 && ncls <= 8;
+}
+
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
               float* stats_ws, cudaStream_t stream, const float* affine, const void* yprev, long long ld_yprev,
-              const float* bnc) {
+              const float* bnc, const Tc3OutConv* oc) {
   Tc3Plan pl;
   if (yprev && (affine || !stats || !stats_ws || !bnc || !aligned16(yprev) ||
                 (ld_yprev * (d->dtype == UNETB200_BF16 ? 2 : 4)) % 16)) {
@@ -731,6 +786,14 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
     rc = encode_act_box(&P.y_map, d->dtype, yprev, d->N, d->Wm, d->Hm, d->B, ld_yprev, (long long)d->Wm * ld_yprev,
                         (long long)d->Hm * d->Wm * ld_yprev, 8, 4, false);
     if (rc) return rc;
+  }
+  if (oc) {
+    if (!affine || !tc3_affine_outconv_supported(d, oc->ncls) || !oc->w || !oc->logits) {
+      set_error("tc3_fprop: the OutConv epilogue needs the folded BatchNorm coefficients, bf16, N = 64 and n_classes <= 8");
+      return UNETB200_E_INVALID;
+    }
+    P.oc_w = oc->w; P.oc_b = oc->b; P.logits = oc->logits; P.ncls = oc->ncls;
+    return tc3_launch<__nv_bfloat16, 64, 3, 3, 2, 2, 3, EPI_AFFINE_OUT>(P, pl.grid, stream);
   }
   if (affine) {
     // BatchNorm-folded inference epilogue: the pair kernel with N block 128 / 64 (the shapes of the path)

@@ -59,9 +59,16 @@ int tc2_wgrad(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
 // CTA-pair tcgen05 engine for the 3x3 convolutions, third generation (conv_tc3.cu)
 int tc3_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, const void* y);
 long long tc3_stats_workspace(const unetb200_gconv_t* d);
+struct Tc3OutConv {            // OutConv fused into the inference epilogue of the last conv (EPI_AFFINE_OUT)
+  const float* w;              // [ncls][64]
+  const float* b;              // [ncls] or null
+  void* logits;                // [B][Hm][Wm][ncls], storage dtype
+  int ncls;
+};
+int tc3_affine_outconv_supported(const unetb200_gconv_t* d, int ncls);
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
               float* stats_ws, cudaStream_t stream, const float* affine = nullptr, const void* yprev = nullptr,
-              long long ld_yprev = 0, const float* bnc = nullptr);
+              long long ld_yprev = 0, const float* bnc = nullptr, const Tc3OutConv* oc = nullptr);
 int tc3_bnbwd_supported(const unetb200_gconv_t* d);
 
 int tc3_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);

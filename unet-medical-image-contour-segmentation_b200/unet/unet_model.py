@@ -72,8 +72,13 @@ class _UNetBase(nn.Module):
         u2 = ck(lambda a, b_: self.up2.run(a, b_, cat=cats[2]), y, x3c)
         u2c, x2c, x1c = cut(u2), cut(x2), cut(x1)
         y = ck(lambda a, b_: self.up3.run(a, b_, cat=cats[1]), u2c, x2c)
-        y = ck(lambda a, b_: self.up4.run(a, b_, cat=cats[0]), y, x1c)
-        out = self.outc.run(y)
+        if not torch.is_grad_enabled() and not self.training:
+            # inference: OutConv rides in the epilogue of the last conv when the fused kernel covers the shape
+            y, fused = self.up4.run(y, x1c, cat=cats[0], outconv=self.outc)
+            out = y if fused else self.outc.run(y)
+        else:
+            y = ck(lambda a, b_: self.up4.run(a, b_, cat=cats[0]), y, x1c)
+            out = self.outc.run(y)
         if taps is not None:
             # cut points of a segmented backward pass (unetb200.ddp.SegmentedStep): name -> (tensor, its cut alias)
             taps.update(x1=(x1, x1c), x2=(x2, x2c), x3=(x3, x3c), x4=(x4, x4c), x5=(x5, x5c), p3=(p3, p3c),

@@ -49,14 +49,21 @@ class DoubleConv(nn.Module):
                    nn.ReLU(inplace=True)]
         self.double_conv = nn.Sequential(*holders)
 
-    def run(self, x, out=None, want_pool=False):
+    def run(self, x, out=None, want_pool=False, outconv=None):
         """x: NHWC compute-dtype tensor.  Returns z or (z, maxpool2(z)); ``out`` = optional
-        caller-owned destination (a channel slice of a concat buffer)."""
+        caller-owned destination (a channel slice of a concat buffer).  ``outconv`` = the OutConv module that follows
+        directly (inference only): when the fused kernel covers the shape the return value is ``(logits, True)``,
+        else ``(z, False)``."""
         c1, bn1, _, c2, bn2, _ = self.double_conv
         if x.shape[1] != c1.in_channels:
             raise ValueError(f"DoubleConv expects {c1.in_channels} input channels, got {x.shape[1]}")
         cfg = _Cfg(bn1=bn1, bn2=bn2, training=self.training, out=out, want_pool=want_pool,
                    save=_needs_graph(self, x))
+        if outconv is not None:
+            if not cfg.save and not _needs_graph(outconv, x):
+                cfg.outconv = (outconv.conv.weight.detach(), outconv.conv.bias.detach() if outconv.conv.bias is not None else None)
+            res = UF.DoubleConvFn.apply(x, c1.weight, bn1.weight, bn1.bias, c2.weight, bn2.weight, bn2.bias, cfg)
+            return res, bool(getattr(cfg, "fused_outconv", False))
         return UF.DoubleConvFn.apply(x, c1.weight, bn1.weight, bn1.bias, c2.weight, bn2.weight, bn2.bias, cfg)
 
     def forward(self, x):
@@ -120,7 +127,7 @@ class Up(nn.Module):
         self.use_attention = use_attention
         self.attention = SpatialAttention() if use_attention else nn.Identity()      # unet_parts.py:76-77
 
-    def run(self, x1, x2, cat=None, out=None, want_pool=False):
+    def run(self, x1, x2, cat=None, out=None, want_pool=False, outconv=None):
         """x2: the skip tensor.  With attention it is the UN-gated encoder output (kept for the gate's backward); the
         gated copy is written into the skip half of ``cat`` when the caller pre-allocated the concat buffer."""
         if self.use_attention:                         # unet_parts.py:91-92
@@ -131,6 +138,8 @@ class Up(nn.Module):
             merged = UF.UpCatBilinearFn.apply(x1, x2, cfg)
         else:
             merged = UF.UpCatConvTFn.apply(x1, x2, self.up.weight, self.up.bias, cfg)
+        if outconv is not None:
+            return self.conv.run(merged, out=out, want_pool=want_pool, outconv=outconv)
         return self.conv.run(merged, out=out, want_pool=want_pool)
 
     def forward(self, x1, x2):

@@ -308,8 +308,36 @@ class recompute_mode:
         return False
 
 
-def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False):
+# eval-mode BatchNorm coefficients (scale / shift from the running statistics), cached per module while the four
+# tensors they come from are unchanged: an inference loop (evaluate.py:43-143, predict.py:22-27) then launches none
+# of the 18 tiny coefficient kernels per forward
+_EVAL_COEFS = {}    # id(bn) -> (weakref(bn), key, coefs)
+
+
+def _eval_coefs(bn, Cout):
+    import weakref
+    parts = (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    key = tuple((t.data_ptr(), t._version, t.dtype, t.device) if t is not None else None for t in parts) + (bn.eps,)
+    ent = _EVAL_COEFS.get(id(bn))
+    if ent is not None and ent[0]() is bn and ent[1] == key and not torch.cuda.is_current_stream_capturing():
+        return ent[2]
+    gamma = _f32c(bn.weight) if bn.weight is not None else None
+    beta = _f32c(bn.bias) if bn.bias is not None else None
+    coefs = ops.bn_eval_coeffs(gamma, beta, bn.running_mean, bn.running_var, bn.eps, Cout)
+    if len(_EVAL_COEFS) > 512:
+        for k in [k for k, e in _EVAL_COEFS.items() if e[0]() is None]:
+            del _EVAL_COEFS[k]
+    if not torch.cuda.is_current_stream_capturing():
+        _EVAL_COEFS[id(bn)] = (weakref.ref(bn), key, coefs)
+    return coefs
+
+
+def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False, outconv=None):
     """x NHWC -> (y raw conv output, z = relu(bn(y)), pooled or None, coefs[4,C]).
+
+    outconv = (weight [K, C, 1, 1], bias or None) with fold=True: when the fused kernel covers the shape, z is the
+    LOGITS of OutConv applied to the activation ([B, K, H, W] view of a packed NHWC tensor) and the 5th return value
+    is True; the activation itself is never written.
 
     fold=True (no backward will follow) with running statistics: BatchNorm + ReLU are folded into the conv epilogue
     (one write of z, no y) when the fused tcgen05 kernel covers the shape."""
@@ -318,18 +346,27 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False):
     cd, dev = x.dtype, x.device
     wp = pack3x3_fprop(w, cd)
     if fold and not (training or bn.running_mean is None) and Cout % 2 == 0:
+        if outconv is not None and out is None and not want_pool:
+            ow, ob = outconv
+            K = ow.shape[0]
+            d = ops.make_gconv(ops._DT[cd], conv_algo(cd), B, H, W, Cin, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(x),
+                               Cout, 1, 1, (0, 0), H, W, Cout)
+            if tuple(ow.shape[1:]) == (Cout, 1, 1) and ops.gconv_fprop_affine_relu_outconv_supported(d, x, wp, K):
+                coefs = _eval_coefs(bn, Cout)
+                logits = torch.empty((B, H, W, K), dtype=cd, device=dev)
+                ops.gconv_fprop_affine_relu_outconv(d, x, wp, coefs, _f32c(ow).view(K, Cout),
+                                                    _f32c(ob) if ob is not None else None, logits)
+                return None, logits.permute(0, 3, 1, 2), None, coefs, True
         z = out if out is not None else ops.empty_nhwc(B, Cout, H, W, cd, dev)
         d = _gconv3x3(x, Cout, z, cd)
         if ops.gconv_fprop_affine_relu_supported(d, x, wp, z):
-            gamma = _f32c(bn.weight) if bn.weight is not None else None
-            beta = _f32c(bn.bias) if bn.bias is not None else None
-            coefs = ops.bn_eval_coeffs(gamma, beta, bn.running_mean, bn.running_var, bn.eps, Cout)
+            coefs = _eval_coefs(bn, Cout)
             ops.gconv_fprop_affine_relu(d, x, wp, coefs, z)
             pooled = None
             if want_pool:
                 pooled = ops.empty_nhwc(B, Cout, H // 2, W // 2, cd, dev)
                 ops.maxpool2_fwd(z, pooled)
-            return None, z, pooled, coefs
+            return None, z, pooled, coefs, False
     y = ops.empty_nhwc(B, Cout, H, W, cd, dev)
     use_batch = training or bn.running_mean is None
     stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if use_batch else None
@@ -342,6 +379,10 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False):
         update = training and bn.running_mean is not None and not _RECOMPUTE[0]
         coefs = ops.bn_finalize(stats, B * H * W, gamma, beta, bn.eps, bn.momentum if update else 0.0,
                                 bn.running_mean if update else None, bn.running_var if update else None, Cout)
+        if update:
+            # the kernel moved the running statistics through raw pointers: tell PyTorch (autograd's saved-tensor
+            # check, the eval-coefficient cache above)
+            torch._C._increment_version([bn.running_mean, bn.running_var])
         if update and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
     else:
@@ -349,7 +390,7 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False):
     z = out if out is not None else ops.empty_nhwc(B, Cout, H, W, cd, dev)
     pooled = ops.empty_nhwc(B, Cout, H // 2, W // 2, cd, dev) if want_pool else None
     ops.bn_relu_apply(y, coefs, z, pooled)
-    return y, z, pooled, coefs
+    return y, z, pooled, coefs, False
 
 
 def _grad_kept_as_is(param, dW):
@@ -481,9 +522,11 @@ class DoubleConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w1, g1, b1, w2, g2, b2, cfg):
         fold = not cfg.save
-        y1, z1, _, c1 = conv_bn_relu_fwd(x, w1, cfg.bn1, cfg.training, fold=fold)
-        y2, z2, pooled, c2 = conv_bn_relu_fwd(z1, w2, cfg.bn2, cfg.training, out=cfg.out, want_pool=cfg.want_pool,
-                                              fold=fold)
+        y1, z1, _, c1, _ = conv_bn_relu_fwd(x, w1, cfg.bn1, cfg.training, fold=fold)
+        y2, z2, pooled, c2, fused_out = conv_bn_relu_fwd(z1, w2, cfg.bn2, cfg.training, out=cfg.out,
+                                                         want_pool=cfg.want_pool, fold=fold,
+                                                         outconv=getattr(cfg, "outconv", None) if fold else None)
+        cfg.fused_outconv = fused_out          # tells the caller whether z2 already holds OutConv's logits
         ctx.batch_stats = (cfg.training or cfg.bn1.running_mean is None, cfg.training or cfg.bn2.running_mean is None)
         ctx.has_pool = pooled is not None
         ctx.colsum = bool(cfg.save) and _WANT_COLSUM.pop(x.data_ptr(), None) == tuple(x.shape)

@@ -407,6 +407,22 @@ def gconv_fprop_affine_relu(d, x, wp, coefs, z):
         _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + tag
 
 
+def gconv_fprop_affine_relu_outconv_supported(d, x, wp, ncls):
+    return (not x3_active(d)) and bool(lib().unetb200_gconv_fprop_affine_relu_outconv_supported(C.byref(d), _p(x), _p(wp), ncls))
+
+
+def gconv_fprop_affine_relu_outconv(d, x, wp, coefs, oc_w, oc_b, logits):
+    """logits = OutConv(relu(conv(x, wp) * scale + shift)) in ONE kernel (inference; the activation is never written)."""
+    flops, tag = gconv_flops(d), _shape_tag(d)
+    ncls = oc_w.shape[0]
+    es = 2 if d.dtype == BF16 else 4
+    _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu_outconv, C.byref(d), _p(x), _p(wp), _p(coefs[2]),
+         _p(oc_w), _p(oc_b), _p(logits), ncls, _stream(), flops=flops,
+         nbytes=float(es) * d.B * d.Hin * d.Win * d.Cin + float(es) * d.B * d.Hm * d.Wm * ncls)
+    if _PROFILE is not None:
+        _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + tag
+
+
 def gconv_dgrad_bnbwd_supported(d, g, wp, gx):
     return (not x3_active(d)) and bool(lib().unetb200_gconv_dgrad_bnbwd_supported(C.byref(d), _p(g), _p(wp), _p(gx)))
 
