@@ -148,8 +148,22 @@ def test_evaluate_host_logic(monkeypatch):
     assert eval_tail.evaluate(Net(3), [], dev, amp=False) == (0, 0, 10)
     with pytest.raises(ValueError):
         eval_tail.evaluate(Net(3), [], dev, amp=False, postprocess=True)
-    with pytest.raises(NotImplementedError):
-        eval_tail.evaluate(Net(3), [], dev, amp=False, epoch_pred_dir="/tmp/x")
+    # epoch_pred_dir: the PNGs of evaluate.py:92-107 / :146-166 (0 / 128 / 255 for classes 0 / 1 / 2; 0 / 255 binary)
+    import tempfile
+    from PIL import Image
+    for ncls in (3, 1):
+        torch.manual_seed(ncls)
+        net = Net(ncls)
+        with tempfile.TemporaryDirectory() as td:
+            eval_tail.evaluate(net, batches, dev, amp=False, epoch_pred_dir=td, postprocess=True, postprocess_fn=erode)
+            names = sorted(os.listdir(td))
+            assert names == ["postprocessed"] + [f"pred_batch{b}_sample{i}.png" for b in range(3) for i in range(2)]
+            assert sorted(os.listdir(os.path.join(td, "postprocessed"))) == names[1:]
+            with torch.inference_mode():
+                lg = net.eval()(batches[1]["image"])
+            want = (torch.sigmoid(lg[1, 0]) > 0.5).numpy().astype(np.uint8) * 255 if ncls == 1 else \
+                np.array([0, 128, 255], dtype=np.uint8)[lg[1].argmax(0).numpy()]
+            assert np.array_equal(np.asarray(Image.open(os.path.join(td, "pred_batch1_sample1.png"))), want)
 
 
 def test_oracle_properties():

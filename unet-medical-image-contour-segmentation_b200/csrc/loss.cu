@@ -35,18 +35,18 @@ __global__ void ce_dice_fwd_kernel(const T* __restrict__ logits, const int64_t* 
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c)
       if (c < C) { z[c] = Elem<T>::ld(logits + p * C + c); mx = fmaxf(mx, z[c]); }
-    float den = 0.f;
+    const int64_t t = target[p];
+    float den = 0.f, zt = 0.f;                          // zt = z_t - max: the exact log-sum-exp form of the cross entropy
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c)
-      if (c < C) { z[c] = expf(z[c] - mx); den += z[c]; }
+      if (c < C) { if (c == t) zt = z[c] - mx; z[c] = expf(z[c] - mx); den += z[c]; }
     const float inv = 1.f / den;
-    const int64_t t = target[p];
     float pt = 0.f, ps = 0.f;
 #pragma unroll
     for (int c = 0; c < kMaxClasses; ++c)
       if (c < C) { float pc = z[c] * inv; ps += pc; if (c == t) pt = pc; }
     if (t >= 0 && t < C) {
-      ce -= logf(fmaxf(pt, 1e-38f));
+      ce += logf(den) - zt;                             // (-log(max(p_t, 1e-38)) saturated near 87.5 for huge margins)
       inter += pt;
       valid += 1.f;
     }

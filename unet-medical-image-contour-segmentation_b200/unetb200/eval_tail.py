@@ -105,18 +105,23 @@ def evaluate(net, dataloader, device, amp, epoch_pred_dir=None, postprocess=Fals
     The OpenCV post-processing (utils/post_process.py) is outside the hot path: pass the
     reference's ``postprocess_mask`` as ``postprocess_fn`` to keep that leg (it then runs on the host on the uint8
     label map this function already produced, evaluate.py:124-139); with ``postprocess=False`` the post-processed
-    score equals the original one (evaluate.py:169-170).  Saving PNGs (``epoch_pred_dir``) is host IO and is not
-    done here."""
-    if epoch_pred_dir is not None:
-        raise NotImplementedError("unetb200.evaluate: saving prediction PNGs is host-side IO; use the reference's "
-                                  "evaluate.py for that (it runs unchanged on this UNet)")
+    score equals the original one (evaluate.py:169-170).  NOTE the default here is ``postprocess=False`` (the
+    reference's is True): the post-processing itself is not part of this package.  ``epoch_pred_dir`` saves the
+    prediction PNGs like evaluate.py:92-107,146-166 (host IO on the uint8 label maps: one device->host copy per batch)."""
     if postprocess and postprocess_fn is None:
         raise ValueError("unetb200.evaluate: postprocess=True needs postprocess_fn (utils.post_process.postprocess_mask)")
     net.eval()
     num_val_batches = len(dataloader)
     scores, scores_post = [], []
+    post_dir = None
+    if epoch_pred_dir is not None:
+        import os
+        os.makedirs(epoch_pred_dir, exist_ok=True)
+        if postprocess:                                   # evaluate.py:38-40
+            post_dir = os.path.join(epoch_pred_dir, "postprocessed")
+            os.makedirs(post_dir, exist_ok=True)
     with torch.autocast(device.type, enabled=amp):
-        for batch in dataloader:
+        for batch_index, batch in enumerate(dataloader):
             image, mask_true = batch['image'], batch['mask']
             image = image.to(device=device, dtype=torch.float32, memory_format=torch.channels_last)
             mask_true = mask_true.to(device=device)
@@ -128,10 +133,14 @@ def evaluate(net, dataloader, device, amp, epoch_pred_dir=None, postprocess=Fals
                 pred, dice, _ = argmax_class_dice(mask_pred, mask_true, c=target_class, index_dtype=torch.uint8)
                 scale = 1
             scores.append(dice)
+            host = pred.cpu().numpy() if (postprocess or epoch_pred_dir is not None) else None
+            if epoch_pred_dir is not None:
+                _save_pngs(host, epoch_pred_dir, batch_index, net.n_classes)
             if postprocess:
                 import numpy as np
-                host = pred.cpu().numpy()
                 post = np.stack([postprocess_fn(m * scale) // scale for m in host]).astype(np.float32)
+                if post_dir is not None:
+                    _save_pngs(post.astype(np.uint8), post_dir, batch_index, net.n_classes)
                 post = torch.from_numpy(post).to(device)
                 if net.n_classes == 1:
                     true = torch.div(mask_true.float(), 2, rounding_mode="floor")
@@ -150,6 +159,21 @@ def evaluate(net, dataloader, device, amp, epoch_pred_dir=None, postprocess=Fals
     total, total_post, mn = torch.stack([s.sum(), sp.sum(), per_batch_min]).tolist()      # the only host read
     n = max(num_val_batches, 1)
     return total / n, total_post / n, min(mn, 10)
+
+
+def _save_pngs(labels, directory, batch_index, n_classes):
+    """evaluate.py:92-107 (binary: 0 / 255) and :146-166 (classes 0 / 1 / 2 -> 0 / 128 / 255): pred_batch{b}_sample{i}.png"""
+    import os
+
+    import numpy as np
+    from PIL import Image
+    lut = np.zeros(256, dtype=np.uint8)
+    if n_classes == 1:
+        lut[1] = 255
+    else:
+        lut[1], lut[2] = 128, 255
+    for i, m in enumerate(labels):
+        Image.fromarray(lut[np.asarray(m, dtype=np.uint8)]).save(os.path.join(directory, f"pred_batch{batch_index}_sample{i}.png"))
 
 
 def predict_img(model, img, device, out_size=None, index_dtype=torch.int64):
