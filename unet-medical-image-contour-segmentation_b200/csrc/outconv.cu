@@ -83,7 +83,7 @@ __global__ void outconv_fwd_scalar_kernel(const T* __restrict__ x, int64_t ld_x,
 // holds the rounded gx in registers, so it also makes the reduction pass of that BatchNorm + ReLU backward
 // (sum gx*mask, sum gx*mask*xhat per channel; unetb200_bn_relu_bwd_reduce) with one extra read of yprev.
 template <typename T, int K, bool BNB>
-__global__ void __launch_bounds__(256) outconv_bwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, (K <= 2 && !BNB) ? 3 : 1) outconv_bwd_vec_kernel(const T* __restrict__ x, int64_t ld_x, const float* __restrict__ w,
                                                               const T* __restrict__ g, T* __restrict__ gx, int64_t ld_gx,
                                                               float* __restrict__ partial, int64_t npix, int C, int LPP,
                                                               const T* __restrict__ yprev, int64_t ld_y,
@@ -323,6 +323,9 @@ static int outconv_bwd_impl(const void* x, int64_t ld_x, const float* w, const v
   int blocks = outconv_blocks(npix);
   if (blocks > 148 * 4 * 2) blocks = 148 * 4 * 2;
   const bool bnb = yprev != nullptr;
+  // n_classes <= 2 (the path: 2 classes) is compiled for three resident blocks per SM (80 registers): one full wave
+  static const bool wave3 = getenv("UNETB200_OUTCONV_WAVE4") == nullptr;
+  if (wave3 && ncls <= 2 && !bnb && blocks > sm_count() * 3) blocks = sm_count() * 3;
   const int KC = ncls * C;
   const int extra = bnb ? 2 * C : 0;
   size_t smem_v = sizeof(float) * (2 * (size_t)KC + ncls + extra + 2048);
