@@ -205,6 +205,15 @@ int unetb200_maxpool2_fwd(const void* x, int64_t ld_x, void* p, int64_t ld_p, in
 int unetb200_maxpool2_bwd(const void* x, int64_t ld_x, const void* gp, int64_t ld_gp, void* gx,
                           int64_t ld_gx, int accumulate, int dtype, int B, int H, int W, int C,
                           void* stream);
+/* The accumulating form of unetb200_maxpool2_bwd (gx += scatter of gp) fused with the reduction pass of the
+ * BatchNorm2d + ReLU backward of the layer that produced x = relu(bn(y)): an encoder stage's output feeds the pool
+ * and the skip connection (unet_model.py:28-36), its gradient is final only after this call and the BatchNorm
+ * backward reads it next, so  sums[0][c] += sum gx*mask, sums[1][c] += sum gx*mask*xhat  (gx as stored; `sums`
+ * zeroed by the caller; see unetb200_bn_relu_bwd_reduce) are made here with one extra read of y. */
+int unetb200_maxpool2_bwd_bnreduce(const void* x, int64_t ld_x, const void* gp, int64_t ld_gp, void* gx,
+                                   int64_t ld_gx, const void* y, int64_t ld_y, const float* scale,
+                                   const float* shift, const float* mean, const float* invstd, double* sums,
+                                   int dtype, int B, int H, int W, int C, void* stream);
 /* g = gz * (y*scale+shift > 0);  sums[0][c] += sum g,  sums[1][c] += sum g*xhat,
  * xhat = (y-mean)*invstd.  `sums` must be zeroed by the caller. */
 int unetb200_bn_relu_bwd_reduce(const void* gz, int64_t ld_gz, const void* y, int64_t ld_y,

@@ -901,8 +901,40 @@ def _outconv_bnbwd_case(B, C, K, H, W, dt_, seed):
     return res
 
 
+def _pool_bnreduce_case(B, C, H, W, dt_, seed):
+    """Accumulating max-pool backward fused with the BatchNorm-backward reduction: gx bit-equal to the plain kernel,
+    sums equal to unetb200_bn_relu_bwd_reduce on that gx."""
+    res = []
+    g = gen(seed)
+    y = rq(torch.randn(B, C, H, W, generator=g), dt_)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    yd = dev_nhwc(y, dt_)
+    stats = torch.stack([y.double().sum((0, 2, 3)), (y.double() ** 2).sum((0, 2, 3))]).reshape(-1).to(DEV)
+    coefs = ops.bn_finalize(stats, B * H * W, gamma.to(DEV), beta.to(DEV), 1e-5, 0.0, None, None, C)
+    x = ops.empty_nhwc(B, C, H, W, dt_, DEV)
+    ops.bn_relu_apply(yd, coefs, x, None)
+    gp = dev_nhwc(rq(torch.randn(B, C, H // 2, W // 2, generator=g), dt_), dt_)
+    g0 = rq(torch.randn(B, C, H, W, generator=g), dt_)
+    ga, gb = in_slice(g0, dt_, 64), in_slice(g0, dt_, 64)            # the skip half of a wider concat-gradient buffer
+    ops.maxpool2_bwd(x, gp, ga, accumulate=True)
+    ref = torch.zeros((2, C), dtype=torch.float64, device=DEV)
+    _lib.check(ops.lib().unetb200_bn_relu_bwd_reduce(ops._p(ga), ops.nhwc_ld(ga), ops._p(yd), ops.nhwc_ld(yd), ops._p(coefs[2]),
+                                                     ops._p(coefs[3]), ops._p(coefs[0]), ops._p(coefs[1]), ops._p(ref),
+                                                     ops.dt(yd), B, H, W, C, ops._stream()), "bn_relu_bwd_reduce")
+    sums = ops.maxpool2_bwd_bnreduce(x, gp, gb, yd, coefs)
+    tag = f"{C}_{B}x{H}x{W}_{str(dt_)[6:]}"
+    res.append((f"pool_bnreduce_gx_bitequal_{tag}", (host(gb) - host(ga)).abs().max().item(), 0.0))
+    scale = ref.abs().max().item() + 1e-30
+    res.append((f"pool_bnreduce_sums_{tag}", (sums - ref).abs().max().item() / scale, 1e-5))
+    return res
+
+
 def check_dgrad_bnbwd():
     out = []
+    out += _pool_bnreduce_case(2, 64, 16, 24, BF, 91)
+    out += _pool_bnreduce_case(1, 128, 9, 7, BF, 92)               # odd sizes: the last row / column has no window
+    out += _pool_bnreduce_case(2, 16, 10, 12, FP, 93)
+    out += _pool_bnreduce_case(1, 6, 8, 8, FP, 94)                  # scalar path
     out += _outconv_bnbwd_case(2, 64, 2, 24, 20, BF, 81)
     out += _outconv_bnbwd_case(1, 64, 4, 33, 17, BF, 82)
     out += _outconv_bnbwd_case(2, 16, 3, 9, 11, FP, 83)

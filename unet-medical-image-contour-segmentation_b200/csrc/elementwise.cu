@@ -398,6 +398,111 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double i
   coef[C + c] = training ? (float)(sgx * inv_count) : 0.f;
 }
 
+
+// Max-pool backward accumulated into the skip gradient (as above, ACC) + the reduction pass of the BatchNorm/ReLU
+// backward of the layer that produced x = relu(bn(y)): an encoder stage's output feeds the pool AND the skip
+// connection, its gradient is final only after this kernel, and the BatchNorm backward reads it right away -- so the
+// sums ride here (one extra read of y instead of a pass over gx and y).  Channel-stationary: a thread owns V channels
+// (coefficients and sums in registers) and walks 2x2 windows; block reduction like bn_relu_bwd_reduce_kernel.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_bnreduce_kernel(const T* __restrict__ x, int64_t ld_x, const T* __restrict__ gp, int64_t ld_gp,
+                             T* __restrict__ gx, int64_t ld_gx, const T* __restrict__ y, int64_t ld_y,
+                             const float* __restrict__ scale, const float* __restrict__ shift,
+                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                             double* __restrict__ sums, int B, int H, int W, int C, int CV, int CVB) {
+  constexpr int RED = (V == 8) ? 512 : 256;
+  __shared__ float red[2][RED];
+  const CsThread t = cs_thread(CV, CVB);
+  const int cvl = threadIdx.x % CVB;
+  float s0[V], s1[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) s0[k] = s1[k] = 0.f;
+  if (t.active) {
+    const int c = t.cv * V;
+    float sc[V], sh[V], mu[V], is[V];
+    ldf<V>(scale + c, sc);
+    ldf<V>(shift + c, sh);
+    ldf<V>(mean + c, mu);
+    ldf<V>(invstd + c, is);
+    const int Hc = (H + 1) >> 1, Wc = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+    const int64_t nwin = (int64_t)B * Hc * Wc;
+    const int64_t stride = (int64_t)gridDim.x * t.lanes;
+    for (int64_t wdx = (int64_t)blockIdx.x * t.lanes + t.lane; wdx < nwin; wdx += stride) {
+      const int j = (int)(wdx % Wc);
+      int64_t r = wdx / Wc;
+      const int i = (int)(r % Hc);
+      const int n = (int)(r / Hc);
+      const bool full = (i < Hp && j < Wp);
+      float g[V], m[V];
+      int arg[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) { m[k] = -INFINITY; arg[k] = 0; g[k] = 0.f; }
+      if (full) {
+        ldv<T, V>(gp + (((int64_t)n * Hp + i) * Wp + j) * ld_gp + c, g);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[V];
+          ldv<T, V>(x + (((int64_t)n * H + 2 * i + (q >> 1)) * W + 2 * j + (q & 1)) * ld_x + c, v);
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            if (v[k] > m[k] || v[k] != v[k]) { m[k] = v[k]; arg[k] = q; }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int h = 2 * i + (q >> 1), w = 2 * j + (q & 1);
+        if (h < H && w < W) {
+          const int64_t pix = ((int64_t)n * H + h) * W + w;
+          float o[V], yv[V];
+          ldv<T, V>(gx + pix * ld_gx + c, o);
+          ldv<T, V>(y + pix * ld_y + c, yv);
+#pragma unroll
+          for (int k = 0; k < V; ++k) o[k] += (full && arg[k] == q) ? g[k] : 0.f;
+          stv<T, V>(gx + pix * ld_gx + c, o);
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            const float gg = (fmaf(yv[k], sc[k], sh[k]) > 0.f) ? Elem<T>::round(o[k]) : 0.f;      // the gradient as stored
+            s0[k] += gg;
+            s1[k] += gg * ((yv[k] - mu[k]) * is[k]);
+          }
+        }
+      }
+    }
+  }
+  const int lanes = t.lanes, lane = t.lane;
+  const int row = CVB * V;
+  const int chunk = RED / row;
+  float fa[2] = {0.f, 0.f}, fb[2] = {0.f, 0.f};
+  for (int base = 0; base < lanes; base += chunk) {
+    __syncthreads();
+    if (t.active && lane >= base && lane < base + chunk) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        red[0][(lane - base) * row + cvl * V + k] = s0[k];
+        red[1][(lane - base) * row + cvl * V + k] = s1[k];
+      }
+    }
+    __syncthreads();
+    const int nl = lanes - base < chunk ? lanes - base : chunk;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = threadIdx.x + u * blockDim.x;
+      if (e < row)
+        for (int l = 0; l < nl; ++l) { fa[u] += red[0][l * row + e]; fb[u] += red[1][l * row + e]; }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int e = threadIdx.x + u * blockDim.x;
+    const int ch = blockIdx.y * CVB * V + e;
+    if (e < row && ch < C) {
+      atomicAdd(sums + ch, (double)fa[u]);
+      atomicAdd(sums + C + ch, (double)fb[u]);
+    }
+  }
+}
+
 // gy = sc*g*mask + A*(y - mu) + B0 with A = -sc*c1*invstd, B0 = -sc*c0 (per channel, in registers)
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
@@ -823,6 +928,32 @@ int unetb200_maxpool2_bwd(const void* x, int64_t ld_x, const void* gp, int64_t l
   }
 #undef GO
   UB_LAUNCH_CHECK("maxpool2_bwd");
+  return 0;
+}
+
+int unetb200_maxpool2_bwd_bnreduce(const void* x, int64_t ld_x, const void* gp, int64_t ld_gp, void* gx, int64_t ld_gx,
+                                   const void* y, int64_t ld_y, const float* scale, const float* shift, const float* mean,
+                                   const float* invstd, double* sums, int dtype, int B, int H, int W, int C, void* stream) {
+  UB_DTYPE_OK(dtype);
+  UB_CHECK_ARG(B > 0 && H >= 2 && W >= 2 && C > 0 && x && gp && gx && y && scale && shift && mean && invstd && sums,
+               "maxpool2_bwd_bnreduce: bad args");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t nwin = (int64_t)B * ((H + 1) / 2) * ((W + 1) / 2);
+#define GO(T, V)                                                                                              \
+  do {                                                                                                        \
+    const int CV = (C + V - 1) / V;                                                                           \
+    CsGeom g_ = cs_geom(CV, nwin, 2, V == 8 ? 64 : 256);                                                      \
+    maxpool2_bwd_bnreduce_kernel<T, V><<<dim3(g_.gx, g_.gy), 256, 0, s>>>(                                    \
+        (const T*)x, ld_x, (const T*)gp, ld_gp, (T*)gx, ld_gx, (const T*)y, ld_y, scale, shift, mean, invstd, \
+        sums, B, H, W, C, CV, g_.CVB);                                                                        \
+  } while (0)
+  if (dtype == UNETB200_BF16) {
+    if (vec_ok<bf16>(C, {ld_x, ld_gp, ld_gx, ld_y}, {x, gp, gx, y})) GO(bf16, 8); else GO(bf16, 1);
+  } else {
+    if (vec_ok<float>(C, {ld_x, ld_gp, ld_gx, ld_y}, {x, gp, gx, y})) GO(float, 8); else GO(float, 1);
+  }
+#undef GO
+  UB_LAUNCH_CHECK("maxpool2_bwd_bnreduce");
   return 0;
 }
 

@@ -86,6 +86,8 @@ PROTOTYPES = {
     "unetb200_sa_backward_workspace": (c_i64, [C.c_int, C.c_int, C.c_int]),
     "unetb200_sa_backward": (C.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, c_p]),
+    "unetb200_maxpool2_bwd_bnreduce": (C.c_int, [c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p,
+                                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),
     "unetb200_f64_to_f32": (C.c_int, [c_p, c_p, C.c_int, c_p]),
     "unetb200_channel_sum": (C.c_int, [c_p, C.c_int, c_i64, c_i64, C.c_int, c_p, c_p, c_p]),
     "unetb200_add_channels": (C.c_int, [c_p, c_i64, c_p, c_i64, C.c_int, c_i64, C.c_int, c_p]),

@@ -555,8 +555,12 @@ class DoubleConvFn(torch.autograd.Function):
                 ops.maxpool2_bwd(z2, gp, gz, accumulate=False)
             elif gz is gz2 and ops.nhwc_ld(gz) > gz.shape[1] and not os.environ.get("UNETB200_NO_INPLACE_SKIP"):
                 # gz2 is the skip half of a concat-gradient buffer produced by our own dgrad: the
-                # pool gradient is accumulated into it in place (skip-gradient sum fused away)
-                ops.maxpool2_bwd(z2, gp, gz, accumulate=True)
+                # pool gradient is accumulated into it in place (skip-gradient sum fused away), and the same pass
+                # makes the reduction of bn2's backward (gz is complete exactly here)
+                if ops.POOL_BNBWD_FUSE and y2 is not None:
+                    sums2 = ops.maxpool2_bwd_bnreduce(z2, gp, gz, y2, c2)
+                else:
+                    ops.maxpool2_bwd(z2, gp, gz, accumulate=True)
             else:
                 t = ops.empty_nhwc(*z2.shape, cd, x.device)
                 ops.maxpool2_bwd(z2, gp, t, accumulate=False)

@@ -572,6 +572,23 @@ def maxpool2_bwd(x, gp, gx, accumulate):
          nbytes=x.numel() * x.element_size() * (3.25 if accumulate else 2.25))
 
 
+# Measured at C2 (4 encoder stages, B = 16): fused 1.18 ms against 0.54 ms + 0.38 ms for the separate reduction
+# passes -- ~110 registers per thread (four coefficient vectors + two sum vectors on top of the pool's own state)
+# leave two blocks per SM and the stream runs at 0.55 of the copy peak -- so the fused form is opt-in; it stays tested.
+POOL_BNBWD_FUSE = _os.environ.get("UNETB200_POOL_BNBWD_FUSE", "0") != "0" and _os.environ.get("UNETB200_NO_BNBWD_FUSE") is None
+
+
+def maxpool2_bwd_bnreduce(x, gp, gx, y, coefs):
+    """gx += max-pool scatter of gp (in place), and the fp64 sums[2, C] of the BatchNorm + ReLU backward of the layer
+    whose raw output is y (x = relu(bn(y)), gx its now complete output gradient) from the same pass."""
+    B, Cc, H, W = x.shape
+    sums = torch.zeros((2, Cc), dtype=torch.float64, device=x.device)
+    _run("maxpool2_bwd", lib().unetb200_maxpool2_bwd_bnreduce, _p(x), nhwc_ld(x), _p(gp), nhwc_ld(gp), _p(gx), nhwc_ld(gx),
+         _p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(sums), dt(x), B, H, W, Cc,
+         _stream(), nbytes=x.numel() * x.element_size() * 4.25)
+    return sums
+
+
 def bn_relu_bwd(gz, y, coefs, training, dgamma=None, dbeta=None, sums=None):
     """Returns (gy, dgamma, dbeta) for z = relu(bn(y)); `dgamma` / `dbeta`: optional fp32 [C] destinations; `sums`:
     the fp64 [2, C] reduction when the kernel that produced gz already made it (gconv_dgrad_bnbwd)."""
