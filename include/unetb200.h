@@ -190,6 +190,12 @@ int unetb200_bn_finalize(const double* stats, int64_t count, const float* gamma,
                          float eps, float momentum, float* running_mean, float* running_var,
                          float* save_mean, float* save_invstd, float* scale, float* shift, int C,
                          void* stream);
+/* The same, and num_batches_tracked[0] += 1 (int64, nullable) from the same launch: nn.BatchNorm2d's step counter
+ * without an elementwise kernel of its own. */
+int unetb200_bn_finalize_track(const double* stats, int64_t count, const float* gamma, const float* beta,
+                               float eps, float momentum, float* running_mean, float* running_var,
+                               float* save_mean, float* save_invstd, float* scale, float* shift,
+                               int64_t* num_batches_tracked, int C, void* stream);
 /* eval mode: scale/shift from the running statistics */
 int unetb200_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* scale, float* shift,

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Side-by-side per-kernel-class table of bench.py JSON lines:  python tools/cmp_bench.py a.json b.json ..."""
 import json
+import signal
 import sys
+
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)      # `| head` is a normal way to read this table
 
 def load(path):
     lines = [ln for ln in open(path) if ln.lstrip().startswith("{")]

@@ -75,8 +75,10 @@ static bool vec_ok(int C, std::initializer_list<int64_t> lds, std::initializer_l
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, double inv_count, double unbias,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float eps, float momentum, float* running_mean, float* running_var,
-                                   float* save_mean, float* save_invstd, float* scale, float* shift, int C) {
+                                   float* save_mean, float* save_invstd, float* scale, float* shift, int C,
+                                   long long* num_batches_tracked) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;      // nn.BatchNorm2d's step counter, same launch
   if (c >= C) return;
   double mean = stats[c] * inv_count;
   double var = stats[C + c] * inv_count - mean * mean;
@@ -830,16 +832,24 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 
 extern "C" {
 
-int unetb200_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float eps,
-                         float momentum, float* running_mean, float* running_var, float* save_mean,
-                         float* save_invstd, float* scale, float* shift, int C, void* stream) {
+int unetb200_bn_finalize_track(const double* stats, int64_t count, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, float* save_mean,
+                               float* save_invstd, float* scale, float* shift, int64_t* num_batches_tracked, int C,
+                               void* stream) {
   UB_CHECK_ARG(C > 0 && count > 0, "bn_finalize: C=%d count=%lld", C, (long long)count);
   double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       stats, 1.0 / (double)count, unbias, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
-      save_invstd, scale, shift, C);
+      save_invstd, scale, shift, C, reinterpret_cast<long long*>(num_batches_tracked));
   UB_LAUNCH_CHECK("bn_finalize");
   return 0;
+}
+
+int unetb200_bn_finalize(const double* stats, int64_t count, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* save_mean,
+                         float* save_invstd, float* scale, float* shift, int C, void* stream) {
+  return unetb200_bn_finalize_track(stats, count, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
+                                    save_invstd, scale, shift, nullptr, C, stream);
 }
 
 int unetb200_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,

@@ -43,6 +43,15 @@ class _UNetBase(nn.Module):
         self.outc = OutConv(b, n_classes)
 
     def forward(self, x):
+        from unetb200 import functional as UF
+        if self._bn_doubles is None:           # 2 C fp64 accumulators (sum, sum of squares) per BatchNorm layer
+            self._bn_doubles = sum(2 * ((m.num_features + 1) // 2 * 2) for m in self.modules() if isinstance(m, nn.BatchNorm2d))
+        with UF.zero_arena(self._bn_doubles if self.training else 0, x.device):
+            return self._forward(x)
+
+    _bn_doubles = None
+
+    def _forward(self, x):
         x = _prep(x, type(self).__name__)
         B, C, H, W = x.shape
         if C != self.n_channels:

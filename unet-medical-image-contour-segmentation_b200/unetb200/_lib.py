@@ -70,6 +70,8 @@ PROTOTYPES = {
     "unetb200_pack_weights_multi": (C.c_int, [C.POINTER(PackJob), C.c_int, C.c_int, c_p]),
     "unetb200_split_tf32": (C.c_int, [c_p, c_i64, c_p, c_i64, C.c_int, C.c_int, c_p]),
     "unetb200_bn_finalize": (C.c_int, [c_p, c_i64, c_p, c_p, C.c_float, C.c_float, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, c_p]),
+    "unetb200_bn_finalize_track": (C.c_int, [c_p, c_i64, c_p, c_p, C.c_float, C.c_float, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                             C.c_int, c_p]),
     "unetb200_bn_eval_coeffs": (C.c_int, [c_p, c_p, c_p, c_p, C.c_float, c_p, c_p, c_p, c_p, C.c_int, c_p]),
     "unetb200_bn_relu_apply": (C.c_int, [c_p, c_i64, c_p, c_p, c_p, c_i64, c_p, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),
     "unetb200_maxpool2_fwd": (C.c_int, [c_p, c_i64, c_p, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p]),

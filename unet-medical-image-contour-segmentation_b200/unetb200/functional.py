@@ -291,6 +291,35 @@ def _gconv3x3(x, Cout, y, dtype):
                           Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(y))
 
 
+# One zero-fill per forward pass for all the BatchNorm statistics accumulators of a network (18 tiny fills otherwise):
+# the model opens an arena (`zero_arena`), conv_bn_relu_fwd takes fp64 slices from it; outside an arena, or when it is
+# exhausted, a slice is an ordinary torch.zeros.
+_ZERO_ARENA = [None, 0]
+
+
+class zero_arena:
+    def __init__(self, n_doubles, device):
+        self.n, self.device = int(n_doubles), device
+
+    def __enter__(self):
+        self.prev = list(_ZERO_ARENA)
+        _ZERO_ARENA[0] = torch.zeros(self.n, dtype=torch.float64, device=self.device) if self.n > 0 else None
+        _ZERO_ARENA[1] = 0
+
+    def __exit__(self, *exc):
+        _ZERO_ARENA[0], _ZERO_ARENA[1] = self.prev
+        return False
+
+
+def zeros_f64(n, device):
+    buf, off = _ZERO_ARENA
+    n2 = (n + 1) // 2 * 2                      # keep slices 16-byte aligned
+    if buf is not None and buf.device == torch.device(device) and off + n2 <= buf.numel() and not _RECOMPUTE[0]:
+        _ZERO_ARENA[1] = off + n2
+        return buf[off:off + n]
+    return torch.zeros(n, dtype=torch.float64, device=device)
+
+
 # Activation re-computation (UNet.use_checkpointing, reference unet_model.py:40-50 / train.py:294-299): while a
 # checkpointed stage is re-run inside the backward pass its BatchNorm layers must normalise with the same batch
 # statistics but leave the running statistics and num_batches_tracked alone (the first run already moved them).
@@ -369,7 +398,7 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False, 
             return None, z, pooled, coefs, False
     y = ops.empty_nhwc(B, Cout, H, W, cd, dev)
     use_batch = training or bn.running_mean is None
-    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=dev) if use_batch else None
+    stats = zeros_f64(2 * Cout, dev) if use_batch else None
     ops.gconv_fprop(_gconv3x3(x, Cout, y, cd), x, wp, None, y, stats)
     gamma = _f32c(bn.weight) if bn.weight is not None else None
     beta = _f32c(bn.bias) if bn.bias is not None else None
@@ -378,13 +407,12 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False, 
             raise ValueError("unetb200: BatchNorm2d(momentum=None) (cumulative average) is not supported")
         update = training and bn.running_mean is not None and not _RECOMPUTE[0]
         coefs = ops.bn_finalize(stats, B * H * W, gamma, beta, bn.eps, bn.momentum if update else 0.0,
-                                bn.running_mean if update else None, bn.running_var if update else None, Cout)
+                                bn.running_mean if update else None, bn.running_var if update else None, Cout,
+                                num_batches_tracked=bn.num_batches_tracked if update else None)
         if update:
             # the kernel moved the running statistics through raw pointers: tell PyTorch (autograd's saved-tensor
             # check, the eval-coefficient cache above)
             torch._C._increment_version([bn.running_mean, bn.running_var])
-        if update and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
     else:
         coefs = ops.bn_eval_coeffs(gamma, beta, bn.running_mean, bn.running_var, bn.eps, Cout)
     z = out if out is not None else ops.empty_nhwc(B, Cout, H, W, cd, dev)

@@ -535,11 +535,18 @@ def gconv_wgrad(d, x, gy, dst, st, sc, sn, sq=0, x_split=None, gy_split=None, de
 # ------------------------------------------------------------------------------------------------
 # BatchNorm / ReLU / pooling
 # ------------------------------------------------------------------------------------------------
-def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, Cc):
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, Cc, num_batches_tracked=None):
+    """`num_batches_tracked`: the module's int64 step counter, incremented by the same launch when given."""
     dev = stats.device
     coefs = torch.empty((4, Cc), dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
-    _run("bn_finalize", lib().unetb200_bn_finalize, _p(stats), count, _p(gamma), _p(beta), eps, momentum,
-         _p(running_mean), _p(running_var), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(coefs[3]), Cc, _stream())
+    nbt = num_batches_tracked
+    if nbt is not None and not (nbt.dtype == torch.int64 and nbt.is_cuda and nbt.numel() == 1):
+        nbt.add_(1)                                                  # a counter the kernel cannot reach (never on the path)
+        nbt = None
+    _run("bn_finalize", lib().unetb200_bn_finalize_track, _p(stats), count, _p(gamma), _p(beta), eps, momentum,
+         _p(running_mean), _p(running_var), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(coefs[3]), _p(nbt), Cc, _stream())
+    if nbt is not None:
+        torch._C._increment_version([nbt])
     return coefs
 
 
