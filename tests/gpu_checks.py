@@ -436,6 +436,71 @@ def check_conv_simt():
     return out
 
 
+def _narrow_case(B, Ci, Co, H, W, seed, slice_in=False):
+    """3x3 conv with narrow channel counts (UNet_S / UNet_T / UNet_SA layers) in bf16: the thread-built-im2col tcgen05
+    kernel -- fprop + BatchNorm statistics, dgrad (the same kernel on rotated / transposed weights) and the folded
+    eval-mode BatchNorm + ReLU epilogue -- against PyTorch-CPU fp32 on the rounded operands."""
+    res = []
+    g = gen(seed)
+    dt_ = BF
+    x = rq(torch.randn(B, Ci, H, W, generator=g), dt_).requires_grad_(True)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Ci ** 0.5)
+    wq = rq(w, dt_).requires_grad_(True)
+    ref = F.conv2d(x, wq, padding=1)
+    gy = rq(torch.randn(ref.shape, generator=g), dt_)
+    ref.backward(gy)
+    tag = f"narrow_{Ci}to{Co}_{B}x{H}x{W}{'_slice' if slice_in else ''}"
+    xd = in_slice(x.detach(), dt_, 16) if slice_in else dev_nhwc(x.detach(), dt_)
+    wdev = w.to(DEV)
+    y = ops.empty_nhwc(B, Co, H, W, dt_, DEV)
+    stats = torch.zeros(2 * Co, dtype=torch.float64, device=DEV)
+
+    def desc(xin, Cout, yout):
+        return ops.make_gconv(ops._DT[dt_], _lib.ALGO_AUTO, B, H, W, xin.shape[1], ops.TAPS3, 1, (0, 0), H, W,
+                              ops.nhwc_ld(xin), Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(yout))
+    used = ops.gconv_fprop(desc(xd, Co, y), xd, UF.pack3x3_fprop(wdev, dt_), None, y, stats)
+    res.append((f"{tag}_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
+    yh = host(y)
+    res.append((f"{tag}_fprop", rel(yh, ref.detach()), 1.2e-2))
+    st = host(stats.float()).reshape(2, Co)
+    res.append((f"{tag}_stats_sum", rel(st[0], yh.sum((0, 2, 3))), 1e-4))
+    res.append((f"{tag}_stats_sq", rel(st[1], (yh ** 2).sum((0, 2, 3))), 1e-4))
+    if Ci >= 8:
+        gyd = dev_nhwc(gy, dt_)
+        gx = ops.empty_nhwc(B, Ci, H, W, dt_, DEV)
+        used = ops.gconv_fprop(desc(gyd, Ci, gx), gyd, UF.pack3x3_dgrad(wdev, dt_), None, gx, None)
+        res.append((f"{tag}_dgrad_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
+        res.append((f"{tag}_dgrad", rel(host(gx), x.grad), 1.2e-2))
+    # folded eval-mode BatchNorm + ReLU
+    sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g) * 0.2
+    coefs = torch.stack([torch.zeros(Co), torch.ones(Co), sc, sh]).to(DEV).contiguous()
+    z = ops.empty_nhwc(B, Co, H, W, dt_, DEV)
+    d = desc(xd, Co, z)
+    ok = ops.gconv_fprop_affine_relu_supported(d, xd, UF.pack3x3_fprop(wdev, dt_), z)
+    res.append((f"{tag}_fold_supported", 0.0 if ok else 1.0, 0.0))
+    if ok:
+        ops.gconv_fprop_affine_relu(d, xd, UF.pack3x3_fprop(wdev, dt_), coefs, z)
+        zref = torch.relu(ref.detach() * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+        res.append((f"{tag}_fold", rel(host(z), zref), 1.2e-2))
+    return res
+
+
+def check_conv_narrow():
+    out = []
+    out += _narrow_case(2, 16, 16, 20, 24, 101)
+    out += _narrow_case(1, 16, 32, 17, 9, 102)                     # ragged: the last tile is partial
+    out += _narrow_case(2, 32, 32, 16, 16, 103, slice_in=True)     # the input is a slice of a concat buffer
+    out += _narrow_case(1, 32, 64, 12, 20, 104)
+    out += _narrow_case(1, 64, 32, 24, 16, 105)
+    out += _narrow_case(2, 32, 16, 33, 7, 106)
+    out += _narrow_case(2, 8, 8, 16, 24, 107)                      # UNet_T: N = 8 rides an N = 16 MMA
+    out += _narrow_case(1, 16, 8, 10, 10, 108)
+    out += _narrow_case(2, 1, 16, 20, 20, 109)                     # first layers of the light variants
+    out += _narrow_case(1, 3, 8, 18, 14, 110)
+    out += _narrow_case(1, 8, 16, 40, 40, 111)
+    return out
+
+
 def check_conv_tc_fprop_small():
     """First contact with the tcgen05 engine: one tile, one N block."""
     return _conv3x3_case(1, 64, 64, 8, 16, BF, _lib.ALGO_TC, 20)
@@ -961,6 +1026,7 @@ GROUPS = {
     "boundary": lambda gd: check_boundary(gd),
     "outconv": lambda gd: check_outconv(),
     "conv_simt": lambda gd: check_conv_simt(),
+    "conv_narrow": lambda gd: check_conv_narrow(),
     "conv_tc_first": lambda gd: check_conv_tc_fprop_small(),
     "conv_tc": lambda gd: check_conv_tc(),
     "conv_tc_tf32": lambda gd: check_conv_tc_tf32(),

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Training-step time of the width variants (UNet_S / UNet_T / UNet_SA, reference unet_model.py:52-189; UNet_S is what
+train.py:253 builds by default) at B = 16, 512x512, bf16, eager launches, with the per-kernel-class profile."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "unet-medical-image-contour-segmentation_b200"))
+import unet.unet_model as UM  # noqa: E402
+from unetb200 import losses as UL, ops  # noqa: E402
+from unetb200.optim import FusedRMSprop  # noqa: E402
+
+dev = torch.device("cuda:0")
+names = sys.argv[1:] or ["UNet_S", "UNet_SA", "UNet_T", "UNet"]
+for name in names:
+    torch.manual_seed(0)
+    m = getattr(UM, name)(1, 2, False).to(dev).to(memory_format=torch.channels_last).train()
+    opt = FusedRMSprop(m.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999)
+    x = torch.rand(16, 1, 512, 512, device=dev).contiguous(memory_format=torch.channels_last)
+    t = torch.randint(0, 2, (16, 512, 512), device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", enabled=True):
+            loss = UL.training_criterion(m(x), t, boundary_coeff=0.2, edge_width=51, edge_weight=7)
+        loss.backward()
+        opt.step(clip_max_norm=1.0)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    with ops.profile() as rec:
+        step()
+        torch.cuda.synchronize()
+    agg = {}
+    for nm, s, e, fl, nb in rec:
+        k = nm.split("[")[0]
+        agg[k] = agg.get(k, 0.0) + s.elapsed_time(e)
+    top = sorted(agg.items(), key=lambda kv: -kv[1])[:8]
+    print(f"{name}: {ms:.2f} ms/step ({16 / ms * 1e3:.0f} img/s, eager);  " + ", ".join(f"{k} {v:.2f}" for k, v in top), flush=True)

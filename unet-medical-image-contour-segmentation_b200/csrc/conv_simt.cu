@@ -673,7 +673,9 @@ int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
   long long n2 = tc2_stats_workspace(d);
   if (n2 > n) n = n2;
   long long n3 = tc3_stats_workspace(d);
-  return n > n3 ? n : n3;
+  if (n3 > n) n = n3;
+  const long long n4 = narrow_tc_stats_rows(d) * 2 * g.N;
+  return n > n4 ? n : n4;
 }
 
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
@@ -686,6 +688,10 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (!stats) stats_ws = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   int algo = d->algo;
+  if (algo != UNETB200_ALGO_SIMT && !bias && narrow_tc_supported(d, x, wp, y)) {      // narrow channel counts: thread-built im2col
+    if (algo_used) *algo_used = UNETB200_ALGO_TC;
+    return narrow_tc_fprop(d, x, wp, y, stats, stats_ws, nullptr, s);
+  }
   if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_fprop_supported(d, x, wp, y) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
   if (algo_used) *algo_used = algo;
   if (algo == UNETB200_ALGO_TC) {
@@ -717,6 +723,7 @@ int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const 
   static const bool wide = getenv("UNETB200_TC3_MAXBN") && atoi(getenv("UNETB200_TC3_MAXBN")) >= 256;
   if (off || d->algo == UNETB200_ALGO_SIMT) return 0;
   if (first_tc_supported(d, z) && aligned16(wp)) return 1;            // first layer: thread-built im2col kernel
+  if (narrow_tc_supported(d, x, wp, z)) return 1;                     // narrow channel counts: the same, generalised
   if (d->N % 128 != 0 && d->N % 64 != 0) return 0;
   if (d->dtype == UNETB200_BF16 && d->N % 256 == 0 && wide) return 0;
   return tc_fprop_supported(d, x, wp, z) && tc3_fprop_supported(d, x, wp, nullptr, z);
@@ -733,6 +740,8 @@ int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, c
                "gconv_fprop + bn_relu_apply instead)");
   if (first_tc_supported(d, z) && aligned16(wp))
     return first_tc_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
+  if (narrow_tc_supported(d, x, wp, z))
+    return narrow_tc_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
   return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift);
 }
 

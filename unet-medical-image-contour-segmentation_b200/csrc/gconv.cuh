@@ -89,6 +89,12 @@ long long first_tc_stats_rows(const unetb200_gconv_t* d);
 int first_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
                    const float* affine, cudaStream_t s);
 
+// 3x3 convolutions with narrow channel counts (C_in, C_out <= 64, bf16) on the tensor cores (conv_narrow.cu)
+int narrow_tc_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+long long narrow_tc_stats_rows(const unetb200_gconv_t* d);
+int narrow_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
+                    const float* affine, cudaStream_t s);
+
 // first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)
 int first_fprop_supported(const unetb200_gconv_t* d, const void* y);
 long long first_fprop_tiles(const unetb200_gconv_t* d);
