@@ -471,6 +471,11 @@ def _narrow_case(B, Ci, Co, H, W, seed, slice_in=False):
         used = ops.gconv_fprop(desc(gyd, Ci, gx), gyd, UF.pack3x3_dgrad(wdev, dt_), None, gx, None)
         res.append((f"{tag}_dgrad_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
         res.append((f"{tag}_dgrad", rel(host(gx), x.grad), 1.2e-2))
+    gyd = dev_nhwc(gy, dt_)
+    dW = torch.empty(Co, Ci, 3, 3, device=DEV)
+    used = ops.gconv_wgrad(desc(xd, Co, gyd), xd, gyd, dW, 1, 9, Ci * 9)
+    res.append((f"{tag}_wgrad_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
+    res.append((f"{tag}_wgrad", rel(host(dW), wq.grad), 5e-3))
     # folded eval-mode BatchNorm + ReLU
     sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g) * 0.2
     coefs = torch.stack([torch.zeros(Co), torch.ones(Co), sc, sh]).to(DEV).contiguous()

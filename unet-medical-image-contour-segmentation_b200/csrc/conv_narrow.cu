@@ -371,4 +371,253 @@ int narrow_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, vo
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ wgrad
+// dW[(t, c)][n] = sum_p x[p + t][c] * g[p][n] for the same narrow layers.  The reduction runs over pixels, so both
+// operands are MN-major: the producers build the SAME im2col tile as above (rows = pixels, 128 bytes = 64 values of
+// k = t * C_in + c) -- read by the tensor core as A^T with M = 128 values of k (two chunk tiles LBO apart), K = 16
+// pixel rows per MMA -- plus the pixel's dY row (N <= 64 channels) as the B tile.  A CTA walks its share of the pixel
+// tiles accumulating ALL of dW in TMEM (ceil(K / 128) blocks x N columns <= 320) and writes one fp32 partial at the
+// end; the partials (one per CTA) go through the ordinary split reduction.
+struct NarrowWParams {
+  const __nv_bfloat16* x;        // [npix][ld_in]
+  const __nv_bfloat16* gy;       // [npix][ld_out]
+  float* partials;               // [grid][9 * Cin][N]
+  long long ld_in, ld_out;
+  long long npix;
+  int H, W, N;
+  int tap_dy[9], tap_dx[9];
+  int ntiles;
+};
+
+template <int CIN, int NT>
+struct NarrowWCfg {
+  static constexpr int K = 9 * CIN, NKC = (K + 63) / 64, MB = (NKC + 1) / 2;
+  static constexpr uint32_t kStage = (NKC + 1) * 16384u;            // im2col chunk tiles + the dY tile
+  static constexpr int STAGES = kStage * 3 <= 200 * 1024 ? 3 : (kStage * 2 <= 200 * 1024 ? 2 : 1);
+  static constexpr int kCols = MB * NT <= 32 ? 32 : (MB * NT <= 64 ? 64 : (MB * NT <= 128 ? 128 : (MB * NT <= 256 ? 256 : 512)));
+  static constexpr int smem = STAGES * (int)kStage + 256 + 1024;
+};
+
+template <int CIN, int NT>
+__global__ void __launch_bounds__(192, 1) narrow_wgrad_kernel(const __grid_constant__ NarrowWParams p) {
+  using Cfg = NarrowWCfg<CIN, NT>;
+  constexpr int K = Cfg::K, NKC = Cfg::NKC, MB = Cfg::MB, STAGES = Cfg::STAGES;
+  constexpr uint32_t kStage = Cfg::kStage;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + STAGES * kStage);
+  uint64_t* a_empty = a_full + STAGES;
+  uint64_t* t_full = a_empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    mbar_init(t_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, Cfg::kCols);
+  for (uint32_t i = threadIdx.x; i < (STAGES * kStage) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);        // K padding / unused dY columns stay zero
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) ++my_tiles;
+
+  if (warp < 4) {
+    const int r = threadIdx.x;
+    uint32_t s = 0, ph = 1;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const long long pix = (long long)tile * 128 + r;
+      const bool live = pix < p.npix;
+      const int j0 = live ? (int)(pix % p.W) : 0;
+      const long long rest = live ? pix / p.W : 0;
+      const int i0 = (int)(rest % p.H);
+      const long long img = rest - i0;
+      mbar_wait(&a_empty[s], ph);
+      const uint32_t row = smem_u32(smem) + s * kStage + r * 128;
+      // the pixel's dY row -> B tile (chunk tile NKC of the stage)
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(p.gy + (live ? pix : 0) * p.ld_out);
+        const int nv = p.N / 8;
+        for (int q = 0; q < nv; ++q) {
+          const uint4 w = live ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + NKC * 16384 + ((q ^ (r & 7)) << 4)), "r"(w.x),
+                       "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+        }
+      }
+      if constexpr (CIN >= 8) {
+        constexpr int VPT = CIN / 8;
+#pragma unroll
+        for (int tr = 0; tr < 3; ++tr) {
+          uint4 v[3 * VPT];
+#pragma unroll
+          for (int tt = 0; tt < 3; ++tt) {
+            const int t = tr * 3 + tt;
+            const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
+            const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+            const uint4* src = reinterpret_cast<const uint4*>(p.x + ((img + yy) * p.W + xx) * p.ld_in);
+#pragma unroll
+            for (int q = 0; q < VPT; ++q) v[tt * VPT + q] = in ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int tt = 0; tt < 3; ++tt)
+#pragma unroll
+            for (int q = 0; q < VPT; ++q) {
+              const int k = (tr * 3 + tt) * CIN + 8 * q;
+              const uint32_t dst = row + (k >> 6) * 16384 + ((((k & 63) >> 3) ^ (r & 7)) << 4);
+              const uint4 w = v[tt * VPT + q];
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w)
+                           : "memory");
+            }
+        }
+      } else {
+        constexpr int KCH = ((K + 15) / 16) * 2;
+        uint32_t v32[KCH * 4];
+#pragma unroll
+        for (int i = 0; i < KCH * 4; ++i) v32[i] = 0u;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
+          const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+          const __nv_bfloat16* src = p.x + ((img + yy) * p.W + xx) * p.ld_in;
+#pragma unroll
+          for (int c = 0; c < CIN; ++c) {
+            const int k = t * CIN + c;
+            const uint32_t val = in ? (uint32_t)__bfloat16_as_ushort(__ldg(src + c)) : 0u;
+            v32[k >> 1] |= val << ((k & 1) * 16);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < KCH; ++c)
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((c ^ (r & 7)) << 4)), "r"(v32[4 * c]),
+                       "r"(v32[4 * c + 1]), "r"(v32[4 * c + 2]), "r"(v32[4 * c + 3]) : "memory");
+      }
+      fence_async_smem();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_full[s])) : "memory");
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    // ---- end of the walk: drain the accumulators, thread = row (value of k) of each 128-row block
+    mbar_wait(t_full, 0);
+    tc_fence_after();
+    float* out = p.partials + (long long)blockIdx.x * K * p.N;
+#pragma unroll 1
+    for (int mb = 0; mb < MB; ++mb) {
+      const int k = mb * 128 + r;
+      const bool dup = (NKC & 1) && mb == MB - 1 && r >= 64;        // odd chunk count: rows 64.. of the last block repeat
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * NT + c0, v);
+        if (k < K && !dup) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c0 + e < p.N) out[(long long)k * p.N + c0 + e] = my_tiles > 0 ? __uint_as_float(v[e]) : 0.f;
+        }
+      }
+    }
+  } else if (warp == 4) {
+    constexpr uint32_t idesc = make_idesc(false, true, true, 128, NT);
+    uint32_t s = 0, ph = 0;
+    int done = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      mbar_wait(&a_full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t base = smem_u32(smem) + s * kStage;
+        const uint64_t db = make_desc(base + NKC * 16384, 16384, 1024, kLayoutSW128);
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          const bool odd_last = (NKC & 1) && mb == MB - 1;
+          const uint64_t da = make_desc(base + 2 * mb * 16384, odd_last ? 0u : 16384u, 1024, kLayoutSW128);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma<false>(tmem_base + mb * NT, da + ((ks * 2048) >> 4), db + ((ks * 2048) >> 4), idesc,
+                        (done > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&a_empty[s]);
+      }
+      __syncwarp();
+      ++done;
+      if (++s == STAGES) { s = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(t_full);
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::kCols);
+  }
+}
+
+static int narrow_wgrad_grid(const unetb200_gconv_t* d, int* ntiles) {
+  const long long npix = (long long)d->B * d->Hm * d->Wm;
+  *ntiles = (int)((npix + 127) / 128);
+  const int slots = sm_count();                         // all of dW lives in a CTA's TMEM: one CTA per SM
+  return *ntiles < slots ? *ntiles : slots;
+}
+
+int narrow_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy) {
+  static const bool off = getenv("UNETB200_NO_NARROW_WGRAD") != nullptr;
+  if (off || !narrow_shape_ok(d)) return 0;
+  if (d->Cin >= 8 && x && !aligned16(x)) return 0;
+  if (gy && !aligned16(gy)) return 0;
+  return 1;
+}
+
+int narrow_wgrad_splits(const unetb200_gconv_t* d) {
+  int nt;
+  return narrow_wgrad_grid(d, &nt);
+}
+
+template <int CIN, int NT>
+static int narrow_wgrad_launch(const NarrowWParams& P, int grid, cudaStream_t s) {
+  constexpr int smem = NarrowWCfg<CIN, NT>::smem;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(&narrow_wgrad_kernel<CIN, NT>), smem, "narrow_wgrad smem attribute"))
+    return rc;
+  narrow_wgrad_kernel<CIN, NT><<<grid, 192, smem, s>>>(P);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "narrow_wgrad launch");
+  return 0;
+}
+
+template <int CIN>
+static int narrow_wgrad_dispatch_n(const NarrowWParams& P, int grid, cudaStream_t s) {
+  const int nt = P.N <= 16 ? 16 : (P.N <= 32 ? 32 : 64);
+  if (nt == 16) return narrow_wgrad_launch<CIN, 16>(P, grid, s);
+  if (nt == 32) return narrow_wgrad_launch<CIN, 32>(P, grid, s);
+  if constexpr (CIN < 64) return narrow_wgrad_launch<CIN, 64>(P, grid, s);
+  set_error("narrow_wgrad: unsupported channel counts");
+  return UNETB200_E_INVALID;
+}
+
+int narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s) {
+  if (!narrow_wgrad_supported(d, x, gy)) { set_error("narrow_wgrad: unsupported shape"); return UNETB200_E_INVALID; }
+  NarrowWParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = (const __nv_bfloat16*)x; P.gy = (const __nv_bfloat16*)gy; P.partials = partials;
+  P.ld_in = d->ld_in; P.ld_out = d->ld_out;
+  P.npix = (long long)d->B * d->Hm * d->Wm;
+  P.H = d->Hm; P.W = d->Wm; P.N = d->N;
+  for (int t = 0; t < 9; ++t) { P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t]; }
+  const int grid = narrow_wgrad_grid(d, &P.ntiles);
+  if (grid != splits) { set_error("narrow_wgrad: the planned split count is %d, got %d", grid, splits); return UNETB200_E_INVALID; }
+  switch (d->Cin) {
+    case 1: return narrow_wgrad_dispatch_n<1>(P, grid, s);
+    case 2: return narrow_wgrad_dispatch_n<2>(P, grid, s);
+    case 3: return narrow_wgrad_dispatch_n<3>(P, grid, s);
+    case 4: return narrow_wgrad_dispatch_n<4>(P, grid, s);
+    case 8: return narrow_wgrad_dispatch_n<8>(P, grid, s);
+    case 16: return narrow_wgrad_dispatch_n<16>(P, grid, s);
+    case 32: return narrow_wgrad_dispatch_n<32>(P, grid, s);
+    default: return narrow_wgrad_dispatch_n<64>(P, grid, s);
+  }
+}
+
 }  // namespace ub

@@ -795,6 +795,11 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
   int rc = gconv_validate(d, &g);
   if (rc) return rc;
   int algo = d->algo;
+  if (algo != UNETB200_ALGO_SIMT && narrow_wgrad_supported(d, nullptr, nullptr)) {      // narrow channel counts
+    if (algo_used) *algo_used = UNETB200_ALGO_TC;
+    if (splits) *splits = narrow_wgrad_splits(d);
+    return 0;
+  }
   if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_wgrad_supported(d, nullptr, nullptr) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
   if (algo == UNETB200_ALGO_TC)
     UB_CHECK_ARG(tc_wgrad_supported(d, nullptr, nullptr), "gconv_wgrad: tcgen05 path requested but shape unsupported");
@@ -817,6 +822,10 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   UB_CHECK_ARG(x && gy && partials && splits >= 1, "gconv_wgrad: null pointer / bad splits");
   cudaStream_t s = (cudaStream_t)stream;
   int algo = d->algo;
+  if (algo != UNETB200_ALGO_SIMT && narrow_wgrad_supported(d, nullptr, nullptr)) {
+    UB_CHECK_ARG(narrow_wgrad_supported(d, x, gy), "gconv_wgrad: the narrow tcgen05 kernel needs 16-byte aligned operands");
+    return narrow_wgrad(d, x, gy, partials, splits, s);
+  }
   if (algo == UNETB200_ALGO_AUTO || algo == UNETB200_ALGO_PREFER_TC) algo = tc_wgrad_supported(d, nullptr, nullptr) ? UNETB200_ALGO_TC : UNETB200_ALGO_SIMT;
   if (algo == UNETB200_ALGO_TC) {
     UB_CHECK_ARG(tc_wgrad_supported(d, x, gy), "gconv_wgrad: tcgen05 path requested but shape/alignment unsupported");

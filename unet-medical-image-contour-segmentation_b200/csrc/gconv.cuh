@@ -95,6 +95,10 @@ long long narrow_tc_stats_rows(const unetb200_gconv_t* d);
 int narrow_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
                     const float* affine, cudaStream_t s);
 
+int narrow_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int narrow_wgrad_splits(const unetb200_gconv_t* d);
+int narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
+
 // first-layer (C_in <= 4) CUDA-core kernels (conv_first.cu)
 int first_fprop_supported(const unetb200_gconv_t* d, const void* y);
 long long first_fprop_tiles(const unetb200_gconv_t* d);
