@@ -46,3 +46,10 @@ for name in names:
         agg[k] = agg.get(k, 0.0) + s.elapsed_time(e)
     top = sorted(agg.items(), key=lambda kv: -kv[1])[:8]
     print(f"{name}: {ms:.2f} ms/step ({16 / ms * 1e3:.0f} img/s, eager);  " + ", ".join(f"{k} {v:.2f}" for k, v in top), flush=True)
+    if os.environ.get("PER_SHAPE"):
+        full = {}
+        for nm, s, e, fl, nb in rec:
+            d = full.setdefault(nm, [0.0, 0, 0.0])
+            d[0] += s.elapsed_time(e); d[1] += 1; d[2] += fl
+        for nm, (t, n, fl) in sorted(full.items(), key=lambda kv: -kv[1][0])[:24]:
+            print(f"    {nm:60s} {t:7.3f} ms  x{n}  {fl / t / 1e9 if t else 0:7.1f} TF/s")
