@@ -239,8 +239,10 @@ _GRAD_SUMS = {}    # data_ptr(g) -> (sums, shape)
 # Column sums of a gradient made by the dgrad that writes it: the ConvTranspose2d bias gradient (unet_parts.py:73) is
 # the per-channel sum of the `up` half of the concat gradient, which the decoder's first conv's dgrad produces -- its
 # epilogue already knows how to sum the tile it stores (the forward BatchNorm statistics path).
-_WANT_COLSUM = {}    # data_ptr(concat buffer) -> shape: registered by UpCatConvTFn.forward, read by DoubleConvFn.forward
-_GRAD_COLSUM = {}    # data_ptr(concat gradient) -> (fp64 stats[2*C], shape)
+# Both hand-offs carry a per-call token, so an entry that was never consumed can never be mistaken for another call's
+# (addresses repeat once the allocator recycles a block).
+_WANT_COLSUM = {}    # data_ptr(concat buffer) -> (shape, token): registered by UpCatConvTFn.forward, read by DoubleConvFn.forward
+_GRAD_COLSUM = {}    # data_ptr(concat gradient) -> (fp64 stats[2*C], shape, token)
 COLSUM_FUSE = os.environ.get("UNETB200_COLSUM_FUSE", "1") != "0"
 
 
@@ -452,7 +454,7 @@ def _vec_dst(param, Cc):
 
 
 def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_params=(None, None), sums=None,
-                     below=None, colsum=False):
+                     below=None, colsum=None):
     """-> (gx or None, dW [Co,Ci,3,3] fp32, dgamma, dbeta, sums_below).  `param`: the Parameter object behind `w`;
     `bn_params`: the BatchNorm weight / bias Parameter objects (only to look up their gradient sinks); `sums`: the
     BatchNorm-backward reduction of THIS stage if the kernel that produced gz already made it; `below` = (y, coefs)
@@ -485,13 +487,13 @@ def conv_bn_relu_bwd(gz, x, y, w, coefs, batch_stats, need_gx, param=None, bn_pa
         if (below is not None and gs is None and _BNBWD_MIN_N <= Cin <= _BNBWD_MAX_N
                 and ops.gconv_dgrad_bnbwd_supported(dd, gy, wd, gx)):
             sums_below = ops.gconv_dgrad_bnbwd(dd, gy, wd, gx, below[0], below[1])
-        elif colsum and gs is None:
+        elif colsum is not None and colsum is not False and gs is None:
             # x is an Up stage's concat buffer: leave the per-channel sums of its gradient for the ConvTranspose bias
             cs = torch.zeros(2 * Cin, dtype=torch.float64, device=x.device)
             ops.gconv_fprop(dd, gy, wd, None, gx, cs, kind="dgrad")
             if len(_GRAD_COLSUM) > 16:
                 _GRAD_COLSUM.clear()
-            _GRAD_COLSUM[gx.data_ptr()] = (cs, tuple(gx.shape))
+            _GRAD_COLSUM[gx.data_ptr()] = (cs, tuple(gx.shape), colsum)
         else:
             ops.gconv_fprop(dd, gy, wd, None, gx, None, kind="dgrad", x_split=gs)
     # after the dgrad, on the side stream: overlaps the (memory-bound) BatchNorm backward of the previous layer
@@ -557,7 +559,8 @@ class DoubleConvFn(torch.autograd.Function):
         cfg.fused_outconv = fused_out          # tells the caller whether z2 already holds OutConv's logits
         ctx.batch_stats = (cfg.training or cfg.bn1.running_mean is None, cfg.training or cfg.bn2.running_mean is None)
         ctx.has_pool = pooled is not None
-        ctx.colsum = bool(cfg.save) and _WANT_COLSUM.pop(x.data_ptr(), None) == tuple(x.shape)
+        want = _WANT_COLSUM.pop(x.data_ptr(), None) if cfg.save else None
+        ctx.colsum = want[1] if (want is not None and want[0] == tuple(x.shape)) else None      # the Up stage's token
         if cfg.save:
             ctx.save_for_backward(x, y1, z1, y2, z2, c1, c2, w1, w2)
             ctx.param_objs = (w1, g1, b1, w2, g2, b2)   # the Parameter objects themselves (.grad / gradient sinks)
@@ -671,7 +674,8 @@ class UpCatConvTFn(torch.autograd.Function):
             if bT is not None and not (dy or dx) and COLSUM_FUSE:
                 if len(_WANT_COLSUM) > 16:
                     _WANT_COLSUM.clear()
-                _WANT_COLSUM[cat.data_ptr()] = tuple(cat.shape)
+                ctx.colsum_token = object()
+                _WANT_COLSUM[cat.data_ptr()] = (tuple(cat.shape), ctx.colsum_token)
         return cat
 
     @staticmethod
@@ -717,7 +721,8 @@ class UpCatConvTFn(torch.autograd.Function):
         cs = _GRAD_COLSUM.pop(g.data_ptr(), None)
         if need[3]:
             dst = _vec_dst(getattr(ctx, "bias_obj", None), Cup)
-            if cs is not None and cs[1] == tuple(g.shape) and not padded and g is gcat:
+            if (cs is not None and cs[1] == tuple(g.shape) and cs[2] is getattr(ctx, "colsum_token", None)
+                    and not padded and g is gcat):
                 dB = ops.f64_to_f32(cs[0][C2:C2 + Cup], dst)      # summed by the dgrad epilogue that wrote g
             else:
                 region = gup if not padded else ops.to_nhwc(
