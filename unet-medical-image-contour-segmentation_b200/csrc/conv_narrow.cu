@@ -27,6 +27,7 @@ struct NarrowParams {
   long long npix;
   int H, W, N;                   // N = real output channels (<= NT)
   int tap_dy[9], tap_dx[9];
+  long long tap_off[9];          // (dy * W + dx) * ld_in, elements
   int ntiles;
 };
 
@@ -35,7 +36,7 @@ constexpr int kNwThreads = 288;
 template <int CIN, int NT>
 struct NarrowCfg {
   static constexpr int K = 9 * CIN, NKC = (K + 63) / 64, KMMA = (K + 15) / 16;
-  static constexpr int STAGES = NKC <= 2 ? 3 : (NKC <= 5 ? 2 : 1);
+  static constexpr int STAGES = NKC <= 2 ? 3 : (NKC <= 5 ? 2 : 1);      // C_in = 16: 2 x 48 KB -> two CTAs per SM gather at once
   static constexpr uint32_t kAStage = NKC * 16384u, kB = NKC * NT * 128u;
   static constexpr int kTmemCols = NT == 64 ? 128 : 64;
   static constexpr int smem = STAGES * (int)kAStage + (int)kB + 4 * 32 * NT * 2 + 2 * 64 * 4 + 256 + 1024;
@@ -50,8 +51,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// C_in <= 16: two CTAs per SM (registers capped at 112, 105 KB of shared memory each): a lone producer warp per
+// scheduler is latency bound, a second CTA doubles what is in flight
 template <int CIN, int NT, int MODE>
-__global__ void __launch_bounds__(kNwThreads, 1) narrow_conv_kernel(const __grid_constant__ NarrowParams p) {
+__global__ void __launch_bounds__(kNwThreads, (CIN <= 16 && NT <= 32) ? 2 : 1) narrow_conv_kernel(const __grid_constant__ NarrowParams p) {
   using Cfg = NarrowCfg<CIN, NT>;
   constexpr int K = Cfg::K, KMMA = Cfg::KMMA, STAGES = Cfg::STAGES;
   constexpr uint32_t kAStage = Cfg::kAStage;
@@ -100,37 +103,45 @@ __global__ void __launch_bounds__(kNwThreads, 1) narrow_conv_kernel(const __grid
     const int r = threadIdx.x;
     uint32_t s = 0, ph = 1;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const long long pix = (long long)tile * 128 + r;
-      const bool live = pix < p.npix;
-      const int j0 = live ? (int)(pix % p.W) : 0;
-      const long long rest = live ? pix / p.W : 0;
-      const int i0 = (int)(rest % p.H);
-      const long long img = rest - i0;                  // b * H
+      // (32-bit index arithmetic: npix < 2^31; a lone producer warp per scheduler is instruction-latency bound)
+      const unsigned pix = (unsigned)tile * 128u + (unsigned)r;
+      const bool live = pix < (unsigned)p.npix;
+      const unsigned rest = live ? pix / (unsigned)p.W : 0u;
+      const int j0 = live ? (int)(pix - rest * (unsigned)p.W) : 0;
+      const int i0 = (int)(rest % (unsigned)p.H);
+      const __nv_bfloat16* pc = p.x + (long long)(live ? pix : 0u) * p.ld_in;      // the pixel itself; taps are offsets from it
       mbar_wait(&a_empty[s], ph);
       const uint32_t row = smem_u32(a_ring) + s * kAStage + r * 128;
       if constexpr (CIN >= 8) {
         constexpr int VPT = CIN / 8;                    // 16-byte vectors per tap
+        // taps per batch: every load of a batch is in flight before the first store (the gather is latency bound:
+        // three taps per batch cost three global round trips per tile, 0.34 ms per full-resolution 16 -> 16 layer)
+        constexpr int TB = CIN <= 8 ? 9 : (CIN <= 32 ? 5 : 3);
 #pragma unroll
-        for (int tr = 0; tr < 3; ++tr) {                // three taps per batch: 3 * VPT loads in flight
-          uint4 v[3 * VPT];
+        for (int t0 = 0; t0 < 9; t0 += TB) {
+          uint4 v[TB * VPT];
 #pragma unroll
-          for (int tt = 0; tt < 3; ++tt) {
-            const int t = tr * 3 + tt;
-            const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
-            const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-            const uint4* src = reinterpret_cast<const uint4*>(p.x + ((img + yy) * p.W + xx) * p.ld_in);
+          for (int tt = 0; tt < TB; ++tt) {
+            const int t = t0 + tt;
+            if (t < 9) {
+              const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
+              const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+              const uint4* src = reinterpret_cast<const uint4*>(pc + p.tap_off[t]);
 #pragma unroll
-            for (int q = 0; q < VPT; ++q) v[tt * VPT + q] = in ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+              for (int q = 0; q < VPT; ++q) v[tt * VPT + q] = in ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+            }
           }
 #pragma unroll
-          for (int tt = 0; tt < 3; ++tt)
+          for (int tt = 0; tt < TB; ++tt)
 #pragma unroll
             for (int q = 0; q < VPT; ++q) {
-              const int k = (tr * 3 + tt) * CIN + 8 * q;         // compile-time
-              const uint32_t dst = row + (k >> 6) * 16384 + ((((k & 63) >> 3) ^ (r & 7)) << 4);
-              const uint4 w = v[tt * VPT + q];
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w)
-                           : "memory");
+              if (t0 + tt < 9) {
+                const int k = (t0 + tt) * CIN + 8 * q;           // compile-time
+                const uint32_t dst = row + (k >> 6) * 16384 + ((((k & 63) >> 3) ^ (r & 7)) << 4);
+                const uint4 w = v[tt * VPT + q];
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w)
+                             : "memory");
+              }
             }
         }
       } else {
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(kNwThreads, 1) narrow_conv_kernel(const __grid
         for (int t = 0; t < 9; ++t) {
           const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
           const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-          const __nv_bfloat16* src = p.x + ((img + yy) * p.W + xx) * p.ld_in;
+          const __nv_bfloat16* src = pc + p.tap_off[t];
 #pragma unroll
           for (int c = 0; c < CIN; ++c) {
             const int k = t * CIN + c;
@@ -303,7 +314,7 @@ int narrow_tc_supported(const unetb200_gconv_t* d, const void* x, const void* wp
 static int narrow_grid(const unetb200_gconv_t* d, int* ntiles) {
   const long long npix = (long long)d->B * d->Hm * d->Wm;
   *ntiles = (int)((npix + 127) / 128);
-  const int per_sm = d->Cin <= 16 ? 2 : 1;              // shared memory per CTA: 60-70 KB up to C_in = 16, more beyond
+  const int per_sm = (d->Cin <= 16 && d->N <= 32) ? 2 : 1;      // see __launch_bounds__ of narrow_conv_kernel
   const int slots = per_sm * sm_count();
   return *ntiles < slots ? *ntiles : slots;
 }
@@ -353,7 +364,10 @@ int narrow_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, vo
   P.ld_in = d->ld_in; P.ld_out = d->ld_out;
   P.npix = (long long)d->B * d->Hm * d->Wm;
   P.H = d->Hm; P.W = d->Wm; P.N = d->N;
-  for (int t = 0; t < 9; ++t) { P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t]; }
+  for (int t = 0; t < 9; ++t) {
+    P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t];
+    P.tap_off[t] = ((long long)d->tap_dy[t] * d->Wm + d->tap_dx[t]) * d->ld_in;
+  }
   const int grid = narrow_grid(d, &P.ntiles);
   int rc;
   switch (d->Cin) {
@@ -386,6 +400,7 @@ struct NarrowWParams {
   long long npix;
   int H, W, N;
   int tap_dy[9], tap_dx[9];
+  long long tap_off[9];
   int ntiles;
 };
 
@@ -431,17 +446,18 @@ __global__ void __launch_bounds__(192, 1) narrow_wgrad_kernel(const __grid_const
     const int r = threadIdx.x;
     uint32_t s = 0, ph = 1;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const long long pix = (long long)tile * 128 + r;
-      const bool live = pix < p.npix;
-      const int j0 = live ? (int)(pix % p.W) : 0;
-      const long long rest = live ? pix / p.W : 0;
-      const int i0 = (int)(rest % p.H);
-      const long long img = rest - i0;
+      // (32-bit index arithmetic: npix < 2^31; a lone producer warp per scheduler is instruction-latency bound)
+      const unsigned pix = (unsigned)tile * 128u + (unsigned)r;
+      const bool live = pix < (unsigned)p.npix;
+      const unsigned rest = live ? pix / (unsigned)p.W : 0u;
+      const int j0 = live ? (int)(pix - rest * (unsigned)p.W) : 0;
+      const int i0 = (int)(rest % (unsigned)p.H);
+      const __nv_bfloat16* pc = p.x + (long long)(live ? pix : 0u) * p.ld_in;      // the pixel itself; taps are offsets from it
       mbar_wait(&a_empty[s], ph);
       const uint32_t row = smem_u32(smem) + s * kStage + r * 128;
       // the pixel's dY row -> B tile (chunk tile NKC of the stage)
       {
-        const uint4* src = reinterpret_cast<const uint4*>(p.gy + (live ? pix : 0) * p.ld_out);
+        const uint4* src = reinterpret_cast<const uint4*>(p.gy + (long long)(live ? pix : 0u) * p.ld_out);
         const int nv = p.N / 8;
         for (int q = 0; q < nv; ++q) {
           const uint4 w = live ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
@@ -451,27 +467,32 @@ __global__ void __launch_bounds__(192, 1) narrow_wgrad_kernel(const __grid_const
       }
       if constexpr (CIN >= 8) {
         constexpr int VPT = CIN / 8;
+        constexpr int TB = CIN <= 16 ? 9 : (CIN == 32 ? 5 : 3);
 #pragma unroll
-        for (int tr = 0; tr < 3; ++tr) {
-          uint4 v[3 * VPT];
+        for (int t0 = 0; t0 < 9; t0 += TB) {
+          uint4 v[TB * VPT];
 #pragma unroll
-          for (int tt = 0; tt < 3; ++tt) {
-            const int t = tr * 3 + tt;
-            const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
-            const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-            const uint4* src = reinterpret_cast<const uint4*>(p.x + ((img + yy) * p.W + xx) * p.ld_in);
+          for (int tt = 0; tt < TB; ++tt) {
+            const int t = t0 + tt;
+            if (t < 9) {
+              const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
+              const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
+              const uint4* src = reinterpret_cast<const uint4*>(pc + p.tap_off[t]);
 #pragma unroll
-            for (int q = 0; q < VPT; ++q) v[tt * VPT + q] = in ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+              for (int q = 0; q < VPT; ++q) v[tt * VPT + q] = in ? __ldg(src + q) : make_uint4(0u, 0u, 0u, 0u);
+            }
           }
 #pragma unroll
-          for (int tt = 0; tt < 3; ++tt)
+          for (int tt = 0; tt < TB; ++tt)
 #pragma unroll
             for (int q = 0; q < VPT; ++q) {
-              const int k = (tr * 3 + tt) * CIN + 8 * q;
-              const uint32_t dst = row + (k >> 6) * 16384 + ((((k & 63) >> 3) ^ (r & 7)) << 4);
-              const uint4 w = v[tt * VPT + q];
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w)
-                           : "memory");
+              if (t0 + tt < 9) {
+                const int k = (t0 + tt) * CIN + 8 * q;           // compile-time
+                const uint32_t dst = row + (k >> 6) * 16384 + ((((k & 63) >> 3) ^ (r & 7)) << 4);
+                const uint4 w = v[tt * VPT + q];
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w)
+                             : "memory");
+              }
             }
         }
       } else {
@@ -483,7 +504,7 @@ __global__ void __launch_bounds__(192, 1) narrow_wgrad_kernel(const __grid_const
         for (int t = 0; t < 9; ++t) {
           const int yy = i0 + p.tap_dy[t], xx = j0 + p.tap_dx[t];
           const bool in = live && yy >= 0 && yy < p.H && xx >= 0 && xx < p.W;
-          const __nv_bfloat16* src = p.x + ((img + yy) * p.W + xx) * p.ld_in;
+          const __nv_bfloat16* src = pc + p.tap_off[t];
 #pragma unroll
           for (int c = 0; c < CIN; ++c) {
             const int k = t * CIN + c;
@@ -605,7 +626,10 @@ int narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float
   P.ld_in = d->ld_in; P.ld_out = d->ld_out;
   P.npix = (long long)d->B * d->Hm * d->Wm;
   P.H = d->Hm; P.W = d->Wm; P.N = d->N;
-  for (int t = 0; t < 9; ++t) { P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t]; }
+  for (int t = 0; t < 9; ++t) {
+    P.tap_dy[t] = d->tap_dy[t]; P.tap_dx[t] = d->tap_dx[t];
+    P.tap_off[t] = ((long long)d->tap_dy[t] * d->Wm + d->tap_dx[t]) * d->ld_in;
+  }
   const int grid = narrow_wgrad_grid(d, &P.ntiles);
   if (grid != splits) { set_error("narrow_wgrad: the planned split count is %d, got %d", grid, splits); return UNETB200_E_INVALID; }
   switch (d->Cin) {
