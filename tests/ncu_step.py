@@ -1,5 +1,5 @@
 """One profiled UNet training step (BASELINE.json configs[1]) for Nsight Compute:
-    ncu --profile-from-start off ... python tests/ncu_step.py [batch] [size]
+    ncu --profile-from-start off ... python tests/ncu_step.py [batch] [size] [UNet|UNet_S|UNet_T|UNet_SA]
 Two warm-up steps run outside the capture range; cudaProfilerStart/Stop bracket the third."""
 import os
 import sys
@@ -15,7 +15,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = unet.UNet(1, 2, False).to(dev).to(memory_format=torch.channels_last).train()
+NAME = sys.argv[3] if len(sys.argv) > 3 else "UNet"
+import unet.unet_model as _UM  # noqa: E402
+model = getattr(_UM, NAME)(1, 2, False).to(dev).to(memory_format=torch.channels_last).train()
 from unetb200.optim import FusedRMSprop  # noqa: E402
 opt = FusedRMSprop(model.parameters(), lr=1e-5, weight_decay=1e-8, momentum=0.999)
 x = torch.rand(B, 1, S, S, device=dev).contiguous(memory_format=torch.channels_last)
