@@ -503,6 +503,13 @@ def check_conv_narrow():
     out += _narrow_case(2, 1, 16, 20, 20, 109)                     # first layers of the light variants
     out += _narrow_case(1, 3, 8, 18, 14, 110)
     out += _narrow_case(1, 8, 16, 40, 40, 111)
+    # the TMA-staged kernels (conv_halo.cu): several tiles per CTA (ring wrap, both accumulator sets), every channel pair
+    out += _narrow_case(8, 16, 16, 256, 256, 112)
+    out += _narrow_case(4, 32, 32, 200, 136, 113)
+    out += _narrow_case(2, 64, 16, 64, 48, 114)
+    out += _narrow_case(2, 16, 64, 40, 56, 115)
+    out += _narrow_case(3, 64, 32, 130, 100, 116)
+    out += _narrow_case(2, 32, 16, 72, 88, 117, slice_in=True)
     return out
 
 

@@ -60,7 +60,7 @@ def test_parts_against_reference_fixtures(G, golden, group):
     _assert_all(G.all_groups()[group](golden))
 
 
-@pytest.mark.parametrize("group", ["unet_fp32", "unet_fp32_b", "unet_tf32", "unet_bf16", "unet_bf16_bil", "unet_infer", "graph_side_stream", "unet_widths", "unet_sa", "checkpointing",
+@pytest.mark.parametrize("group", ["unet_fp32", "unet_fp32_b", "unet_tf32", "unet_bf16", "unet_bf16_bil", "unet_ragged", "unet_infer", "graph_side_stream", "unet_widths", "unet_sa", "checkpointing",
                                    "north_star_tf32x3", "segments", "prepack", "north_star_bf16", "north_star_bf16_b", "full_c2", "full_c3", "full_c5"])
 def test_unet_training_step(G, golden, group):
     _assert_all(G.all_groups()[group](golden))

@@ -4,6 +4,8 @@
 //                                        resident in shared memory, with and without concurrent bulk-copy fills
 //   tools/build/umma_probe check         (a) cta_group::2 GEMM against a host reference,
 //                                        (b) descriptors whose start address / SBO are not 1024-byte aligned
+//   tools/build/umma_probe checknarrow   (d) K-major 32 / 64-byte swizzle with shifted starts, (e) MN-major 32 / 64-byte
+//                                        swizzle with pixel-shifted M atoms and row-shifted N atoms (conv_halo.cu)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -457,7 +459,220 @@ __global__ void __launch_bounds__(128, 1) mn_kernel(const __nv_bfloat16* X, cons
   if (warp == 1) tmem_dealloc(tmem_base, 64);
 }
 
+
+// ---------------------------------------------------------------- check (d): K-major 32 / 64-byte swizzle, shifted starts
+// Pixel rows of P bytes (P / 2 bf16 channels) written with the P-byte swizzle as a function of the absolute
+// shared-memory address (16-byte chunk index XOR address bits [7, 7 + log2(P / 16))).  A = 128 rows addressed as
+// start + (m / 8) * sbo + (m % 8) * P, start = base + start_row * P (not atom aligned); B = 16 x (P / 2), K-major.
+constexpr uint32_t kLayoutSW64 = 4, kLayoutSW32 = 6;
+template <int P>
+__global__ void __launch_bounds__(128, 1) shiftn_kernel(const __nv_bfloat16* X, const __nv_bfloat16* B, float* D, int rows,
+                                                         int start_row, int sbo) {
+  constexpr int CPR = P / 16, MASK = CPR - 1, CH = P / 2;
+  constexpr uint32_t LAYOUT = P == 64 ? kLayoutSW64 : kLayoutSW32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sx = smem;
+  uint8_t* sb = smem + 49152;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 49152 + 8192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < rows * CPR; i += blockDim.x) {
+    const int r = i / CPR, c = i % CPR;
+    const uint32_t addr = smem_u32(sx) + r * P;
+    *reinterpret_cast<uint4*>(sx + r * P + ((c ^ ((addr >> 7) & MASK)) << 4)) =
+        *reinterpret_cast<const uint4*>(X + (size_t)r * CH + c * 8);
+  }
+  for (int i = threadIdx.x; i < 16 * CPR; i += blockDim.x) {
+    const int r = i / CPR, c = i % CPR;
+    const uint32_t addr = smem_u32(sb) + r * P;
+    *reinterpret_cast<uint4*>(sb + r * P + ((c ^ ((addr >> 7) & MASK)) << 4)) = *reinterpret_cast<const uint4*>(B + (size_t)r * CH + c * 8);
+  }
+  if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(false, false, false, 128, 16);
+    const uint64_t a0 = make_desc(smem_u32(sx) + start_row * P, 16, sbo, LAYOUT);
+    const uint64_t b0 = make_desc(smem_u32(sb), 16, 8 * P, LAYOUT);
+    if (elect_one()) {
+      for (int kk = 0; kk < P / 32; ++kk) umma<false>(tmem_base, a0 + 2 * kk, b0 + 2 * kk, idesc, kk > 0);
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+    for (int e = 0; e < 16; ++e) D[(size_t)(warp * 32 + lane) * 16 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 32);
+}
+
+// ---------------------------------------------------------------- check (e): MN-major 32 / 64-byte swizzle, stacked shifts
+// wgrad form for narrow layers.  X: box of box_w-pixel rows, PX bytes per pixel; G: box of gbox_w-pixel rows, PG bytes
+// per pixel.  A (MN-major): M = 128 = (256 / PX) atoms of PX / 2 channels, LBO = PX: atom h is the box shifted by h
+// pixels; B (MN-major): N = 3 atoms of PG / 2 channels, LBO = gbox_w * PG: atom s is the box shifted by s rows.
+// K = 16 pixels = 2 groups of 8 pixels, `rowk` ? one image row apart : consecutive.
+template <int PX, int PG>
+__global__ void __launch_bounds__(128, 1) mnn_kernel(const __nv_bfloat16* X, const __nv_bfloat16* G, float* D, int xrows,
+                                                      int grows, int box_w, int gbox_w, int xstart, int gstart, int rowk) {
+  constexpr int CX = PX / 16, CG = PG / 16;
+  constexpr uint32_t LX = PX == 128 ? kLayoutSW128 : (PX == 64 ? kLayoutSW64 : kLayoutSW32);
+  constexpr uint32_t LG = PG == 128 ? kLayoutSW128 : (PG == 64 ? kLayoutSW64 : kLayoutSW32);
+  constexpr int NN = 3 * (PG / 2);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sx = smem;
+  uint8_t* sg = smem + 49152;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 49152 + 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < xrows * CX; i += blockDim.x) {
+    const int r = i / CX, c = i % CX;
+    const uint32_t addr = smem_u32(sx) + r * PX;
+    *reinterpret_cast<uint4*>(sx + r * PX + ((c ^ ((addr >> 7) & (CX - 1))) << 4)) = *reinterpret_cast<const uint4*>(X + (size_t)r * (PX / 2) + c * 8);
+  }
+  for (int i = threadIdx.x; i < grows * CG; i += blockDim.x) {
+    const int r = i / CG, c = i % CG;
+    const uint32_t addr = smem_u32(sg) + r * PG;
+    *reinterpret_cast<uint4*>(sg + r * PG + ((c ^ ((addr >> 7) & (CG - 1))) << 4)) = *reinterpret_cast<const uint4*>(G + (size_t)r * (PG / 2) + c * 8);
+  }
+  if (warp == 0 && lane == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc(false, true, true, 128, NN);
+    if (elect_one()) {
+      const uint64_t da = make_desc(smem_u32(sx) + xstart * PX, PX, rowk ? box_w * PX : 8 * PX, LX);
+      const uint64_t db = make_desc(smem_u32(sg) + gstart * PG, gbox_w * PG, rowk ? gbox_w * PG : 8 * PG, LG);
+      umma<false>(tmem_base, da, db, idesc, 0);
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < NN; c0 += 16) {
+    uint32_t v[32];
+    // 16 columns at a time (x32 load of a 32-column aligned window would overrun NN = 48)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(tmem_base + ((uint32_t)(warp * 32) << 16) + c0) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int e = 0; e < 16; ++e) D[(size_t)(warp * 32 + lane) * NN + c0 + e] = __uint_as_float(v[e]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+template <int P>
+static void run_check_narrow_k() {
+  const int rows = 640, CH = P / 2;
+  std::vector<__nv_bfloat16> hX(rows * CH), hB(16 * CH);
+  std::vector<float> fX(rows * CH), fB(16 * CH);
+  srand(5);
+  for (size_t i = 0; i < hX.size(); ++i) { fX[i] = bf((rand() % 31 - 15) / 8.f); hX[i] = __float2bfloat16(fX[i]); }
+  for (size_t i = 0; i < hB.size(); ++i) { fB[i] = bf((rand() % 9 - 4) / 4.f); hB[i] = __float2bfloat16(fB[i]); }
+  __nv_bfloat16 *dX, *dB; float* dD;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dB, hB.size() * 2)); CK(cudaMalloc(&dD, 128 * 16 * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  const int smem = 49152 + 8192 + 1024 + 256;
+  CK(cudaFuncSetAttribute(shiftn_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int sbo_rows : {8, 10, 18, 34}) {
+    for (int start_row : {0, 1, 3, 8, 19}) {
+      CK(cudaMemset(dD, 0xff, 128 * 16 * 4));
+      shiftn_kernel<P><<<1, 128, smem>>>(dX, dB, dD, rows, start_row, sbo_rows * P);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("check(d) P=%d sbo_rows=%d start=%d: CUDA error %s\n", P, sbo_rows, start_row, cudaGetErrorString(e)); exit(1); }
+      std::vector<float> hD(128 * 16);
+      CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+      double maxerr = 0;
+      for (int m = 0; m < 128; ++m) {
+        const int r = start_row + (m / 8) * sbo_rows + (m % 8);
+        for (int n = 0; n < 16; ++n) {
+          double ref = 0;
+          for (int k = 0; k < CH; ++k) ref += (double)fX[r * CH + k] * fB[n * CH + k];
+          double er = fabs(ref - hD[m * 16 + n]);
+          if (!(er <= maxerr)) maxerr = er;
+        }
+      }
+      printf("check(d) K-major SW%d sbo=%2d rows start_row=%2d: max abs err %.3g %s\n", P, sbo_rows, start_row, maxerr,
+             maxerr < 1e-3 ? "OK" : "MISMATCH");
+    }
+  }
+}
+
+template <int PX, int PG>
+static void run_check_narrow_mn() {
+  const int xrows = 24 * 16, grows = 24 * 16, CX = PX / 2, CGc = PG / 2, NN = 3 * CGc;
+  std::vector<__nv_bfloat16> hX(xrows * CX), hG(grows * CGc);
+  std::vector<float> fX(xrows * CX), fG(grows * CGc);
+  srand(7);
+  for (size_t i = 0; i < hX.size(); ++i) { fX[i] = bf((rand() % 31 - 15) / 8.f); hX[i] = __float2bfloat16(fX[i]); }
+  for (size_t i = 0; i < hG.size(); ++i) { fG[i] = bf((rand() % 9 - 4) / 4.f); hG[i] = __float2bfloat16(fG[i]); }
+  __nv_bfloat16 *dX, *dG; float* dD;
+  CK(cudaMalloc(&dX, hX.size() * 2)); CK(cudaMalloc(&dG, hG.size() * 2)); CK(cudaMalloc(&dD, 128 * NN * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dG, hG.data(), hG.size() * 2, cudaMemcpyHostToDevice));
+  const int smem = 49152 + 32768 + 1024 + 256;
+  CK(cudaFuncSetAttribute(mnn_kernel<PX, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  struct Case { int box_w, gbox_w, xstart, gstart, rowk; };
+  const Case cases[] = {{24, 16, 0, 0, 0}, {24, 16, 25, 16, 0}, {24, 16, 51, 35, 0}, {18, 16, 0, 0, 1}, {18, 16, 19, 16, 1}, {19, 16, 40, 8, 1}};
+  for (const Case& c : cases) {
+    CK(cudaMemset(dD, 0xff, 128 * NN * 4));
+    mnn_kernel<PX, PG><<<1, 128, smem>>>(dX, dG, dD, xrows, grows, c.box_w, c.gbox_w, c.xstart, c.gstart, c.rowk);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("check(e) PX=%d PG=%d: CUDA error %s\n", PX, PG, cudaGetErrorString(e)); exit(1); }
+    std::vector<float> hD(128 * NN);
+    CK(cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0;
+    for (int m = 0; m < 128; ++m) {
+      const int h = m / CX, ch = m % CX;
+      for (int n = 0; n < NN; ++n) {
+        const int sft = n / CGc, co = n % CGc;
+        double ref = 0;
+        for (int k = 0; k < 16; ++k) {
+          const int xo = c.rowk ? (k / 8) * c.box_w + (k % 8) : k;
+          const int go = c.rowk ? (k / 8) * c.gbox_w + (k % 8) : k;
+          ref += (double)fX[(c.xstart + xo + h) * CX + ch] * fG[(c.gstart + go + sft * c.gbox_w) * CGc + co];
+        }
+        const double er = fabs(ref - hD[m * NN + n]);
+        if (!(er <= maxerr)) maxerr = er;
+      }
+    }
+    printf("check(e) MN-major X SW%d G SW%d box_w=%d xstart=%d gstart=%d rowk=%d: max abs err %.3g %s\n", PX, PG, c.box_w,
+           c.xstart, c.gstart, c.rowk, maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
+  }
+}
+
+static void run_check_narrow() {
+  run_check_narrow_k<32>();
+  run_check_narrow_k<64>();
+  run_check_narrow_mn<32, 32>();
+  run_check_narrow_mn<64, 32>();
+  run_check_narrow_mn<32, 64>();
+  run_check_narrow_mn<64, 64>();
+  run_check_narrow_mn<128, 64>();
+}
 
 static void run_check() {
   // (a)
@@ -573,6 +788,7 @@ int main(int argc, char** argv) {
   const char* mode = argc > 1 ? argv[1] : "all";
   if (!strcmp(mode, "check") || !strcmp(mode, "all")) run_check();
   if (!strcmp(mode, "checkmn") || !strcmp(mode, "all")) run_check_mn();
+  if (!strcmp(mode, "checknarrow") || !strcmp(mode, "all")) run_check_narrow();
   if (!strcmp(mode, "rate") || !strcmp(mode, "all")) run_rate();
   if (!strcmp(mode, "rate2") || !strcmp(mode, "all")) run_rate2();
   return 0;

@@ -675,7 +675,9 @@ int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
   long long n3 = tc3_stats_workspace(d);
   if (n3 > n) n = n3;
   const long long n4 = narrow_tc_stats_rows(d) * 2 * g.N;
-  return n > n4 ? n : n4;
+  if (n4 > n) n = n4;
+  const long long n5 = halo_stats_rows(d) * 2 * g.N;
+  return n > n5 ? n : n5;
 }
 
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
@@ -688,6 +690,10 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (!stats) stats_ws = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   int algo = d->algo;
+  if (algo != UNETB200_ALGO_SIMT && !bias && halo_fprop_supported(d, x, wp, y)) {     // 16 / 32 / 64 channels: TMA halo box
+    if (algo_used) *algo_used = UNETB200_ALGO_TC;
+    return halo_fprop(d, x, wp, y, stats, stats_ws, nullptr, s);
+  }
   if (algo != UNETB200_ALGO_SIMT && !bias && narrow_tc_supported(d, x, wp, y)) {      // narrow channel counts: thread-built im2col
     if (algo_used) *algo_used = UNETB200_ALGO_TC;
     return narrow_tc_fprop(d, x, wp, y, stats, stats_ws, nullptr, s);
@@ -723,6 +729,7 @@ int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const 
   static const bool wide = getenv("UNETB200_TC3_MAXBN") && atoi(getenv("UNETB200_TC3_MAXBN")) >= 256;
   if (off || d->algo == UNETB200_ALGO_SIMT) return 0;
   if (first_tc_supported(d, z) && aligned16(wp)) return 1;            // first layer: thread-built im2col kernel
+  if (halo_fprop_supported(d, x, wp, z)) return 1;                    // 16 / 32 / 64 channels: TMA halo box
   if (narrow_tc_supported(d, x, wp, z)) return 1;                     // narrow channel counts: the same, generalised
   if (d->N % 128 != 0 && d->N % 64 != 0) return 0;
   if (d->dtype == UNETB200_BF16 && d->N % 256 == 0 && wide) return 0;
@@ -740,6 +747,8 @@ int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, c
                "gconv_fprop + bn_relu_apply instead)");
   if (first_tc_supported(d, z) && aligned16(wp))
     return first_tc_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
+  if (halo_fprop_supported(d, x, wp, z))
+    return halo_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
   if (narrow_tc_supported(d, x, wp, z))
     return narrow_tc_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
   return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift);
@@ -795,6 +804,11 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
   int rc = gconv_validate(d, &g);
   if (rc) return rc;
   int algo = d->algo;
+  if (algo != UNETB200_ALGO_SIMT && halo_wgrad_supported(d, nullptr, nullptr)) {        // 16 / 32 / 64 channels: TMA boxes
+    if (algo_used) *algo_used = UNETB200_ALGO_TC;
+    if (splits) *splits = halo_wgrad_splits(d);
+    return 0;
+  }
   if (algo != UNETB200_ALGO_SIMT && narrow_wgrad_supported(d, nullptr, nullptr)) {      // narrow channel counts
     if (algo_used) *algo_used = UNETB200_ALGO_TC;
     if (splits) *splits = narrow_wgrad_splits(d);
@@ -822,6 +836,10 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   UB_CHECK_ARG(x && gy && partials && splits >= 1, "gconv_wgrad: null pointer / bad splits");
   cudaStream_t s = (cudaStream_t)stream;
   int algo = d->algo;
+  if (algo != UNETB200_ALGO_SIMT && halo_wgrad_supported(d, nullptr, nullptr)) {
+    UB_CHECK_ARG(halo_wgrad_supported(d, x, gy), "gconv_wgrad: the TMA-staged narrow kernel needs 16-byte aligned operands");
+    return halo_wgrad(d, x, gy, partials, splits, s);
+  }
   if (algo != UNETB200_ALGO_SIMT && narrow_wgrad_supported(d, nullptr, nullptr)) {
     UB_CHECK_ARG(narrow_wgrad_supported(d, x, gy), "gconv_wgrad: the narrow tcgen05 kernel needs 16-byte aligned operands");
     return narrow_wgrad(d, x, gy, partials, splits, s);

@@ -95,6 +95,14 @@ long long narrow_tc_stats_rows(const unetb200_gconv_t* d);
 int narrow_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
                     const float* affine, cudaStream_t s);
 
+// TMA-staged tcgen05 kernels for 16 / 32 / 64 channels on either side (conv_halo.cu)
+int halo_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+long long halo_stats_rows(const unetb200_gconv_t* d);
+int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
+               const float* affine, cudaStream_t s);
+int halo_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int halo_wgrad_splits(const unetb200_gconv_t* d);
+int halo_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
 int narrow_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int narrow_wgrad_splits(const unetb200_gconv_t* d);
 int narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
