@@ -390,7 +390,7 @@ def _convT_case(B, Ci, Co, h, w_, pad, dt_, algo, seed):
                        off, H, W, ops.nhwc_ld(cat))
     d.algo = algo
     used = ops.gconv_fprop(d, xd, UF.packT_fprop(w.to(DEV), dt_), b.to(DEV), upv, None)
-    assert used == algo
+    assert used == algo or algo == _lib.ALGO_AUTO
     res.append((f"convT_fprop_{tag}", rel(host(upv), ref.detach()), tol))
     res.append((f"convT_fprop_{tag}_skip_untouched", host(ops.channel_slice(cat, 0, Co)).abs().max().item(), 0.0))
     gcat = ops.empty_nhwc(B, 2 * Co, H, W, dt_, DEV)
@@ -510,6 +510,14 @@ def check_conv_narrow():
     out += _narrow_case(2, 16, 64, 40, 56, 115)
     out += _narrow_case(3, 64, 32, 130, 100, 116)
     out += _narrow_case(2, 32, 16, 72, 88, 117, slice_in=True)
+    # narrow ConvTranspose2d (conv_halo_t.cu): partial tiles in both directions, rows past the image (h % 8 != 0) that
+    # the 5-D quadrant view reads from the next image, several tiles per CTA, padded destination (fprop only)
+    out += _convT_case(2, 32, 16, 24, 40, (0, 0), BF, _lib.ALGO_TC, 120)
+    out += _convT_case(3, 64, 32, 20, 16, (0, 0), BF, _lib.ALGO_TC, 121)
+    out += _convT_case(1, 32, 32, 9, 7, (0, 0), BF, _lib.ALGO_TC, 122)
+    out += _convT_case(2, 64, 16, 8, 16, (0, 0), BF, _lib.ALGO_TC, 123)
+    out += _convT_case(16, 32, 16, 128, 128, (0, 0), BF, _lib.ALGO_TC, 124)
+    out += _convT_case(2, 32, 16, 5, 6, (1, 2), BF, _lib.ALGO_AUTO, 125)
     return out
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Training-step time of the width variants (UNet_S / UNet_T / UNet_SA, reference unet_model.py:52-189; UNet_S is what
-train.py:253 builds by default) at B = 16, 512x512, bf16, eager launches, with the per-kernel-class profile."""
+train.py:253 builds by default) at B = 16, 512x512, bf16, as a CUDA graph and with eager launches, with the per-kernel-class profile."""
 import os
 import sys
 
@@ -37,6 +37,27 @@ for name in names:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
+    # the same step replayed as a CUDA graph (what bench.py times): eager launches are CPU-bound on the light variants
+    from unetb200.graph import GraphedStep
+
+    def gstep(xx, tt):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", enabled=True):
+            loss = UL.training_criterion(m(xx), tt, boundary_coeff=0.2, edge_width=51, edge_weight=7)
+        loss.backward()
+        opt.step(clip_max_norm=1.0)
+        return loss.detach()
+    gs = GraphedStep(gstep, (x, t), warmup=2)
+    for _ in range(3):
+        gs.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        gs.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    gms = e0.elapsed_time(e1) / 20
+    del gs
     with ops.profile() as rec:
         step()
         torch.cuda.synchronize()
@@ -45,7 +66,7 @@ for name in names:
         k = nm.split("[")[0]
         agg[k] = agg.get(k, 0.0) + s.elapsed_time(e)
     top = sorted(agg.items(), key=lambda kv: -kv[1])[:8]
-    print(f"{name}: {ms:.2f} ms/step ({16 / ms * 1e3:.0f} img/s, eager);  " + ", ".join(f"{k} {v:.2f}" for k, v in top), flush=True)
+    print(f"{name}: graph {gms:.2f} ms/step ({16 / gms * 1e3:.0f} img/s), eager {ms:.2f} ms/step;  " + ", ".join(f"{k} {v:.2f}" for k, v in top), flush=True)
     if os.environ.get("PER_SHAPE"):
         full = {}
         for nm, s, e, fl, nb in rec:

@@ -690,6 +690,14 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (!stats) stats_ws = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   int algo = d->algo;
+  if (algo != UNETB200_ALGO_SIMT && !stats && halo_t_fprop_supported(d, x, wp, y)) {  // narrow ConvTranspose2d
+    if (algo_used) *algo_used = UNETB200_ALGO_TC;
+    return halo_t_fprop(d, x, wp, bias, y, s);
+  }
+  if (algo != UNETB200_ALGO_SIMT && !stats && !bias && halo_t_dgrad_supported(d, x, wp, y)) {      // ... and its dgrad
+    if (algo_used) *algo_used = UNETB200_ALGO_TC;
+    return halo_t_dgrad(d, x, wp, y, s);
+  }
   if (algo != UNETB200_ALGO_SIMT && !bias && halo_fprop_supported(d, x, wp, y)) {     // 16 / 32 / 64 channels: TMA halo box
     if (algo_used) *algo_used = UNETB200_ALGO_TC;
     return halo_fprop(d, x, wp, y, stats, stats_ws, nullptr, s);
@@ -809,6 +817,11 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
     if (splits) *splits = halo_wgrad_splits(d);
     return 0;
   }
+  if (algo != UNETB200_ALGO_SIMT && halo_t_wgrad_supported(d, nullptr, nullptr)) {      // narrow ConvTranspose2d
+    if (algo_used) *algo_used = UNETB200_ALGO_TC;
+    if (splits) *splits = halo_t_wgrad_splits(d);
+    return 0;
+  }
   if (algo != UNETB200_ALGO_SIMT && narrow_wgrad_supported(d, nullptr, nullptr)) {      // narrow channel counts
     if (algo_used) *algo_used = UNETB200_ALGO_TC;
     if (splits) *splits = narrow_wgrad_splits(d);
@@ -839,6 +852,10 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   if (algo != UNETB200_ALGO_SIMT && halo_wgrad_supported(d, nullptr, nullptr)) {
     UB_CHECK_ARG(halo_wgrad_supported(d, x, gy), "gconv_wgrad: the TMA-staged narrow kernel needs 16-byte aligned operands");
     return halo_wgrad(d, x, gy, partials, splits, s);
+  }
+  if (algo != UNETB200_ALGO_SIMT && halo_t_wgrad_supported(d, nullptr, nullptr)) {
+    UB_CHECK_ARG(halo_t_wgrad_supported(d, x, gy), "gconv_wgrad: the TMA-staged narrow kernel needs 16-byte aligned operands");
+    return halo_t_wgrad(d, x, gy, partials, splits, s);
   }
   if (algo != UNETB200_ALGO_SIMT && narrow_wgrad_supported(d, nullptr, nullptr)) {
     UB_CHECK_ARG(narrow_wgrad_supported(d, x, gy), "gconv_wgrad: the narrow tcgen05 kernel needs 16-byte aligned operands");

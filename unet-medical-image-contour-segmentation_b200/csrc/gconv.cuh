@@ -103,6 +103,14 @@ int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y
 int halo_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int halo_wgrad_splits(const unetb200_gconv_t* d);
 int halo_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
+// ConvTranspose2d(k=2, s=2) with narrow channel counts (conv_halo_t.cu)
+int halo_t_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+int halo_t_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y, cudaStream_t s);
+int halo_t_dgrad_supported(const unetb200_gconv_t* d, const void* g, const void* wp, const void* gx);
+int halo_t_dgrad(const unetb200_gconv_t* d, const void* g, const void* wp, void* gx, cudaStream_t s);
+int halo_t_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int halo_t_wgrad_splits(const unetb200_gconv_t* d);
+int halo_t_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
 int narrow_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int narrow_wgrad_splits(const unetb200_gconv_t* d);
 int narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);

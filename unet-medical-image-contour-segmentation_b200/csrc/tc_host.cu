@@ -70,6 +70,25 @@ int encode_act_box_sw(CUtensorMap* m, const void* base, int C, int W, int H, int
   }
   return 0;
 }
+int encode_bf16_box(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims, const unsigned long long* strides_bytes,
+                    const unsigned* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return UNETB200_E_CUDA; }
+  if (rank < 2 || rank > 5 || (box[0] != 16 && box[0] != 32 && box[0] != 64)) { set_error("encode_bf16_box: rank %d box %u", rank, box[0]); return UNETB200_E_INVALID; }
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box[0] == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box[0] == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(bf16 box rank %d, inner %u) failed: %d", rank, box[0], (int)r);
+    return UNETB200_E_CUDA;
+  }
+  return 0;
+}
 int encode_weights(CUtensorMap* m, int dtype, const void* base, int K, int N, int box_n) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return UNETB200_E_CUDA; }
