@@ -459,7 +459,9 @@ def _narrow_case(B, Ci, Co, H, W, seed, slice_in=False):
         return ops.make_gconv(ops._DT[dt_], _lib.ALGO_AUTO, B, H, W, xin.shape[1], ops.TAPS3, 1, (0, 0), H, W,
                               ops.nhwc_ld(xin), Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(yout))
     used = ops.gconv_fprop(desc(xd, Co, y), xd, UF.pack3x3_fprop(wdev, dt_), None, y, stats)
-    res.append((f"{tag}_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
+    # C_in = 1 -> 8 / 16 / 32 channels is the CUDA-core first-layer kernel (conv_first_narrow.cu: K = 9, HBM-bound)
+    want = _lib.ALGO_SIMT if (Ci == 1 and Co in (8, 16, 32)) else _lib.ALGO_TC
+    res.append((f"{tag}_on_tensor_cores", 0.0 if used == want else 1.0, 0.0))
     yh = host(y)
     res.append((f"{tag}_fprop", rel(yh, ref.detach()), 1.2e-2))
     st = host(stats.float()).reshape(2, Co)
@@ -474,7 +476,7 @@ def _narrow_case(B, Ci, Co, H, W, seed, slice_in=False):
     gyd = dev_nhwc(gy, dt_)
     dW = torch.empty(Co, Ci, 3, 3, device=DEV)
     used = ops.gconv_wgrad(desc(xd, Co, gyd), xd, gyd, dW, 1, 9, Ci * 9)
-    res.append((f"{tag}_wgrad_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
+    res.append((f"{tag}_wgrad_on_tensor_cores", 0.0 if used == want else 1.0, 0.0))
     res.append((f"{tag}_wgrad", rel(host(dW), wq.grad), 5e-3))
     # folded eval-mode BatchNorm + ReLU
     sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g) * 0.2
@@ -501,6 +503,10 @@ def check_conv_narrow():
     out += _narrow_case(2, 8, 8, 16, 24, 107)                      # UNet_T: N = 8 rides an N = 16 MMA
     out += _narrow_case(1, 16, 8, 10, 10, 108)
     out += _narrow_case(2, 1, 16, 20, 20, 109)                     # first layers of the light variants
+    out += _narrow_case(3, 1, 16, 200, 300, 118)                   # ... several tiles per block, ragged in both directions
+    out += _narrow_case(2, 1, 8, 37, 530, 119)
+    out += _narrow_case(2, 1, 32, 64, 100, 126)
+    out += _narrow_case(1, 3, 16, 24, 24, 127)                     # RGB input stays on the im2col kernel
     out += _narrow_case(1, 3, 8, 18, 14, 110)
     out += _narrow_case(1, 8, 16, 40, 40, 111)
     # the TMA-staged kernels (conv_halo.cu): several tiles per CTA (ring wrap, both accumulator sets), every channel pair

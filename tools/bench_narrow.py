@@ -15,7 +15,7 @@ from unetb200 import functional as UF  # noqa: E402
 DEV, BF = "cuda", torch.bfloat16
 PEAK = 6.5e12
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-shapes = [(16, 16, 512), (32, 16, 512), (16, 32, 256), (32, 32, 256), (64, 32, 256), (32, 64, 128), (8, 8, 512), (16, 8, 512)]
+shapes = [(1, 16, 512), (1, 8, 512), (16, 16, 512), (32, 16, 512), (16, 32, 256), (32, 32, 256), (64, 32, 256), (32, 64, 128), (8, 8, 512), (16, 8, 512)]
 
 
 def timed(fn, n=10):

@@ -677,7 +677,9 @@ int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
   const long long n4 = narrow_tc_stats_rows(d) * 2 * g.N;
   if (n4 > n) n = n4;
   const long long n5 = halo_stats_rows(d) * 2 * g.N;
-  return n > n5 ? n : n5;
+  if (n5 > n) n = n5;
+  const long long n6 = first_narrow_rows(d) * 2 * g.N;
+  return n > n6 ? n : n6;
 }
 
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
@@ -697,6 +699,10 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   if (algo != UNETB200_ALGO_SIMT && !stats && !bias && halo_t_dgrad_supported(d, x, wp, y)) {      // ... and its dgrad
     if (algo_used) *algo_used = UNETB200_ALGO_TC;
     return halo_t_dgrad(d, x, wp, y, s);
+  }
+  if (!bias && first_narrow_supported(d, y)) {          // C_in = 1 -> 8 / 16 / 32 channels
+    if (algo_used) *algo_used = UNETB200_ALGO_SIMT;
+    return first_narrow_fprop(d, x, wp, y, stats, stats_ws, nullptr, s);
   }
   if (algo != UNETB200_ALGO_SIMT && !bias && halo_fprop_supported(d, x, wp, y)) {     // 16 / 32 / 64 channels: TMA halo box
     if (algo_used) *algo_used = UNETB200_ALGO_TC;
@@ -737,6 +743,7 @@ int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const 
   static const bool wide = getenv("UNETB200_TC3_MAXBN") && atoi(getenv("UNETB200_TC3_MAXBN")) >= 256;
   if (off || d->algo == UNETB200_ALGO_SIMT) return 0;
   if (first_tc_supported(d, z) && aligned16(wp)) return 1;            // first layer: thread-built im2col kernel
+  if (first_narrow_supported(d, z)) return 1;                         // C_in = 1 -> 8 / 16 / 32 channels
   if (halo_fprop_supported(d, x, wp, z)) return 1;                    // 16 / 32 / 64 channels: TMA halo box
   if (narrow_tc_supported(d, x, wp, z)) return 1;                     // narrow channel counts: the same, generalised
   if (d->N % 128 != 0 && d->N % 64 != 0) return 0;
@@ -755,6 +762,8 @@ int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, c
                "gconv_fprop + bn_relu_apply instead)");
   if (first_tc_supported(d, z) && aligned16(wp))
     return first_tc_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
+  if (first_narrow_supported(d, z))
+    return first_narrow_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
   if (halo_fprop_supported(d, x, wp, z))
     return halo_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream);
   if (narrow_tc_supported(d, x, wp, z))
@@ -812,6 +821,11 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
   int rc = gconv_validate(d, &g);
   if (rc) return rc;
   int algo = d->algo;
+  if (first_narrow_supported(d, nullptr)) {               // C_in = 1 -> 8 / 16 / 32 channels
+    if (algo_used) *algo_used = UNETB200_ALGO_SIMT;
+    if (splits) *splits = first_narrow_wgrad_splits(d);
+    return 0;
+  }
   if (algo != UNETB200_ALGO_SIMT && halo_wgrad_supported(d, nullptr, nullptr)) {        // 16 / 32 / 64 channels: TMA boxes
     if (algo_used) *algo_used = UNETB200_ALGO_TC;
     if (splits) *splits = halo_wgrad_splits(d);
@@ -849,6 +863,10 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   UB_CHECK_ARG(x && gy && partials && splits >= 1, "gconv_wgrad: null pointer / bad splits");
   cudaStream_t s = (cudaStream_t)stream;
   int algo = d->algo;
+  if (first_narrow_supported(d, nullptr)) {
+    UB_CHECK_ARG(first_narrow_supported(d, gy), "gconv_wgrad: the first-layer kernel needs a 16-byte aligned gradient");
+    return first_narrow_wgrad(d, x, gy, partials, splits, s);
+  }
   if (algo != UNETB200_ALGO_SIMT && halo_wgrad_supported(d, nullptr, nullptr)) {
     UB_CHECK_ARG(halo_wgrad_supported(d, x, gy), "gconv_wgrad: the TMA-staged narrow kernel needs 16-byte aligned operands");
     return halo_wgrad(d, x, gy, partials, splits, s);

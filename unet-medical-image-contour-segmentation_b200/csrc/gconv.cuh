@@ -103,6 +103,13 @@ int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y
 int halo_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int halo_wgrad_splits(const unetb200_gconv_t* d);
 int halo_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
+// first layer of the light variants: C_in = 1 -> 8 / 16 / 32 channels, CUDA cores (conv_first_narrow.cu)
+int first_narrow_supported(const unetb200_gconv_t* d, const void* y);
+long long first_narrow_rows(const unetb200_gconv_t* d);
+int first_narrow_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
+                       const float* affine, cudaStream_t s);
+int first_narrow_wgrad_splits(const unetb200_gconv_t* d);
+int first_narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
 // ConvTranspose2d(k=2, s=2) with narrow channel counts (conv_halo_t.cu)
 int halo_t_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
 int halo_t_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y, cudaStream_t s);
