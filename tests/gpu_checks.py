@@ -527,6 +527,66 @@ def check_conv_narrow():
     return out
 
 
+def _guarded_nhwc(B, Cc, H, W, dtype, guard=8192, fill=3.0):
+    """Logical [B, C, H, W] NHWC view in the middle of a flat buffer whose `guard` elements either side hold a
+    sentinel: an out-of-bounds store of a kernel shows up as a changed guard (compute-sanitizer is not available on
+    the GPU pool)."""
+    n = B * H * W * Cc
+    flat = torch.full((guard + n + guard,), fill, dtype=dtype, device=DEV)
+    view = flat[guard:guard + n].view(B, H, W, Cc).permute(0, 3, 1, 2)
+    return flat, view, guard
+
+
+def _guards_intact(flat, guard, fill=3.0):
+    return 0.0 if bool((flat[:guard] == fill).all()) and bool((flat[-guard:] == fill).all()) else 1.0
+
+
+def check_narrow_bounds():
+    """Stores of the TMA-staged narrow kernels stay inside their tensors on ragged shapes (partial tiles in both
+    directions, rows of a tile past the image, the last tile of the last image)."""
+    res = []
+    g = gen(130)
+    for (B, Ci, Co, H, W) in [(2, 16, 16, 20, 24), (1, 16, 32, 17, 9), (3, 64, 32, 35, 50), (2, 1, 8, 37, 530), (2, 1, 16, 9, 130),
+                              (1, 32, 64, 5, 3)]:
+        x = dev_nhwc(torch.randn(B, Ci, H, W, generator=g), BF)
+        w = torch.randn(Co, Ci, 3, 3, generator=g).to(DEV) / (3 * Ci ** 0.5)
+        flat, y, gd = _guarded_nhwc(B, Co, H, W, BF)
+        stats = torch.zeros(2 * Co, dtype=torch.float64, device=DEV)
+        d = ops.make_gconv(ops._DT[BF], _lib.ALGO_AUTO, B, H, W, Ci, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(x), Co, 1, 1,
+                           (0, 0), H, W, ops.nhwc_ld(y))
+        ops.gconv_fprop(d, x, UF.pack3x3_fprop(w, BF), None, y, stats)
+        torch.cuda.synchronize()
+        res.append((f"bounds_fprop_{Ci}to{Co}_{B}x{H}x{W}", _guards_intact(flat, gd), 0.0))
+        ref = F.conv2d(host(x), rq(w.cpu(), BF), padding=1)
+        res.append((f"bounds_fprop_{Ci}to{Co}_{B}x{H}x{W}_values", rel(host(y), ref), 1.2e-2))
+        if Ci >= 8:
+            gy = dev_nhwc(torch.randn(B, Co, H, W, generator=g), BF)
+            flat2, gx, gd2 = _guarded_nhwc(B, Ci, H, W, BF)
+            dd = ops.make_gconv(ops._DT[BF], _lib.ALGO_AUTO, B, H, W, Co, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(gy), Ci, 1, 1,
+                                (0, 0), H, W, ops.nhwc_ld(gx))
+            ops.gconv_fprop(dd, gy, UF.pack3x3_dgrad(w, BF), None, gx, None)
+            torch.cuda.synchronize()
+            res.append((f"bounds_dgrad_{Ci}to{Co}_{B}x{H}x{W}", _guards_intact(flat2, gd2), 0.0))
+    for (B, Ci, Co, h, w_) in [(2, 32, 16, 9, 7), (1, 64, 32, 3, 20), (3, 32, 32, 8, 16)]:
+        x = dev_nhwc(torch.randn(B, Ci, h, w_, generator=g), BF)
+        wT = torch.randn(Ci, Co, 2, 2, generator=g).to(DEV) / (Ci ** 0.5)
+        b = torch.randn(Co, generator=g).to(DEV)
+        H, W = 2 * h, 2 * w_
+        flat, up, gd = _guarded_nhwc(B, Co, H, W, BF)
+        d = ops.make_gconv(ops._DT[BF], _lib.ALGO_AUTO, B, h, w_, Ci, ops.TAPS1, 1, (0, 0), h, w_, ops.nhwc_ld(x), 4 * Co, 4, 2,
+                           (0, 0), H, W, ops.nhwc_ld(up))
+        ops.gconv_fprop(d, x, UF.packT_fprop(wT, BF), b, up, None)
+        flat2, gx, gd2 = _guarded_nhwc(B, Ci, h, w_, BF)
+        gup = dev_nhwc(torch.randn(B, Co, H, W, generator=g), BF)
+        dd = ops.make_gconv(ops._DT[BF], _lib.ALGO_AUTO, B, h, w_, Co, ops.TAPS_Q, 2, (0, 0), H, W, ops.nhwc_ld(gup), Ci, 1, 1,
+                            (0, 0), h, w_, ops.nhwc_ld(gx))
+        ops.gconv_fprop(dd, gup, UF.packT_dgrad(wT, BF), None, gx, None)
+        torch.cuda.synchronize()
+        res.append((f"bounds_convT_fprop_{Ci}to{Co}_{B}x{h}x{w_}", _guards_intact(flat, gd), 0.0))
+        res.append((f"bounds_convT_dgrad_{Ci}to{Co}_{B}x{h}x{w_}", _guards_intact(flat2, gd2), 0.0))
+    return res
+
+
 def check_conv_tc_fprop_small():
     """First contact with the tcgen05 engine: one tile, one N block."""
     return _conv3x3_case(1, 64, 64, 8, 16, BF, _lib.ALGO_TC, 20)
@@ -1053,6 +1113,7 @@ GROUPS = {
     "outconv": lambda gd: check_outconv(),
     "conv_simt": lambda gd: check_conv_simt(),
     "conv_narrow": lambda gd: check_conv_narrow(),
+    "narrow_bounds": lambda gd: check_narrow_bounds(),
     "conv_tc_first": lambda gd: check_conv_tc_fprop_small(),
     "conv_tc": lambda gd: check_conv_tc(),
     "conv_tc_tf32": lambda gd: check_conv_tc_tf32(),

@@ -50,7 +50,7 @@ def test_conv_simt(G, golden):
     _assert_all(G.all_groups()["conv_simt"](golden))
 
 
-@pytest.mark.parametrize("group", ["conv_tc_first", "conv_tc", "conv_tc_tf32", "conv_tc_x3", "conv_layouts", "conv_bnfold", "dgrad_bnbwd", "conv_narrow"])
+@pytest.mark.parametrize("group", ["conv_tc_first", "conv_tc", "conv_tc_tf32", "conv_tc_x3", "conv_layouts", "conv_bnfold", "dgrad_bnbwd", "conv_narrow", "narrow_bounds"])
 def test_conv_tcgen05(G, golden, group):
     _assert_all(G.all_groups()[group](golden))
 

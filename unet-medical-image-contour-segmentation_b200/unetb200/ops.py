@@ -54,7 +54,15 @@ def lib():
     return _lib.load()
 
 
+# torch.cuda.current_stream() costs ~18 us of Python per call (device-index plumbing, an environment lookup in
+# is_available); the light variants issue ~230 launches per step and are launch-bound when run eagerly
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    if _raw_stream is not None and _cur_device is not None:
+        return C.c_void_p(_raw_stream(_cur_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -283,9 +291,12 @@ TAPS_Q = [(0, 0), (0, 1), (1, 0), (1, 1)]
 _ALGO_NAME = {ALGO_SIMT: "simt", ALGO_TC: "tc"}
 
 
+_FORCED_ALGO = {"simt": ALGO_SIMT, "tc": ALGO_TC}.get(os.environ.get("UNETB200_ALGO", "").lower(), None)
+
+
 def forced_algo():
-    v = os.environ.get("UNETB200_ALGO", "").lower()
-    return {"simt": ALGO_SIMT, "tc": ALGO_TC}.get(v, None)
+    """UNETB200_ALGO=simt|tc (read once at import): every convolution on one engine, for A/B runs."""
+    return _FORCED_ALGO
 
 
 def make_gconv(dtype, algo, B, Hm, Wm, Cin, taps, in_scale, in_off, Hin, Win, ld_in, N, nquad, out_scale, out_off,
@@ -307,7 +318,7 @@ def make_gconv(dtype, algo, B, Hm, Wm, Cin, taps, in_scale, in_off, Hin, Win, ld
 
 def _shape_tag(d):
     """Per-layer profile names when UNETB200_PROFILE_SHAPES is set (bench.py --per-layer)."""
-    if not os.environ.get("UNETB200_PROFILE_SHAPES"):
+    if _PROFILE is None or not os.environ.get("UNETB200_PROFILE_SHAPES"):
         return ""
     return f"[M={d.B * d.Hm * d.Wm},N={d.N},K={d.ntaps * d.Cin}]"
 
