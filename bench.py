@@ -573,9 +573,10 @@ def bench_train(ctx):
             torch.cuda.current_stream().wait_event(ev)
             x.record_stream(torch.cuda.current_stream())
             t.record_stream(torch.cuda.current_stream())
+            loss = step(x, t)                 # asynchronous launch (graph replay)
             if i + 1 < n:
-                nxt = prefetch()
-            out = step(x, t).item()
+                nxt = prefetch()              # issued while the step runs: no host work between the loss read and the next launch
+            out = loss.item()
         return out
 
     first_loss = None
