@@ -173,6 +173,11 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+def _prow(t, i):
+    """pointer to row i of a 2-D tensor (no view tensor is created: ~3 us each on the launch path)"""
+    return C.c_void_p(t.data_ptr() + i * t.stride(0) * t.element_size())
+
+
 def dt(t):
     try:
         return _DT[t.dtype]
@@ -412,7 +417,7 @@ def gconv_fprop_affine_relu(d, x, wp, coefs, z):
         x = x3_split(x)
         wp = x3_split_rows(wp, d.N * d.ntaps, d.Cin)
         d = _x3_desc(d, ld_in=3 * d.Cin)
-    _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu, C.byref(d), _p(x), _p(wp), _p(coefs[2]), _p(z),
+    _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu, C.byref(d), _p(x), _p(wp), _prow(coefs, 2), _p(z),
          _stream(), flops=flops, nbytes=nbytes)
     if _PROFILE is not None:
         _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + tag
@@ -427,7 +432,7 @@ def gconv_fprop_affine_relu_outconv(d, x, wp, coefs, oc_w, oc_b, logits):
     flops, tag = gconv_flops(d), _shape_tag(d)
     ncls = oc_w.shape[0]
     es = 2 if d.dtype == BF16 else 4
-    _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu_outconv, C.byref(d), _p(x), _p(wp), _p(coefs[2]),
+    _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu_outconv, C.byref(d), _p(x), _p(wp), _prow(coefs, 2),
          _p(oc_w), _p(oc_b), _p(logits), ncls, _stream(), flops=flops,
          nbytes=float(es) * d.B * d.Hin * d.Win * d.Cin + float(es) * d.B * d.Hm * d.Wm * ncls)
     if _PROFILE is not None:
@@ -555,7 +560,7 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_
         nbt.add_(1)                                                  # a counter the kernel cannot reach (never on the path)
         nbt = None
     _run("bn_finalize", lib().unetb200_bn_finalize_track, _p(stats), count, _p(gamma), _p(beta), eps, momentum,
-         _p(running_mean), _p(running_var), _p(coefs[0]), _p(coefs[1]), _p(coefs[2]), _p(coefs[3]), _p(nbt), Cc, _stream())
+         _p(running_mean), _p(running_var), _prow(coefs, 0), _prow(coefs, 1), _prow(coefs, 2), _prow(coefs, 3), _p(nbt), Cc, _stream())
     if nbt is not None:
         torch._C._increment_version([nbt])
     return coefs
@@ -564,7 +569,7 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, Cc):
     coefs = torch.empty((4, Cc), dtype=torch.float32, device=running_mean.device)
     _run("bn_eval_coeffs", lib().unetb200_bn_eval_coeffs, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
-         eps, _p(coefs[2]), _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), Cc, _stream())
+         eps, _prow(coefs, 2), _prow(coefs, 3), _prow(coefs, 0), _prow(coefs, 1), Cc, _stream())
     return coefs
 
 
@@ -572,7 +577,7 @@ def bn_relu_apply(y, coefs, z, pooled=None):
     B, Cc, H, W = y.shape
     es = y.element_size()
     _run("bn_relu_apply_pool" if pooled is not None else "bn_relu_apply", lib().unetb200_bn_relu_apply, _p(y),
-         nhwc_ld(y), _p(coefs[2]), _p(coefs[3]), _p(z), nhwc_ld(z), _p(pooled),
+         nhwc_ld(y), _prow(coefs, 2), _prow(coefs, 3), _p(z), nhwc_ld(z), _p(pooled),
          nhwc_ld(pooled) if pooled is not None else 0, dt(y), B, H, W, Cc, _stream(),
          nbytes=y.numel() * es * (2.25 if pooled is not None else 2.0))
 
@@ -602,7 +607,7 @@ def maxpool2_bwd_bnreduce(x, gp, gx, y, coefs):
     B, Cc, H, W = x.shape
     sums = torch.zeros((2, Cc), dtype=torch.float64, device=x.device)
     _run("maxpool2_bwd", lib().unetb200_maxpool2_bwd_bnreduce, _p(x), nhwc_ld(x), _p(gp), nhwc_ld(gp), _p(gx), nhwc_ld(gx),
-         _p(y), nhwc_ld(y), _p(coefs[2]), _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(sums), dt(x), B, H, W, Cc,
+         _p(y), nhwc_ld(y), _prow(coefs, 2), _prow(coefs, 3), _prow(coefs, 0), _prow(coefs, 1), _p(sums), dt(x), B, H, W, Cc,
          _stream(), nbytes=x.numel() * x.element_size() * 4.25)
     return sums
 
@@ -616,8 +621,8 @@ def bn_relu_bwd(gz, y, coefs, training, dgamma=None, dbeta=None, sums=None):
     L = lib()
     if sums is None:
         sums = torch.zeros((2, Cc), dtype=torch.float64, device=dev)
-        _run("bn_relu_bwd_reduce", L.unetb200_bn_relu_bwd_reduce, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]),
-             _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(sums), dt(y), B, H, W, Cc, _stream(),
+        _run("bn_relu_bwd_reduce", L.unetb200_bn_relu_bwd_reduce, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _prow(coefs, 2),
+             _prow(coefs, 3), _prow(coefs, 0), _prow(coefs, 1), _p(sums), dt(y), B, H, W, Cc, _stream(),
              nbytes=2.0 * y.numel() * es)
     if dgamma is None:
         dgamma = torch.empty(Cc, dtype=torch.float32, device=dev)
@@ -627,8 +632,8 @@ def bn_relu_bwd(gz, y, coefs, training, dgamma=None, dbeta=None, sums=None):
     _run("bn_bwd_finalize", L.unetb200_bn_bwd_finalize, _p(sums), B * H * W, 1 if training else 0, _p(dgamma),
          _p(dbeta), _p(coef), Cc, _stream())
     gy = empty_nhwc(B, Cc, H, W, y.dtype, dev)
-    _run("bn_relu_bwd_apply", L.unetb200_bn_relu_bwd_apply, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _p(coefs[2]),
-         _p(coefs[3]), _p(coefs[0]), _p(coefs[1]), _p(coef), _p(gy), nhwc_ld(gy), dt(y), B, H, W, Cc, _stream(),
+    _run("bn_relu_bwd_apply", L.unetb200_bn_relu_bwd_apply, _p(gz), nhwc_ld(gz), _p(y), nhwc_ld(y), _prow(coefs, 2),
+         _prow(coefs, 3), _prow(coefs, 0), _prow(coefs, 1), _p(coef), _p(gy), nhwc_ld(gy), dt(y), B, H, W, Cc, _stream(),
          nbytes=3.0 * y.numel() * es)
     return gy, dgamma, dbeta
 
