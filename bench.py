@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=None, help="images per GPU (default 16 train, 8 infer)")
     ap.add_argument("--size", type=int, default=None, help="default 512 train, 1024 infer")
     ap.add_argument("--bilinear", action="store_true")
+    ap.add_argument("--model", default="UNet", choices=["UNet", "UNet_S", "UNet_T", "UNet_SA"],
+                    help="UNet = BASELINE.json's model (the metric); the width variants of unet_model.py:52-189 (UNet_S is "
+                         "what train.py:253 builds) run the same step for comparison, off the BASELINE metric")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -73,16 +76,30 @@ def parse():
 
 
 def metric_name(a):
-    return f"unet{a.size}_{'train' if a.workload == 'train' else 'infer'}_images_per_sec"
+    return f"{a.model.lower()}{a.size}_{'train' if a.workload == 'train' else 'infer'}_images_per_sec"
+
+
+def model_class(pkg, a):
+    """`UNet` from the package itself, the width variants from its unet_model module (the reference's __init__ exports
+    UNet only)."""
+    if a.model == "UNet":
+        return pkg.UNet
+    mod = sys.modules.get(pkg.__name__ + ".unet_model")
+    if mod is None:
+        import importlib
+        mod = importlib.import_module(pkg.__name__ + ".unet_model")
+    return getattr(mod, a.model)
 
 
 def workload_text(a, per_gpu=True):
     if a.workload == "train":
-        return (f"UNet(1,2,bilinear={a.bilinear}) {a.precision} training step, batch {a.batch}/GPU, {a.size}x{a.size}, "
-                "CE+dice+0.2*boundary_loss(51,7), clip_grad_norm, RMSprop (BASELINE.json "
-                f"{'configs[2]' if a.bilinear else 'configs[1]; configs[3] when n_gpus > 1'})")
-    return (f"UNet(3,4,bilinear={a.bilinear}).eval() {a.precision} predict.py-style inference (forward + resize + argmax), "
-            f"batch {a.batch}/GPU, {a.size}x{a.size} (BASELINE.json configs[4]; replicas when n_gpus > 1)")
+        which = (f"BASELINE.json {'configs[2]' if a.bilinear else 'configs[1]; configs[3] when n_gpus > 1'}" if a.model == "UNet"
+                 else "width variant of unet_model.py:52-189, same step as configs[1], off the BASELINE metric")
+        return (f"{a.model}(1,2,bilinear={a.bilinear}) {a.precision} training step, batch {a.batch}/GPU, {a.size}x{a.size}, "
+                f"CE+dice+0.2*boundary_loss(51,7), clip_grad_norm, RMSprop ({which})")
+    which = "BASELINE.json configs[4]" if a.model == "UNet" else "width variant, off the BASELINE metric"
+    return (f"{a.model}(3,4,bilinear={a.bilinear}).eval() {a.precision} predict.py-style inference (forward + resize + argmax), "
+            f"batch {a.batch}/GPU, {a.size}x{a.size} ({which}; replicas when n_gpus > 1)")
 
 
 def measured_peaks():
@@ -145,9 +162,11 @@ class ReferenceStep:
         torch.manual_seed(0)
         if mods is not None:
             refunet, self.dice, self.bnd = mods
-            self.model = refunet.UNet(a.nc, a.ncls, a.bilinear)
+            self.model = model_class(refunet, a)(a.nc, a.ncls, a.bilinear)
             self.dice_loss, self.boundary_loss = self.dice.dice_loss, self.bnd.boundary_loss
         else:
+            if a.model != "UNet":
+                raise RuntimeError("bench.py --model variants need the reference modules in baseline/_ref for their baseline legs")
             from oracle import unet_oracle as O           # the pinned restatement (baseline leg only)
             self.O = O
             self.state = O.build_state(a.nc, a.ncls, a.bilinear, seed=0)
@@ -381,6 +400,8 @@ def roofline_tables(a, rec, peaks, nsteps):
     kd, sd = kernels[dom], summ[dom]
     traffic, traffic_src = None, None
     try:                                  # DRAM bytes per launch of that kernel class from the committed ncu pass
+        if a.model != "UNet" or a.workload != "train":
+            raise LookupError("the committed ncu pass is of BASELINE configs[1]")
         import glob
         tj = sorted(glob.glob(os.path.join(ROOT, "profiles", "kernel_traffic_r*.json")))[-1]
         with open(tj) as f:
@@ -514,7 +535,7 @@ def bench_train(ctx):
     from unetb200 import losses as UL
     B, S, amp = a.batch, a.size, ctx["amp"]
     torch.manual_seed(0)
-    model = ctx["unet"].UNet(1, 2, a.bilinear).to(dev).to(memory_format=torch.channels_last).train()
+    model = model_class(ctx["unet"], a)(1, 2, a.bilinear).to(dev).to(memory_format=torch.channels_last).train()
     if world > 1:
         ddp.broadcast_module_state(model)
     bucket_mb = int(os.environ.get("UNETB200_DDP_BUCKET_MB", "32"))
@@ -652,7 +673,7 @@ def bench_train(ctx):
     # that feeds the optimizer stale gradients shows here)
     line["loss_sane"] = bool(first_loss is not None and last_loss == last_loss and last_loss < 1.2 * first_loss)
     peaks = measured_peaks()
-    gf_img = GFLOP_PER_IMG.get(("train", a.bilinear, S))
+    gf_img = GFLOP_PER_IMG.get(("train", a.bilinear, S)) if a.model == "UNet" else None
     if gf_img:
         conv_tf = gf_img * 1e9 * line["value"] / world / 1e12
         line["step_conv_tflops_per_gpu"] = conv_tf
@@ -687,7 +708,7 @@ def bench_infer(ctx):
     from unetb200 import eval_tail as UE
     B, S, amp = a.batch, a.size, ctx["amp"]
     torch.manual_seed(0)
-    model = ctx["unet"].UNet(a.nc, a.ncls, a.bilinear).to(dev).to(memory_format=torch.channels_last).eval()
+    model = model_class(ctx["unet"], a)(a.nc, a.ncls, a.bilinear).to(dev).to(memory_format=torch.channels_last).eval()
     img_h, msk_h = synthetic(a, rank)
     img_h = img_h.pin_memory()
     img_d = img_h.to(dev).contiguous(memory_format=torch.channels_last)
@@ -748,7 +769,7 @@ def bench_infer(ctx):
     line = _base_line(ctx, ms, ms_e2e, launches_per_step * a.steps, clocks, img_h.numel() * 4, out_h.numel() * 8)
     line["cuda_graph"] = graph_note
     peaks = measured_peaks()
-    gf_img = GFLOP_PER_IMG.get(("infer", a.bilinear, S))
+    gf_img = GFLOP_PER_IMG.get(("infer", a.bilinear, S)) if a.model == "UNet" else None
     if gf_img and a.nc == 3 and a.ncls == 4:
         conv_tf = gf_img * 1e9 * line["value"] / world / 1e12
         line["step_conv_tflops_per_gpu"] = conv_tf
