@@ -516,6 +516,10 @@ def check_conv_narrow():
     out += _narrow_case(2, 16, 64, 40, 56, 115)
     out += _narrow_case(3, 64, 32, 130, 100, 116)
     out += _narrow_case(2, 32, 16, 72, 88, 117, slice_in=True)
+    # 8-channel tensors (UNet_T) ride the 16-channel instantiation: TMA zero-fills the upper half of the 32-byte rows
+    out += _narrow_case(4, 8, 8, 200, 136, 131)
+    out += _narrow_case(2, 16, 8, 130, 100, 132)
+    out += _narrow_case(2, 8, 32, 64, 48, 133)
     # narrow ConvTranspose2d (conv_halo_t.cu): partial tiles in both directions, rows past the image (h % 8 != 0) that
     # the 5-D quadrant view reads from the next image, several tiles per CTA, padded destination (fprop only)
     out += _convT_case(2, 32, 16, 24, 40, (0, 0), BF, _lib.ALGO_TC, 120)
@@ -547,7 +551,7 @@ def check_narrow_bounds():
     res = []
     g = gen(130)
     for (B, Ci, Co, H, W) in [(2, 16, 16, 20, 24), (1, 16, 32, 17, 9), (3, 64, 32, 35, 50), (2, 1, 8, 37, 530), (2, 1, 16, 9, 130),
-                              (1, 32, 64, 5, 3)]:
+                              (1, 32, 64, 5, 3), (2, 8, 8, 21, 19), (1, 16, 8, 33, 40)]:
         x = dev_nhwc(torch.randn(B, Ci, H, W, generator=g), BF)
         w = torch.randn(Co, Ci, 3, 3, generator=g).to(DEV) / (3 * Ci ** 0.5)
         flat, y, gd = _guarded_nhwc(B, Co, H, W, BF)

@@ -34,6 +34,8 @@ struct HaloParams {
   int H, W;
   int tiles_w, tiles_h, ntiles;
   int tap_pix[9];                // (dy + 1) * 18 + dx + 1
+  int cin_real, n_real;          // 8-channel tensors ride the 16-channel instantiation: TMA zero-fills channels 8..15 of
+                                 // a pixel row (the box is wider than the tensor), weight rows / columns 8..15 are zero
 };
 
 constexpr int kHaloThreads = 320;
@@ -86,12 +88,14 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
     const int t = r / (CIN / 8), c = r - t * (CIN / 8);
     const uint32_t off = t * Cfg::kBTile + n * P;
     const uint32_t addr = smem_u32(b_tile) + off;
-    *reinterpret_cast<uint4*>(b_tile + off + ((c ^ ((addr >> 7) & CMASK)) << 4)) =
-        *reinterpret_cast<const uint4*>(p.wp + (size_t)n * 9 * CIN + t * CIN + c * 8);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < p.n_real && c * 8 < p.cin_real)
+      v = *reinterpret_cast<const uint4*>(p.wp + (size_t)n * 9 * p.cin_real + t * p.cin_real + c * 8);
+    *reinterpret_cast<uint4*>(b_tile + off + ((c ^ ((addr >> 7) & CMASK)) << 4)) = v;
   }
   if (MODE == 1 && threadIdx.x < 128) {
     const int c = threadIdx.x & 63, which = threadIdx.x >> 6;
-    coef[threadIdx.x] = c < NT ? p.affine[which * NT + c] : 0.f;
+    coef[threadIdx.x] = c < p.n_real ? p.affine[which * p.n_real + c] : 0.f;
   }
   fence_async_smem();
   tc_fence_before();
@@ -202,7 +206,7 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
                        : "r"(stg + rr * RS + ((ch ^ swz(rr)) << 4)) : "memory");
           const int yy = y0 + (rr >> 3), xx = x0 + (rr & 7);
-          if (yy < p.H && xx < p.W)
+          if (yy < p.H && xx < p.W && ch * 8 < p.n_real)
             *reinterpret_cast<uint4*>(p.y + (((long long)b * p.H + yy) * p.W + xx) * p.ld_out + ch * 8) = q;
         }
       }
@@ -223,10 +227,10 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
         s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
         s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
       }
-      float* dst = p.stats_ws + ((long long)blockIdx.x * 8 + e) * 2 * NT;
-      if (grp == 0) {
+      float* dst = p.stats_ws + ((long long)blockIdx.x * 8 + e) * 2 * p.n_real;
+      if (grp == 0 && 2 * pair < p.n_real) {
         dst[2 * pair] = s0; dst[2 * pair + 1] = s1;
-        dst[NT + 2 * pair] = q0; dst[NT + 2 * pair + 1] = q1;
+        dst[p.n_real + 2 * pair] = q0; dst[p.n_real + 2 * pair + 1] = q1;
       }
     }
   }
@@ -239,7 +243,8 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
 }
 
 // ------------------------------------------------------------------------------------------ host side (fprop)
-static bool halo_ch_ok(int c) { return c == 16 || c == 32 || c == 64; }
+static bool halo_ch_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
+static int halo_ch_pad(int c) { return c < 16 ? 16 : c; }          // 8 channels ride the 16-channel instantiation
 
 static bool halo_shape_ok(const unetb200_gconv_t* d) {
   static const bool off = getenv("UNETB200_NO_HALO") != nullptr;
@@ -268,6 +273,7 @@ template <int CIN, int NT>
 static int halo_ctas() { return HaloCfg<CIN, NT>::CTAS; }
 
 static int halo_ctas_per_sm(int cin, int n) {
+  cin = halo_ch_pad(cin); n = halo_ch_pad(n);
   if (cin == 16) return n == 16 ? halo_ctas<16, 16>() : (n == 32 ? halo_ctas<16, 32>() : halo_ctas<16, 64>());
   if (cin == 32) return n == 16 ? halo_ctas<32, 16>() : (n == 32 ? halo_ctas<32, 32>() : halo_ctas<32, 64>());
   return n == 16 ? halo_ctas<64, 16>() : halo_ctas<64, 32>();
@@ -322,6 +328,7 @@ int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y
   if (int rc = encode_act_box_sw(&P.x_map, x, d->Cin, d->Wm, d->Hm, d->B, d->ld_in, (long long)d->Wm * d->ld_in,
                                  (long long)d->Hm * d->Wm * d->ld_in, kHaloBW, kHaloBW))
     return rc;
+  P.cin_real = d->Cin; P.n_real = d->N;
   P.wp = (const __nv_bfloat16*)wp; P.y = (__nv_bfloat16*)y;
   P.affine = affine;
   P.stats_ws = (stats && !affine) ? stats_ws : nullptr;
@@ -330,10 +337,10 @@ int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y
   for (int t = 0; t < 9; ++t) P.tap_pix[t] = (d->tap_dy[t] + 1) * kHaloBW + d->tap_dx[t] + 1;
   const int grid = halo_grid(d, &P.tiles_w, &P.tiles_h, &P.ntiles);
   int rc;
-  switch (d->Cin) {
-    case 16: rc = halo_dispatch_n<16>(P, d->N, grid, affine != nullptr, s); break;
-    case 32: rc = halo_dispatch_n<32>(P, d->N, grid, affine != nullptr, s); break;
-    default: rc = halo_dispatch_n<64>(P, d->N, grid, affine != nullptr, s); break;
+  switch (halo_ch_pad(d->Cin)) {
+    case 16: rc = halo_dispatch_n<16>(P, halo_ch_pad(d->N), grid, affine != nullptr, s); break;
+    case 32: rc = halo_dispatch_n<32>(P, halo_ch_pad(d->N), grid, affine != nullptr, s); break;
+    default: rc = halo_dispatch_n<64>(P, halo_ch_pad(d->N), grid, affine != nullptr, s); break;
   }
   if (rc) return rc;
   if (P.stats_ws) return launch_stats_reduce(stats_ws, (long long)grid * 8, 2 * d->N, stats, s);
@@ -353,6 +360,7 @@ struct HaloWParams {
   float* partials;               // [grid][9 * Cin][N]
   int tiles_w, tiles_h, ntiles;
   int tap_of[9];                 // [(dy + 1) * 3 + dx + 1] -> tap index of the descriptor
+  int cin_real, n_real;          // 8-channel operands: atoms of 16 channels whose upper half TMA zero-fills
 };
 
 template <int CIN, int NT>
@@ -450,7 +458,7 @@ __global__ void __launch_bounds__(192, HaloWCfg<CIN, NT>::CTAS) halo_wgrad_kerne
     const int m = threadIdx.x;
     mbar_wait(t_full, 0);
     tc_fence_after();
-    float* out = p.partials + (long long)blockIdx.x * K * NT;
+    float* out = p.partials + (long long)blockIdx.x * 9 * p.cin_real * p.n_real;
 #pragma unroll 1
     for (int mb = 0; mb < NMMA; ++mb) {
       const int h = (CIN == 64 ? 2 * mb : 0) + m / CIN, c = m % CIN;
@@ -461,12 +469,13 @@ __global__ void __launch_bounds__(192, HaloWCfg<CIN, NT>::CTAS) halo_wgrad_kerne
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t v[16];
           halo_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + mb * 3 * NT + sft * NT + c0, v);
-          if (h < 3) {
-            float4* dst = reinterpret_cast<float4*>(out + ((long long)t * CIN + c) * NT + c0);
+          if (h < 3 && c < p.cin_real) {
+            float4* dst = reinterpret_cast<float4*>(out + ((long long)t * p.cin_real + c) * p.n_real + c0);
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
-                                   __uint_as_float(v[4 * e + 3]));
+              if (c0 + 4 * e < p.n_real)
+                dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                     __uint_as_float(v[4 * e + 3]));
           }
         }
       }
@@ -484,6 +493,7 @@ template <int CIN, int NT>
 static int halo_w_ctas() { return HaloWCfg<CIN, NT>::CTAS; }
 
 static int halo_w_ctas_per_sm(int cin, int n) {
+  cin = halo_ch_pad(cin); n = halo_ch_pad(n);
   if (cin == 16) return n == 16 ? halo_w_ctas<16, 16>() : (n == 32 ? halo_w_ctas<16, 32>() : halo_w_ctas<16, 64>());
   if (cin == 32) return n == 16 ? halo_w_ctas<32, 16>() : (n == 32 ? halo_w_ctas<32, 32>() : halo_w_ctas<32, 64>());
   return n == 16 ? halo_w_ctas<64, 16>() : halo_w_ctas<64, 32>();
@@ -541,13 +551,14 @@ int halo_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* 
                                  (long long)d->Hm * d->Wm * d->ld_out, 16, kHaloBW))
     return rc;
   P.partials = partials;
+  P.cin_real = d->Cin; P.n_real = d->N;
   for (int t = 0; t < 9; ++t) P.tap_of[(d->tap_dy[t] + 1) * 3 + d->tap_dx[t] + 1] = t;
   const int grid = halo_wgrad_grid(d, &P.tiles_w, &P.tiles_h, &P.ntiles);
   if (grid != splits) { set_error("halo_wgrad: the planned split count is %d, got %d", grid, splits); return UNETB200_E_INVALID; }
-  switch (d->Cin) {
-    case 16: return halo_wgrad_dispatch_n<16>(P, d->N, grid, s);
-    case 32: return halo_wgrad_dispatch_n<32>(P, d->N, grid, s);
-    default: return halo_wgrad_dispatch_n<64>(P, d->N, grid, s);
+  switch (halo_ch_pad(d->Cin)) {
+    case 16: return halo_wgrad_dispatch_n<16>(P, halo_ch_pad(d->N), grid, s);
+    case 32: return halo_wgrad_dispatch_n<32>(P, halo_ch_pad(d->N), grid, s);
+    default: return halo_wgrad_dispatch_n<64>(P, halo_ch_pad(d->N), grid, s);
   }
 }
 
