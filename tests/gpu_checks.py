@@ -528,6 +528,9 @@ def check_conv_narrow():
     out += _convT_case(2, 64, 16, 8, 16, (0, 0), BF, _lib.ALGO_TC, 123)
     out += _convT_case(16, 32, 16, 128, 128, (0, 0), BF, _lib.ALGO_TC, 124)
     out += _convT_case(2, 32, 16, 5, 6, (1, 2), BF, _lib.ALGO_AUTO, 125)
+    out += _convT_case(2, 16, 8, 24, 40, (0, 0), BF, _lib.ALGO_TC, 134)          # UNet_T's last up-sampler (padded instantiation)
+    out += _convT_case(3, 16, 8, 9, 7, (0, 0), BF, _lib.ALGO_TC, 135)
+    out += _convT_case(8, 16, 8, 128, 128, (0, 0), BF, _lib.ALGO_TC, 136)
     return out
 
 
@@ -571,7 +574,7 @@ def check_narrow_bounds():
             ops.gconv_fprop(dd, gy, UF.pack3x3_dgrad(w, BF), None, gx, None)
             torch.cuda.synchronize()
             res.append((f"bounds_dgrad_{Ci}to{Co}_{B}x{H}x{W}", _guards_intact(flat2, gd2), 0.0))
-    for (B, Ci, Co, h, w_) in [(2, 32, 16, 9, 7), (1, 64, 32, 3, 20), (3, 32, 32, 8, 16)]:
+    for (B, Ci, Co, h, w_) in [(2, 32, 16, 9, 7), (1, 64, 32, 3, 20), (3, 32, 32, 8, 16), (2, 16, 8, 9, 7)]:
         x = dev_nhwc(torch.randn(B, Ci, h, w_, generator=g), BF)
         wT = torch.randn(Ci, Co, 2, 2, generator=g).to(DEV) / (Ci ** 0.5)
         b = torch.randn(Co, generator=g).to(DEV)

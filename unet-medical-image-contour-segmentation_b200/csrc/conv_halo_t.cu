@@ -27,6 +27,7 @@ struct HaloTParams {
   long long ld_out, npix;
   int h, w, Hout, Wout, off_y, off_x;
   int ntiles;
+  int cup_real;                  // C_out = 8 rides the CUP = 16 instantiation (weight rows 8..15 of a quadrant are zero)
 };
 
 template <int C1, int CUP>
@@ -67,11 +68,13 @@ __global__ void __launch_bounds__(kHtThreads, HaloTCfg<C1, CUP>::CTAS) halo_t_fp
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   for (int e = threadIdx.x; e < NT * (C1 / 8); e += blockDim.x) {
     const int n = e / (C1 / 8), c = e - n * (C1 / 8);
+    const int q = n / CUP, co = n % CUP;
     const uint32_t addr = smem_u32(b_tile) + n * P;
-    *reinterpret_cast<uint4*>(b_tile + n * P + ((c ^ ((addr >> 7) & CMASK)) << 4)) =
-        *reinterpret_cast<const uint4*>(p.wp + (size_t)n * C1 + c * 8);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (co < p.cup_real) v = *reinterpret_cast<const uint4*>(p.wp + (size_t)(q * p.cup_real + co) * C1 + c * 8);
+    *reinterpret_cast<uint4*>(b_tile + n * P + ((c ^ ((addr >> 7) & CMASK)) << 4)) = v;
   }
-  if (threadIdx.x < 64) sbias[threadIdx.x] = (p.bias && threadIdx.x < CUP) ? p.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < 64) sbias[threadIdx.x] = (p.bias && threadIdx.x < p.cup_real) ? p.bias[threadIdx.x] : 0.f;
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(kHtThreads, HaloTCfg<C1, CUP>::CTAS) halo_t_fp
             o.y = halo_pack(__uint_as_float(v[c8 * 8 + 2]) + sbias[co + 2], __uint_as_float(v[c8 * 8 + 3]) + sbias[co + 3]);
             o.z = halo_pack(__uint_as_float(v[c8 * 8 + 4]) + sbias[co + 4], __uint_as_float(v[c8 * 8 + 5]) + sbias[co + 5]);
             o.w = halo_pack(__uint_as_float(v[c8 * 8 + 6]) + sbias[co + 6], __uint_as_float(v[c8 * 8 + 7]) + sbias[co + 7]);
-            *reinterpret_cast<uint4*>(dst + qx * p.ld_out + co) = o;
+            if (co < p.cup_real) *reinterpret_cast<uint4*>(dst + qx * p.ld_out + co) = o;
           }
         }
       }
@@ -166,6 +169,7 @@ struct HaloTDParams {
   __nv_bfloat16* gx;             // [B][h][w][ld_out]
   long long ld_out;
   int h, w, tiles_w, tiles_h, ntiles;
+  int cup_real, c1_real;         // 16 -> 8: the (CUP, C1) = (16, 32) instantiation, upper halves zero
 };
 
 template <int CUP, int C1>
@@ -209,8 +213,10 @@ __global__ void __launch_bounds__(kHtThreads, HaloTDCfg<CUP, C1>::CTAS) halo_t_d
     const int q = r / (CUP / 8), c = r - q * (CUP / 8);
     const uint32_t off = q * Cfg::kBQ + n * PG;
     const uint32_t addr = smem_u32(b_tile) + off;
-    *reinterpret_cast<uint4*>(b_tile + off + ((c ^ ((addr >> 7) & CMASK)) << 4)) =
-        *reinterpret_cast<const uint4*>(p.wp + (size_t)n * 4 * CUP + q * CUP + c * 8);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < p.c1_real && c * 8 < p.cup_real)
+      v = *reinterpret_cast<const uint4*>(p.wp + (size_t)n * 4 * p.cup_real + q * p.cup_real + c * 8);
+    *reinterpret_cast<uint4*>(b_tile + off + ((c ^ ((addr >> 7) & CMASK)) << 4)) = v;
   }
   fence_async_smem();
   tc_fence_before();
@@ -280,6 +286,7 @@ __global__ void __launch_bounds__(kHtThreads, HaloTDCfg<CUP, C1>::CTAS) halo_t_d
         __nv_bfloat16* dst = p.gx + (((long long)b * p.h + y) * p.w + x) * p.ld_out + half * HC;
 #pragma unroll
         for (int c8 = 0; c8 < HC / 8; ++c8) {
+          if (half * HC + c8 * 8 >= p.c1_real) break;
           uint4 o;
           o.x = halo_pack(__uint_as_float(v[c8 * 8 + 0]), __uint_as_float(v[c8 * 8 + 1]));
           o.y = halo_pack(__uint_as_float(v[c8 * 8 + 2]), __uint_as_float(v[c8 * 8 + 3]));
@@ -305,6 +312,7 @@ struct HaloTWParams {
   CUtensorMap g_map;             // 5-D {CUP, 2, w, 2, B h}, box {CUP, 1, 16, 1, 8}
   float* partials;               // [grid][C1][4 CUP]
   int h, tiles_w, tiles_h, ntiles;
+  int cup_real;                  // C_out = 8: quadrant atoms of 16 channels whose upper half TMA zero-fills
 };
 
 template <int C1, int CUP>
@@ -386,19 +394,23 @@ __global__ void __launch_bounds__(192, HaloTWCfg<C1, CUP>::CTAS) halo_t_wgrad_ke
     if (elect_one()) umma_commit(t_full);
     __syncwarp();
   } else if (warp * 32 < C1) {
-    const int m = threadIdx.x;           // row = input channel
+    const int m = threadIdx.x;           // row = input channel (rows >= C1 repeat the atom: not read)
     mbar_wait(t_full, 0);
     tc_fence_after();
-    float* out = p.partials + ((long long)blockIdx.x * C1 + m) * NN;
+    float* out = p.partials + ((long long)blockIdx.x * C1 + m) * 4 * p.cup_real;
 #pragma unroll 1
     for (int c0 = 0; c0 < NN; c0 += 16) {
       uint32_t v[16];
       halo_tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
-      float4* dst = reinterpret_cast<float4*>(out + c0);
+      const int q = c0 / CUP, co0 = c0 % CUP;          // 16 columns never straddle a quadrant (CUP >= 16)
+      if (m < C1) {
+        float4* dst = reinterpret_cast<float4*>(out + q * p.cup_real + co0);
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
-                             __uint_as_float(v[4 * e + 3]));
+        for (int e = 0; e < 4; ++e)
+          if (co0 + 4 * e < p.cup_real)
+            dst[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]),
+                                 __uint_as_float(v[4 * e + 3]));
+      }
     }
   }
   tc_fence_before();
@@ -410,7 +422,10 @@ __global__ void __launch_bounds__(192, HaloTWCfg<C1, CUP>::CTAS) halo_t_wgrad_ke
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static bool halo_t_pair_ok(int c1, int cup) { return (c1 == 32 && cup == 16) || (c1 == 64 && cup == 32) || (c1 == 32 && cup == 32) || (c1 == 64 && cup == 16); }
+static bool halo_t_pair_ok(int c1, int cup) {
+  return (c1 == 32 && cup == 16) || (c1 == 64 && cup == 32) || (c1 == 32 && cup == 32) || (c1 == 64 && cup == 16) ||
+         (c1 == 16 && cup == 8);           // UNet_T's last up-sampler: padded instantiations, see *_real
+}
 
 static bool halo_t_off() {
   static const bool off = getenv("UNETB200_NO_HALO") != nullptr || getenv("UNETB200_NO_HALO_T") != nullptr;
@@ -465,7 +480,7 @@ static int encode_quadrants(CUtensorMap* m, const void* g, int cup, int w, int h
   const unsigned long long dims[5] = {(unsigned long long)cup, 2ULL, (unsigned long long)w, 2ULL, (unsigned long long)B * h};
   const unsigned long long st[4] = {(unsigned long long)(ld * 2), (unsigned long long)(2 * ld * 2), (unsigned long long)(W * ld * 2),
                                     (unsigned long long)(2 * W * ld * 2)};
-  const unsigned box[5] = {(unsigned)cup, 1u, 16u, 1u, 8u};
+  const unsigned box[5] = {(unsigned)(cup < 16 ? 16 : cup), 1u, 16u, 1u, 8u};      // 8 channels: zero-filled upper half
   return encode_bf16_box(m, g, 5, dims, st, box);
 }
 
@@ -499,6 +514,8 @@ int halo_t_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const
   P.ld_out = d->ld_out;
   P.h = d->Hm; P.w = d->Wm; P.Hout = d->Hout; P.Wout = d->Wout; P.off_y = d->out_off_y; P.off_x = d->out_off_x;
   P.ntiles = (int)((P.npix + 127) / 128);
+  P.cup_real = cup;
+  if (d->Cin == 16) return halo_t_fprop_launch<16, 16>(P, s);
   if (d->Cin == 32 && cup == 16) return halo_t_fprop_launch<32, 16>(P, s);
   if (d->Cin == 32 && cup == 32) return halo_t_fprop_launch<32, 32>(P, s);
   if (d->Cin == 64 && cup == 16) return halo_t_fprop_launch<64, 16>(P, s);
@@ -528,6 +545,8 @@ int halo_t_dgrad(const unetb200_gconv_t* d, const void* g, const void* wp, void*
   P.h = d->Hm; P.w = d->Wm;
   P.tiles_w = (d->Wm + 15) / 16; P.tiles_h = (d->Hm + 7) / 8;
   P.ntiles = d->B * P.tiles_w * P.tiles_h;
+  P.cup_real = d->Cin; P.c1_real = d->N;
+  if (d->Cin == 8) return halo_t_dgrad_launch<16, 32>(P, s);
   if (d->Cin == 16 && d->N == 32) return halo_t_dgrad_launch<16, 32>(P, s);
   if (d->Cin == 32 && d->N == 32) return halo_t_dgrad_launch<32, 32>(P, s);
   if (d->Cin == 16 && d->N == 64) return halo_t_dgrad_launch<16, 64>(P, s);
@@ -542,6 +561,7 @@ static int halo_t_wgrad_grid(const unetb200_gconv_t* d, int* tiles_w, int* tiles
   *tiles_h = (d->Hm + 7) / 8;
   *ntiles = d->B * *tiles_w * *tiles_h;
   const int cup = d->N / 4;
+  if (d->Cin == 16) { const int sl = halo_t_w_ctas<16, 16>() * sm_count(); return *ntiles < sl ? *ntiles : sl; }
   const int per = d->Cin == 32 ? (cup == 16 ? halo_t_w_ctas<32, 16>() : halo_t_w_ctas<32, 32>())
                                : (cup == 16 ? halo_t_w_ctas<64, 16>() : halo_t_w_ctas<64, 32>());
   const int slots = per * sm_count();
@@ -580,8 +600,10 @@ int halo_t_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float
   if (int rc = encode_quadrants(&P.g_map, gy, cup, d->Wm, d->Hm, d->B, d->ld_out)) return rc;
   P.partials = partials;
   P.h = d->Hm;
+  P.cup_real = cup;
   const int grid = halo_t_wgrad_grid(d, &P.tiles_w, &P.tiles_h, &P.ntiles);
   if (grid != splits) { set_error("halo_t_wgrad: the planned split count is %d, got %d", grid, splits); return UNETB200_E_INVALID; }
+  if (d->Cin == 16) return halo_t_wgrad_launch<16, 16>(P, grid, s);
   if (d->Cin == 32 && cup == 16) return halo_t_wgrad_launch<32, 16>(P, grid, s);
   if (d->Cin == 32 && cup == 32) return halo_t_wgrad_launch<32, 32>(P, grid, s);
   if (d->Cin == 64 && cup == 16) return halo_t_wgrad_launch<64, 16>(P, grid, s);
