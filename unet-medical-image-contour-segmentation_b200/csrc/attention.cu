@@ -59,35 +59,86 @@ __global__ void sa_stats_scalar_kernel(const T* __restrict__ x, int64_t ld, floa
   }
 }
 
-// gate[p] = sigmoid(sum_{ch,ky,kx} w[ch][ky][kx] * stats[p + (ky-3, kx-3)][ch]), zero padding; one thread per pixel
+// gate[p] = sigmoid(sum_{ch,ky,kx} w[ch][ky][kx] * stats[p + (ky-3, kx-3)][ch]), zero padding.
+// Tiled: a block owns an 8 x 32 pixel tile, the
+// (8 + 6) x (32 + 6) x 2 halo of the statistics map sits in shared memory (zeros outside the image add nothing), a
+// thread owns one pixel.  (First version: one thread per pixel with 49 bounds-checked 8-byte global loads -- 0.23 ms per
+// full-resolution gate where the map is 34 MB; the transposed stencil of the backward pass likewise, 0.42 -> 0.2 ms.)
+constexpr int kSgTH = 8, kSgTW = 32;
 template <typename T>
-__global__ void __launch_bounds__(256) sa_gate_kernel(const float* __restrict__ stats, const float* __restrict__ w,
-                                                      float* __restrict__ gate, int B, int H, int W) {
+__global__ void __launch_bounds__(256) sa_gate_tiled_kernel(const float* __restrict__ stats, const float* __restrict__ w,
+                                                            float* __restrict__ gate, int B, int H, int W, int tiles_h,
+                                                            int tiles_w) {
   __shared__ float sw[kSaTaps];
+  __shared__ float sst[2][kSgTH + 2 * kSaR][kSgTW + 2 * kSaR + 1];
   for (int i = threadIdx.x; i < kSaTaps; i += blockDim.x) sw[i] = Elem<T>::round(w[i]);
-  __syncthreads();
-  const int64_t npix = (int64_t)B * H * W;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(p % W);
-    const int64_t r = p / W;
-    const int i = (int)(r % H);
-    const int64_t img = (r / H) * H * W;
-    float a = 0.f;
-#pragma unroll
-    for (int ky = 0; ky < kSaK; ++ky) {
-      const int yy = i + ky - kSaR;
-      if (yy < 0 || yy >= H) continue;
-#pragma unroll
-      for (int kx = 0; kx < kSaK; ++kx) {
-        const int xx = j + kx - kSaR;
-        if (xx < 0 || xx >= W) continue;
-        const float2 st = *reinterpret_cast<const float2*>(stats + 2 * (img + (int64_t)yy * W + xx));
-        a = fmaf(sw[ky * kSaK + kx], st.x, a);
-        a = fmaf(sw[kSaK * kSaK + ky * kSaK + kx], st.y, a);
-      }
-    }
-    gate[p] = Elem<T>::round(sigmoidf_(Elem<T>::round(a)));
+  int rest = blockIdx.x;
+  const int tj = rest % tiles_w;
+  rest /= tiles_w;
+  const int ti = rest % tiles_h;
+  const int b = rest / tiles_h;
+  const int i0 = ti * kSgTH, j0 = tj * kSgTW;
+  const float* stb = stats + 2LL * b * H * W;
+  constexpr int HH = kSgTH + 2 * kSaR, HW = kSgTW + 2 * kSaR;
+  for (int e = threadIdx.x; e < HH * HW; e += blockDim.x) {
+    const int i = e / HW, j = e - i * HW;
+    const int yy = i0 + i - kSaR, xx = j0 + j - kSaR;
+    float2 v = make_float2(0.f, 0.f);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *reinterpret_cast<const float2*>(stb + 2 * ((long long)yy * W + xx));
+    sst[0][i][j] = v.x;
+    sst[1][i][j] = v.y;
   }
+  __syncthreads();
+  const int ty = threadIdx.x / kSgTW, tx = threadIdx.x % kSgTW;
+  const int yy = i0 + ty, xx = j0 + tx;
+  if (yy >= H || xx >= W) return;
+  float a = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < kSaK; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < kSaK; ++kx) {
+      a = fmaf(sw[ky * kSaK + kx], sst[0][ty + ky][tx + kx], a);
+      a = fmaf(sw[kSaK * kSaK + ky * kSaK + kx], sst[1][ty + ky][tx + kx], a);
+    }
+  gate[(long long)b * H * W + (long long)yy * W + xx] = Elem<T>::round(sigmoidf_(Elem<T>::round(a)));
+}
+
+// (dmean, dmax)[q] = sum_{ky,kx} w[ch][ky][kx] * da[q - (ky-3, kx-3)]: the transposed 7x7 conv of the backward pass as a
+// tiled stencil (da halo in shared memory), written as a float2 map that sa_bwd_dx streams.
+template <typename T>
+__global__ void __launch_bounds__(256) sa_bwd_dstats_kernel(const float* __restrict__ da, const float* __restrict__ w,
+                                                            float* __restrict__ dstats, int B, int H, int W, int tiles_h,
+                                                            int tiles_w) {
+  __shared__ float sw[kSaTaps];
+  __shared__ float sda[kSgTH + 2 * kSaR][kSgTW + 2 * kSaR + 1];
+  for (int i = threadIdx.x; i < kSaTaps; i += blockDim.x) sw[i] = Elem<T>::round(w[i]);
+  int rest = blockIdx.x;
+  const int tj = rest % tiles_w;
+  rest /= tiles_w;
+  const int ti = rest % tiles_h;
+  const int b = rest / tiles_h;
+  const int i0 = ti * kSgTH, j0 = tj * kSgTW;
+  const float* dab = da + (long long)b * H * W;
+  constexpr int HH = kSgTH + 2 * kSaR, HW = kSgTW + 2 * kSaR;
+  for (int e = threadIdx.x; e < HH * HW; e += blockDim.x) {
+    const int i = e / HW, j = e - i * HW;
+    const int yy = i0 + i - kSaR, xx = j0 + j - kSaR;
+    sda[i][j] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? dab[(long long)yy * W + xx] : 0.f;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / kSgTW, tx = threadIdx.x % kSgTW;
+  const int yy = i0 + ty, xx = j0 + tx;
+  if (yy >= H || xx >= W) return;
+  float dmean = 0.f, dmax = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < kSaK; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < kSaK; ++kx) {
+      const float d = sda[ty + 2 * kSaR - ky][tx + 2 * kSaR - kx];
+      dmean = fmaf(sw[ky * kSaK + kx], d, dmean);
+      dmax = fmaf(sw[kSaK * kSaK + ky * kSaK + kx], d, dmax);
+    }
+  *reinterpret_cast<float2*>(dstats + 2 * ((long long)b * H * W + (long long)yy * W + xx)) = make_float2(dmean, dmax);
 }
 
 // out[p][c] = x[p][c] * gate[p]
@@ -195,37 +246,21 @@ __global__ void sa_bwd_dw_reduce_kernel(const float* __restrict__ partial, int n
 template <typename T>
 __global__ void __launch_bounds__(256) sa_bwd_dx_kernel(const T* __restrict__ g, int64_t ld_g, const T* __restrict__ x,
                                                         int64_t ld_x, const float* __restrict__ gate,
-                                                        const float* __restrict__ da, const float* __restrict__ w,
+                                                        const float* __restrict__ dstats,
                                                         T* __restrict__ dx, int64_t ld_dx, int B, int H, int W, int C,
                                                         int LPP) {
-  __shared__ float sw[kSaTaps];
-  for (int i = threadIdx.x; i < kSaTaps; i += blockDim.x) sw[i] = Elem<T>::round(w[i]);
-  __syncthreads();
   const int sub = threadIdx.x % LPP, ppb = blockDim.x / LPP;
   const int64_t npix = (int64_t)B * H * W;
   const float inv_c = 1.f / (float)C;
   for (int64_t base = (int64_t)blockIdx.x * ppb; base < npix; base += (int64_t)gridDim.x * ppb) {
     const int64_t p = base + threadIdx.x / LPP;
     const bool live = p < npix;
-    // the 49 taps of the transposed conv are split over the LPP lanes of the pixel
+    // (dmean, dmax) of the pixel from the map sa_bwd_dstats_kernel made (every lane of the pixel reads the same 8 bytes)
     float dmean = 0.f, dmax = 0.f;
     if (live) {
-      const int j = (int)(p % W);
-      const int64_t r = p / W;
-      const int i = (int)(r % H);
-      const int64_t img = (r / H) * H * W;
-      for (int t = sub; t < kSaK * kSaK; t += LPP) {
-        const int ky = t / kSaK, kx = t - ky * kSaK;
-        const int yy = i - (ky - kSaR), xx = j - (kx - kSaR);
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const float d = da[img + (int64_t)yy * W + xx];
-        dmean = fmaf(sw[t], d, dmean);
-        dmax = fmaf(sw[kSaK * kSaK + t], d, dmax);
-      }
-    }
-    for (int o = LPP >> 1; o > 0; o >>= 1) {
-      dmean += __shfl_xor_sync(0xffffffffu, dmean, o);
-      dmax += __shfl_xor_sync(0xffffffffu, dmax, o);
+      const float2 ds = *reinterpret_cast<const float2*>(dstats + 2 * p);
+      dmean = ds.x;
+      dmax = ds.y;
     }
     if (LPP * 8 == C) {
       float xv[8], gv[8];
@@ -299,11 +334,14 @@ int unetb200_sa_forward(const void* x, int64_t ld_x, const float* w, float* stat
   const size_t esz = dtype == UNETB200_BF16 ? 2 : 4;
   const bool vec = sa_vec(C, {ld_x, ld_out}, {x, out}, esz);
   const int LPP = vec ? C / 8 : 1;
+  const int gth = (H + kSgTH - 1) / kSgTH, gtw = (W + kSgTW - 1) / kSgTW;
+  const int64_t gblocks = (int64_t)B * gth * gtw;
+  UB_CHECK_ARG(gblocks < (1LL << 31), "sa_forward: too many tiles");
 #define UB_SA_T(T)                                                                                                    \
   do {                                                                                                                \
     if (vec) sa_stats_kernel<T><<<sa_blocks(npix, 256 / LPP), 256, 0, s>>>((const T*)x, ld_x, stats, npix, C, LPP);   \
     else sa_stats_scalar_kernel<T><<<sa_blocks(npix, 256), 256, 0, s>>>((const T*)x, ld_x, stats, npix, C);           \
-    sa_gate_kernel<T><<<sa_blocks(npix, 256), 256, 0, s>>>(stats, w, gate, B, H, W);                                  \
+    sa_gate_tiled_kernel<T><<<(unsigned)gblocks, 256, 0, s>>>(stats, w, gate, B, H, W, gth, gtw);                      \
     if (vec) sa_apply_kernel<T, 8><<<sa_blocks(npix * (C / 8), 256), 256, 0, s>>>((const T*)x, ld_x, gate, (T*)out, ld_out, npix, C / 8); \
     else sa_apply_kernel<T, 1><<<sa_blocks(npix * C, 256), 256, 0, s>>>((const T*)x, ld_x, gate, (T*)out, ld_out, npix, C); \
   } while (0)
@@ -317,7 +355,7 @@ int unetb200_sa_forward(const void* x, int64_t ld_x, const float* w, float* stat
 int64_t unetb200_sa_backward_workspace(int B, int H, int W) {
   const int64_t npix = (int64_t)B * H * W;
   const int64_t blocks = (int64_t)B * ((H + kSaTH - 1) / kSaTH) * ((W + kSaTW - 1) / kSaTW);
-  return npix + blocks * kSaTaps + 64;           // floats: da map + dw partials
+  return 3 * npix + blocks * kSaTaps + 64;       // floats: (dmean, dmax) map + da map + dw partials
 }
 
 int unetb200_sa_backward(const void* g, int64_t ld_g, const void* x, int64_t ld_x, const float* w, const float* stats,
@@ -332,8 +370,12 @@ int unetb200_sa_backward(const void* g, int64_t ld_g, const void* x, int64_t ld_
   const size_t esz = dtype == UNETB200_BF16 ? 2 : 4;
   const bool vec = sa_vec(C, {ld_g, ld_x, ld_dx}, {g, x, dx}, esz);
   const int LPP = vec ? C / 8 : 1;
-  float* da = workspace;
-  float* partial = workspace + npix;
+  float* dstats = workspace;                     // float2 per pixel (first: 8-byte aligned for any npix)
+  float* da = workspace + 2 * npix;
+  float* partial = workspace + 3 * npix;
+  const int gth = (H + kSgTH - 1) / kSgTH, gtw = (W + kSgTW - 1) / kSgTW;
+  const int64_t gblocks = (int64_t)B * gth * gtw;
+  UB_CHECK_ARG(gblocks < (1LL << 31), "sa_backward: too many tiles");
   const int tiles_h = (H + kSaTH - 1) / kSaTH, tiles_w = (W + kSaTW - 1) / kSaTW;
   const int64_t blocks = (int64_t)B * tiles_h * tiles_w;
   UB_CHECK_ARG(blocks < (1LL << 31), "sa_backward: too many tiles");
@@ -342,7 +384,8 @@ int unetb200_sa_backward(const void* g, int64_t ld_g, const void* x, int64_t ld_
     sa_bwd_dgate_kernel<T><<<sa_blocks(npix, 256 / LPP), 256, 0, s>>>((const T*)g, ld_g, (const T*)x, ld_x, gate, da, npix, C, LPP); \
     sa_bwd_dw_kernel<<<(unsigned)blocks, 128, 0, s>>>(da, stats, partial, B, H, W, tiles_h, tiles_w);                 \
     sa_bwd_dw_reduce_kernel<<<(kSaTaps + 7) / 8, 256, 0, s>>>(partial, (int)blocks, dw);                              \
-    sa_bwd_dx_kernel<T><<<sa_blocks(npix, 256 / LPP), 256, 0, s>>>((const T*)g, ld_g, (const T*)x, ld_x, gate, da, w, (T*)dx, ld_dx, B, H, W, C, LPP); \
+    sa_bwd_dstats_kernel<T><<<(unsigned)gblocks, 256, 0, s>>>(da, w, dstats, B, H, W, gth, gtw);                      \
+    sa_bwd_dx_kernel<T><<<sa_blocks(npix, 256 / LPP), 256, 0, s>>>((const T*)g, ld_g, (const T*)x, ld_x, gate, dstats, (T*)dx, ld_dx, B, H, W, C, LPP); \
   } while (0)
   if (dtype == UNETB200_BF16) UB_SA_B(bf16);
   else UB_SA_B(float);

@@ -667,7 +667,7 @@ def sa_backward(g, x, w, stats, gate, dx, dw):
     B, Cc, H, W = x.shape
     ws = torch.empty(lib().unetb200_sa_backward_workspace(B, H, W), dtype=torch.float32, device=x.device)
     _run("sa_backward", lib().unetb200_sa_backward, _p(g), nhwc_ld(g), _p(x), nhwc_ld(x), _p(w), _p(stats), _p(gate),
-         _p(dx), nhwc_ld(dx), _p(dw), _p(ws), dt(x), B, H, W, Cc, _stream(), kernels=4,
+         _p(dx), nhwc_ld(dx), _p(dw), _p(ws), dt(x), B, H, W, Cc, _stream(), kernels=5,
          nbytes=5.0 * x.numel() * x.element_size())
 
 
