@@ -84,10 +84,14 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float v[4]) {
 // ------------------------------------------------------------------------------------------
 // fprop: D[128 x 64] tile per block, 256 threads, 8x4 micro-tile, K chunks of 16
 // ------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
+// FBN_ = 64 / 32 / 16 output channels per block (narrow layers: a 64-wide tile wastes 3/4 of its FMAs at N = 16);
+// the block keeps 256 threads with an 8 x 4 micro-tile, so FBM_ = 8 * 256 / (FBN_ / 4) = 128 / 256 / 512 pixels.
+template <typename T, bool VEC, int FBN_>
 __global__ void __launch_bounds__(256)
 gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ wp, const float* __restrict__ bias,
                         T* __restrict__ y, float* __restrict__ stats_ws) {
+  constexpr int TX = FBN_ / 4, TY = 256 / TX, FBM_ = TY * 8;
+  constexpr int FBM = FBM_, FBN = FBN_;   // (shadow the file-scope defaults inside this kernel)
   __shared__ __align__(16) float As[FBK][FBM + 4];
   __shared__ __align__(16) float Bs[FBK][FBN + 4];
   __shared__ int pb[FBM], pi[FBM], pj[FBM];
@@ -102,7 +106,7 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
     pb[t] = b; pi[t] = i; pj[t] = j;
   }
   __syncthreads();
-  const int tx = tid & 15, ty = tid >> 4;
+  const int tx = tid % TX, ty = tid / TX;
   float acc[8][4];
 #pragma unroll
   for (int r = 0; r < 8; ++r)
@@ -111,8 +115,8 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
 
   for (int k0 = 0; k0 < d.K; k0 += FBK) {
     if (VEC) {
-      {  // A: thread -> pixel tid/2, 8 channels
-        const int ml = tid >> 1, kv = (tid & 1) * 8;
+      for (int it = tid; it < FBM * 2; it += 256) {  // A: item -> pixel it/2, 8 channels
+        const int ml = it >> 1, kv = (it & 1) * 8;
         const int k = k0 + kv;
         const int t = k / d.Cin, c = k - t * d.Cin;
         float v[8];
@@ -125,7 +129,7 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
 #pragma unroll
         for (int e = 0; e < 8; ++e) As[kv + e][ml] = v[e];
       }
-      {  // B: thread -> row n tid/4, 4 consecutive k
+      if (tid < FBN * 4) {  // B: thread -> row n tid/4, 4 consecutive k
         const int nl = tid >> 2, k4 = (tid & 3) * 4;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (n0 + nl < d.N) load4<T>(wp + (long long)(n0 + nl) * d.K + k0 + k4, v);
@@ -134,7 +138,7 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
       }
     } else {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
+      for (int r = 0; r < FBM / 16; ++r) {
         const int e = tid + r * 256;
         const int kl = e & 15, ml = e >> 4;
         const int k = k0 + kl;
@@ -146,9 +150,7 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
         }
         As[kl][ml] = v;
       }
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int e = tid + r * 256;
+      for (int e = tid; e < FBN * 16; e += 256) {
         const int kl = e & 15, nl = e >> 4;
         const int k = k0 + kl;
         float v = 0.f;
@@ -205,11 +207,15 @@ gconv_fprop_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
   if (stats_ws) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      // the two ty rows of a warp first, then shared-memory atomics across the 8 warps
-      float a = s1[c] + __shfl_xor_sync(0xffffffffu, s1[c], 16);
-      float b = s2[c] + __shfl_xor_sync(0xffffffffu, s2[c], 16);
-      // per-warp partials, summed in a fixed order below (float atomics would make the statistics run-dependent)
-      if ((tid & 16) == 0) { wstat[tid >> 5][0][tx * 4 + c] = a; wstat[tid >> 5][1][tx * 4 + c] = b; }
+      // the ty rows of a warp first (lanes with the same tx), then the 8 warps in a fixed order below (float atomics
+      // would make the statistics run-dependent)
+      float a = s1[c], b = s2[c];
+#pragma unroll
+      for (int o = TX; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if ((tid & 31) < TX) { wstat[tid >> 5][0][tx * 4 + c] = a; wstat[tid >> 5][1][tx * 4 + c] = b; }
     }
     __syncthreads();
     // per-tile partials [tile][2][N]: plain stores, reduced by stats_reduce_kernel (no global atomics)
@@ -255,10 +261,13 @@ int launch_stats_reduce(const float* ws, long long ntiles, int C2, double* stats
 // ------------------------------------------------------------------------------------------
 // wgrad: dWp[64 k x 64 n] tile per block, reduction over a slice of m, 4x4 micro-tile
 // ------------------------------------------------------------------------------------------
-template <typename T, bool VEC>
+// WBN_ = 64 / 32 / 16 columns per block; 256 threads with a 4 x 4 micro-tile, so WBK_ = 4 * 256 / (WBN_ / 4) = 64 / 128 / 256 rows
+template <typename T, bool VEC, int WBN_>
 __global__ void __launch_bounds__(256)
 gconv_wgrad_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ partials,
                         long long m_per_split) {
+  constexpr int TN = WBN_ / 4, TK = 256 / TN, WBK_ = TK * 4;
+  constexpr int WBK = WBK_, WBN = WBN_;   // (shadow the file-scope defaults inside this kernel)
   __shared__ __align__(16) float As[WBM][WBK + 4];
   __shared__ __align__(16) float Gs[WBM][WBN + 4];
   const int tid = threadIdx.x;
@@ -266,7 +275,7 @@ gconv_wgrad_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
   const long long mb = (long long)blockIdx.z * m_per_split;
   long long me = mb + m_per_split;
   if (me > d.M) me = d.M;
-  const int tk = tid >> 4, tn = tid & 15;
+  const int tk = tid / TN, tn = tid % TN;
   float acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -275,50 +284,57 @@ gconv_wgrad_simt_kernel(GconvDev d, const T* __restrict__ x, const T* __restrict
 
   for (long long m0 = mb; m0 < me; m0 += WBM) {
     if (VEC) {
-      const int ml = tid >> 4, q4 = (tid & 15) * 4;
-      const long long m = m0 + ml;
-      float va[4] = {0.f, 0.f, 0.f, 0.f}, vg[4] = {0.f, 0.f, 0.f, 0.f};
-      if (m < me) {
-        int b, i, j;
-        decode_m(d, m, b, i, j);
-        const int k = k0 + q4;
-        if (k < d.K) {
-          const int t = k / d.Cin, c = k - t * d.Cin;
-          long long off = src_offset(d, b, i, j, t);
-          if (off >= 0) load4<T>(x + off + c, va);
-        }
-        const int n = n0 + q4;
-        if (n < d.N) {
-          const int q = n / d.Cq, co = n - q * d.Cq;
-          load4<T>(gy + dst_offset(d, b, i, j, q) + co, vg);
-        }
-      }
-      *reinterpret_cast<float4*>(&As[ml][q4]) = make_float4(va[0], va[1], va[2], va[3]);
-      *reinterpret_cast<float4*>(&Gs[ml][q4]) = make_float4(vg[0], vg[1], vg[2], vg[3]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int e = tid + r * 256;
-        const int ml = e >> 6, kl = e & 63;
+      constexpr int AV = WBK / 4, GV = WBN / 4;          // float4 items per pixel
+      for (int it = tid; it < WBM * (AV + GV); it += 256) {
+        const int ml = it / (AV + GV), r = it - ml * (AV + GV);
         const long long m = m0 + ml;
-        float va = 0.f, vg = 0.f;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (m < me) {
           int b, i, j;
           decode_m(d, m, b, i, j);
-          const int k = k0 + kl;
-          if (k < d.K) {
-            const int t = k / d.Cin, c = k - t * d.Cin;
-            long long off = src_offset(d, b, i, j, t);
-            if (off >= 0) va = Elem<T>::ld(x + off + c);
-          }
-          const int n = n0 + kl;
-          if (n < d.N) {
-            const int q = n / d.Cq, co = n - q * d.Cq;
-            vg = Elem<T>::ld(gy + dst_offset(d, b, i, j, q) + co);
+          if (r < AV) {
+            const int k = k0 + r * 4;
+            if (k < d.K) {
+              const int t = k / d.Cin, c = k - t * d.Cin;
+              long long off = src_offset(d, b, i, j, t);
+              if (off >= 0) load4<T>(x + off + c, v);
+            }
+          } else {
+            const int n = n0 + (r - AV) * 4;
+            if (n < d.N) {
+              const int q = n / d.Cq, co = n - q * d.Cq;
+              load4<T>(gy + dst_offset(d, b, i, j, q) + co, v);
+            }
           }
         }
-        As[ml][kl] = va;
-        Gs[ml][kl] = vg;
+        if (r < AV) *reinterpret_cast<float4*>(&As[ml][r * 4]) = make_float4(v[0], v[1], v[2], v[3]);
+        else *reinterpret_cast<float4*>(&Gs[ml][(r - AV) * 4]) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+      for (int e = tid; e < WBM * (WBK + WBN); e += 256) {
+        const int ml = e / (WBK + WBN), r = e - ml * (WBK + WBN);
+        const long long m = m0 + ml;
+        float v = 0.f;
+        if (m < me) {
+          int b, i, j;
+          decode_m(d, m, b, i, j);
+          if (r < WBK) {
+            const int k = k0 + r;
+            if (k < d.K) {
+              const int t = k / d.Cin, c = k - t * d.Cin;
+              long long off = src_offset(d, b, i, j, t);
+              if (off >= 0) v = Elem<T>::ld(x + off + c);
+            }
+          } else {
+            const int n = n0 + r - WBK;
+            if (n < d.N) {
+              const int q = n / d.Cq, co = n - q * d.Cq;
+              v = Elem<T>::ld(gy + dst_offset(d, b, i, j, q) + co);
+            }
+          }
+        }
+        if (r < WBK) As[ml][r] = v;
+        else Gs[ml][r - WBK] = v;
       }
     }
     __syncthreads();
@@ -645,8 +661,13 @@ static bool simt_vec_ok(const unetb200_gconv_t* d, const void* x, const void* wp
          (reinterpret_cast<uintptr_t>(y) % (4 * esz)) == 0;
 }
 
+static int simt_fbn(int N) { return N <= 16 ? 16 : (N <= 32 ? 32 : 64); }
+static int simt_fbm(int N) { return 8 * 256 / (simt_fbn(N) / 4); }
+static int simt_wbk(int N) { return 4 * 256 / (simt_fbn(N) / 4); }
+
 static int simt_wgrad_splits(const GconvDev& g) {
-  long long tiles = (long long)((g.K + WBK - 1) / WBK) * ((g.N + WBN - 1) / WBN);
+  const int wbn = simt_fbn(g.N), wbk = simt_wbk(g.N);
+  long long tiles = (long long)((g.K + wbk - 1) / wbk) * ((g.N + wbn - 1) / wbn);
   long long want = ((long long)sm_count() * 6 + tiles - 1) / tiles;
   long long max_by_m = (g.M + 255) / 256;
   if (want > max_by_m) want = max_by_m;
@@ -721,17 +742,20 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   }
   UB_CHECK_ARG(algo == UNETB200_ALGO_SIMT, "gconv_fprop: unknown algo %d", algo);
   if (!bias && first_fprop_supported(d, y)) return first_fprop(d, g, x, wp, y, stats, stats_ws, s);
-  dim3 grid((unsigned)((g.M + FBM - 1) / FBM), (unsigned)((g.N + FBN - 1) / FBN));
+  const int fbn = simt_fbn(g.N), fbm = simt_fbm(g.N);
+  dim3 grid((unsigned)((g.M + fbm - 1) / fbm), (unsigned)((g.N + fbn - 1) / fbn));
   const bool vec = simt_vec_ok(d, x, wp, y) && (g.K % 4 == 0);
+#define UB_SIMT_F(T, V, BN) gconv_fprop_simt_kernel<T, V, BN><<<grid, 256, 0, s>>>(g, (const T*)x, (const T*)wp, bias, (T*)y, stats_ws)
+#define UB_SIMT_FN(T, V) do { if (fbn == 16) UB_SIMT_F(T, V, 16); else if (fbn == 32) UB_SIMT_F(T, V, 32); else UB_SIMT_F(T, V, 64); } while (0)
   if (d->dtype == UNETB200_BF16) {
-    if (vec) gconv_fprop_simt_kernel<bf16, true><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats_ws);
-    else gconv_fprop_simt_kernel<bf16, false><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)wp, bias, (bf16*)y, stats_ws);
+    if (vec) UB_SIMT_FN(bf16, true); else UB_SIMT_FN(bf16, false);
   } else {
-    if (vec) gconv_fprop_simt_kernel<float, true><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats_ws);
-    else gconv_fprop_simt_kernel<float, false><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)wp, bias, (float*)y, stats_ws);
+    if (vec) UB_SIMT_FN(float, true); else UB_SIMT_FN(float, false);
   }
+#undef UB_SIMT_FN
+#undef UB_SIMT_F
   UB_LAUNCH_CHECK("gconv_fprop_simt");
-  if (stats) return launch_stats_reduce(stats_ws, (g.M + FBM - 1) / FBM, 2 * g.N, stats, s);
+  if (stats) return launch_stats_reduce(stats_ws, (g.M + fbm - 1) / fbm, 2 * g.N, stats, s);
   return 0;
 }
 
@@ -900,18 +924,21 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
   }
   long long mper = (g.M + splits - 1) / splits;
   mper = (mper + WBM - 1) / WBM * WBM;
-  dim3 grid((unsigned)((g.K + WBK - 1) / WBK), (unsigned)((g.N + WBN - 1) / WBN), (unsigned)splits);
+  const int wbn = simt_fbn(g.N), wbk = simt_wbk(g.N);
+  dim3 grid((unsigned)((g.K + wbk - 1) / wbk), (unsigned)((g.N + wbn - 1) / wbn), (unsigned)splits);
   const size_t esz = d->dtype == UNETB200_BF16 ? 2 : 4;
   const bool vec = d->Cin % 4 == 0 && g.Cq % 4 == 0 && d->ld_in % 4 == 0 && d->ld_out % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(x) % (4 * esz)) == 0 &&
                    (reinterpret_cast<uintptr_t>(gy) % (4 * esz)) == 0;
+#define UB_SIMT_W(T, V, BN) gconv_wgrad_simt_kernel<T, V, BN><<<grid, 256, 0, s>>>(g, (const T*)x, (const T*)gy, partials, mper)
+#define UB_SIMT_WN(T, V) do { if (wbn == 16) UB_SIMT_W(T, V, 16); else if (wbn == 32) UB_SIMT_W(T, V, 32); else UB_SIMT_W(T, V, 64); } while (0)
   if (d->dtype == UNETB200_BF16) {
-    if (vec) gconv_wgrad_simt_kernel<bf16, true><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)gy, partials, mper);
-    else gconv_wgrad_simt_kernel<bf16, false><<<grid, 256, 0, s>>>(g, (const bf16*)x, (const bf16*)gy, partials, mper);
+    if (vec) UB_SIMT_WN(bf16, true); else UB_SIMT_WN(bf16, false);
   } else {
-    if (vec) gconv_wgrad_simt_kernel<float, true><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)gy, partials, mper);
-    else gconv_wgrad_simt_kernel<float, false><<<grid, 256, 0, s>>>(g, (const float*)x, (const float*)gy, partials, mper);
+    if (vec) UB_SIMT_WN(float, true); else UB_SIMT_WN(float, false);
   }
+#undef UB_SIMT_WN
+#undef UB_SIMT_W
   UB_LAUNCH_CHECK("gconv_wgrad_simt");
   return 0;
 }
