@@ -492,6 +492,22 @@ def _narrow_case(B, Ci, Co, H, W, seed, slice_in=False):
     return res
 
 
+def _wgrad_f32_narrow_case(B, Ci, Co, H, W, seed):
+    """exact-fp32 weight gradient of a narrow 3x3 layer (conv_simt_narrow.cu) against PyTorch-CPU fp32"""
+    g = gen(seed)
+    x = torch.randn(B, Ci, H, W, generator=g).requires_grad_(True)
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Ci ** 0.5)).requires_grad_(True)
+    ref = F.conv2d(x, w, padding=1)
+    gy = torch.randn(ref.shape, generator=g)
+    ref.backward(gy)
+    xd, gyd = dev_nhwc(x.detach(), FP), dev_nhwc(gy, FP)
+    dW = torch.empty(Co, Ci, 3, 3, device=DEV)
+    d = ops.make_gconv(ops._DT[FP], _lib.ALGO_SIMT, B, H, W, Ci, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(xd), Co, 1, 1,
+                       (0, 0), H, W, ops.nhwc_ld(gyd))
+    ops.gconv_wgrad(d, xd, gyd, dW, 1, 9, Ci * 9)
+    return [(f"wgrad_f32_narrow_{Ci}to{Co}_{B}x{H}x{W}", rel(host(dW), w.grad), 2e-5)]
+
+
 def check_conv_narrow():
     out = []
     out += _narrow_case(2, 16, 16, 20, 24, 101)
@@ -520,6 +536,11 @@ def check_conv_narrow():
     out += _narrow_case(4, 8, 8, 200, 136, 131)
     out += _narrow_case(2, 16, 8, 130, 100, 132)
     out += _narrow_case(2, 8, 32, 64, 48, 133)
+    # the same layers without autocast: exact-fp32 weight gradient on the CUDA cores, several tiles per block, ragged
+    for i, (B, Ci, Co, H, W) in enumerate([(2, 16, 16, 40, 70), (8, 16, 16, 256, 256), (2, 16, 32, 33, 20), (1, 32, 16, 9, 50),
+                                           (3, 32, 32, 64, 48), (1, 64, 32, 24, 17), (2, 32, 64, 16, 16), (1, 16, 64, 20, 36),
+                                           (1, 64, 16, 10, 9)]):
+        out += _wgrad_f32_narrow_case(B, Ci, Co, H, W, 140 + i)
     # narrow ConvTranspose2d (conv_halo_t.cu): partial tiles in both directions, rows past the image (h % 8 != 0) that
     # the 5-D quadrant view reads from the next image, several tiles per CTA, padded destination (fprop only)
     out += _convT_case(2, 32, 16, 24, 40, (0, 0), BF, _lib.ALGO_TC, 120)

@@ -874,6 +874,7 @@ int unetb200_gconv_wgrad_plan(const unetb200_gconv_t* d, int* splits, int* algo_
       *splits = tc4_wgrad_preferred(d) ? tc4_wgrad_splits(d)
                 : tc3_wgrad_supported(d, nullptr, nullptr) ? tc3_wgrad_splits(d) : tc2_wgrad_splits(d);
     else if (first_wgrad_supported(d, nullptr)) *splits = first_wgrad_splits(d);
+    else if (wgrad_narrow_f32_supported(d, nullptr, nullptr)) *splits = wgrad_narrow_f32_splits(d);
     else *splits = simt_wgrad_splits(g);
   }
   return 0;
@@ -921,6 +922,10 @@ int unetb200_gconv_wgrad(const unetb200_gconv_t* d, const void* x, const void* g
     UB_CHECK_ARG(first_wgrad_supported(d, gy) && splits == first_wgrad_splits(d),
                  "gconv_wgrad: first-layer kernel needs 16-byte aligned dY and the planned split count");
     return first_wgrad(d, g, x, gy, partials, splits, s);
+  }
+  if (wgrad_narrow_f32_supported(d, nullptr, nullptr)) {
+    UB_CHECK_ARG(wgrad_narrow_f32_supported(d, x, gy), "gconv_wgrad: the narrow fp32 kernel needs 16-byte aligned operands");
+    return wgrad_narrow_f32(d, x, gy, partials, splits, s);
   }
   long long mper = (g.M + splits - 1) / splits;
   mper = (mper + WBM - 1) / WBM * WBM;

@@ -110,6 +110,10 @@ int first_narrow_fprop(const unetb200_gconv_t* d, const void* x, const void* wp,
                        const float* affine, cudaStream_t s);
 int first_narrow_wgrad_splits(const unetb200_gconv_t* d);
 int first_narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
+// exact-fp32 wgrad of the narrow 3x3 layers on the CUDA cores (conv_simt_narrow.cu)
+int wgrad_narrow_f32_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
+int wgrad_narrow_f32_splits(const unetb200_gconv_t* d);
+int wgrad_narrow_f32(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
 // ConvTranspose2d(k=2, s=2) with narrow channel counts (conv_halo_t.cu)
 int halo_t_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
 int halo_t_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y, cudaStream_t s);
