@@ -505,7 +505,22 @@ def _wgrad_f32_narrow_case(B, Ci, Co, H, W, seed):
     d = ops.make_gconv(ops._DT[FP], _lib.ALGO_SIMT, B, H, W, Ci, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(xd), Co, 1, 1,
                        (0, 0), H, W, ops.nhwc_ld(gyd))
     ops.gconv_wgrad(d, xd, gyd, dW, 1, 9, Ci * 9)
-    return [(f"wgrad_f32_narrow_{Ci}to{Co}_{B}x{H}x{W}", rel(host(dW), w.grad), 2e-5)]
+    res = [(f"wgrad_f32_narrow_{Ci}to{Co}_{B}x{H}x{W}", rel(host(dW), w.grad), 2e-5)]
+    # forward (+ BatchNorm statistics) and data gradient through the same exact-fp32 CUDA-core kernel
+    y = ops.empty_nhwc(B, Co, H, W, FP, DEV)
+    stats = torch.zeros(2 * Co, dtype=torch.float64, device=DEV)
+    ops.gconv_fprop(d, xd, UF.pack3x3_fprop(w.detach().to(DEV), FP), None, y, stats)
+    yh = host(y)
+    res.append((f"fprop_f32_narrow_{Ci}to{Co}_{B}x{H}x{W}", rel(yh, ref.detach()), 2e-5))
+    st = host(stats.float()).reshape(2, Co)
+    res.append((f"fprop_f32_narrow_{Ci}to{Co}_{B}x{H}x{W}_stats_sum", rel(st[0], yh.sum((0, 2, 3))), 1e-4))
+    res.append((f"fprop_f32_narrow_{Ci}to{Co}_{B}x{H}x{W}_stats_sq", rel(st[1], (yh ** 2).sum((0, 2, 3))), 1e-4))
+    gx = ops.empty_nhwc(B, Ci, H, W, FP, DEV)
+    dd = ops.make_gconv(ops._DT[FP], _lib.ALGO_SIMT, B, H, W, Co, ops.TAPS3, 1, (0, 0), H, W, ops.nhwc_ld(gyd), Ci, 1, 1,
+                        (0, 0), H, W, ops.nhwc_ld(gx))
+    ops.gconv_fprop(dd, gyd, UF.pack3x3_dgrad(w.detach().to(DEV), FP), None, gx, None)
+    res.append((f"dgrad_f32_narrow_{Ci}to{Co}_{B}x{H}x{W}", rel(host(gx), x.grad), 2e-5))
+    return res
 
 
 def check_conv_narrow():

@@ -700,7 +700,9 @@ int64_t unetb200_gconv_stats_workspace(const unetb200_gconv_t* d) {
   const long long n5 = halo_stats_rows(d) * 2 * g.N;
   if (n5 > n) n = n5;
   const long long n6 = first_narrow_rows(d) * 2 * g.N;
-  return n > n6 ? n : n6;
+  if (n6 > n) n = n6;
+  const long long n7 = fprop_narrow_f32_rows(d) * 2 * g.N;
+  return n > n7 ? n : n7;
 }
 
 int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, const float* bias, void* y,
@@ -742,6 +744,7 @@ int unetb200_gconv_fprop(const unetb200_gconv_t* d, const void* x, const void* w
   }
   UB_CHECK_ARG(algo == UNETB200_ALGO_SIMT, "gconv_fprop: unknown algo %d", algo);
   if (!bias && first_fprop_supported(d, y)) return first_fprop(d, g, x, wp, y, stats, stats_ws, s);
+  if (!bias && fprop_narrow_f32_supported(d, x, wp, y)) return fprop_narrow_f32(d, x, wp, y, stats, stats_ws, s);
   const int fbn = simt_fbn(g.N), fbm = simt_fbm(g.N);
   dim3 grid((unsigned)((g.M + fbm - 1) / fbm), (unsigned)((g.N + fbn - 1) / fbn));
   const bool vec = simt_vec_ok(d, x, wp, y) && (g.K % 4 == 0);

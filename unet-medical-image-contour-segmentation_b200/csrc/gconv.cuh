@@ -111,6 +111,10 @@ int first_narrow_fprop(const unetb200_gconv_t* d, const void* x, const void* wp,
 int first_narrow_wgrad_splits(const unetb200_gconv_t* d);
 int first_narrow_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
 // exact-fp32 wgrad of the narrow 3x3 layers on the CUDA cores (conv_simt_narrow.cu)
+int fprop_narrow_f32_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
+long long fprop_narrow_f32_rows(const unetb200_gconv_t* d);
+int fprop_narrow_f32(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
+                     cudaStream_t s);
 int wgrad_narrow_f32_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int wgrad_narrow_f32_splits(const unetb200_gconv_t* d);
 int wgrad_narrow_f32(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
