@@ -18,7 +18,7 @@ constexpr int kWnH = 8;
 template <int CIN, int N>
 struct WnCfg {
   static constexpr int NG = N / 8, THREADS = CIN * NG;
-  static constexpr int TW = (CIN == 16 && N == 16) ? 32 : ((CIN >= 64 || (CIN == 32 && N == 64)) ? 8 : 16);
+  static constexpr int TW = (CIN >= 64 || (CIN == 32 && N == 64)) ? 8 : 16;
   static constexpr int XS = (kWnH + 2) * (TW + 2) * CIN, GS = kWnH * TW * N;     // floats
   static constexpr int smem = (XS + GS) * 4;
 };
