@@ -523,6 +523,51 @@ def _wgrad_f32_narrow_case(B, Ci, Co, H, W, seed):
     return res
 
 
+def _narrow_tf32_case(B, Ci, Co, H, W, seed):
+    """fp32 tensors through the TF32 form of the TMA-staged narrow kernel (fprop + statistics, dgrad, folded eval
+    BatchNorm + ReLU) against PyTorch-CPU fp32; the weight gradient of these layers is the exact CUDA-core kernel."""
+    res = []
+    g = gen(seed)
+    x = torch.randn(B, Ci, H, W, generator=g).requires_grad_(True)
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) / (3 * Ci ** 0.5)).requires_grad_(True)
+    ref = F.conv2d(x, w, padding=1)
+    gy = torch.randn(ref.shape, generator=g)
+    ref.backward(gy)
+    tag = f"narrow_tf32_{Ci}to{Co}_{B}x{H}x{W}"
+    xd, gyd, wdev = dev_nhwc(x.detach(), FP), dev_nhwc(gy, FP), w.detach().to(DEV)
+    y = ops.empty_nhwc(B, Co, H, W, FP, DEV)
+    stats = torch.zeros(2 * Co, dtype=torch.float64, device=DEV)
+
+    def desc(xin, Cout, yout):
+        return ops.make_gconv(ops._DT[FP], _lib.ALGO_PREFER_TC, B, H, W, xin.shape[1], ops.TAPS3, 1, (0, 0), H, W,
+                              ops.nhwc_ld(xin), Cout, 1, 1, (0, 0), H, W, ops.nhwc_ld(yout))
+    used = ops.gconv_fprop(desc(xd, Co, y), xd, UF.pack3x3_fprop(wdev, FP), None, y, stats)
+    res.append((f"{tag}_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
+    yh = host(y)
+    res.append((f"{tag}_fprop", rel(yh, ref.detach()), 2e-3))
+    st = host(stats.float()).reshape(2, Co)
+    res.append((f"{tag}_stats_sum", rel(st[0], yh.sum((0, 2, 3))), 1e-4))
+    res.append((f"{tag}_stats_sq", rel(st[1], (yh ** 2).sum((0, 2, 3))), 1e-4))
+    gx = ops.empty_nhwc(B, Ci, H, W, FP, DEV)
+    used = ops.gconv_fprop(desc(gyd, Ci, gx), gyd, UF.pack3x3_dgrad(wdev, FP), None, gx, None)
+    res.append((f"{tag}_dgrad_on_tensor_cores", 0.0 if used == _lib.ALGO_TC else 1.0, 0.0))
+    res.append((f"{tag}_dgrad", rel(host(gx), x.grad), 2e-3))
+    dW = torch.empty(Co, Ci, 3, 3, device=DEV)
+    ops.gconv_wgrad(desc(xd, Co, gyd), xd, gyd, dW, 1, 9, Ci * 9)
+    res.append((f"{tag}_wgrad_exact", rel(host(dW), w.grad), 2e-5 if min(Ci, Co) >= 16 else 2e-4))
+    sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g) * 0.2
+    coefs = torch.stack([torch.zeros(Co), torch.ones(Co), sc, sh]).to(DEV).contiguous()
+    z = ops.empty_nhwc(B, Co, H, W, FP, DEV)
+    d = desc(xd, Co, z)
+    ok = ops.gconv_fprop_affine_relu_supported(d, xd, UF.pack3x3_fprop(wdev, FP), z)
+    res.append((f"{tag}_fold_supported", 0.0 if ok else 1.0, 0.0))
+    if ok:
+        ops.gconv_fprop_affine_relu(d, xd, UF.pack3x3_fprop(wdev, FP), coefs, z)
+        zref = torch.relu(ref.detach() * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1))
+        res.append((f"{tag}_fold", rel(host(z), zref), 2e-3))
+    return res
+
+
 def check_conv_narrow():
     out = []
     out += _narrow_case(2, 16, 16, 20, 24, 101)
@@ -556,6 +601,10 @@ def check_conv_narrow():
                                            (3, 32, 32, 64, 48), (1, 64, 32, 24, 17), (2, 32, 64, 16, 16), (1, 16, 64, 20, 36),
                                            (1, 64, 16, 10, 9)]):
         out += _wgrad_f32_narrow_case(B, Ci, Co, H, W, 140 + i)
+    # ... and with TF32 allowed: fprop / dgrad on the tensor cores from fp32 tensors (64 / 128-byte swizzle rows)
+    for i, (B, Ci, Co, H, W) in enumerate([(2, 16, 16, 40, 70), (8, 16, 16, 256, 256), (2, 16, 32, 33, 20), (1, 32, 16, 9, 50),
+                                           (4, 32, 32, 200, 136), (2, 8, 8, 37, 41), (1, 8, 16, 24, 24), (2, 32, 8, 16, 48)]):
+        out += _narrow_tf32_case(B, Ci, Co, H, W, 160 + i)
     # narrow ConvTranspose2d (conv_halo_t.cu): partial tiles in both directions, rows past the image (h % 8 != 0) that
     # the 5-D quadrant view reads from the next image, several tiles per CTA, padded destination (fprop only)
     out += _convT_case(2, 32, 16, 24, 40, (0, 0), BF, _lib.ALGO_TC, 120)

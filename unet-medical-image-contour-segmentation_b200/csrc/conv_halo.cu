@@ -26,8 +26,8 @@ namespace ub {
 // ------------------------------------------------------------------------------------------ fprop / dgrad
 struct HaloParams {
   CUtensorMap x_map;             // {Cin, W, H, B}, box {Cin, 18, 18, 1}
-  const __nv_bfloat16* wp;       // packed [N][9 * Cin], tap order of the descriptor
-  __nv_bfloat16* y;              // [B][H][W][ld_out]
+  const void* wp;                // packed [N][9 * Cin], tap order of the descriptor (bf16, or fp32 for the TF32 form)
+  void* y;                       // [B][H][W][ld_out]
   const float* affine;           // MODE 1: scale[N] then shift[N]
   float* stats_ws;               // MODE 0: [grid * 8][2][N] or null
   long long ld_out;
@@ -41,24 +41,29 @@ struct HaloParams {
 constexpr int kHaloThreads = 320;
 constexpr int kHaloBW = 18;
 
-template <int CIN, int NT>
+// ES = 2: bf16 operands (kind::f16, K = 16 per MMA); ES = 4: fp32 operands read as TF32 (kind::tf32, K = 8 per MMA --
+// the same 32 bytes; a 16 / 32-channel fp32 pixel row is a 64 / 128-byte swizzle row), fp32 output.  Used without
+// autocast when TF32 is allowed (UNET_B200_PRECISION=tf32, the default when torch allows TF32 in cuDNN).
+template <int CIN, int NT, int ES = 2>
 struct HaloCfg {
-  static constexpr int P = 2 * CIN;
+  static constexpr int P = ES * CIN;
   static constexpr uint32_t kBox = kHaloBW * kHaloBW * P;
   static constexpr uint32_t kStage = (kBox + 1023) / 1024 * 1024;
   static constexpr uint32_t kBTile = NT * P < 1024 ? 1024u : (uint32_t)(NT * P);
-  static constexpr int RS = NT * 2;
+  static constexpr int RS = NT * ES;
   static constexpr uint32_t kEpi = 8 * 32 * RS;
   static constexpr int kFixed = 9 * (int)kBTile + (int)kEpi + 128 * 4 + 256 + 1024;
-  static constexpr int STAGES = CIN == 16 ? 4 : 3;
+  static constexpr int STAGES = P == 32 ? 4 : 3;
   static constexpr int smem = STAGES * (int)kStage + kFixed;
   static constexpr int CTAS = smem <= 110 * 1024 ? 2 : 1;
   static constexpr int kTmemCols = 4 * NT;
 };
 
-template <int CIN, int NT, int MODE>
-__global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_conv_kernel(const __grid_constant__ HaloParams p) {
-  using Cfg = HaloCfg<CIN, NT>;
+template <int CIN, int NT, int MODE, int ES = 2>
+__global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT, ES>::CTAS) halo_conv_kernel(const __grid_constant__ HaloParams p) {
+  using Cfg = HaloCfg<CIN, NT, ES>;
+  constexpr bool TF32 = ES == 4;
+  constexpr int EPC = 16 / ES;                          // elements per 16-byte chunk
   constexpr int P = Cfg::P, STAGES = Cfg::STAGES, RS = Cfg::RS;
   constexpr uint32_t LAYOUT = halo_layout<P>();
   constexpr int CMASK = P / 16 - 1;
@@ -83,14 +88,15 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   // weights: row n of tap tile t holds Wp[n][t * CIN .. + CIN), swizzled like a TMA write would
-  for (int e = threadIdx.x; e < NT * 9 * (CIN / 8); e += blockDim.x) {
-    const int n = e / (9 * (CIN / 8)), r = e - n * (9 * (CIN / 8));
-    const int t = r / (CIN / 8), c = r - t * (CIN / 8);
+  for (int e = threadIdx.x; e < NT * 9 * (P / 16); e += blockDim.x) {
+    const int n = e / (9 * (P / 16)), r = e - n * (9 * (P / 16));
+    const int t = r / (P / 16), c = r - t * (P / 16);
     const uint32_t off = t * Cfg::kBTile + n * P;
     const uint32_t addr = smem_u32(b_tile) + off;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (n < p.n_real && c * 8 < p.cin_real)
-      v = *reinterpret_cast<const uint4*>(p.wp + (size_t)n * 9 * p.cin_real + t * p.cin_real + c * 8);
+    if (n < p.n_real && c * EPC < p.cin_real)
+      v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.wp) +
+                                          ((size_t)n * 9 * p.cin_real + t * p.cin_real + c * EPC) * ES);
     *reinterpret_cast<uint4*>(b_tile + off + ((c ^ ((addr >> 7) & CMASK)) << 4)) = v;
   }
   if (MODE == 1 && threadIdx.x < 128) {
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc(false, false, false, 128, NT);
+    constexpr uint32_t idesc = make_idesc(TF32, false, false, 128, NT);
     const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_tile);
     uint32_t s = 0, ph = 0, acc = 0, pacc = 1;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -134,8 +140,8 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
           for (int t = 0; t < 9; ++t) {
             const uint32_t a0 = a_base + s * Cfg::kStage + (p.tap_pix[t] + 8 * strip) * P;
 #pragma unroll
-            for (int kk = 0; kk < CIN / 16; ++kk)
-              umma<false>(d, make_desc(a0 + kk * 32, 16, kHaloBW * P, LAYOUT),
+            for (int kk = 0; kk < P / 32; ++kk)               // 32 bytes of K per MMA: 16 bf16 or 8 tf32 values
+              umma<TF32>(d, make_desc(a0 + kk * 32, 16, kHaloBW * P, LAYOUT),
                           make_desc(b_base + t * Cfg::kBTile + kk * 32, 16, 8 * P, LAYOUT), idesc, (t | kk) ? 1u : 0u);
           }
         }
@@ -150,10 +156,11 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
     // ------------------------------------------------ epilogue: warp drains TMEM lanes [32 (warp % 4), +32) of one strip
     const int e = warp - 2, strip = e >> 2, quad = warp & 3;
     const uint32_t stg = smem_u32(stage) + e * 32 * RS;
-    auto swz = [](int row) { return NT == 64 ? (row & 7) : (NT == 32 ? ((row >> 1) & 3) : 0); };
-    constexpr int PP = NT / 2, G = 32 / PP;             // channel pairs per row; row groups for the statistics
+    auto swz = [](int row) { return RS == 128 ? (row & 7) : (RS == 64 ? ((row >> 1) & 3) : 0); };
+    // statistics lanes: bf16 -> a lane owns a channel PAIR (one 32-bit word of the staged row), fp32 -> one channel
+    constexpr int PP = TF32 ? NT : NT / 2, G = 32 / PP;     // lanes per row; row groups
     const int pair = lane % PP, grp = lane / PP;
-    constexpr int cpr = NT / 8;                         // 16-byte chunks per stored row
+    constexpr int cpr = RS / 16;                        // 16-byte chunks per stored row
     uint32_t acc = 0, pacc = 0;
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -176,21 +183,34 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&t_empty[acc])) : "memory");
         }
-        uint32_t o[W / 2];
+        if constexpr (TF32) {
 #pragma unroll
-        for (int c = 0; c < W / 2; ++c) {
-          float v0 = __uint_as_float(v[2 * c]), v1 = __uint_as_float(v[2 * c + 1]);
-          if (MODE == 1) {
-            const int ch = h * 32 + 2 * c;
-            v0 = fmaxf(fmaf(v0, coef[ch], coef[64 + ch]), 0.f);
-            v1 = fmaxf(fmaf(v1, coef[ch + 1], coef[64 + ch + 1]), 0.f);
+          for (int c = 0; c < W; ++c) {
+            float v0 = __uint_as_float(v[c]);
+            if (MODE == 1) v0 = fmaxf(fmaf(v0, coef[h * 32 + c], coef[64 + h * 32 + c]), 0.f);
+            v[c] = live ? __float_as_uint(v0) : 0u;
           }
-          o[c] = live ? halo_pack(v0, v1) : 0u;
-        }
 #pragma unroll
-        for (int c = 0; c < W / 8; ++c)
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * RS + (((h * 4 + c) ^ swz(lane)) << 4)),
-                       "r"(o[4 * c]), "r"(o[4 * c + 1]), "r"(o[4 * c + 2]), "r"(o[4 * c + 3]) : "memory");
+          for (int c = 0; c < W / 4; ++c)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * RS + (((h * 8 + c) ^ swz(lane)) << 4)),
+                         "r"(v[4 * c]), "r"(v[4 * c + 1]), "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
+        } else {
+          uint32_t o[W / 2];
+#pragma unroll
+          for (int c = 0; c < W / 2; ++c) {
+            float v0 = __uint_as_float(v[2 * c]), v1 = __uint_as_float(v[2 * c + 1]);
+            if (MODE == 1) {
+              const int ch = h * 32 + 2 * c;
+              v0 = fmaxf(fmaf(v0, coef[ch], coef[64 + ch]), 0.f);
+              v1 = fmaxf(fmaf(v1, coef[ch + 1], coef[64 + ch + 1]), 0.f);
+            }
+            o[c] = live ? halo_pack(v0, v1) : 0u;
+          }
+#pragma unroll
+          for (int c = 0; c < W / 8; ++c)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * RS + (((h * 4 + c) ^ swz(lane)) << 4)),
+                         "r"(o[4 * c]), "r"(o[4 * c + 1]), "r"(o[4 * c + 2]), "r"(o[4 * c + 3]) : "memory");
+        }
       }
       if (++acc == 2) { acc = 0; pacc ^= 1; }
       __syncwarp();
@@ -206,8 +226,9 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
                        : "r"(stg + rr * RS + ((ch ^ swz(rr)) << 4)) : "memory");
           const int yy = y0 + (rr >> 3), xx = x0 + (rr & 7);
-          if (yy < p.H && xx < p.W && ch * 8 < p.n_real)
-            *reinterpret_cast<uint4*>(p.y + (((long long)b * p.H + yy) * p.W + xx) * p.ld_out + ch * 8) = q;
+          if (yy < p.H && xx < p.W && ch * EPC < p.n_real)
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.y) +
+                                      ((((long long)b * p.H + yy) * p.W + xx) * p.ld_out + ch * EPC) * ES) = q;
         }
       }
       if (MODE == 0 && p.stats_ws) {
@@ -216,8 +237,13 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
           uint32_t u;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u)
                        : "r"(stg + rr * RS + ((((pair >> 2) ^ swz(rr)) << 4) | ((pair & 3) << 2))) : "memory");
-          const float a = __uint_as_float(u << 16), bq = __uint_as_float(u & 0xffff0000u);
-          s0 += a; q0 = fmaf(a, a, q0); s1 += bq; q1 = fmaf(bq, bq, q1);
+          if constexpr (TF32) {
+            const float a = __uint_as_float(u);
+            s0 += a; q0 = fmaf(a, a, q0);
+          } else {
+            const float a = __uint_as_float(u << 16), bq = __uint_as_float(u & 0xffff0000u);
+            s0 += a; q0 = fmaf(a, a, q0); s1 += bq; q1 = fmaf(bq, bq, q1);
+          }
         }
       }
     }
@@ -228,9 +254,13 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
         s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
       }
       float* dst = p.stats_ws + ((long long)blockIdx.x * 8 + e) * 2 * p.n_real;
-      if (grp == 0 && 2 * pair < p.n_real) {
-        dst[2 * pair] = s0; dst[2 * pair + 1] = s1;
-        dst[p.n_real + 2 * pair] = q0; dst[p.n_real + 2 * pair + 1] = q1;
+      if constexpr (TF32) {
+        if (grp == 0 && pair < p.n_real) { dst[pair] = s0; dst[p.n_real + pair] = q0; }
+      } else {
+        if (grp == 0 && 2 * pair < p.n_real) {
+          dst[2 * pair] = s0; dst[2 * pair + 1] = s1;
+          dst[p.n_real + 2 * pair] = q0; dst[p.n_real + 2 * pair + 1] = q1;
+        }
       }
     }
   }
@@ -246,15 +276,24 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT>::CTAS) halo_con
 static bool halo_ch_ok(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
 static int halo_ch_pad(int c) { return c < 16 ? 16 : c; }          // 8 channels ride the 16-channel instantiation
 
-static bool halo_shape_ok(const unetb200_gconv_t* d) {
+// fp32 (TF32 on the tensor cores, fprop / dgrad only): 8 / 16 / 32 channels on either side -- a 64-channel fp32 row is two
+// swizzle rows, and tcgen05 has no MN-major 32-bit layout for 64-byte rows (the weight gradient stays exact fp32 on the
+// CUDA cores, conv_simt_narrow.cu)
+static bool halo_shape_ok(const unetb200_gconv_t* d, bool wgrad = false) {
   static const bool off = getenv("UNETB200_NO_HALO") != nullptr;
-  if (off || d->dtype != UNETB200_BF16) return false;
+  static const bool off32 = getenv("UNETB200_NO_HALO_TF32") != nullptr;
+  if (off || (d->dtype != UNETB200_BF16 && d->dtype != UNETB200_F32)) return false;
+  if (d->dtype == UNETB200_F32) {
+    if (wgrad || off32 || (d->algo != UNETB200_ALGO_TC && d->algo != UNETB200_ALGO_PREFER_TC)) return false;
+    if (d->Cin > 32 || d->N > 32) return false;
+  }
   if (d->ntaps != 9 || d->in_scale != 1 || d->out_scale != 1 || d->nquad != 1) return false;
   if (d->in_off_y || d->in_off_x || d->out_off_y || d->out_off_x) return false;
   if (d->Hm != d->Hout || d->Wm != d->Wout || d->Hm != d->Hin || d->Wm != d->Win) return false;
   if (!halo_ch_ok(d->Cin) || !halo_ch_ok(d->N)) return false;
   if (d->Cin == 64 && d->N == 64) return false;                    // the CTA-pair kernel (conv_tc3.cu) covers 64 -> 64
-  if ((d->ld_in % 8) || (d->ld_out % 8)) return false;
+  const int vec = d->dtype == UNETB200_BF16 ? 8 : 4;               // 16-byte pixel strides
+  if ((d->ld_in % vec) || (d->ld_out % vec)) return false;
   bool seen[9] = {false};
   for (int t = 0; t < 9; ++t) {
     const int dy = d->tap_dy[t], dx = d->tap_dx[t];
@@ -269,11 +308,15 @@ int halo_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* w
   return aligned16(x) && aligned16(wp) && aligned16(y);
 }
 
-template <int CIN, int NT>
-static int halo_ctas() { return HaloCfg<CIN, NT>::CTAS; }
+template <int CIN, int NT, int ES = 2>
+static int halo_ctas() { return HaloCfg<CIN, NT, ES>::CTAS; }
 
-static int halo_ctas_per_sm(int cin, int n) {
+static int halo_ctas_per_sm(int cin, int n, bool f32 = false) {
   cin = halo_ch_pad(cin); n = halo_ch_pad(n);
+  if (f32) {
+    if (cin == 16) return n == 16 ? halo_ctas<16, 16, 4>() : halo_ctas<16, 32, 4>();
+    return n == 16 ? halo_ctas<32, 16, 4>() : halo_ctas<32, 32, 4>();
+  }
   if (cin == 16) return n == 16 ? halo_ctas<16, 16>() : (n == 32 ? halo_ctas<16, 32>() : halo_ctas<16, 64>());
   if (cin == 32) return n == 16 ? halo_ctas<32, 16>() : (n == 32 ? halo_ctas<32, 32>() : halo_ctas<32, 64>());
   return n == 16 ? halo_ctas<64, 16>() : halo_ctas<64, 32>();
@@ -283,7 +326,7 @@ static int halo_grid(const unetb200_gconv_t* d, int* tiles_w, int* tiles_h, int*
   *tiles_w = (d->Wm + 15) / 16;
   *tiles_h = (d->Hm + 15) / 16;
   *ntiles = d->B * *tiles_w * *tiles_h;
-  const int slots = halo_ctas_per_sm(d->Cin, d->N) * sm_count();
+  const int slots = halo_ctas_per_sm(d->Cin, d->N, d->dtype == UNETB200_F32) * sm_count();
   return *ntiles < slots ? *ntiles : slots;
 }
 
@@ -293,13 +336,13 @@ long long halo_stats_rows(const unetb200_gconv_t* d) {
   return (long long)halo_grid(d, &tw, &th, &nt) * 8;
 }
 
-template <int CIN, int NT, int MODE>
+template <int CIN, int NT, int MODE, int ES = 2>
 static int halo_launch(const HaloParams& P, int grid, cudaStream_t s) {
-  constexpr int smem = HaloCfg<CIN, NT>::smem;
+  constexpr int smem = HaloCfg<CIN, NT, ES>::smem;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(&halo_conv_kernel<CIN, NT, MODE>), smem, "halo_conv smem attribute"))
+  if (int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(&halo_conv_kernel<CIN, NT, MODE, ES>), smem, "halo_conv smem attribute"))
     return rc;
-  halo_conv_kernel<CIN, NT, MODE><<<grid, kHaloThreads, smem, s>>>(P);
+  halo_conv_kernel<CIN, NT, MODE, ES><<<grid, kHaloThreads, smem, s>>>(P);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "halo_conv launch");
   return 0;
@@ -320,16 +363,23 @@ static int halo_dispatch_n(const HaloParams& P, int n, int grid, bool affine, cu
   return UNETB200_E_INVALID;
 }
 
+template <int CIN>
+static int halo_dispatch_n32(const HaloParams& P, int n, int grid, bool affine, cudaStream_t s) {
+  if (affine) return n == 16 ? halo_launch<CIN, 16, 1, 4>(P, grid, s) : halo_launch<CIN, 32, 1, 4>(P, grid, s);
+  return n == 16 ? halo_launch<CIN, 16, 0, 4>(P, grid, s) : halo_launch<CIN, 32, 0, 4>(P, grid, s);
+}
+
 int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
                const float* affine, cudaStream_t s) {
   if (!halo_fprop_supported(d, x, wp, y)) { set_error("halo_fprop: unsupported shape"); return UNETB200_E_INVALID; }
   HaloParams P;
   memset(&P, 0, sizeof(P));
+  const bool f32 = d->dtype == UNETB200_F32;
   if (int rc = encode_act_box_sw(&P.x_map, x, d->Cin, d->Wm, d->Hm, d->B, d->ld_in, (long long)d->Wm * d->ld_in,
-                                 (long long)d->Hm * d->Wm * d->ld_in, kHaloBW, kHaloBW))
+                                 (long long)d->Hm * d->Wm * d->ld_in, kHaloBW, kHaloBW, f32 ? 4 : 2))
     return rc;
   P.cin_real = d->Cin; P.n_real = d->N;
-  P.wp = (const __nv_bfloat16*)wp; P.y = (__nv_bfloat16*)y;
+  P.wp = wp; P.y = y;
   P.affine = affine;
   P.stats_ws = (stats && !affine) ? stats_ws : nullptr;
   P.ld_out = d->ld_out;
@@ -337,6 +387,10 @@ int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y
   for (int t = 0; t < 9; ++t) P.tap_pix[t] = (d->tap_dy[t] + 1) * kHaloBW + d->tap_dx[t] + 1;
   const int grid = halo_grid(d, &P.tiles_w, &P.tiles_h, &P.ntiles);
   int rc;
+  if (f32) {
+    rc = halo_ch_pad(d->Cin) == 16 ? halo_dispatch_n32<16>(P, halo_ch_pad(d->N), grid, affine != nullptr, s)
+                                   : halo_dispatch_n32<32>(P, halo_ch_pad(d->N), grid, affine != nullptr, s);
+  } else
   switch (halo_ch_pad(d->Cin)) {
     case 16: rc = halo_dispatch_n<16>(P, halo_ch_pad(d->N), grid, affine != nullptr, s); break;
     case 32: rc = halo_dispatch_n<32>(P, halo_ch_pad(d->N), grid, affine != nullptr, s); break;
@@ -509,7 +563,7 @@ static int halo_wgrad_grid(const unetb200_gconv_t* d, int* tiles_w, int* tiles_h
 
 int halo_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy) {
   static const bool off = getenv("UNETB200_NO_HALO_WGRAD") != nullptr;
-  if (off || !halo_shape_ok(d)) return 0;
+  if (off || !halo_shape_ok(d, true)) return 0;
   if ((x && !aligned16(x)) || (gy && !aligned16(gy))) return 0;
   return 1;
 }

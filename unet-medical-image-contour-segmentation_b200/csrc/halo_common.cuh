@@ -9,7 +9,7 @@ template <int P>
 __host__ __device__ constexpr uint32_t halo_layout() { return P == 128 ? kLayoutSW128 : (P == 64 ? kLayoutSW64 : kLayoutSW32); }
 
 int encode_act_box_sw(CUtensorMap* m, const void* base, int C, int W, int H, int B, long long sw, long long sh, long long sb,
-                      int box_w, int box_h);
+                      int box_w, int box_h, int esz = 2);
 
 __device__ __forceinline__ void halo_tmem_ld16(uint32_t taddr, uint32_t v[16]) {
   asm volatile(

@@ -52,19 +52,21 @@ int encode_act_box(CUtensorMap* m, int dtype, const void* base, int C, int W, in
 // bf16 NHWC view {C, W, H, B} with C = 16 / 32 / 64 channels: a {C, box_w, box_h, 1} box whose 2C-byte pixel rows are
 // written with the 32 / 64 / 128-byte swizzle (conv_halo.cu)
 int encode_act_box_sw(CUtensorMap* m, const void* base, int C, int W, int H, int B, long long sw, long long sh, long long sb,
-                      int box_w, int box_h) {
+                      int box_w, int box_h, int esz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not found"); return UNETB200_E_CUDA; }
   if (C != 8 && C != 16 && C != 32 && C != 64) { set_error("encode_act_box_sw: C = %d", C); return UNETB200_E_INVALID; }
-  // C = 8: the box is 16 channels wide on an 8-channel tensor -- TMA zero-fills the upper half of every 32-byte row
+  // C = 8: the box is 16 channels wide on an 8-channel tensor -- TMA zero-fills the upper half of every row
   const int box_c = C < 16 ? 16 : C;
+  const int row_bytes = box_c * esz;               // 32 / 64 / 128: the swizzle width (bf16: esz 2, fp32 read as TF32: esz 4)
+  if ((esz != 2 && esz != 4) || row_bytes > 128) { set_error("encode_act_box_sw: C = %d esz = %d", C, esz); return UNETB200_E_INVALID; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)(sw * 2), (cuuint64_t)(sh * 2), (cuuint64_t)(sb * 2)};
+  cuuint64_t strides[3] = {(cuuint64_t)(sw * esz), (cuuint64_t)(sh * esz), (cuuint64_t)(sb * esz)};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+  CUresult r = enc(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(narrow activation C=%d W=%d H=%d B=%d sw=%lld) failed: %d", C, W, H, B, sw, (int)r);
