@@ -18,7 +18,9 @@ constexpr int kWnH = 8;
 template <int CIN, int N>
 struct WnCfg {
   static constexpr int NG = N / 8, THREADS = CIN * NG;
-  static constexpr int TW = (CIN >= 64 || (CIN == 32 && N == 64)) ? 8 : 16;
+  // small blocks (<= 2 warps) take 8-column tiles: 10 KB of shared memory each, so 16 blocks (the register limit at 128
+  // registers) are resident -- at 9 blocks of one warp the FMA pipe was 41 % active (ncu), two warps per scheduler
+  static constexpr int TW = (CIN >= 64 || (CIN == 32 && N == 64) || CIN * (N / 8) <= 64) ? 8 : 16;
   static constexpr int XS = (kWnH + 2) * (TW + 2) * CIN, GS = kWnH * TW * N;     // floats
   static constexpr int smem = (XS + GS) * 4;
 };
@@ -263,7 +265,7 @@ template <int CIN, int N>
 static int wn_tw() { return WnCfg<CIN, N>::TW; }
 template <int CIN, int N>
 static int wn_bps() {                       // resident blocks per SM: shared memory and threads
-  int by_smem = (200 * 1024) / (WnCfg<CIN, N>::smem + 1024), by_thr = 1536 / WnCfg<CIN, N>::THREADS;
+  int by_smem = (200 * 1024) / (WnCfg<CIN, N>::smem + 1024), by_thr = 512 / WnCfg<CIN, N>::THREADS;   // 128 registers per thread
   int b = by_smem < by_thr ? by_smem : by_thr;
   return b < 1 ? 1 : (b > 16 ? 16 : b);
 }
