@@ -310,6 +310,10 @@ def make_gconv(dtype, algo, B, Hm, Wm, Cin, taps, in_scale, in_off, Hin, Win, ld
     d.dtype = dtype
     fa = forced_algo()
     d.algo = fa if fa is not None else algo
+    if dtype == F32 and d.algo == _lib.ALGO_PREFER_TC and Cin < 16 and x3_mode():
+        # fp32 exactness mode: layers too narrow for the 3-term split (x3_active needs C_in >= 16) stay on the exact
+        # CUDA-core kernels instead of the plain-TF32 narrow kernel
+        d.algo = ALGO_SIMT
     d.B, d.Hm, d.Wm, d.Cin, d.ntaps = B, Hm, Wm, Cin, len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
