@@ -107,6 +107,17 @@ int unetb200_gconv_fprop_affine_relu_supported(const unetb200_gconv_t* d, const 
 int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, const void* wp,
                                      const float* scale_shift, void* z, void* stream);
 
+/* The same with MaxPool2d(2) of the activation as a second output (Down under .eval(): unet_parts.py:26-37 reads the
+ * DoubleConv output the kernel just produced): pooled[b][i][j][n] = max over the 2x2 window of z, floor semantics
+ * ([B][Hm/2][Wm/2] pixels, pixel stride ld_pooled elements, bf16).  The separate pooling pass (2.5 B per element)
+ * disappears.  _supported: the CTA-pair tcgen05 kernel covers the shape (bf16, C_in and N multiples of 64); otherwise run
+ * unetb200_gconv_fprop_affine_relu + unetb200_maxpool2_fwd. */
+int unetb200_gconv_fprop_affine_relu_pool_supported(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                                    const void* z, const void* pooled, int64_t ld_pooled);
+int unetb200_gconv_fprop_affine_relu_pool(const unetb200_gconv_t* d, const void* x, const void* wp,
+                                          const float* scale_shift, void* z, void* pooled, int64_t ld_pooled,
+                                          void* stream);
+
 /* The last conv of the network in inference, fused with OutConv (unet_model.py:25,37; unet_parts.py:100-106):
  * logits[p][k] = sum_c relu(gconv(x, Wp)[p][c] * scale[c] + shift[c]) * oc_w[k][c] + oc_b[k], the activation rounded
  * to `dtype` before the 1x1 conv like the stand-alone kernels; the 64-channel activation is never written.  The

@@ -798,6 +798,34 @@ int unetb200_gconv_fprop_affine_relu(const unetb200_gconv_t* d, const void* x, c
   return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift);
 }
 
+// the same with MaxPool2d(2) of the activation as a second output (Down: unet_parts.py:26-37 under .eval()): the CTA-pair
+// kernel only -- a warp's 4 x 8 pixel patch of the epilogue holds whole 2 x 2 windows
+int unetb200_gconv_fprop_affine_relu_pool_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* z,
+                                                    const void* pooled, int64_t ld_pooled) {
+  GconvDev g;
+  if (gconv_validate(d, &g)) return 0;
+  static const bool off = getenv("UNETB200_NO_POOL_FOLD") != nullptr;
+  if (off || d->dtype != UNETB200_BF16 || !pooled || (ld_pooled & 1) || (reinterpret_cast<uintptr_t>(pooled) & 3)) return 0;
+  if (!unetb200_gconv_fprop_affine_relu_supported(d, x, wp, z)) return 0;
+  if ((first_tc_supported(d, z) && aligned16(wp)) || first_narrow_supported(d, z) || halo_fprop_supported(d, x, wp, z) ||
+      narrow_tc_supported(d, x, wp, z))
+    return 0;                                      // those shapes run on other kernels
+  return d->Hm >= 2 && d->Wm >= 2;
+}
+
+int unetb200_gconv_fprop_affine_relu_pool(const unetb200_gconv_t* d, const void* x, const void* wp, const float* scale_shift,
+                                          void* z, void* pooled, int64_t ld_pooled, void* stream) {
+  GconvDev g;
+  int rc = gconv_validate(d, &g);
+  if (rc) return rc;
+  UB_CHECK_ARG(x && wp && z && scale_shift && pooled, "gconv_fprop_affine_relu_pool: null pointer");
+  UB_CHECK_ARG(unetb200_gconv_fprop_affine_relu_pool_supported(d, x, wp, z, pooled, ld_pooled),
+               "gconv_fprop_affine_relu_pool: shape not covered (query _supported first and run gconv_fprop_affine_relu + "
+               "maxpool2_fwd instead)");
+  return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift, nullptr, 0, nullptr, nullptr, pooled,
+                   (long long)ld_pooled);
+}
+
 // dgrad of a 3x3 convolution + the reduction pass of the BatchNorm/ReLU backward of the layer that produced its input
 int unetb200_gconv_dgrad_bnbwd_supported(const unetb200_gconv_t* d, const void* g, const void* wp, const void* gx) {
   GconvDev gd;

@@ -174,6 +174,10 @@ struct alignas(64) Tc3Params {
   const float* oc_b;
   void* logits;
   int ncls;
+  // AFFINE bf16 kernels, optional: MaxPool2d(2) of the activation as a second output (Down's pool reads what this
+  // epilogue just staged: a warp's 4 x 8 pixel patch holds whole 2 x 2 windows), [B][Hm/2][Wm/2][ld_pool] bf16
+  void* pooled;
+  long long ld_pool;
 };
 
 constexpr uint32_t kA3Stage = 44032;    // 43 KB >= the largest halo box: 34 rows x 10 px x 128 B
@@ -501,6 +505,30 @@ __global__ void __launch_bounds__(kTc3Threads, 1) tc3_conv_kernel(const __grid_c
             tma_store_4d(&p.o_map, buf, n0 + cb * EPR, pj0, pi0, b);
             tma_store_commit();
           }
+          if constexpr (AFFINE && !OUTC && !TF32) {
+            if (p.pooled) {
+              // lane = 32-bit word (two channels) of the 128-byte row; pooled pixel (py, px) of the patch = max over rows
+              // 16 py + 2 px + {0, 1, 8, 9}.  The activations are >= 0 (ReLU), so the unsigned 16-bit SIMD maximum of the
+              // bf16 bit patterns is the bf16 maximum.
+              const int Hp = p.Hm >> 1, Wp = p.Wm >> 1;
+              const int gy0 = pi0 >> 1, gx0 = pj0 >> 1;
+#pragma unroll
+              for (int py = 0; py < 2; ++py)
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                  const int r0 = 16 * py + 2 * px;
+                  uint32_t m = 0u;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const int r = r0 + (k & 1) + 8 * (k >> 1);
+                    m = __vmaxu2(m, lds_u32(buf_s + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2))));
+                  }
+                  if (valid && gy0 + py < Hp && gx0 + px < Wp)
+                    reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.pooled) +
+                                                (((long long)b * Hp + gy0 + py) * Wp + gx0 + px) * p.ld_pool + n0 + cb * EPR)[lane] = m;
+                }
+            }
+          }
           if constexpr (BNBWD) {
             // lane = 32-bit word of the 128-byte row (one fp32 / two bf16 channels), over the 32 rows (pixels) of the
             // patch: g from the staged (rounded) tile, yprev from the TMA-fetched patch (same swizzle); rows outside
@@ -740,8 +768,12 @@ int tc3_affine_outconv_supported(const unetb200_gconv_t* d, int ncls) {
 
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
               float* stats_ws, cudaStream_t stream, const float* affine, const void* yprev, long long ld_yprev,
-              const float* bnc, const Tc3OutConv* oc) {
+              const float* bnc, const Tc3OutConv* oc, void* pooled, long long ld_pool) {
   Tc3Plan pl;
+  if (pooled && (!affine || oc || d->dtype != UNETB200_BF16 || (ld_pool & 1) || (reinterpret_cast<uintptr_t>(pooled) & 3))) {
+    set_error("tc3_fprop: the pooled second output needs the bf16 affine epilogue and 4-byte aligned rows");
+    return UNETB200_E_INVALID;
+  }
   if (yprev && (affine || !stats || !stats_ws || !bnc || !aligned16(yprev) ||
                 (ld_yprev * (d->dtype == UNETB200_BF16 ? 2 : 4)) % 16)) {
     set_error("tc3_fprop: the BatchNorm-backward epilogue needs sums, a workspace, coefficients and 16-byte aligned yprev rows");
@@ -782,6 +814,7 @@ int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const
   P.affine = affine;
   P.N = d->N;
   P.bnc = bnc;
+  P.pooled = pooled; P.ld_pool = ld_pool;
   if (yprev) {
     rc = encode_act_box(&P.y_map, d->dtype, yprev, d->N, d->Wm, d->Hm, d->B, ld_yprev, (long long)d->Wm * ld_yprev,
                         (long long)d->Hm * d->Wm * ld_yprev, 8, 4, false);

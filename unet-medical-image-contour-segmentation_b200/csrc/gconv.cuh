@@ -68,7 +68,8 @@ struct Tc3OutConv {            // OutConv fused into the inference epilogue of t
 int tc3_affine_outconv_supported(const unetb200_gconv_t* d, int ncls);
 int tc3_fprop(const unetb200_gconv_t* d, const GconvDev& g, const void* x, const void* wp, void* y, double* stats,
               float* stats_ws, cudaStream_t stream, const float* affine = nullptr, const void* yprev = nullptr,
-              long long ld_yprev = 0, const float* bnc = nullptr, const Tc3OutConv* oc = nullptr);
+              long long ld_yprev = 0, const float* bnc = nullptr, const Tc3OutConv* oc = nullptr, void* pooled = nullptr,
+              long long ld_pool = 0);
 int tc3_bnbwd_supported(const unetb200_gconv_t* d);
 
 int tc3_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);

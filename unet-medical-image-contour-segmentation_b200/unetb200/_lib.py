@@ -57,6 +57,8 @@ PROTOTYPES = {
     "unetb200_gconv_fprop": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p, c_p, C.POINTER(C.c_int), c_p]),
     "unetb200_gconv_fprop_affine_relu_supported": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p]),
     "unetb200_gconv_fprop_affine_relu": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p]),
+    "unetb200_gconv_fprop_affine_relu_pool_supported": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, C.c_int64]),
+    "unetb200_gconv_fprop_affine_relu_pool": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p, C.c_int64, c_p]),
     "unetb200_gconv_fprop_affine_relu_outconv_supported": (C.c_int, [C.POINTER(GConv), c_p, c_p, C.c_int]),
     "unetb200_gconv_fprop_affine_relu_outconv": (C.c_int, [C.POINTER(GConv), c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, c_p]),
     "unetb200_wgrad_reduce_multi": (C.c_int, [C.POINTER(ReduceJob), C.c_int, c_p]),

@@ -392,11 +392,13 @@ def conv_bn_relu_fwd(x, w, bn, training, out=None, want_pool=False, fold=False, 
         d = _gconv3x3(x, Cout, z, cd)
         if ops.gconv_fprop_affine_relu_supported(d, x, wp, z):
             coefs = _eval_coefs(bn, Cout)
-            ops.gconv_fprop_affine_relu(d, x, wp, coefs, z)
-            pooled = None
-            if want_pool:
-                pooled = ops.empty_nhwc(B, Cout, H // 2, W // 2, cd, dev)
-                ops.maxpool2_fwd(z, pooled)
+            pooled = ops.empty_nhwc(B, Cout, H // 2, W // 2, cd, dev) if want_pool else None
+            if pooled is not None and ops.gconv_fprop_affine_relu_pool_supported(d, x, wp, z, pooled):
+                ops.gconv_fprop_affine_relu(d, x, wp, coefs, z, pooled)      # the pool rides in the conv epilogue
+            else:
+                ops.gconv_fprop_affine_relu(d, x, wp, coefs, z)
+                if pooled is not None:
+                    ops.maxpool2_fwd(z, pooled)
             return None, z, pooled, coefs, False
     y = ops.empty_nhwc(B, Cout, H, W, cd, dev)
     use_batch = training or bn.running_mean is None

@@ -413,10 +413,23 @@ def gconv_fprop_affine_relu_supported(d, x, wp, z):
     return bool(lib().unetb200_gconv_fprop_affine_relu_supported(C.byref(d), _p(x), _p(wp), _p(z)))
 
 
-def gconv_fprop_affine_relu(d, x, wp, coefs, z):
-    """z = relu(conv(x, wp) * scale + shift) in the tcgen05 epilogue (inference; coefs rows 2, 3 = scale, shift)."""
+def gconv_fprop_affine_relu_pool_supported(d, x, wp, z, pooled):
+    return (not x3_active(d)) and bool(lib().unetb200_gconv_fprop_affine_relu_pool_supported(
+        C.byref(d), _p(x), _p(wp), _p(z), _p(pooled), nhwc_ld(pooled)))
+
+
+def gconv_fprop_affine_relu(d, x, wp, coefs, z, pooled=None):
+    """z = relu(conv(x, wp) * scale + shift) in the tcgen05 epilogue (inference; coefs rows 2, 3 = scale, shift);
+    pooled (query gconv_fprop_affine_relu_pool_supported first) = MaxPool2d(2)(z) from the same epilogue."""
     flops, nbytes = gconv_flops(d), gconv_bytes(d, 2 if d.dtype == BF16 else 4)
     tag = _shape_tag(d)
+    if pooled is not None:
+        _run("conv_fprop_bnfold", lib().unetb200_gconv_fprop_affine_relu_pool, C.byref(d), _p(x), _p(wp), _prow(coefs, 2),
+             _p(z), _p(pooled), nhwc_ld(pooled), _stream(), flops=flops,
+             nbytes=nbytes + float(pooled.numel()) * pooled.element_size())
+        if _PROFILE is not None:
+            _PROFILE[-1][0] = "conv_fprop_bnfold_tc" + tag
+        return
     if x3_active(d):
         x = x3_split(x)
         wp = x3_split_rows(wp, d.N * d.ntaps, d.Cin)
