@@ -574,6 +574,7 @@ GROUPS = {
     "unet_bf16": lambda gd: gate(1, 2, False, 2, 128, 128, "bf16", boundary_coeff=0.2) + gate(3, 4, False, 1, 160, 96, "bf16"),
     # sizes that are not multiples of 16: the pools floor, Up pads x1 to the skip (unet_parts.py:85-88), odd widths
     "unet_ragged": lambda gd: gate(1, 2, False, 2, 100, 84, "fp32") + gate(1, 2, True, 1, 72, 100, "fp32")
-                   + gate(3, 4, False, 2, 200, 136, "bf16") + infer_gate(1, 2, False, 1, 90, 122, "fp32"),
+                   + gate(3, 4, False, 2, 200, 136, "bf16") + infer_gate(1, 2, False, 1, 90, 122, "fp32")
+                   + width_gate("UNet_S", 1, 2, False, 2, 100, 84, "bf16") + width_gate("UNet_T", 1, 2, False, 1, 72, 100, "fp32"),
     "unet_bf16_bil": lambda gd: gate(1, 2, True, 2, 128, 128, "bf16") + gate(1, 2, False, 4, 256, 256, "bf16", fused=False),
 }
