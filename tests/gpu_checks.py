@@ -1185,6 +1185,15 @@ def check_dgrad_bnbwd():
     out += _dgrad_bnbwd_case(2, 64, 64, 16, 24, BF, 71)
     out += _dgrad_bnbwd_case(1, 128, 128, 20, 12, BF, 72)
     out += _dgrad_bnbwd_case(2, 128, 256, 9, 7, BF, 73)            # ragged tiles: rows outside the M grid must not count
+    # narrow layers: the TMA-staged kernel's epilogue (conv_halo.cu, MODE 2), partial tiles, several tiles per CTA,
+    # 8-channel tensors, yprev as a channel slice
+    out += _dgrad_bnbwd_case(2, 16, 16, 40, 70, BF, 170)
+    out += _dgrad_bnbwd_case(8, 16, 16, 256, 256, BF, 171)
+    out += _dgrad_bnbwd_case(2, 32, 32, 33, 20, BF, 172)
+    out += _dgrad_bnbwd_case(1, 16, 32, 9, 50, BF, 173)
+    out += _dgrad_bnbwd_case(2, 32, 64, 24, 24, BF, 174)
+    out += _dgrad_bnbwd_case(2, 8, 8, 37, 41, BF, 175)
+    out += _dgrad_bnbwd_case(2, 32, 16, 16, 48, BF, 176, slice_y=True)
     out += _dgrad_bnbwd_case(3, 64, 128, 20, 8, BF, 74)            # stacked sub-tile geometry (W <= 8)
     out += _dgrad_bnbwd_case(2, 64, 64, 40, 36, BF, 75, slice_y=True)
     out += _dgrad_bnbwd_case(1, 256, 128, 33, 17, BF, 76)

@@ -36,6 +36,12 @@ struct HaloParams {
   int tap_pix[9];                // (dy + 1) * 18 + dx + 1
   int cin_real, n_real;          // 8-channel tensors ride the 16-channel instantiation: TMA zero-fills channels 8..15 of
                                  // a pixel row (the box is wider than the tensor), weight rows / columns 8..15 are zero
+  // MODE 2 (bf16 dgrad whose output g is the gradient of z = relu(bn(yprev))): the raw conv output of the layer below and
+  // its BatchNorm coefficients [4][N] = mean, invstd, scale, shift; stats_ws then receives sum(g * mask) and
+  // sum(g * mask * xhat) per channel -- the reduction pass of unetb200_bn_relu_bwd_reduce
+  const __nv_bfloat16* yprev;
+  long long ld_y;
+  const float* bnc;
 };
 
 constexpr int kHaloThreads = 320;
@@ -163,11 +169,35 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT, ES>::CTAS) halo
     constexpr int cpr = RS / 16;                        // 16-byte chunks per stored row
     uint32_t acc = 0, pacc = 0;
     float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+    float bmu[2] = {0.f, 0.f}, bis[2] = {0.f, 0.f}, bsc[2] = {0.f, 0.f}, bsh[2] = {0.f, 0.f};
+    if constexpr (MODE == 2) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int ch = 2 * pair + k;
+        if (ch < p.n_real) {
+          bmu[k] = __ldg(p.bnc + ch); bis[k] = __ldg(p.bnc + p.n_real + ch);
+          bsc[k] = __ldg(p.bnc + 2 * p.n_real + ch); bsh[k] = __ldg(p.bnc + 3 * p.n_real + ch);
+        }
+      }
+    }
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
       const int ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
       const int y0 = ty * 16 + quad * 4, x0 = tx * 16 + strip * 8;       // row m = 8 * y + x of the strip
       const bool live = (y0 + (lane >> 3)) < p.H && (x0 + (lane & 7)) < p.W;
+      // MODE 2: this lane's yprev words (rows grp, grp + G, ...; channel pair `pair`) are requested before the wait for
+      // the accumulators, so their latency hides behind the MMAs of the tile
+      uint32_t yv[MODE == 2 ? 32 / G : 1];
+      if constexpr (MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < 32 / G; ++i) {
+          const int rr = grp + i * G;
+          const int yy = y0 + (rr >> 3), xx = x0 + (rr & 7);
+          yv[i] = 0u;
+          if (yy < p.H && xx < p.W && 2 * pair < p.n_real)
+            yv[i] = __ldg(reinterpret_cast<const uint32_t*>(p.yprev + (((long long)b * p.H + yy) * p.W + xx) * p.ld_y) + pair);
+        }
+      }
       mbar_wait(&t_full[acc], pacc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (acc * 2 + strip) * NT;
@@ -231,6 +261,21 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT, ES>::CTAS) halo
                                       ((((long long)b * p.H + yy) * p.W + xx) * p.ld_out + ch * EPC) * ES) = q;
         }
       }
+      if constexpr (MODE == 2) {
+#pragma unroll
+        for (int i = 0; i < 32 / G; ++i) {
+          const int rr = grp + i * G;
+          uint32_t u;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u)
+                       : "r"(stg + rr * RS + ((((pair >> 2) ^ swz(rr)) << 4) | ((pair & 3) << 2))) : "memory");
+          // rows outside the image were staged as zeros and fetched no yprev: they add nothing
+          const float ya = __uint_as_float(yv[i] << 16), yb = __uint_as_float(yv[i] & 0xffff0000u);
+          const float ga = (fmaf(ya, bsc[0], bsh[0]) > 0.f) ? __uint_as_float(u << 16) : 0.f;
+          const float gb = (fmaf(yb, bsc[1], bsh[1]) > 0.f) ? __uint_as_float(u & 0xffff0000u) : 0.f;
+          s0 += ga; q0 += ga * ((ya - bmu[0]) * bis[0]);
+          s1 += gb; q1 += gb * ((yb - bmu[1]) * bis[1]);
+        }
+      }
       if (MODE == 0 && p.stats_ws) {
 #pragma unroll
         for (int rr = grp; rr < 32; rr += G) {
@@ -247,7 +292,7 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT, ES>::CTAS) halo
         }
       }
     }
-    if (MODE == 0 && p.stats_ws) {
+    if ((MODE == 0 || MODE == 2) && p.stats_ws) {
 #pragma unroll
       for (int o = PP; o < 32; o <<= 1) {               // combine the row groups (fixed order)
         s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
@@ -369,11 +414,24 @@ static int halo_dispatch_n32(const HaloParams& P, int n, int grid, bool affine, 
   return n == 16 ? halo_launch<CIN, 16, 0, 4>(P, grid, s) : halo_launch<CIN, 32, 0, 4>(P, grid, s);
 }
 
+// dgrad + BatchNorm-backward reduction (MODE 2): bf16, at most 32 output channels (the prefetched yprev words live in
+// registers: 32 / G per lane)
+int halo_bnbwd_supported(const unetb200_gconv_t* d, const void* g, const void* wp, const void* gx) {
+  static const bool off = getenv("UNETB200_NO_HALO_BNBWD") != nullptr;
+  return !off && d->dtype == UNETB200_BF16 && d->N <= 32 && halo_fprop_supported(d, g, wp, gx);
+}
+
 int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
-               const float* affine, cudaStream_t s) {
+               const float* affine, cudaStream_t s, const void* yprev, long long ld_yprev, const float* bnc) {
   if (!halo_fprop_supported(d, x, wp, y)) { set_error("halo_fprop: unsupported shape"); return UNETB200_E_INVALID; }
+  if (yprev && (!halo_bnbwd_supported(d, x, wp, y) || affine || !stats || !stats_ws || !bnc || (ld_yprev & 1) ||
+                (reinterpret_cast<uintptr_t>(yprev) & 3))) {
+    set_error("halo_fprop: the BatchNorm-backward epilogue needs bf16, N <= 32, sums, a workspace and coefficients");
+    return UNETB200_E_INVALID;
+  }
   HaloParams P;
   memset(&P, 0, sizeof(P));
+  P.yprev = (const __nv_bfloat16*)yprev; P.ld_y = ld_yprev; P.bnc = bnc;
   const bool f32 = d->dtype == UNETB200_F32;
   if (int rc = encode_act_box_sw(&P.x_map, x, d->Cin, d->Wm, d->Hm, d->B, d->ld_in, (long long)d->Wm * d->ld_in,
                                  (long long)d->Hm * d->Wm * d->ld_in, kHaloBW, kHaloBW, f32 ? 4 : 2))
@@ -387,7 +445,12 @@ int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y
   for (int t = 0; t < 9; ++t) P.tap_pix[t] = (d->tap_dy[t] + 1) * kHaloBW + d->tap_dx[t] + 1;
   const int grid = halo_grid(d, &P.tiles_w, &P.tiles_h, &P.ntiles);
   int rc;
-  if (f32) {
+  if (yprev) {
+    const int cp = halo_ch_pad(d->Cin), np = halo_ch_pad(d->N);
+    if (cp == 16) rc = np == 16 ? halo_launch<16, 16, 2>(P, grid, s) : halo_launch<16, 32, 2>(P, grid, s);
+    else if (cp == 32) rc = np == 16 ? halo_launch<32, 16, 2>(P, grid, s) : halo_launch<32, 32, 2>(P, grid, s);
+    else rc = np == 16 ? halo_launch<64, 16, 2>(P, grid, s) : halo_launch<64, 32, 2>(P, grid, s);
+  } else if (f32) {
     rc = halo_ch_pad(d->Cin) == 16 ? halo_dispatch_n32<16>(P, halo_ch_pad(d->N), grid, affine != nullptr, s)
                                    : halo_dispatch_n32<32>(P, halo_ch_pad(d->N), grid, affine != nullptr, s);
   } else

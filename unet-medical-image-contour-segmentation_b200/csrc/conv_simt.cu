@@ -832,6 +832,7 @@ int unetb200_gconv_dgrad_bnbwd_supported(const unetb200_gconv_t* d, const void* 
   if (gconv_validate(d, &gd)) return 0;
   static const bool off = getenv("UNETB200_NO_BNBWD_FUSE") != nullptr;
   if (off || d->algo == UNETB200_ALGO_SIMT) return 0;
+  if (halo_bnbwd_supported(d, g, wp, gx)) return 1;                   // narrow layers: the TMA-staged kernel's epilogue
   return tc_fprop_supported(d, g, wp, gx) && tc3_fprop_supported(d, g, wp, nullptr, gx) && tc3_bnbwd_supported(d);
 }
 
@@ -845,6 +846,8 @@ int unetb200_gconv_dgrad_bnbwd(const unetb200_gconv_t* d, const void* g, const v
   UB_CHECK_ARG(unetb200_gconv_dgrad_bnbwd_supported(d, g, wp, gx),
                "gconv_dgrad_bnbwd: shape not covered by the fused kernel (query _supported first and run gconv_fprop + "
                "bn_relu_bwd_reduce instead)");
+  if (halo_bnbwd_supported(d, g, wp, gx))
+    return halo_fprop(d, g, wp, gx, sums, ws, nullptr, (cudaStream_t)stream, yprev, (long long)ld_yprev, coefs);
   return tc3_fprop(d, gd, g, wp, gx, sums, ws, (cudaStream_t)stream, nullptr, yprev, (long long)ld_yprev, coefs);
 }
 

@@ -100,7 +100,9 @@ int narrow_tc_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, vo
 int halo_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y);
 long long halo_stats_rows(const unetb200_gconv_t* d);
 int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
-               const float* affine, cudaStream_t s);
+               const float* affine, cudaStream_t s, const void* yprev = nullptr, long long ld_yprev = 0,
+               const float* bnc = nullptr);
+int halo_bnbwd_supported(const unetb200_gconv_t* d, const void* g, const void* wp, const void* gx);
 int halo_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int halo_wgrad_splits(const unetb200_gconv_t* d);
 int halo_wgrad(const unetb200_gconv_t* d, const void* x, const void* gy, float* partials, int splits, cudaStream_t s);
