@@ -599,7 +599,8 @@ def check_conv_narrow():
     # the same layers without autocast: exact-fp32 weight gradient on the CUDA cores, several tiles per block, ragged
     for i, (B, Ci, Co, H, W) in enumerate([(2, 16, 16, 40, 70), (8, 16, 16, 256, 256), (2, 16, 32, 33, 20), (1, 32, 16, 9, 50),
                                            (3, 32, 32, 64, 48), (1, 64, 32, 24, 17), (2, 32, 64, 16, 16), (1, 16, 64, 20, 36),
-                                           (1, 64, 16, 10, 9)]):
+                                           (1, 64, 16, 10, 9), (2, 8, 8, 37, 41), (1, 8, 16, 24, 24), (2, 16, 8, 16, 48),
+                                           (1, 8, 32, 20, 20), (1, 64, 8, 9, 9), (4, 8, 8, 128, 128)]):
         out += _wgrad_f32_narrow_case(B, Ci, Co, H, W, 140 + i)
     # ... and with TF32 allowed: fprop / dgrad on the tensor cores from fp32 tensors (64 / 128-byte swizzle rows)
     for i, (B, Ci, Co, H, W) in enumerate([(2, 16, 16, 40, 70), (8, 16, 16, 256, 256), (2, 16, 32, 33, 20), (1, 32, 16, 9, 50),

@@ -17,10 +17,12 @@ constexpr int kWnH = 8;
 
 template <int CIN, int N>
 struct WnCfg {
-  static constexpr int NG = N / 8, THREADS = CIN * NG;
+  // TPB threads = one (input channel, 8-output-channel group) each; below a warp (8-channel tensors of UNet_T) LANES
+  // copies of them share the block, walking interleaved pixel columns, and are combined by shuffles at the end
+  static constexpr int NG = N / 8, TPB = CIN * NG, LANES = TPB >= 32 ? 1 : 32 / TPB, THREADS = TPB * LANES;
   // small blocks (<= 2 warps) take 8-column tiles: 10 KB of shared memory each, so 16 blocks (the register limit at 128
   // registers) are resident -- at 9 blocks of one warp the FMA pipe was 41 % active (ncu), two warps per scheduler
-  static constexpr int TW = (CIN >= 64 || (CIN == 32 && N == 64) || CIN * (N / 8) <= 64) ? 8 : 16;
+  static constexpr int TW = (CIN >= 64 || (CIN == 32 && N == 64) || TPB <= 64) ? 8 : 16;
   static constexpr int XS = (kWnH + 2) * (TW + 2) * CIN, GS = kWnH * TW * N;     // floats
   static constexpr int smem = (XS + GS) * 4;
 };
@@ -41,7 +43,9 @@ __global__ void __launch_bounds__(WnCfg<CIN, N>::THREADS) wgrad_narrow_f32_kerne
   extern __shared__ __align__(16) float wn_smem[];
   float* xs = wn_smem;                       // [kWnH + 2][TW + 2][CIN]
   float* gs = wn_smem + Cfg::XS;             // [kWnH][TW][N]
-  const int cin = threadIdx.x % CIN, ng = threadIdx.x / CIN;
+  constexpr int TPB = Cfg::TPB, LANES = Cfg::LANES;
+  const int cl = threadIdx.x / TPB, tq = threadIdx.x % TPB;        // column lane; (cin, ng) index
+  const int cin = tq % CIN, ng = tq / CIN;
   float acc[3][3][8];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(WnCfg<CIN, N>::THREADS) wgrad_narrow_f32_kerne
     }
     __syncthreads();
 #pragma unroll 1
-    for (int col = 0; col < TW; ++col) {
+    for (int col = cl; col < TW; col += LANES) {
       float win[3][3];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -96,6 +100,17 @@ __global__ void __launch_bounds__(WnCfg<CIN, N>::THREADS) wgrad_narrow_f32_kerne
         for (int c = 0; c < 3; ++c) { win[0][c] = win[1][c]; win[1][c] = win[2][c]; }
       }
     }
+  }
+  if constexpr (LANES > 1) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int o = TPB; o < 32; o <<= 1) acc[a][c][k] += __shfl_xor_sync(0xffffffffu, acc[a][c][k], o);
+    if (cl != 0) return;
   }
   float* out = p.partials + (long long)blockIdx.x * 9 * CIN * N;
 #pragma unroll
@@ -236,7 +251,8 @@ __global__ void __launch_bounds__(FnfCfg<CIN, N>::THREADS) fprop_narrow_f32_kern
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static bool wn_ch(int c) { return c == 16 || c == 32 || c == 64; }
+static bool wn_ch(int c) { return c == 8 || c == 16 || c == 32 || c == 64; }
+static bool fnf_ch(int c) { return c == 16 || c == 32 || c == 64; }
 
 static bool wn_shape_ok(const unetb200_gconv_t* d) {
   static const bool off = getenv("UNETB200_NO_SIMT_NARROW") != nullptr;
@@ -272,11 +288,13 @@ static int wn_bps() {                       // resident blocks per SM: shared me
 
 #define UB_WN_CASES(X)                                                                                            \
   X(16, 16) X(16, 32) X(16, 64) X(32, 16) X(32, 32) X(32, 64) X(64, 16) X(64, 32)
+#define UB_WN8_CASES(X) X(8, 8) X(8, 16) X(8, 32) X(8, 64) X(16, 8) X(32, 8) X(64, 8)
 
 static int wn_grid(const unetb200_gconv_t* d, WnParams* P) {
   int tw = 16, bps = 1;
 #define UB_WN_Q(C, NN) if (d->Cin == C && d->N == NN) { tw = wn_tw<C, NN>(); bps = wn_bps<C, NN>(); }
   UB_WN_CASES(UB_WN_Q)
+  UB_WN8_CASES(UB_WN_Q)
 #undef UB_WN_Q
   P->tiles_w = (d->Wm + tw - 1) / tw;
   P->tiles_h = (d->Hm + kWnH - 1) / kWnH;
@@ -312,6 +330,7 @@ int wgrad_narrow_f32(const unetb200_gconv_t* d, const void* x, const void* gy, f
   if (grid != splits) { set_error("wgrad_narrow_f32: the planned split count is %d, got %d", grid, splits); return UNETB200_E_INVALID; }
 #define UB_WN_L(C, NN) if (d->Cin == C && d->N == NN) return wn_launch<C, NN>(P, grid, s);
   UB_WN_CASES(UB_WN_L)
+  UB_WN8_CASES(UB_WN_L)
 #undef UB_WN_L
   set_error("wgrad_narrow_f32: unsupported channel counts");
   return UNETB200_E_INVALID;
@@ -319,7 +338,7 @@ int wgrad_narrow_f32(const unetb200_gconv_t* d, const void* x, const void* gy, f
 
 // ---- fprop / dgrad host side
 int fprop_narrow_f32_supported(const unetb200_gconv_t* d, const void* x, const void* wp, const void* y) {
-  if (!wn_shape_ok(d)) return 0;
+  if (!wn_shape_ok(d) || !fnf_ch(d->Cin) || !fnf_ch(d->N)) return 0;
   if ((x && !aligned16(x)) || (y && !aligned16(y)) || (wp && (reinterpret_cast<uintptr_t>(wp) & 3))) return 0;
   return 1;
 }
@@ -344,7 +363,7 @@ static int fnf_grid(const unetb200_gconv_t* d, FnfParams* P) {
 }
 
 long long fprop_narrow_f32_rows(const unetb200_gconv_t* d) {
-  if (!wn_shape_ok(d)) return 0;
+  if (!wn_shape_ok(d) || !fnf_ch(d->Cin) || !fnf_ch(d->N)) return 0;
   FnfParams P;
   return fnf_grid(d, &P);
 }
