@@ -988,7 +988,10 @@ def check_conv_bnfold():
         for (B, Ci, Co, H, W, dt_, sliced, pool) in ((2, 64, 64, 40, 36, BF, False, False), (1, 128, 128, 32, 48, BF, True, True),
                                                     (2, 64, 128, 16, 8, BF, False, True), (1, 256, 64, 24, 24, BF, True, False),
                                                     (1, 64, 128, 20, 28, FP, False, True), (3, 128, 256, 8, 8, BF, False, False),
-                                                    (2, 64, 64, 18, 22, BF, False, True), (1, 64, 128, 17, 21, BF, False, True)):
+                                                    (2, 64, 64, 18, 22, BF, False, True), (1, 64, 128, 17, 21, BF, False, True),
+                                                    # narrow layers: the pool rides in the TMA-staged kernel's epilogue too
+                                                    (2, 16, 16, 40, 36, BF, False, True), (1, 32, 32, 18, 22, BF, False, True),
+                                                    (1, 16, 8, 17, 21, BF, False, True), (2, 32, 64, 16, 24, BF, True, True)):
             x = rq(torch.randn(B, Ci, H, W, generator=g), dt_ if dt_ == BF else FP)
             w = torch.randn(Co, Ci, 3, 3, generator=g) * (2.0 / (9 * Ci)) ** 0.5
             bn = torch.nn.BatchNorm2d(Co)

@@ -42,6 +42,10 @@ struct HaloParams {
   const __nv_bfloat16* yprev;
   long long ld_y;
   const float* bnc;
+  // MODE 1, bf16, optional: MaxPool2d(2) of the activation as a second output, [B][H/2][W/2][ld_pool] (a warp's 4 x 8
+  // pixel patch holds whole 2 x 2 windows; conv_tc3.cu does the same for the wide layers)
+  __nv_bfloat16* pooled;
+  long long ld_pool;
 };
 
 constexpr int kHaloThreads = 320;
@@ -261,6 +265,30 @@ __global__ void __launch_bounds__(kHaloThreads, HaloCfg<CIN, NT, ES>::CTAS) halo
                                       ((((long long)b * p.H + yy) * p.W + xx) * p.ld_out + ch * EPC) * ES) = q;
         }
       }
+      if constexpr (MODE == 1 && !TF32) {
+        if (p.pooled) {
+          // 8 pooled pixels x NT / 2 channel-pair words per patch; activations are >= 0, so the unsigned 16-bit SIMD
+          // maximum of the bf16 bit patterns is the bf16 maximum
+          const int Hp = p.H >> 1, Wp = p.W >> 1;
+#pragma unroll
+          for (int idx = lane; idx < 8 * (NT / 2); idx += 32) {
+            const int pp = idx / (NT / 2), w = idx % (NT / 2);
+            const int r0 = 16 * (pp >> 2) + 2 * (pp & 3);
+            uint32_t m = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = r0 + (k & 1) + 8 * (k >> 1);
+              uint32_t u;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(u)
+                           : "r"(stg + rr * RS + ((((w >> 2) ^ swz(rr)) << 4) | ((w & 3) << 2))) : "memory");
+              m = __vmaxu2(m, u);
+            }
+            const int gy = (y0 >> 1) + (pp >> 2), gx = (x0 >> 1) + (pp & 3);
+            if (gy < Hp && gx < Wp && 2 * w < p.n_real)
+              reinterpret_cast<uint32_t*>(p.pooled + (((long long)b * Hp + gy) * Wp + gx) * p.ld_pool)[w] = m;
+          }
+        }
+      }
       if constexpr (MODE == 2) {
 #pragma unroll
         for (int i = 0; i < 32 / G; ++i) {
@@ -422,8 +450,13 @@ int halo_bnbwd_supported(const unetb200_gconv_t* d, const void* g, const void* w
 }
 
 int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
-               const float* affine, cudaStream_t s, const void* yprev, long long ld_yprev, const float* bnc) {
+               const float* affine, cudaStream_t s, const void* yprev, long long ld_yprev, const float* bnc, void* pooled,
+               long long ld_pool) {
   if (!halo_fprop_supported(d, x, wp, y)) { set_error("halo_fprop: unsupported shape"); return UNETB200_E_INVALID; }
+  if (pooled && (!affine || d->dtype != UNETB200_BF16 || (ld_pool & 1) || (reinterpret_cast<uintptr_t>(pooled) & 3))) {
+    set_error("halo_fprop: the pooled second output needs the bf16 affine epilogue and 4-byte aligned rows");
+    return UNETB200_E_INVALID;
+  }
   if (yprev && (!halo_bnbwd_supported(d, x, wp, y) || affine || !stats || !stats_ws || !bnc || (ld_yprev & 1) ||
                 (reinterpret_cast<uintptr_t>(yprev) & 3))) {
     set_error("halo_fprop: the BatchNorm-backward epilogue needs bf16, N <= 32, sums, a workspace and coefficients");
@@ -432,6 +465,7 @@ int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y
   HaloParams P;
   memset(&P, 0, sizeof(P));
   P.yprev = (const __nv_bfloat16*)yprev; P.ld_y = ld_yprev; P.bnc = bnc;
+  P.pooled = (__nv_bfloat16*)pooled; P.ld_pool = ld_pool;
   const bool f32 = d->dtype == UNETB200_F32;
   if (int rc = encode_act_box_sw(&P.x_map, x, d->Cin, d->Wm, d->Hm, d->B, d->ld_in, (long long)d->Wm * d->ld_in,
                                  (long long)d->Hm * d->Wm * d->ld_in, kHaloBW, kHaloBW, f32 ? 4 : 2))

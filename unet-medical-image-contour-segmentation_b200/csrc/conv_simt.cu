@@ -807,10 +807,9 @@ int unetb200_gconv_fprop_affine_relu_pool_supported(const unetb200_gconv_t* d, c
   static const bool off = getenv("UNETB200_NO_POOL_FOLD") != nullptr;
   if (off || d->dtype != UNETB200_BF16 || !pooled || (ld_pooled & 1) || (reinterpret_cast<uintptr_t>(pooled) & 3)) return 0;
   if (!unetb200_gconv_fprop_affine_relu_supported(d, x, wp, z)) return 0;
-  if ((first_tc_supported(d, z) && aligned16(wp)) || first_narrow_supported(d, z) || halo_fprop_supported(d, x, wp, z) ||
-      narrow_tc_supported(d, x, wp, z))
-    return 0;                                      // those shapes run on other kernels
-  return d->Hm >= 2 && d->Wm >= 2;
+  if ((first_tc_supported(d, z) && aligned16(wp)) || first_narrow_supported(d, z)) return 0;   // first-layer kernels: no
+  if (!halo_fprop_supported(d, x, wp, z) && narrow_tc_supported(d, x, wp, z)) return 0;        // thread-built im2col: no
+  return d->Hm >= 2 && d->Wm >= 2;                 // the TMA-staged narrow kernel and the CTA-pair kernel: yes
 }
 
 int unetb200_gconv_fprop_affine_relu_pool(const unetb200_gconv_t* d, const void* x, const void* wp, const float* scale_shift,
@@ -822,6 +821,9 @@ int unetb200_gconv_fprop_affine_relu_pool(const unetb200_gconv_t* d, const void*
   UB_CHECK_ARG(unetb200_gconv_fprop_affine_relu_pool_supported(d, x, wp, z, pooled, ld_pooled),
                "gconv_fprop_affine_relu_pool: shape not covered (query _supported first and run gconv_fprop_affine_relu + "
                "maxpool2_fwd instead)");
+  if (halo_fprop_supported(d, x, wp, z))
+    return halo_fprop(d, x, wp, z, nullptr, nullptr, scale_shift, (cudaStream_t)stream, nullptr, 0, nullptr, pooled,
+                      (long long)ld_pooled);
   return tc3_fprop(d, g, x, wp, z, nullptr, nullptr, (cudaStream_t)stream, scale_shift, nullptr, 0, nullptr, nullptr, pooled,
                    (long long)ld_pooled);
 }

@@ -101,7 +101,7 @@ int halo_fprop_supported(const unetb200_gconv_t* d, const void* x, const void* w
 long long halo_stats_rows(const unetb200_gconv_t* d);
 int halo_fprop(const unetb200_gconv_t* d, const void* x, const void* wp, void* y, double* stats, float* stats_ws,
                const float* affine, cudaStream_t s, const void* yprev = nullptr, long long ld_yprev = 0,
-               const float* bnc = nullptr);
+               const float* bnc = nullptr, void* pooled = nullptr, long long ld_pool = 0);
 int halo_bnbwd_supported(const unetb200_gconv_t* d, const void* g, const void* wp, const void* gx);
 int halo_wgrad_supported(const unetb200_gconv_t* d, const void* x, const void* gy);
 int halo_wgrad_splits(const unetb200_gconv_t* d);
